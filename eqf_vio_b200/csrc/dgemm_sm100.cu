@@ -1,0 +1,363 @@
+// dgemm_sm100.cu — see dgemm_sm100.cuh.  Hand-written sm_100a kernel:
+//   * operands staged by TMA (cp.async.bulk.tensor.{2d,3d}, SASS UTMALDG) with SWIZZLE_128B into a
+//     STAGES-deep shared-memory ring; full/empty mbarriers; one producer warp, N consumer warps;
+//   * consumers read conflict-free 8-byte fragments and issue DMMA.8x8x4, accumulators in registers;
+//   * fused epilogue: alpha/beta, optional diagonal add (the T*P term of the Riccati step,
+//     reference eqf_vio/src/VIOFilter.cpp:162-167,188).
+//
+// Shared-memory tile layouts (BK = 16 doubles = 128 B, one swizzle row):
+//   "MN-major" operand (A always; B when transB): TMA 3-D box {16 (m_in), 16 (k), BM/16 (m_out)}
+//      byte(m,k) = (m>>4)*2048 + k*128 + ((((m&15)>>1) ^ (k&7)) << 4) + (m&1)*8
+//   "K-major" operand (B when !transB): TMA 2-D box {16 (k), BN (n)}
+//      byte(k,n) = n*128 + (((k>>1) ^ (n&7)) << 4) + (k&1)*8
+// Within a 16-deep k tile the four k4 MMAs (j = 0..3) use k(t,j) with t = lane&3:
+//      k = ((t1^j1)<<3) | (t1<<2) | (t0<<1) | (t0^j0)
+// which makes every fragment LDS.64 hit 16 distinct 8-byte slots per half-warp for BOTH layouts.
+#include "dgemm_sm100.cuh"
+
+#include <cudaTypedefs.h>  // PFN_cuTensorMapEncodeTiled
+#include <stdio.h>
+
+namespace eqvio {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+struct KernelParams {
+    int M, N, K;
+    double* D;
+    int ldd;
+    const double* Cin;
+    int ldcin;
+    double alpha, beta;
+    int add_diag;  // D[m][m] += T * Pd(class of m)
+    double T;
+    double Pd[5];
+};
+
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_>
+struct TileCfg {
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+    static constexpr int BK = 16;
+    static constexpr int NWM = BM / WM, NWN = BN / WN;
+    static constexpr int CONSUMER_WARPS = NWM * NWN;
+    static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+    static constexpr int A_BYTES = BM * BK * 8;
+    static constexpr int B_BYTES = BN * BK * 8;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024;  // + barriers + align slack
+    static_assert(WM % 16 == 0 && WN % 8 == 0, "warp tile granularity");
+    static_assert(BM % 16 == 0 && BN % 16 == 0, "CTA tile granularity");
+};
+
+__device__ __forceinline__ double process_diag(const KernelParams& p, int m) {
+    // index map of Sigma (eqf_vio/src/VIOFilter.cpp:163-167)
+    return m < 3 ? p.Pd[0] : m < 6 ? p.Pd[1] : m < 8 ? p.Pd[2] : m < 11 ? p.Pd[3] : p.Pd[4];
+}
+
+template <class Cfg, bool TRANSB>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
+dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KernelParams p) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
+    constexpr int MB = WM / 8, NB = WN / 8;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
+    uint8_t* smem = smem_raw + (base - raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    const int KT = (p.K + 15) >> 4;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], Cfg::CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == Cfg::CONSUMER_WARPS) {
+        // ===== producer warp: one lane drives TMA =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+                uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+                uint8_t* sb = sa + Cfg::A_BYTES;
+                tma_load_3d(sa, &tmA, 0, kt * 16, tile_m * (BM / 16), &full[s]);
+                if (TRANSB)
+                    tma_load_3d(sb, &tmB, 0, kt * 16, tile_n * (BN / 16), &full[s]);
+                else
+                    tma_load_2d(sb, &tmB, kt * 16, tile_n * BN, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const int wm = warp % Cfg::NWM, wn = warp / Cfg::NWM;
+    const int g = lane >> 2, t = lane & 3, t1 = t >> 1, t0 = t & 1;
+
+    double acc[MB][NB][2];
+#pragma unroll
+    for (int i = 0; i < MB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // per-thread fragment offsets at j = 0 (see layout comment at the top of the file)
+    const int k0 = (t1 << 3) | (t1 << 2) | (t0 << 1) | t0;
+    // MN-major: m = 16*mo + mi, mi = g (+8 for odd 8-row blocks)
+    const uint32_t mn_off0 = (uint32_t)(k0 * 128 + (((g >> 1) ^ (k0 & 7)) << 4) + (g & 1) * 8);
+    // K-major: row n (n&7 == g), chunk (k>>1)^g
+    const uint32_t km_off0 = (uint32_t)(g * 128 + ((((k0 >> 1) ^ g) & 7) << 4) + (k0 & 1) * 8);
+
+    const uint32_t a_warp = (uint32_t)((wm * WM / 16) * 2048);
+    const uint32_t b_warp = TRANSB ? (uint32_t)((wn * WN / 16) * 2048) : (uint32_t)(wn * WN * 128);
+    // note: for TRANSB with WN % 16 == 8 the warp's first 8-column block may start mid-atom
+    const int b_half = TRANSB ? ((wn * WN) & 8) >> 3 : 0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        const uint32_t sa = base + s * Cfg::STAGE_BYTES + a_warp;
+        const uint32_t sb = base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + b_warp;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int j1 = j >> 1, j0 = j & 1;
+            // XOR constants move k by (j1<<3 | j0): k*128 bits [7,10], chunk bit j0 for MN-major;
+            // chunk bit (j1<<2) and half bit j0 for K-major
+            const uint32_t mn_x = (uint32_t)((((j1 << 3) | j0) << 7) | (j0 << 4));
+            const uint32_t km_x = (uint32_t)((j1 << 6) | (j0 << 3));
+            double af[MB], bf[NB];
+#pragma unroll
+            for (int i = 0; i < MB; ++i) {
+                const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((i & 1) << 6)) + (uint32_t)((i >> 1) * 2048);
+                af[i] = lds_f64(sa + off);
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                if (TRANSB) {
+                    const int blk = i + b_half;
+                    const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((blk & 1) << 6)) + (uint32_t)((blk >> 1) * 2048);
+                    bf[i] = lds_f64(sb + off);
+                } else {
+                    const uint32_t off = (km_off0 ^ km_x) + (uint32_t)(i * 1024);
+                    bf[i] = lds_f64(sb + off);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < MB; ++i)
+#pragma unroll
+                for (int jn = 0; jn < NB; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i], bf[jn]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // ===== epilogue: registers -> global =====
+    const int m_base = tile_m * BM + wm * WM + g;
+    const int n_base = tile_n * BN + wn * WN + 2 * t;
+#pragma unroll
+    for (int jn = 0; jn < NB; ++jn) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int n = n_base + jn * 8 + c;
+            if (n >= p.N) continue;
+#pragma unroll
+            for (int i = 0; i < MB; ++i) {
+                const int m = m_base + i * 8;
+                if (m >= p.M) continue;
+                double v = p.alpha * acc[i][jn][c];
+                if (p.beta != 0.0) v += p.beta * p.Cin[(size_t)m + (size_t)p.ldcin * n];
+                if (p.add_diag && m == n) v += p.T * process_diag(p, m);
+                p.D[(size_t)m + (size_t)p.ldd * n] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+using Cfg128x128 = TileCfg<128, 128, 64, 32, 4, 1>;
+using Cfg128x64 = TileCfg<128, 64, 32, 32, 4, 2>;
+using Cfg64x64 = TileCfg<64, 64, 32, 32, 4, 3>;
+using Cfg32x32 = TileCfg<32, 32, 16, 16, 4, 4>;
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// 3-D map of an MN-major operand X (R x K, element (r,k) at X[r + k*ld]): dims {16, K, ceil(R/16)}.
+static CUresult encode_mn_major(CUtensorMap* map, const double* X, int R, int K, int ld, int box_r) {
+    cuuint64_t dims[3] = {16, (cuuint64_t)K, (cuuint64_t)((R + 15) / 16)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, 128};
+    cuuint32_t box[3] = {16, 16, (cuuint32_t)(box_r / 16)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return get_encode()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(X), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+// 2-D map of a K-major operand B (K x N, element (k,n) at B[k + n*ld]): dims {K, N}.
+static CUresult encode_k_major(CUtensorMap* map, const double* X, int K, int N, int ld, int box_n) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {16, (cuuint32_t)box_n};
+    cuuint32_t estr[2] = {1, 1};
+    return get_encode()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(X), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+template <class Cfg>
+static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
+    if (!get_encode()) return cudaErrorNotSupported;
+    CUtensorMap tmA, tmB;
+    if (encode_mn_major(&tmA, g.A, g.M, g.K, g.lda, Cfg::BM) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    CUresult rb = g.transB ? encode_mn_major(&tmB, g.B, g.N, g.K, g.ldb, Cfg::BN)
+                           : encode_k_major(&tmB, g.B, g.K, g.N, g.ldb, Cfg::BN);
+    if (rb != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    KernelParams p;
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.D = g.D; p.ldd = g.ldd;
+    p.Cin = g.epi.Cin; p.ldcin = g.epi.ldcin;
+    p.alpha = g.epi.alpha;
+    p.beta = g.epi.Cin ? g.epi.beta : 0.0;
+    p.add_diag = g.epilogue == EPI_RICCATI;
+    p.T = g.epi.T;
+    for (int i = 0; i < 5; ++i) p.Pd[i] = g.epi.Pd[i];
+    dim3 grid((g.M + Cfg::BM - 1) / Cfg::BM, (g.N + Cfg::BN - 1) / Cfg::BN);
+    cudaError_t e;
+    if (g.transB) {
+        auto k = dgemm_dmma_tma_kernel<Cfg, true>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        k<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    } else {
+        auto k = dgemm_dmma_tma_kernel<Cfg, false>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        k<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    }
+    return cudaGetLastError();
+}
+
+int dgemm_num_configs() { return 4; }
+const char* dgemm_config_name(int cfg) {
+    switch (cfg) {
+        case 0: return "128x128x16 (8 DMMA warps 64x32, 4 stages)";
+        case 1: return "128x64x16 (8 DMMA warps 32x32, 4 stages)";
+        case 2: return "64x64x16 (4 DMMA warps 32x32, 4 stages)";
+        case 3: return "32x32x16 (4 DMMA warps 16x16, 4 stages)";
+    }
+    return "?";
+}
+
+// Pick the tile shape that minimises waves * per-wave time on 148 SMs.  An SM retires 64 fp64
+// FMA/clk (measured, profiles/r01_dmma_microbench.md) however many CTAs share it, so the model is
+// time ~ ceil(tiles / (148*occ)) * occ * BM*BN / eff.
+int dgemm_pick_config(int M, int N, int K) {
+    (void)K;
+    static const int bm[4] = {128, 128, 64, 32}, bn[4] = {128, 64, 64, 32}, occ[4] = {1, 2, 3, 4};
+    static const double eff[4] = {1.0, 0.97, 0.92, 0.70};
+    int best = 0;
+    double best_t = 1e300;
+    for (int c = 0; c < 4; ++c) {
+        long tiles = (long)((M + bm[c] - 1) / bm[c]) * ((N + bn[c] - 1) / bn[c]);
+        long slots = 148L * occ[c];
+        long waves = (tiles + slots - 1) / slots;
+        long resident = tiles < slots ? (tiles + 147) / 148 : occ[c];  // CTAs sharing an SM in a wave
+        double t = (double)waves * (double)resident * bm[c] * bn[c] / eff[c];
+        if (t < best_t) { best_t = t; best = c; }
+    }
+    return best;
+}
+
+cudaError_t dgemm_launch(const GemmProblem& g, cudaStream_t stream, int force_config) {
+    if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+    int cfg = force_config >= 0 ? force_config : dgemm_pick_config(g.M, g.N, g.K);
+    switch (cfg) {
+        case 0: return launch_cfg<Cfg128x128>(g, stream);
+        case 1: return launch_cfg<Cfg128x64>(g, stream);
+        case 2: return launch_cfg<Cfg64x64>(g, stream);
+        default: return launch_cfg<Cfg32x32>(g, stream);
+    }
+}
+
+}  // namespace eqvio

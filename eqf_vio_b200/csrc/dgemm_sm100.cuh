@@ -1,0 +1,57 @@
+// dgemm_sm100.cuh — fp64 GEMM for sm_100a: TMA-staged (cp.async.bulk.tensor, SWIZZLE_128B) operand
+// tiles in shared memory, an mbarrier full/empty ring fed by one producer warp, and DMMA.8x8x4
+// (mma.sync.aligned.m8n8k4.f64 — the only native fp64 tensor shape on sm_100a; larger PTX shapes
+// decompose into it) issued by the consumer warps with accumulators in registers.  tcgen05 has no
+// f64 kind, so there is no TMEM path for this arithmetic.
+//
+// Computes, column-major:   D = alpha * A * op(B) + beta * Cin   (+ optional Riccati epilogue)
+//   A   : M x K, element (m,k) at A[m + k*lda]                      ("M-major")
+//   B   : transB == 0 : K x N, element (k,n) at B[k + n*ldb]        ("K-major")
+//         transB == 1 : N x K, element (n,k) at B[n + k*ldb]        ("N-major"), op(B) = B^T
+//   Cin, D : M x N column-major; D may alias Cin (each element is read then written by one thread).
+//
+// These are the reference's dense Sigma contractions (eqf_vio/src/VIOFilter.cpp:188-189, 276-277,
+// 297; eqf_vio/src/EqFMatrices.cpp:239) which Eigen evaluates as general dynamic GEMMs.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace eqvio {
+
+enum GemmEpilogue : int {
+    EPI_AXPBY = 0,   // D = alpha*acc + beta*Cin
+    EPI_RICCATI = 1  // D = acc + T*(Pdiag[m]*(m==n) + sum_j Rd[j]*Bb[m,j]*Bb[n,j])   (VIOFilter.cpp:188-189)
+};
+
+struct GemmEpilogueArgs {
+    double alpha, beta;
+    const double* Cin;
+    int ldcin;
+    // Riccati epilogue
+    double T;
+    const double* Bb;  // n x 6 column-major, leading dimension ldbb
+    int ldbb;
+    double Rd[6];      // diag(velOmegaVariance x3, velAccelVariance x3)
+    double Pd[5];      // process variances: biasOmega, biasAccel, gravity, velocity, point
+};
+
+struct GemmProblem {
+    int M, N, K;
+    const double* A; int lda;
+    const double* B; int ldb; int transB;
+    double* D; int ldd;
+    int epilogue;
+    GemmEpilogueArgs epi;
+};
+
+// Host API.  All pointers are device pointers; A, B must be 16-byte aligned with even lda/ldb and
+// be readable up to the next multiple of 16 rows (the library's buffers are padded accordingly).
+// Returns cudaSuccess or the launch / encode error.  `flops_out` (optional) receives 2*M*N*K.
+cudaError_t dgemm_launch(const GemmProblem& p, cudaStream_t stream, int force_config = -1);
+// Which tile configuration dgemm_launch would pick (for DESIGN.md / tests).
+int dgemm_pick_config(int M, int N, int K);
+const char* dgemm_config_name(int cfg);
+int dgemm_num_configs();
+
+}  // namespace eqvio

@@ -1,0 +1,971 @@
+// eqvio_capi.cu — host side of the B200 EqF-VIO hot path and its C ABI (include/eqvio.h).
+//
+// One handle owns one CUDA stream and every buffer of a filter session; Sigma, F, C, K, the landmark
+// arrays and the SE(3) x R^3 state stay resident in HBM.  The host keeps only what the reference keeps
+// in plain scalars/ids (currentTime, accumulatedTime, initialisedFlag, landmark ids), so an IMU tick
+// is a handful of stream-ordered launches with the sample passed as kernel arguments and no copy or
+// synchronisation; a vision frame copies the bearings in and synchronises only if the outlier test
+// can fire (threshold < 2) — everything else is stream-ordered.
+//
+// Dense products follow the reference's association (eqf_vio/src/VIOFilter.cpp:188-189, 276-277, 297):
+//   (F Sigma) F^T, (C Sigma) C^T, (Sigma C^T) S^-1, (K C) Sigma.
+// The two explicit inverses are replaced by a blocked Cholesky sweep on an augmented buffer:
+//   S^-1 = X X^T with X = L^-T carried as appended identity rows; bundleLift needs only
+//   Y^T Sigma_sub^-1 Y for five vectors, obtained as Z^T Z with Z^T = Y^T L^-T appended the same way.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/eqvio.h"
+#include "dgemm_sm100.cuh"
+#include "kernels_api.cuh"
+
+using namespace eqvio;
+
+#define CU_TRY(expr)                                   \
+    do {                                               \
+        cudaError_t _e = (expr);                       \
+        if (_e != cudaSuccess) {                       \
+            set_error(_e, #expr, __LINE__);            \
+            return EQVIO_ERR_CUDA;                     \
+        }                                              \
+    } while (0)
+
+static thread_local char g_last_error[512] = "";
+static void set_error(cudaError_t e, const char* what, int line) {
+    snprintf(g_last_error, sizeof g_last_error, "%s at eqvio_capi.cu:%d: %s", what, line, cudaGetErrorString(e));
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct ProfEvent { cudaEvent_t a, b; double flops; };
+
+struct eqvio_filter {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    eqvio_settings_t s;
+    // host-side scalars of the reference class (VIOFilter.h:49-55)
+    bool initialised = false;
+    double currentTime = -1;
+    double accTime = 0;
+    std::vector<int> ids;  // X.id == xi0.bodyLandmarks[*].id
+    int N = 0;
+    // capacity-derived layout
+    int cap = 0, ld = 0, ldm = 0, ld2m = 0;
+    // device state
+    BaseState* st = nullptr;
+    StepScratch* sc = nullptr;
+    Landmarks L{nullptr, 0}, L2{nullptr, 0};
+    double *Sigma = nullptr, *Sigma2 = nullptr, *F = nullptr, *W = nullptr, *Bb = nullptr, *Aug = nullptr;
+    double *C = nullptr, *CS = nullptr, *SCt = nullptr, *K = nullptr, *Saug = nullptr, *Sinv = nullptr;
+    double *delta = nullptr, *gamma = nullptr, *y_in = nullptr, *y = nullptr, *scratch = nullptr, *Gamma = nullptr;
+    int *d_flags = nullptr, *d_map = nullptr;
+    // pinned staging
+    double* h_stage = nullptr;  // bearings in / state out
+    int* h_istage = nullptr;
+    size_t h_stage_doubles = 0, h_istage_ints = 0;
+    cudaEvent_t stage_free = nullptr;
+    int layoutN = -1;  // N for which F/W/C zero structure was prepared
+    // instrumentation
+    long long launches = 0;
+    bool profiling = false;
+    std::vector<ProfEvent> prof;
+    long long prof_launches = 0;
+    double prof_ms = 0, prof_flops = 0;
+};
+
+typedef eqvio_filter Filter;
+
+static int n_of(int N) { return EQVIO_SIGMA_BASE_SIZE + 3 * N; }
+
+// ------------------------------------------------------------------------------------------------
+// memory
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
+
+static void free_device(Filter* f) {
+    cudaFree(f->L.base); cudaFree(f->L2.base);
+    cudaFree(f->Sigma); cudaFree(f->Sigma2); cudaFree(f->F); cudaFree(f->W); cudaFree(f->Bb); cudaFree(f->Aug);
+    cudaFree(f->C); cudaFree(f->CS); cudaFree(f->SCt); cudaFree(f->K); cudaFree(f->Saug); cudaFree(f->Sinv);
+    cudaFree(f->delta); cudaFree(f->gamma); cudaFree(f->y_in); cudaFree(f->y); cudaFree(f->scratch); cudaFree(f->Gamma);
+    cudaFree(f->d_flags); cudaFree(f->d_map);
+    f->L.base = f->L2.base = nullptr;
+    f->Sigma = f->Sigma2 = f->F = f->W = f->Bb = f->Aug = f->C = f->CS = f->SCt = f->K = f->Saug = f->Sinv = nullptr;
+    f->delta = f->gamma = f->y_in = f->y = f->scratch = f->Gamma = nullptr;
+    f->d_flags = f->d_map = nullptr;
+}
+
+// (Re)allocate every capacity-dependent buffer for `cap` landmarks, preserving Sigma (n x n) and the
+// landmark arrays of the current N.
+static int ensure_capacity(Filter* f, int needN) {
+    if (needN <= f->cap) return EQVIO_OK;
+    int cap = f->cap ? f->cap : 64;
+    while (cap < needN) cap *= 2;
+    const int ld = round_up(n_of(cap), 16) + 16;
+    const int ldm = round_up(2 * cap, 16) + 16;
+    const int ld2m = round_up(4 * cap, 16) + 32;
+    const size_t nn = (size_t)ld * (ld + 32);
+    Filter o = *f;  // old pointers
+    Landmarks L{nullptr, cap}, L2{nullptr, cap};
+    double *Sigma, *Sigma2, *F, *W, *Bb, *Aug, *C, *CS, *SCt, *K, *Saug, *Sinv, *delta, *gamma, *y_in, *y, *scratch, *Gamma;
+    int *d_flags, *d_map;
+    CU_TRY(dalloc(&L.base, (size_t)LM_FIELDS * cap));
+    CU_TRY(dalloc(&L2.base, (size_t)LM_FIELDS * cap));
+    CU_TRY(dalloc(&Sigma, nn)); CU_TRY(dalloc(&Sigma2, nn)); CU_TRY(dalloc(&F, nn)); CU_TRY(dalloc(&W, nn));
+    CU_TRY(dalloc(&Aug, nn));
+    CU_TRY(dalloc(&Bb, (size_t)ld * 8));
+    CU_TRY(dalloc(&C, (size_t)ldm * (ld + 32))); CU_TRY(dalloc(&CS, (size_t)ldm * (ld + 32)));
+    CU_TRY(dalloc(&SCt, (size_t)ld * (ldm + 32))); CU_TRY(dalloc(&K, (size_t)ld * (ldm + 32)));
+    CU_TRY(dalloc(&Saug, (size_t)ld2m * (ldm + 32))); CU_TRY(dalloc(&Sinv, (size_t)ldm * (ldm + 32)));
+    CU_TRY(dalloc(&delta, (size_t)ldm)); CU_TRY(dalloc(&gamma, (size_t)ld)); CU_TRY(dalloc(&Gamma, (size_t)ld));
+    CU_TRY(dalloc(&y_in, (size_t)3 * cap + 8)); CU_TRY(dalloc(&y, (size_t)3 * cap + 8)); CU_TRY(dalloc(&scratch, (size_t)cap + 8));
+    CU_TRY(dalloc(&d_flags, (size_t)cap + 8)); CU_TRY(dalloc(&d_map, (size_t)ld + 8));
+    cudaStream_t s = f->stream;
+    CU_TRY(cudaMemsetAsync(Sigma, 0, nn * 8, s)); CU_TRY(cudaMemsetAsync(Sigma2, 0, nn * 8, s));
+    CU_TRY(cudaMemsetAsync(Aug, 0, nn * 8, s));
+    CU_TRY(cudaMemsetAsync(CS, 0, (size_t)ldm * (ld + 32) * 8, s));
+    CU_TRY(cudaMemsetAsync(SCt, 0, (size_t)ld * (ldm + 32) * 8, s)); CU_TRY(cudaMemsetAsync(K, 0, (size_t)ld * (ldm + 32) * 8, s));
+    CU_TRY(cudaMemsetAsync(Saug, 0, (size_t)ld2m * (ldm + 32) * 8, s)); CU_TRY(cudaMemsetAsync(Sinv, 0, (size_t)ldm * (ldm + 32) * 8, s));
+    CU_TRY(cudaMemsetAsync(L.base, 0, (size_t)LM_FIELDS * cap * 8, s)); CU_TRY(cudaMemsetAsync(L2.base, 0, (size_t)LM_FIELDS * cap * 8, s));
+    CU_TRY(cudaMemsetAsync(gamma, 0, (size_t)ld * 8, s)); CU_TRY(cudaMemsetAsync(delta, 0, (size_t)ldm * 8, s));
+    if (o.Sigma) {
+        const int n = n_of(f->N);
+        CU_TRY(cudaMemcpy2DAsync(Sigma, (size_t)ld * 8, o.Sigma, (size_t)o.ld * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice, s));
+        for (int k = 0; k < LM_FIELDS; ++k)
+            CU_TRY(cudaMemcpyAsync(L.base + (size_t)k * cap, o.L.base + (size_t)k * o.cap, (size_t)f->N * 8, cudaMemcpyDeviceToDevice, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        free_device(&o);
+    }
+    f->cap = cap; f->ld = ld; f->ldm = ldm; f->ld2m = ld2m;
+    f->L = L; f->L2 = L2;
+    f->Sigma = Sigma; f->Sigma2 = Sigma2; f->F = F; f->W = W; f->Bb = Bb; f->Aug = Aug;
+    f->C = C; f->CS = CS; f->SCt = SCt; f->K = K; f->Saug = Saug; f->Sinv = Sinv;
+    f->delta = delta; f->gamma = gamma; f->y_in = y_in; f->y = y; f->scratch = scratch; f->Gamma = Gamma;
+    f->d_flags = d_flags; f->d_map = d_map;
+    f->layoutN = -1;
+    // pinned staging sized for the capacity
+    size_t need_d = (size_t)LM_FIELDS * cap + 3 * (size_t)cap + 256, need_i = (size_t)ld + cap + 64;
+    if (need_d > f->h_stage_doubles) {
+        if (f->h_stage) cudaFreeHost(f->h_stage);
+        CU_TRY(cudaMallocHost((void**)&f->h_stage, need_d * 8));
+        f->h_stage_doubles = need_d;
+    }
+    if (need_i > f->h_istage_ints) {
+        if (f->h_istage) cudaFreeHost(f->h_istage);
+        CU_TRY(cudaMallocHost((void**)&f->h_istage, need_i * 4));
+        f->h_istage_ints = need_i;
+    }
+    return EQVIO_OK;
+}
+
+// Zero structure of the dense operands depends on N only: F = I outside the blocks rewritten every
+// tick, W / F padding columns [n, n16) must be zero, C is zero outside its 2x3 blocks.
+static int prepare_layout(Filter* f) {
+    if (f->layoutN == f->N) return EQVIO_OK;
+    const size_t nn = (size_t)f->ld * (f->ld + 32);
+    cudaStream_t s = f->stream;
+    CU_TRY(cudaMemsetAsync(f->F, 0, nn * 8, s));
+    CU_TRY(cudaMemsetAsync(f->W, 0, nn * 8, s));
+    CU_TRY(cudaMemsetAsync(f->Bb, 0, (size_t)f->ld * 8 * 8, s));
+    CU_TRY(cudaMemsetAsync(f->C, 0, (size_t)f->ldm * (f->ld + 32) * 8, s));
+    launch_set_diag_one(s, f->F, f->ld, n_of(f->N));
+    f->launches += 1;
+    f->layoutN = f->N;
+    return EQVIO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM wrapper with launch counting and optional event bracketing
+// ------------------------------------------------------------------------------------------------
+static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                double beta, const double* Cin, int ldcin, double* D, int ldd, int riccati_diag = 0, double T = 0.0) {
+    GemmProblem g;
+    g.M = M; g.N = N; g.K = K;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.transB = transB;
+    g.D = D; g.ldd = ldd;
+    g.epilogue = riccati_diag ? EPI_RICCATI : EPI_AXPBY;
+    g.epi.alpha = alpha; g.epi.beta = beta; g.epi.Cin = Cin; g.epi.ldcin = ldcin;
+    g.epi.T = T; g.epi.Bb = nullptr; g.epi.ldbb = 0;
+    for (int i = 0; i < 6; ++i) g.epi.Rd[i] = 0;
+    g.epi.Pd[0] = f->s.biasOmegaProcessVariance; g.epi.Pd[1] = f->s.biasAccelProcessVariance;
+    g.epi.Pd[2] = f->s.gravityProcessVariance; g.epi.Pd[3] = f->s.velocityProcessVariance;
+    g.epi.Pd[4] = f->s.pointProcessVariance;
+    ProfEvent pe;
+    if (f->profiling) {
+        cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
+        pe.flops = 2.0 * M * N * K;
+        cudaEventRecord(pe.a, f->stream);
+    }
+    CU_TRY(dgemm_launch(g, f->stream));
+    if (f->profiling) { cudaEventRecord(pe.b, f->stream); f->prof.push_back(pe); }
+    f->launches += 1;
+    return EQVIO_OK;
+}
+
+// Blocked Cholesky of the k x k SPD matrix at the top of Aug with r appended rows (-> R L^-T).
+static int chol_augmented(Filter* f, double* Aug, int lda, int k, int r) {
+    for (int j = 0; j < k; j += 64) {
+        const int nb = std::min(64, k - j);
+        launch_potrf_diag(f->stream, Aug, lda, j, nb, &f->st->flags);
+        launch_trsm_rows(f->stream, Aug, lda, j, nb, j + nb, k + r);
+        f->launches += 2;
+        if (j + nb < k) {
+            double* P = Aug + (j + nb) + (size_t)lda * j;
+            double* T22 = Aug + (j + nb) + (size_t)lda * (j + nb);
+            int st = gemm(f, 1, k + r - (j + nb), k - (j + nb), nb, -1.0, P, lda, P, lda, 1.0, T22, lda, T22, lda);
+            if (st) return st;
+        }
+    }
+    return EQVIO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// steps
+// ------------------------------------------------------------------------------------------------
+static RiccatiOut riccati_out(Filter* f) {
+    RiccatiOut ro;
+    ro.F = f->F; ro.W = f->W; ro.Bb = f->Bb; ro.ld = f->ld; ro.n = n_of(f->N); ro.n16 = round_up(n_of(f->N), 16);
+    return ro;
+}
+
+// The two Sigma GEMMs of the Riccati step (VIOFilter.cpp:188-189); F, B_b already built.
+static int riccati_gemms(Filter* f, double T) {
+    const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld;
+    int st = gemm(f, 0, n, n, n, 1.0, f->F, ld, f->Sigma, ld, 0.0, nullptr, 0, f->W, ld);  // W = F Sigma
+    if (st) return st;
+    // Sigma = [W | T B_b R] [F | B_b]^T + T P      (K runs over n16 + 6 columns; [n, n16) are zero)
+    return gemm(f, 1, n, n, n16 + 6, 1.0, f->W, ld, f->F, ld, 0.0, nullptr, 0, f->Sigma, ld, 1, T);
+}
+
+// integrateUpToTime, VIOFilter.cpp:146-209.  Returns 1 integrated, 0 skipped, <0 error.
+// `raw` (may be null) is the IMU sample to latch afterwards (processIMUData :129-130).
+static int integrate(Filter* f, double newTime, bool doRiccati, const double* omega, const double* accel, bool do_init,
+                     bool latch) {
+    ImuArgs a;
+    memset(&a, 0, sizeof a);
+    if (omega) for (int i = 0; i < 3; ++i) { a.omega[i] = omega[i]; a.accel[i] = accel[i]; }
+    a.stamp = newTime;
+    a.do_init = do_init; a.do_latch = latch;
+    a.discrete_lift = f->s.useDiscreteVelocityLift;
+    int integrated = 0;
+    if (f->currentTime >= 0) {
+        const double dt = newTime - f->currentTime;
+        if (dt > 0) {
+            integrated = 1;
+            f->accTime += dt;
+            a.do_integrate = 1; a.dt = dt;
+            if (doRiccati) { a.do_riccati = 1; a.T = f->accTime; }
+        }
+    }
+    if (!a.do_init && !a.do_integrate && !a.do_latch) return 0;
+    if (a.do_riccati) { int st = prepare_layout(f); if (st) return st; }
+    RiccatiOut ro = riccati_out(f);
+    launch_step_prepare(f->stream, f->st, f->sc, a, ro);
+    f->launches += 1;
+    if (a.do_integrate) {
+        if (f->N > 0) { launch_feature_step(f->stream, f->st, f->sc, f->L, f->N, a.do_riccati, a.discrete_lift, ro); f->launches += 1; }
+        if (a.do_riccati) {
+            int st = riccati_gemms(f, a.T);
+            if (st) return st;
+            f->accTime = 0.0;
+        }
+        f->currentTime = newTime;
+    }
+    return integrated;
+}
+
+// compaction after landmark removal: keep[] = surviving landmark indices (ascending)
+static int compact(Filter* f, const std::vector<int>& keep) {
+    const int newN = (int)keep.size(), n_new = n_of(newN);
+    int* hm = f->h_istage;
+    cudaEventSynchronize(f->stage_free);
+    for (int i = 0; i < 11; ++i) hm[i] = i;
+    for (int i = 0; i < newN; ++i)
+        for (int k = 0; k < 3; ++k) hm[11 + 3 * i + k] = 11 + 3 * keep[i] + k;
+    int* hk = hm + n_new;
+    for (int i = 0; i < newN; ++i) hk[i] = keep[i];
+    CU_TRY(cudaMemcpyAsync(f->d_map, hm, (size_t)(n_new + newN) * 4, cudaMemcpyHostToDevice, f->stream));
+    cudaEventRecord(f->stage_free, f->stream);
+    launch_gather_sigma(f->stream, f->Sigma, f->Sigma2, f->ld, f->d_map, n_new);
+    launch_gather_landmarks(f->stream, f->L.base, f->L2.base, f->cap, f->d_map + n_new, newN);
+    f->launches += 2;
+    std::swap(f->Sigma, f->Sigma2);
+    std::swap(f->L, f->L2);
+    std::vector<int> nid(newN);
+    for (int i = 0; i < newN; ++i) nid[i] = f->ids[keep[i]];
+    f->ids.swap(nid);
+    f->N = newN;
+    return EQVIO_OK;
+}
+
+// The measurement update, VIOFilter.cpp:264-297, on matched bearings f->y (3N, device).
+// want_lift = 0 stops after gamma / Sigma update (kernel-level entry point).
+static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
+    const int N = f->N, n = n_of(N), m = 2 * N, p = 5 + 3 * N, ld = f->ld, ldm = f->ldm;
+    int st = prepare_layout(f);
+    if (st) return st;
+    cudaStream_t s = f->stream;
+    launch_build_C_delta(s, f->st, f->L, N, f->y, f->C, ldm, f->delta);
+    f->launches += 1;
+    // S = (C Sigma) C^T + Q                                        VIOFilter.cpp:276
+    if ((st = gemm(f, 0, m, n, n, 1.0, f->C, ldm, f->Sigma, ld, 0.0, nullptr, 0, f->CS, ldm))) return st;
+    if ((st = gemm(f, 1, m, m, n, 1.0, f->CS, ldm, f->C, ldm, 0.0, nullptr, 0, f->Saug, f->ld2m))) return st;
+    launch_add_diag_const(s, f->Saug, f->ld2m, m, f->s.measurementVariance);
+    // S^-1 = X X^T, X = L^-T from the augmented Cholesky sweep       (S.inverse(), :277)
+    launch_set_identity_rows(s, f->Saug, f->ld2m, m, m);
+    f->launches += 2;
+    if ((st = chol_augmented(f, f->Saug, f->ld2m, m, m))) return st;
+    const double* X = f->Saug + m;
+    if ((st = gemm(f, 1, m, m, m, 1.0, X, f->ld2m, X, f->ld2m, 0.0, nullptr, 0, f->Sinv, ldm))) return st;
+    // K = (Sigma C^T) S^-1                                           :277
+    if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
+    if ((st = gemm(f, 0, n, m, m, 1.0, f->SCt, ld, f->Sinv, ldm, 0.0, nullptr, 0, f->K, ld))) return st;
+    launch_gemv(s, f->K, ld, n, m, f->delta, f->gamma);  // :279
+    f->launches += 1;
+    if (do_lift) {
+        const int use_lift = f->s.useInnovationLift, discrete = f->s.useDiscreteInnovationLift;
+        if (use_lift) {
+            // bundleLift with the PRIOR Sigma block (:285 precedes :297)
+            launch_lift_prepare(s, f->st, f->sc, f->gamma);
+            launch_copy_block(s, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
+            launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, p);
+            f->launches += 3;
+            if ((st = chol_augmented(f, f->Aug, ld, p, 5))) return st;
+        }
+        launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, p, use_lift, discrete, stamp, nullptr, 1);
+        launch_lift_apply(s, f->st, f->L, N, f->gamma, use_lift ? discrete : 0);
+        f->launches += 2;
+    }
+    if (do_sigma) {
+        // Sigma <- Sigma - (K C) Sigma                                :297
+        if ((st = gemm(f, 0, n, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, f->W, ld))) return st;
+        if ((st = gemm(f, 0, n, n, n, -1.0, f->W, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld))) return st;
+        std::swap(f->Sigma, f->Sigma2);
+        // W's columns [0, n) now hold K C; the Riccati step rewrites them (W = F Sigma) before use.
+    }
+    return EQVIO_OK;
+}
+
+static int read_flags(Filter* f, int* flags) {
+    CU_TRY(cudaMemcpyAsync(f->h_istage, &f->st->flags, 4, cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    *flags = f->h_istage[0];
+    return EQVIO_OK;
+}
+static int flags_to_status(int flags) {
+    if (flags & FLAG_SINGULAR) return EQVIO_ERR_SINGULAR_CHART;
+    if (flags & FLAG_NOT_SPD) return EQVIO_ERR_NOT_SPD;
+    if (flags & FLAG_NAN) return EQVIO_ERR_NAN;
+    return EQVIO_OK;
+}
+
+static int init_state(Filter* f) {
+    // VIOFilter::VIOFilter(const Settings&), VIOFilter.cpp:60-73 + member defaults VIOFilter.h:46-55
+    BaseState b;
+    memset(&b, 0, sizeof b);
+    b.pose0 = se3_identity(); b.vel0 = v3(0, 0, 0);
+    b.cam.x = v3(f->s.cameraOffset[0], f->s.cameraOffset[1], f->s.cameraOffset[2]);
+    b.cam.R.w = f->s.cameraOffset[3]; b.cam.R.x = f->s.cameraOffset[4]; b.cam.R.y = f->s.cameraOffset[5]; b.cam.R.z = f->s.cameraOffset[6];
+    b.XA = se3_identity(); b.Xw = v3(0, 0, 0);
+    for (int i = 0; i < 3; ++i) { b.bias[i] = f->s.initialOmegaBias[i]; b.bias[3 + i] = f->s.initialAccelBias[i]; }
+    StepScratch sc;
+    memset(&sc, 0, sizeof sc);
+    for (int i = 0; i < 3; ++i) { sc.Rd[i] = f->s.velOmegaVariance; sc.Rd[3 + i] = f->s.velAccelVariance; }
+    CU_TRY(cudaMemcpyAsync(f->st, &b, sizeof b, cudaMemcpyHostToDevice, f->stream));
+    CU_TRY(cudaMemcpyAsync(f->sc, &sc, sizeof sc, cudaMemcpyHostToDevice, f->stream));
+    const size_t nn = (size_t)f->ld * (f->ld + 32);
+    CU_TRY(cudaMemsetAsync(f->Sigma, 0, nn * 8, f->stream));
+    double d[11];
+    for (int i = 0; i < 3; ++i) { d[i] = f->s.initialBiasOmegaVariance; d[3 + i] = f->s.initialBiasAccelVariance; d[8 + i] = f->s.initialVelocityVariance; }
+    d[6] = d[7] = f->s.initialGravityVariance;
+    CU_TRY(cudaMemcpy2DAsync(f->Sigma, (size_t)(f->ld + 1) * 8, d, 8, 8, 11, cudaMemcpyHostToDevice, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    f->initialised = false; f->currentTime = -1; f->accTime = 0; f->N = 0; f->ids.clear(); f->layoutN = -1;
+    return EQVIO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int eqvio_settings_default(eqvio_settings_t* s) {
+    if (!s) return EQVIO_ERR_ARG;
+    memset(s, 0, sizeof *s);
+    s->biasOmegaProcessVariance = s->biasAccelProcessVariance = s->gravityProcessVariance = 0.001;
+    s->velocityProcessVariance = s->pointProcessVariance = 0.001;
+    s->velOmegaVariance = s->velAccelVariance = s->measurementVariance = 0.1;
+    s->initialGravityVariance = s->initialVelocityVariance = s->initialPointVariance = 1.0;
+    s->initialBiasOmegaVariance = s->initialBiasAccelVariance = 1.0;
+    s->initialSceneDepth = 1.0;
+    s->outlierThreshold = 0.01;
+    s->useInnovationLift = s->useDiscreteInnovationLift = s->useDiscreteVelocityLift = 1;
+    s->fastRiccati = 0;
+    s->cameraOffset[3] = 1.0;
+    return EQVIO_OK;
+}
+
+int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* out) {
+    if (!settings || !out) return EQVIO_ERR_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        snprintf(g_last_error, sizeof g_last_error, "no CUDA device %d (found %d): the B200 path has no CPU fallback", device, count);
+        return EQVIO_ERR_NO_DEVICE;
+    }
+    CU_TRY(cudaSetDevice(device));
+    Filter* f = new Filter();
+    f->device = device;
+    f->s = *settings;
+    CU_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&f->stage_free, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(f->stage_free, f->stream));
+    CU_TRY(dalloc(&f->st, 1));
+    CU_TRY(dalloc(&f->sc, 1));
+    int st = ensure_capacity(f, 64);
+    if (st) return st;
+    st = init_state(f);
+    if (st) return st;
+    *out = f;
+    return EQVIO_OK;
+}
+
+int eqvio_destroy(eqvio_handle_t f) {
+    if (!f) return EQVIO_ERR_ARG;
+    cudaSetDevice(f->device);
+    cudaStreamSynchronize(f->stream);
+    for (auto& e : f->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    free_device(f);
+    cudaFree(f->st); cudaFree(f->sc);
+    if (f->h_stage) cudaFreeHost(f->h_stage);
+    if (f->h_istage) cudaFreeHost(f->h_istage);
+    cudaEventDestroy(f->stage_free);
+    cudaStreamDestroy(f->stream);
+    delete f;
+    return EQVIO_OK;
+}
+
+int eqvio_reset(eqvio_handle_t f) {
+    // VIOFilter::reset(), VIOFilter.cpp:84-91: xi0 = VIOState(), X = Identity, Sigma = I(11), time = -1.
+    if (!f) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    int st = init_state(f);
+    if (st) return st;
+    double ones[11];
+    for (int i = 0; i < 11; ++i) ones[i] = 1.0;
+    CU_TRY(cudaMemcpy2DAsync(f->Sigma, (size_t)(f->ld + 1) * 8, ones, 8, 8, 11, cudaMemcpyHostToDevice, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return EQVIO_OK;
+}
+
+int eqvio_process_imu(eqvio_handle_t f, double stamp, const double omega[3], const double accel[3]) {
+    if (!f || !omega || !accel) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    const bool do_init = !f->initialised;  // VIOFilter.cpp:122-124
+    f->initialised = true;
+    int r = integrate(f, stamp, !f->s.fastRiccati, omega, accel, do_init, true);
+    if (r < 0) return r;
+    f->currentTime = stamp;  // :130
+    return r == 1 ? EQVIO_OK : EQVIO_SKIPPED_DT;
+}
+
+static int process_vision_impl(Filter* f, double stamp, int nmeas, const int* mids, const double* y_host, const double* y_dev) {
+    CU_TRY(cudaSetDevice(f->device));
+    int r = integrate(f, stamp, true, nullptr, nullptr, false, false);  // VIOFilter.cpp:234
+    if (r < 0) return r;
+    if (r == 0) return EQVIO_SKIPPED_DT;
+    if (!f->initialised) return EQVIO_NOT_INITIALISED;
+    for (int i = 1; i < nmeas; ++i)
+        if (mids[i] < mids[i - 1]) return EQVIO_ERR_UNSORTED;
+    cudaStream_t s = f->stream;
+    // removeOldLandmarks, VIOFilter.cpp:393-419
+    {
+        std::vector<int> keep;
+        keep.reserve(f->N);
+        for (int i = 0; i < f->N; ++i)
+            if (std::binary_search(mids, mids + nmeas, f->ids[i])) keep.push_back(i);
+        if ((int)keep.size() != f->N) { int st = compact(f, keep); if (st) return st; }
+    }
+    int st = ensure_capacity(f, std::max(nmeas, f->N));
+    if (st) return st;
+    // matchMeasurementsToState, VIOFilter.cpp:211-230: order[idx] = index into the measurement
+    std::vector<int> order(nmeas);
+    {
+        std::unordered_map<int, int> pos;
+        pos.reserve(f->N * 2 + 1);
+        for (int i = 0; i < f->N; ++i) pos.emplace(f->ids[i], i);
+        int newPos = f->N - 1;
+        for (int j = 0; j < nmeas; ++j) {
+            auto it = pos.find(mids[j]);
+            const int idx = it != pos.end() ? it->second : ++newPos;
+            order[idx] = j;
+        }
+    }
+    // bring the bearings in: `src` keeps the caller's order, f->y receives the matched order
+    const double* src = y_dev;
+    if (y_host) {
+        cudaEventSynchronize(f->stage_free);
+        memcpy(f->h_stage, y_host, (size_t)3 * nmeas * 8);
+        CU_TRY(cudaMemcpyAsync(f->y_in, f->h_stage, (size_t)3 * nmeas * 8, cudaMemcpyHostToDevice, s));
+        cudaEventRecord(f->stage_free, s);
+        src = f->y_in;
+    }
+    auto gather = [&](const std::vector<int>& ord) -> int {
+        bool identity = true;
+        for (size_t i = 0; i < ord.size(); ++i)
+            if (ord[i] != (int)i) { identity = false; break; }
+        if (ord.empty()) return EQVIO_OK;
+        if (identity) {
+            CU_TRY(cudaMemcpyAsync(f->y, src, ord.size() * 24, cudaMemcpyDeviceToDevice, s));
+            return EQVIO_OK;
+        }
+        cudaEventSynchronize(f->stage_free);
+        memcpy(f->h_istage, ord.data(), ord.size() * 4);
+        CU_TRY(cudaMemcpyAsync(f->d_map, f->h_istage, ord.size() * 4, cudaMemcpyHostToDevice, s));
+        cudaEventRecord(f->stage_free, s);
+        launch_gather_bearings(s, src, f->y, f->d_map, (int)ord.size());
+        f->launches += 1;
+        return EQVIO_OK;
+    };
+    if ((st = gather(order))) return st;
+    // removeOutliers, VIOFilter.cpp:429-443.  |y - yhat| <= 2 for unit vectors: a threshold >= 2 can never fire.
+    if (f->N > 0 && f->s.outlierThreshold < 2.0) {
+        launch_outlier_flags(s, f->L, f->N, f->y, f->s.outlierThreshold, f->d_flags);
+        f->launches += 1;
+        cudaEventSynchronize(f->stage_free);
+        int* hf = f->h_istage;
+        CU_TRY(cudaMemcpyAsync(hf, f->d_flags, (size_t)f->N * 4, cudaMemcpyDeviceToHost, s));
+        CU_TRY(cudaStreamSynchronize(s));
+        std::vector<int> keep, order2;
+        for (int i = 0; i < f->N; ++i)
+            if (!hf[i]) { keep.push_back(i); order2.push_back(order[i]); }
+        if ((int)keep.size() != f->N) {
+            for (int i = f->N; i < nmeas; ++i) order2.push_back(order[i]);
+            if ((st = compact(f, keep))) return st;
+            order.swap(order2);
+            nmeas = (int)order.size();
+            if ((st = gather(order))) return st;
+        }
+    }
+    // addNewLandmarks, VIOFilter.cpp:345-391
+    if (nmeas > f->N) {
+        const int oldN = f->N, newN = nmeas - oldN;
+        launch_add_landmarks(s, f->L, oldN, newN, f->y, f->s.initialSceneDepth, f->scratch);
+        launch_grow_sigma(s, f->Sigma, f->ld, n_of(oldN), n_of(nmeas), f->s.initialPointVariance);
+        f->launches += 2;
+        for (int i = oldN; i < nmeas; ++i) f->ids.push_back(mids[order[i]]);
+        f->N = nmeas;
+    }
+    if (nmeas == 0) return EQVIO_EMPTY_MEASUREMENT;
+    return update(f, stamp, true, true);
+}
+
+int eqvio_process_vision(eqvio_handle_t f, double stamp, int n, const int* ids, const double* bearings) {
+    if (!f || n < 0 || (n > 0 && (!ids || !bearings))) return EQVIO_ERR_ARG;
+    return process_vision_impl(f, stamp, n, ids, bearings, nullptr);
+}
+int eqvio_process_vision_dev(eqvio_handle_t f, double stamp, int n, const int* ids, const double* bearings_dev) {
+    if (!f || n < 0 || (n > 0 && (!ids || !bearings_dev))) return EQVIO_ERR_ARG;
+    return process_vision_impl(f, stamp, n, ids, nullptr, bearings_dev);
+}
+
+int eqvio_set_inertial_points(eqvio_handle_t f, int n, const int* ids, const double* points) {
+    if (!f || n < 0 || (n > 0 && (!ids || !points))) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    int st = ensure_capacity(f, n);
+    if (st) return st;
+    cudaEventSynchronize(f->stage_free);
+    memcpy(f->h_stage, points, (size_t)3 * n * 8);
+    CU_TRY(cudaMemcpyAsync(f->y_in, f->h_stage, (size_t)3 * n * 8, cudaMemcpyHostToDevice, f->stream));
+    cudaEventRecord(f->stage_free, f->stream);
+    launch_set_inertial_points(f->stream, f->st, f->L, n, f->y_in);
+    // Sigma: identity * initialPointVariance with the 11 x 11 base block kept (VIOFilter.cpp:113-117)
+    launch_grow_sigma(f->stream, f->Sigma, f->ld, 11, n_of(n), f->s.initialPointVariance);
+    f->launches += 2;
+    f->ids.assign(ids, ids + n);
+    f->N = n;
+    return EQVIO_OK;
+}
+
+int eqvio_get_time(eqvio_handle_t f, double* t) {
+    if (!f || !t) return EQVIO_ERR_ARG;
+    *t = f->currentTime;
+    return EQVIO_OK;
+}
+int eqvio_get_num_landmarks(eqvio_handle_t f, int* n) {
+    if (!f || !n) return EQVIO_ERR_ARG;
+    *n = f->N;
+    return EQVIO_OK;
+}
+
+static int fetch_base(Filter* f, BaseState* b) {
+    cudaEventSynchronize(f->stage_free);
+    CU_TRY(cudaMemcpyAsync(f->h_stage, f->st, sizeof(BaseState), cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    memcpy(b, f->h_stage, sizeof(BaseState));
+    return EQVIO_OK;
+}
+static int fetch_landmarks(Filter* f, std::vector<double>& lm) {
+    lm.resize((size_t)LM_FIELDS * std::max(f->N, 1));
+    if (f->N == 0) return EQVIO_OK;
+    for (int k = 0; k < LM_FIELDS; ++k)
+        CU_TRY(cudaMemcpyAsync(f->h_stage + (size_t)k * f->N, f->L.base + (size_t)k * f->cap, (size_t)f->N * 8, cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    memcpy(lm.data(), f->h_stage, (size_t)LM_FIELDS * f->N * 8);
+    return EQVIO_OK;
+}
+static void pose7(double* o, const Se3& P) {
+    o[0] = P.x.x; o[1] = P.x.y; o[2] = P.x.z; o[3] = P.R.w; o[4] = P.R.x; o[5] = P.R.y; o[6] = P.R.z;
+}
+
+int eqvio_get_state(eqvio_handle_t f, double pose[7], double velocity[3], double cam_offset[7], int* n, int cap, int* ids,
+                    double* landmarks) {
+    if (!f) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    BaseState b;
+    int st = fetch_base(f, &b);
+    if (st) return st;
+    // stateGroupAction(X, xi0), VIOGroup.cpp:23-45
+    if (pose) pose7(pose, b.pose0 * b.XA);
+    if (velocity) { V3 v = rotate_inv(b.XA.R, b.vel0 - b.Xw); velocity[0] = v.x; velocity[1] = v.y; velocity[2] = v.z; }
+    if (cam_offset) pose7(cam_offset, b.cam);
+    if (n) *n = f->N;
+    if ((ids || landmarks) && f->N > 0) {
+        std::vector<double> lm;
+        if ((st = fetch_landmarks(f, lm))) return st;
+        const int N = f->N;
+        for (int i = 0; i < N && i < cap; ++i) {
+            if (ids) ids[i] = f->ids[i];
+            if (landmarks) {
+                Sot3 Q; Q.R.w = lm[3 * N + i]; Q.R.x = lm[4 * N + i]; Q.R.y = lm[5 * N + i]; Q.R.z = lm[6 * N + i]; Q.a = lm[7 * N + i];
+                V3 q = inverse(Q) * v3(lm[i], lm[N + i], lm[2 * N + i]);
+                landmarks[3 * i] = q.x; landmarks[3 * i + 1] = q.y; landmarks[3 * i + 2] = q.z;
+            }
+        }
+    }
+    return flags_to_status(b.flags);
+}
+
+int eqvio_get_pose_record(eqvio_handle_t f, double rec[8]) {
+    if (!f || !rec) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    cudaEventSynchronize(f->stage_free);
+    CU_TRY(cudaMemcpyAsync(f->h_stage, f->st->pose_record, 64, cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    memcpy(rec, f->h_stage, 64);
+    return EQVIO_OK;
+}
+int eqvio_pose_record_dev(eqvio_handle_t f, double** dev_ptr) {
+    if (!f || !dev_ptr) return EQVIO_ERR_ARG;
+    *dev_ptr = f->st->pose_record;
+    return EQVIO_OK;
+}
+
+int eqvio_get_covariance(eqvio_handle_t f, double* dst, int ld) {
+    if (!f || !dst || ld < n_of(f->N)) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    const int n = n_of(f->N);
+    CU_TRY(cudaMemcpy2DAsync(dst, (size_t)ld * 8, f->Sigma, (size_t)f->ld * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return EQVIO_OK;
+}
+int eqvio_get_bias(eqvio_handle_t f, double bias[6]) {
+    if (!f || !bias) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    BaseState b;
+    int st = fetch_base(f, &b);
+    if (st) return st;
+    memcpy(bias, b.bias, 48);
+    return EQVIO_OK;
+}
+
+size_t eqvio_snapshot_size(int N) {
+    size_t n = n_of(N);
+    return EQVIO_SNAPSHOT_HEADER + EQVIO_SNAPSHOT_PER_LANDMARK * (size_t)N + n * n;
+}
+static void put_se3(double* d, const Se3& P) { d[0] = P.R.w; d[1] = P.R.x; d[2] = P.R.y; d[3] = P.R.z; d[4] = P.x.x; d[5] = P.x.y; d[6] = P.x.z; }
+static void take_se3(Se3* P, const double* d) { P->R.w = d[0]; P->R.x = d[1]; P->R.y = d[2]; P->R.z = d[3]; P->x = v3(d[4], d[5], d[6]); }
+
+int eqvio_get_snapshot(eqvio_handle_t f, double* d, size_t cap) {
+    if (!f || !d || cap < eqvio_snapshot_size(f->N)) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    BaseState b;
+    int st = fetch_base(f, &b);
+    if (st) return st;
+    const int N = f->N;
+    d[0] = N; d[1] = f->currentTime; d[2] = f->initialised ? 1.0 : 0.0; d[3] = f->accTime;
+    memcpy(d + 4, b.bias, 48);
+    memcpy(d + 10, b.curOmega, 24); memcpy(d + 13, b.curAccel, 24);
+    memcpy(d + 16, b.accOmega, 24); memcpy(d + 19, b.accAccel, 24);
+    put_se3(d + 22, b.pose0);
+    d[29] = b.vel0.x; d[30] = b.vel0.y; d[31] = b.vel0.z;
+    put_se3(d + 32, b.cam);
+    put_se3(d + 39, b.XA);
+    d[46] = b.Xw.x; d[47] = b.Xw.y; d[48] = b.Xw.z;
+    std::vector<double> lm;
+    if ((st = fetch_landmarks(f, lm))) return st;
+    double* Lp = d + EQVIO_SNAPSHOT_HEADER;
+    for (int i = 0; i < N; ++i, Lp += EQVIO_SNAPSHOT_PER_LANDMARK) {
+        Lp[0] = f->ids[i];
+        Lp[1] = lm[i]; Lp[2] = lm[N + i]; Lp[3] = lm[2 * N + i];
+        Lp[4] = lm[3 * N + i]; Lp[5] = lm[4 * N + i]; Lp[6] = lm[5 * N + i]; Lp[7] = lm[6 * N + i]; Lp[8] = lm[7 * N + i];
+    }
+    return eqvio_get_covariance(f, Lp, n_of(N));
+}
+
+int eqvio_set_snapshot(eqvio_handle_t f, const double* d, size_t len) {
+    if (!f || !d || len < EQVIO_SNAPSHOT_HEADER) return EQVIO_ERR_ARG;
+    const int N = (int)d[0];
+    if (N < 0 || len < eqvio_snapshot_size(N)) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    int st = ensure_capacity(f, std::max(N, 1));
+    if (st) return st;
+    BaseState b;
+    if ((st = fetch_base(f, &b))) return st;
+    f->N = N; f->currentTime = d[1]; f->initialised = d[2] != 0.0; f->accTime = d[3];
+    memcpy(b.bias, d + 4, 48);
+    memcpy(b.curOmega, d + 10, 24); memcpy(b.curAccel, d + 13, 24);
+    memcpy(b.accOmega, d + 16, 24); memcpy(b.accAccel, d + 19, 24);
+    take_se3(&b.pose0, d + 22);
+    b.vel0 = v3(d[29], d[30], d[31]);
+    take_se3(&b.cam, d + 32);
+    take_se3(&b.XA, d + 39);
+    b.Xw = v3(d[46], d[47], d[48]);
+    b.flags = 0;
+    CU_TRY(cudaMemcpy(f->st, &b, sizeof b, cudaMemcpyHostToDevice));
+    f->ids.resize(N);
+    std::vector<double> lm((size_t)LM_FIELDS * std::max(N, 1));
+    const double* Lp = d + EQVIO_SNAPSHOT_HEADER;
+    for (int i = 0; i < N; ++i, Lp += EQVIO_SNAPSHOT_PER_LANDMARK) {
+        f->ids[i] = (int)Lp[0];
+        lm[i] = Lp[1]; lm[N + i] = Lp[2]; lm[2 * N + i] = Lp[3];
+        lm[3 * N + i] = Lp[4]; lm[4 * N + i] = Lp[5]; lm[5 * N + i] = Lp[6]; lm[6 * N + i] = Lp[7]; lm[7 * N + i] = Lp[8];
+    }
+    for (int k = 0; k < LM_FIELDS && N > 0; ++k)
+        CU_TRY(cudaMemcpy(f->L.base + (size_t)k * f->cap, lm.data() + (size_t)k * N, (size_t)N * 8, cudaMemcpyHostToDevice));
+    const int n = n_of(N);
+    CU_TRY(cudaMemset(f->Sigma, 0, (size_t)f->ld * (f->ld + 32) * 8));
+    CU_TRY(cudaMemcpy2D(f->Sigma, (size_t)f->ld * 8, Lp, (size_t)n * 8, (size_t)n * 8, n, cudaMemcpyHostToDevice));
+    f->layoutN = -1;
+    return EQVIO_OK;
+}
+
+// ---- kernel-level entry points ----
+static int upload_bearings(Filter* f, const double* bearings) {
+    cudaEventSynchronize(f->stage_free);
+    memcpy(f->h_stage, bearings, (size_t)3 * f->N * 8);
+    CU_TRY(cudaMemcpyAsync(f->y, f->h_stage, (size_t)3 * f->N * 8, cudaMemcpyHostToDevice, f->stream));
+    cudaEventRecord(f->stage_free, f->stream);
+    return EQVIO_OK;
+}
+
+// Builds F and B_b for (T, omega) without touching the filter state: the state kernels are run with
+// do_integrate on a scratch copy is avoided by saving / restoring the small state and landmark arrays.
+static int build_FB_only(Filter* f, double T, const double omega[3]) {
+    // Save the mutable state that k_step_prepare / k_feature_step would change.
+    BaseState saved;
+    int st = fetch_base(f, &saved);
+    if (st) return st;
+    CU_TRY(cudaMemcpyAsync(f->L2.base, f->L.base, (size_t)LM_FIELDS * f->cap * 8, cudaMemcpyDeviceToDevice, f->stream));
+    // Make accumulated velocity / T reproduce the requested mean omega with dt -> tiny propagate that we discard.
+    BaseState tmp = saved;
+    for (int i = 0; i < 3; ++i) { tmp.accOmega[i] = omega[i] * T; tmp.accAccel[i] = 0; tmp.curOmega[i] = 0; tmp.curAccel[i] = 0; }
+    CU_TRY(cudaMemcpyAsync(f->st, &tmp, sizeof tmp, cudaMemcpyHostToDevice, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    if ((st = prepare_layout(f))) return st;
+    ImuArgs a;
+    memset(&a, 0, sizeof a);
+    a.do_integrate = 1; a.do_riccati = 1; a.dt = 0.0; a.T = T; a.discrete_lift = 1;
+    RiccatiOut ro = riccati_out(f);
+    launch_step_prepare(f->stream, f->st, f->sc, a, ro);
+    if (f->N > 0) launch_feature_step(f->stream, f->st, f->sc, f->L, f->N, 1, 1, ro);
+    f->launches += 2;
+    // restore
+    CU_TRY(cudaMemcpyAsync(f->st, &saved, sizeof saved, cudaMemcpyHostToDevice, f->stream));
+    CU_TRY(cudaMemcpyAsync(f->L.base, f->L2.base, (size_t)LM_FIELDS * f->cap * 8, cudaMemcpyDeviceToDevice, f->stream));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return EQVIO_OK;
+}
+
+int eqvio_build_FB(eqvio_handle_t f, double T, const double omega[3], double* F, double* Bb) {
+    if (!f || !omega) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    int st = build_FB_only(f, T, omega);
+    if (st) return st;
+    const int n = n_of(f->N);
+    if (F) CU_TRY(cudaMemcpy2D(F, (size_t)n * 8, f->F, (size_t)f->ld * 8, (size_t)n * 8, n, cudaMemcpyDeviceToHost));
+    if (Bb) CU_TRY(cudaMemcpy2D(Bb, (size_t)n * 8, f->Bb, (size_t)f->ld * 8, (size_t)n * 8, 6, cudaMemcpyDeviceToHost));
+    int flags = 0;
+    if ((st = read_flags(f, &flags))) return st;
+    return flags_to_status(flags);
+}
+
+int eqvio_riccati_propagate(eqvio_handle_t f, double T, const double omega[3]) {
+    if (!f || !omega) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    int st = build_FB_only(f, T, omega);
+    if (st) return st;
+    if ((st = riccati_gemms(f, T))) return st;
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    return EQVIO_OK;
+}
+
+int eqvio_build_C_delta(eqvio_handle_t f, const double* bearings, double* C, double* delta) {
+    if (!f || !bearings) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    int st = prepare_layout(f);
+    if (st) return st;
+    if ((st = upload_bearings(f, bearings))) return st;
+    launch_build_C_delta(f->stream, f->st, f->L, f->N, f->y, f->C, f->ldm, f->delta);
+    f->launches += 1;
+    const int n = n_of(f->N), m = 2 * f->N;
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    if (C) CU_TRY(cudaMemcpy2D(C, (size_t)m * 8, f->C, (size_t)f->ldm * 8, (size_t)m * 8, n, cudaMemcpyDeviceToHost));
+    if (delta) CU_TRY(cudaMemcpy(delta, f->delta, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    return EQVIO_OK;
+}
+
+int eqvio_gain_update(eqvio_handle_t f, const double* bearings, double* K, double* gamma) {
+    if (!f || !bearings) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    int st = upload_bearings(f, bearings);
+    if (st) return st;
+    if ((st = update(f, f->currentTime, false, true))) return st;
+    const int n = n_of(f->N), m = 2 * f->N;
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    if (K) CU_TRY(cudaMemcpy2D(K, (size_t)n * 8, f->K, (size_t)f->ld * 8, (size_t)n * 8, m, cudaMemcpyDeviceToHost));
+    if (gamma) CU_TRY(cudaMemcpy(gamma, f->gamma, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    int flags = 0;
+    if ((st = read_flags(f, &flags))) return st;
+    return flags_to_status(flags);
+}
+
+int eqvio_bundle_lift(eqvio_handle_t f, const double* gamma_eqf, double* Gamma) {
+    if (!f || !gamma_eqf || !Gamma) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    const int N = f->N, p = 5 + 3 * N, ld = f->ld;
+    std::vector<double> g(n_of(N), 0.0);
+    memcpy(g.data() + 6, gamma_eqf, (size_t)p * 8);
+    CU_TRY(cudaMemcpy(f->gamma, g.data(), g.size() * 8, cudaMemcpyHostToDevice));
+    cudaStream_t s = f->stream;
+    launch_lift_prepare(s, f->st, f->sc, f->gamma);
+    launch_copy_block(s, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
+    launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, p);
+    f->launches += 3;
+    int st = chol_augmented(f, f->Aug, ld, p, 5);
+    if (st) return st;
+    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, p, 1, 1, f->currentTime, f->Gamma, 0);
+    f->launches += 1;
+    CU_TRY(cudaStreamSynchronize(s));
+    CU_TRY(cudaMemcpy(Gamma, f->Gamma, 48, cudaMemcpyDeviceToHost));
+    memcpy(Gamma + 6, gamma_eqf + 2, (size_t)(3 + 3 * N) * 8);  // EqFMatrices.cpp:246-249
+    int flags = 0;
+    if ((st = read_flags(f, &flags))) return st;
+    return flags_to_status(flags);
+}
+
+int eqvio_dgemm(int device, int transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                double beta, double* C, int ldc, int reps, float* ms) {
+    if (M < 0 || N < 0 || K < 0 || !A || !B || !C) return EQVIO_ERR_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return EQVIO_ERR_NO_DEVICE;
+    CU_TRY(cudaSetDevice(device));
+    const int brow = transB ? N : K, bcol = transB ? K : N;
+    const int dlda = round_up(std::max(M, 1), 16) + 16, dldb = round_up(std::max(brow, 1), 16) + 16, dldc = round_up(std::max(M, 1), 16);
+    double *dA, *dB, *dC, *dD;
+    CU_TRY(dalloc(&dA, (size_t)dlda * (K + 32))); CU_TRY(dalloc(&dB, (size_t)dldb * (bcol + 32)));
+    CU_TRY(dalloc(&dC, (size_t)dldc * (N + 1))); CU_TRY(dalloc(&dD, (size_t)dldc * (N + 1)));
+    CU_TRY(cudaMemset(dA, 0, (size_t)dlda * (K + 32) * 8)); CU_TRY(cudaMemset(dB, 0, (size_t)dldb * (bcol + 32) * 8));
+    if (M && K) CU_TRY(cudaMemcpy2D(dA, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)M * 8, K, cudaMemcpyHostToDevice));
+    if (brow && bcol) CU_TRY(cudaMemcpy2D(dB, (size_t)dldb * 8, B, (size_t)ldb * 8, (size_t)brow * 8, bcol, cudaMemcpyHostToDevice));
+    if (M && N) CU_TRY(cudaMemcpy2D(dC, (size_t)dldc * 8, C, (size_t)ldc * 8, (size_t)M * 8, N, cudaMemcpyHostToDevice));
+    GemmProblem g;
+    g.M = M; g.N = N; g.K = K; g.A = dA; g.lda = dlda; g.B = dB; g.ldb = dldb; g.transB = transB; g.D = dD; g.ldd = dldc;
+    g.epilogue = EPI_AXPBY;
+    memset(&g.epi, 0, sizeof g.epi);
+    g.epi.alpha = alpha; g.epi.beta = beta; g.epi.Cin = dC; g.epi.ldcin = dldc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int force = -1;
+    if (const char* env = getenv("EQVIO_GEMM_CONFIG")) force = atoi(env);
+    CU_TRY(dgemm_launch(g, 0, force));
+    CU_TRY(cudaDeviceSynchronize());
+    if (reps > 1) {
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < reps; ++i) CU_TRY(dgemm_launch(g, 0, force));
+        cudaEventRecord(e1, 0);
+        CU_TRY(cudaEventSynchronize(e1));
+        float t;
+        cudaEventElapsedTime(&t, e0, e1);
+        if (ms) *ms = t / reps;
+    } else if (ms) *ms = 0;
+    if (M && N) CU_TRY(cudaMemcpy2D(C, (size_t)ldc * 8, dD, (size_t)dldc * 8, (size_t)M * 8, N, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dD);
+    return EQVIO_OK;
+}
+
+// ---- instrumentation ----
+int eqvio_synchronize(eqvio_handle_t f) {
+    if (!f) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    int flags = 0;
+    int st = read_flags(f, &flags);
+    if (st) return st;
+    return flags_to_status(flags);
+}
+int eqvio_launch_count(eqvio_handle_t f, long long* count, int reset) {
+    if (!f || !count) return EQVIO_ERR_ARG;
+    *count = f->launches;
+    if (reset) f->launches = 0;
+    return EQVIO_OK;
+}
+int eqvio_profile_enable(eqvio_handle_t f, int on) {
+    if (!f) return EQVIO_ERR_ARG;
+    f->profiling = on != 0;
+    return EQVIO_OK;
+}
+int eqvio_profile_read(eqvio_handle_t f, long long* gemm_launches, double* gemm_ms, double* gemm_flops, int reset) {
+    if (!f) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    for (auto& e : f->prof) {
+        float t = 0;
+        cudaEventElapsedTime(&t, e.a, e.b);
+        f->prof_ms += t; f->prof_flops += e.flops; f->prof_launches += 1;
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    f->prof.clear();
+    if (gemm_launches) *gemm_launches = f->prof_launches;
+    if (gemm_ms) *gemm_ms = f->prof_ms;
+    if (gemm_flops) *gemm_flops = f->prof_flops;
+    if (reset) { f->prof_launches = 0; f->prof_ms = 0; f->prof_flops = 0; }
+    return EQVIO_OK;
+}
+int eqvio_stream(eqvio_handle_t f, void** stream) {
+    if (!f || !stream) return EQVIO_ERR_ARG;
+    *stream = (void*)f->stream;
+    return EQVIO_OK;
+}
+const char* eqvio_status_string(int status) {
+    switch (status) {
+        case EQVIO_OK: return "ok";
+        case EQVIO_SKIPPED_DT: return "skipped: dt <= 0 or no previous stamp";
+        case EQVIO_NOT_INITIALISED: return "skipped: filter not initialised";
+        case EQVIO_EMPTY_MEASUREMENT: return "skipped: empty measurement";
+        case EQVIO_ERR_ARG: return "invalid argument";
+        case EQVIO_ERR_CUDA: return g_last_error[0] ? g_last_error : "CUDA error";
+        case EQVIO_ERR_NAN: return "NaN in Sigma or X";
+        case EQVIO_ERR_SINGULAR_CHART: return "SO3FromVectors: the vectors cannot be exactly opposing";
+        case EQVIO_ERR_NOT_SPD: return "Cholesky failed: matrix not positive definite";
+        case EQVIO_ERR_NO_DEVICE: return g_last_error[0] ? g_last_error : "no CUDA device";
+        case EQVIO_ERR_UNSORTED: return "bearings are not sorted by ascending id";
+    }
+    return "unknown status";
+}
+const char* eqvio_version(void) { return "eqvio-b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

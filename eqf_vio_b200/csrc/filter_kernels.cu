@@ -1,0 +1,706 @@
+// filter_kernels.cu — O(N) kernels of the EqF-VIO hot path (everything except the dense GEMMs):
+//   k_step_prepare      base rows of F/B_b, derived step quantities, X.A / X.w propagate, velocity latch
+//   k_feature_step      one warp per feature: F / B_b landmark rows + Q_i propagate
+//   k_build_C_delta     one warp per feature: 2x3 C block + innovation delta_i
+//   k_gemv              gamma = K delta
+//   k_lift_prepare / k_lift_features / k_lift_solve / k_lift_apply   bundleLift + discrete lift + X <- Delta X
+//   k_potrf_diag / k_trsm_rows   panel kernels of the blocked Cholesky used for S^-1 and Sigma_sub^-1
+//   bookkeeping: outlier flags, Sigma / landmark compaction, median depth + landmark append
+#include "filter_kernels.cuh"
+#include "kernels_api.cuh"
+
+namespace eqvio {
+
+#define GRAV 9.81  // GRAVITY_CONSTANT, eqf_vio/include/eqf_vio/IMUVelocity.h:22
+
+__device__ __forceinline__ V3 ld3(const double* p) { return v3(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st3(double* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+__device__ __forceinline__ Sot3 load_Q(const Landmarks& L, int i) {
+    Sot3 Q;
+    Q.R.w = L.Q(0)[i]; Q.R.x = L.Q(1)[i]; Q.R.y = L.Q(2)[i]; Q.R.z = L.Q(3)[i]; Q.a = L.Q(4)[i];
+    return Q;
+}
+__device__ __forceinline__ void store_Q(const Landmarks& L, int i, Sot3 Q) {
+    L.Q(0)[i] = Q.R.w; L.Q(1)[i] = Q.R.x; L.Q(2)[i] = Q.R.y; L.Q(3)[i] = Q.R.z; L.Q(4)[i] = Q.a;
+}
+__device__ __forceinline__ V3 load_q0(const Landmarks& L, int i) { return v3(L.q0(0)[i], L.q0(1)[i], L.q0(2)[i]); }
+
+// ------------------------------------------------------------------------------------------------
+// k_step_prepare — single thread.  processIMUData / integrateUpToTime bookkeeping that is O(1):
+//   VIOFilter.cpp:120-131 (unbias, initialise, latch), :154-155 (accumulate), :162-185 base rows of
+//   A/B (EqFMatrices.cpp:289, 364-368), :196-203 with liftVelocityDiscrete (VIOGroup.cpp:209-243)
+//   / liftVelocity (VIOGroup.cpp:178-207) for the SE(3) x R^3 part, X <- X * lift (VIOGroup.cpp:92-97).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_step_prepare(BaseState* st, StepScratch* sc, ImuArgs a, RiccatiOut ro) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int sing = 0;
+    V3 uo = v3(a.omega[0] - st->bias[0], a.omega[1] - st->bias[1], a.omega[2] - st->bias[2]);
+    V3 ua = v3(a.accel[0] - st->bias[3], a.accel[1] - st->bias[4], a.accel[2] - st->bias[5]);
+    if (a.do_init) {  // initialiseFromIMUData, VIOFilter.cpp:133-144
+        st->pose0 = se3_identity();
+        st->vel0 = v3(0, 0, 0);
+        st->pose0.R = so3_from_vectors(normalized(ua), v3(0, 0, 1), &sing);
+    }
+    if (a.do_integrate) {
+        const V3 co = ld3(st->curOmega), ca = ld3(st->curAccel);
+        V3 ao = ld3(st->accOmega) + co * a.dt, aa = ld3(st->accAccel) + ca * a.dt;
+        const Se3 XA = st->XA;
+        const V3 eta0 = rotate_inv(st->pose0.R, v3(0, 0, 1));       // projectToManifold, VIOState.cpp:90
+        const V3 eta_hat = rotate_inv(XA.R, eta0);                  // VIOGroup.cpp:49
+        const V3 v_hat = rotate_inv(XA.R, st->vel0 - st->Xw);       // VIOGroup.cpp:25,50
+        const Se3 camInvT = inverse(st->cam);
+        const M3 RA = to_matrix(XA.R);
+        if (a.do_riccati) {
+            const V3 om = ao * (1.0 / a.T);
+            const int ld = ro.ld, n16 = ro.n16;
+            double* F = ro.F; double* W = ro.W; double* Bb = ro.Bb;
+            sc->T = a.T;
+            // A0[2:5,0:2] = -g * stereoSphereChartInvDiff(0, eta0)   (EqFMatrices.cpp:289)
+            M32 D = stereo_sphere_chart_inv_diff(0.0, 0.0, eta0, &sing);
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 2; ++c) F[(8 + r) + (size_t)ld * (6 + c)] = (-D.m[r][c] * GRAV) * a.T;
+            const M3 RIC = to_matrix(st->cam.R);
+            sc->RICt_RAt = transpose(RIC) * transpose(RA);
+            V3 omC, vC;
+            se3_adjoint_apply(camInvT, om, v_hat, &omC, &vC);       // EqFMatrices.cpp:302-304
+            sc->vC = vC;
+            // B rows (EqFMatrices.cpp:364-368)
+            M23 Dg = stereo_sphere_chart_diff(eta0, eta0, &sing);
+            M3 RAse = RA * skew(eta_hat);
+            double Bbase[5][6];
+            for (int r = 0; r < 2; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    Bbase[r][c] = Dg.m[r][0] * RAse.m[0][c] + Dg.m[r][1] * RAse.m[1][c] + Dg.m[r][2] * RAse.m[2][c];
+                    Bbase[r][3 + c] = 0.0;
+                }
+            M3 RAsv = RA * skew(v_hat);
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) { Bbase[2 + r][c] = RAsv.m[r][c]; Bbase[2 + r][3 + c] = RA.m[r][c]; }
+            for (int r = 0; r < 5; ++r)
+                for (int c = 0; c < 6; ++c) {
+                    const double b = Bbase[r][c];
+                    F[(6 + r) + (size_t)ld * c] = -b * a.T;                           // A_b = [[0,0],[-Bt,A0t]]; F = I + A_b T
+                    Bb[(6 + r) + (size_t)ld * c] = b;
+                    F[(6 + r) + (size_t)ld * (n16 + c)] = b;                          // [F | B_b]
+                    W[(6 + r) + (size_t)ld * (n16 + c)] = a.T * (b * sc->Rd[c]);      // [F Sigma | T B_b R]
+                }
+            sc->RT_IC = to_matrix(q_inverse(st->cam.R));
+            sc->RT_IC_sx = sc->RT_IC * skew(st->cam.x);
+            ao = v3(0, 0, 0); aa = v3(0, 0, 0);  // VIOFilter.cpp:192-193
+        }
+        st3(st->accOmega, ao); st3(st->accAccel, aa);
+        // state propagate of the SE(3) x R^3 part
+        sc->dt = a.dt;
+        V3 omC, vC;
+        se3_adjoint_apply(camInvT, co, v_hat, &omC, &vC);
+        if (a.discrete_lift) {
+            Se3 LA = se3_exp(co * a.dt, v_hat * a.dt);
+            V3 inner = v_hat + a.dt * (-cross(co, v_hat) + ca - eta_hat * GRAV);
+            V3 Lw = v_hat - rotate(LA.R, inner);
+            sc->camInv = se3_exp(omC * (-a.dt), vC * (-a.dt));
+            st->Xw = st->Xw + rotate(XA.R, Lw);
+            st->XA = XA * LA;
+        } else {
+            sc->omC = omC; sc->vCcur = vC;
+            V3 u = -ca + eta_hat * GRAV;
+            Se3 EA = se3_exp(co * a.dt, v_hat * a.dt);
+            st->Xw = st->Xw + rotate(XA.R, u * a.dt);
+            st->XA = XA * EA;
+        }
+    }
+    if (a.do_latch) { st3(st->curOmega, uo); st3(st->curAccel, ua); }
+    if (sing) atomicOr(&st->flags, FLAG_SINGULAR);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_feature_step — one warp per feature.  Lanes 0..2 each build one 3x3 block, lane 3 propagates
+// Q_i; the blocks go through a per-warp shared staging area so that the stores to F / B_b are issued
+// by 27 + 9 lanes side by side (rows of one feature are contiguous in every column).
+//   A_iv, A_ii : EqFStateMatrixA_euclid_impl, EqFMatrices.cpp:292-312
+//   B_i        : EqFInputMatrixB_euclid_impl, EqFMatrices.cpp:371-377
+//   F, B_b     : VIOFilter.cpp:177-185
+//   Q_i <- Q_i * lift.Q_i : liftVelocityDiscrete VIOGroup.cpp:231-240 / liftVelocity :192-199, product :104-107
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_feature_step(BaseState* st, const StepScratch* sc, Landmarks L, int N,
+                                                      int do_riccati, int discrete_lift, RiccatiOut ro) {
+    __shared__ double stage[8][40];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + wib;
+    if (i >= N) return;
+    double* sm = stage[wib];
+    const Sot3 Q = load_Q(L, i);
+    const V3 q0 = load_q0(L, i);
+    const V3 qh = inverse(Q) * q0;  // VIOGroup.cpp:39-44
+    if (do_riccati) {
+        if (lane < 3) {
+            const M3 Qhat = as_matrix3(Q);
+            M3 blk;
+            if (lane == 0) {
+                blk = Qhat * (skew(qh) * sc->RT_IC + sc->RT_IC_sx);                       // B_i
+            } else if (lane == 1) {
+                blk = (Qhat * sc->RICt_RAt) * -1.0;                                       // A_iv
+            } else {
+                const V3 vC = sc->vC;
+                M3 inner = skew(qh) * skew(vC) + outer(vC, qh) * -2.0 + outer(qh, vC);
+                blk = ((Qhat * inner) * inverse(Qhat)) * (-1.0 / dot(qh, qh));            // A_ii
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sm[lane * 9 + c * 3 + r] = blk.m[r][c];      // column-major 3x3
+        }
+        __syncwarp();
+        const double T = sc->T;
+        const int ld = ro.ld, row0 = 11 + 3 * i;
+        if (lane < 27) {
+            const int b = lane / 9, e = lane % 9, c = e / 3, r = e % 3;
+            const double v = sm[lane];
+            double* F = ro.F;
+            if (b == 0) {
+                F[(row0 + r) + (size_t)ld * c] = -v * T;
+                ro.Bb[(row0 + r) + (size_t)ld * c] = v;
+                F[(row0 + r) + (size_t)ld * (ro.n16 + c)] = v;
+                ro.W[(row0 + r) + (size_t)ld * (ro.n16 + c)] = T * (v * sc->Rd[c]);
+            } else if (b == 1) {
+                F[(row0 + r) + (size_t)ld * (8 + c)] = v * T;
+            } else {
+                F[(row0 + r) + (size_t)ld * (row0 + c)] = v * T + (r == c ? 1.0 : 0.0);
+            }
+        }
+    }
+    if (lane == 3) {
+        int sing = 0;
+        Sot3 dQ;
+        if (discrete_lift) {
+            const V3 p1 = sc->camInv * qh;
+            dQ.R = so3_from_vectors(normalized(p1), normalized(qh), &sing);
+            dQ.a = norm(qh) / norm(p1);
+        } else {
+            const double n2 = dot(qh, qh), dt = sc->dt;
+            const V3 w = sc->omC + (skew(qh) * sc->vCcur) / n2;
+            dQ = sot3_exp(w * dt, dt * (dot(qh, sc->vCcur) / n2));
+        }
+        store_Q(L, i, Q * dQ);
+        if (sing) atomicOr(&st->flags, FLAG_SINGULAR);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_build_C_delta — one warp per feature (lane 0 computes, lanes 0..5 / 0..1 store).
+//   y0 = measureSystemState(xi0)            VIOState.cpp:58-70
+//   ye = outputGroupAction(X^-1, y)         VIOGroup.cpp:71-90, 124-134
+//   delta_i = stereoSphereChart(ye, y0)     VisionMeasurement.cpp:24-34
+//   C0_i = 1/|q0| chartDiff(y0,y0)(I - y0 y0^T)   EqFMatrices.cpp:332-338; C = [0, C0] VIOFilter.cpp:272-273
+// C is m x n column-major with leading dimension ldc; only the 2x3 block of feature i is written.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_C_delta(BaseState* st, Landmarks L, int N, const double* bearings,
+                                                       double* C, int ldc, double* delta) {
+    __shared__ double stage[8][8];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + wib;
+    if (i >= N) return;
+    double* sm = stage[wib];
+    if (lane == 0) {
+        int sing = 0;
+        const V3 q0 = load_q0(L, i);
+        const V3 y0 = normalized(q0);
+        const Sot3 Q = load_Q(L, i);
+        if (delta && bearings) {
+            const V3 y = v3(bearings[3 * i], bearings[3 * i + 1], bearings[3 * i + 2]);
+            const V3 ye = rotate(q_inverse(q_inverse(Q.R)), y);
+            stereo_sphere_chart(ye, y0, sm + 6, &sing);
+        }
+        M23 D = stereo_sphere_chart_diff(y0, y0, &sing);
+        M3 proj = m3_identity() + outer(y0, y0) * -1.0;
+        const double sc = 1 / norm(q0);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                sm[c * 2 + r] = (sc * D.m[r][0]) * proj.m[0][c] + (sc * D.m[r][1]) * proj.m[1][c] + (sc * D.m[r][2]) * proj.m[2][c];
+        if (sing) atomicOr(&st->flags, FLAG_SINGULAR);
+    }
+    __syncwarp();
+    if (C && lane < 6) C[(2 * i + (lane & 1)) + (size_t)ldc * (11 + 3 * i + (lane >> 1))] = sm[lane];
+    if (delta && bearings && lane < 2) delta[2 * i + lane] = sm[6 + lane];
+}
+
+// gamma = K delta  (VIOFilter.cpp:279).  K is n x m column-major.  Block = 32 rows x 8 column groups.
+__global__ void __launch_bounds__(256) k_gemv(const double* K, int ldk, int n, int m, const double* x, double* y) {
+    __shared__ double red[8][33];
+    const int rx = threadIdx.x & 31, cy = threadIdx.x >> 5;
+    const int r = blockIdx.x * 32 + rx;
+    double s = 0.0;
+    if (r < n)
+        for (int c = cy; c < m; c += 8) s += K[r + (size_t)ldk * c] * x[c];
+    red[cy][rx] = s;
+    __syncthreads();
+    if (cy == 0 && r < n) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][rx];
+        y[r] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Innovation lift.  gamma is the biased innovation (n entries): gamma[0:6] bias, gamma[6:] EqF part.
+// k_lift_prepare: O(1) parts of bundleLift (EqFMatrices.cpp:173-213): DeltaU default, KPara, KPerp,
+//   R_C, Ad(P0), P_hat T_IC.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_lift_prepare(BaseState* st, StepScratch* sc, const double* gamma) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int sing = 0;
+    const V3 eta0 = normalized(rotate_inv(st->pose0.R, v3(0, 0, 1)));
+    sc->eta0n = eta0;
+    const double* g = gamma + 6;
+    M32 D = stereo_sphere_chart_inv_diff(0.0, 0.0, eta0, &sing);
+    V3 t = v3(D.m[0][0] * g[0] + D.m[0][1] * g[1], D.m[1][0] * g[0] + D.m[1][1] * g[1], D.m[2][0] * g[0] + D.m[2][1] * g[1]);
+    V3 Om = -(skew(eta0) * t);  // :187
+    // DUF = KPerp * DeltaU with KPerp = diag(I - eta eta^T, 0)  (:201-206, :212)
+    M3 P = m3_identity() + outer(eta0, eta0) * -1.0;
+    V3 duf = P * Om;
+    sc->DUF[0] = duf.x; sc->DUF[1] = duf.y; sc->DUF[2] = duf.z; sc->DUF[3] = sc->DUF[4] = sc->DUF[5] = 0.0;
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 4; ++c) sc->KPara[r][c] = 0.0;
+    sc->KPara[0][0] = eta0.x; sc->KPara[1][0] = eta0.y; sc->KPara[2][0] = eta0.z;
+    sc->KPara[3][1] = sc->KPara[4][2] = sc->KPara[5][3] = 1.0;
+    const Se3 Phat = st->pose0 * st->XA;
+    sc->RC = Phat.R * st->cam.R;
+    sc->RCt = to_matrix(q_inverse(sc->RC));
+    sc->PT = Phat * st->cam;
+    // Ad(P0), SE3.cpp:95-103
+    M3 R = to_matrix(st->pose0.R), sxR = skew(st->pose0.x) * R;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            sc->AdP0[r][c] = R.m[r][c]; sc->AdP0[r][3 + c] = 0.0;
+            sc->AdP0[3 + r][c] = sxR.m[r][c]; sc->AdP0[3 + r][3 + c] = R.m[r][c];
+        }
+    if (sing) atomicOr(&st->flags, FLAG_SINGULAR);
+}
+
+// k_lift_features: per feature, Y_i = D_i [M_i | obs_i] (3 x 5) with (EqFMatrices.cpp:218-236)
+//   M_i = [-[p_i]x, I] Ad(P0) KPara,  obs_i = -R_C Q_i^-1 gamma_qi - [-[p_i]x, I] Ad(P0) DUF,  D_i = Qhat_i R_C^T.
+// Written transposed as the 5 appended rows of the augmented Cholesky buffer:
+//   Aug[p + c, 5 + 3i + r] = Y_i[r][c]   (first five columns of the appended rows are zero).
+__global__ void __launch_bounds__(128) k_lift_features(const StepScratch* sc, Landmarks L, int N, const double* gamma,
+                                                       double* Aug, int lda, int p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 5)
+        for (int c = 0; c < 5; ++c) Aug[(p + c) + (size_t)lda * i] = 0.0;
+    if (i >= N) return;
+    const Sot3 Q = load_Q(L, i);
+    const V3 q0 = load_q0(L, i);
+    const V3 qh = inverse(Q) * q0;
+    const V3 pH = sc->PT * qh;
+    const double* gq = gamma + 11 + 3 * i;
+    const V3 alpha = -rotate(sc->RC, inverse(Q) * v3(gq[0], gq[1], gq[2]));
+    // pHatMat * AdP0 (3 x 6)
+    M3 nsp = skew(pH) * -1.0;
+    double pmAd[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+            pmAd[r][c] = nsp.m[r][0] * sc->AdP0[0][c] + nsp.m[r][1] * sc->AdP0[1][c] + nsp.m[r][2] * sc->AdP0[2][c] + sc->AdP0[3 + r][c];
+    double MO[3][5];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s += pmAd[r][k] * sc->DUF[k];
+        MO[r][4] = v3_get(alpha, r) - s;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double m = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) m += pmAd[r][k] * sc->KPara[k][c];
+            MO[r][c] = m;
+        }
+    }
+    const M3 Dm = as_matrix3(Q) * sc->RCt;
+#pragma unroll
+    for (int c = 0; c < 5; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            Aug[(p + c) + (size_t)lda * (5 + 3 * i + r)] = Dm.m[r][0] * MO[0][c] + Dm.m[r][1] * MO[1][c] + Dm.m[r][2] * MO[2][c];
+}
+
+// 4x4 Householder QR solve (EqFMatrices.cpp:240-242)
+__device__ void qr_solve4(double A[4][4], double b[4], double x[4]) {
+    for (int k = 0; k < 4; ++k) {
+        double tail2 = 0;
+        for (int r = k + 1; r < 4; ++r) tail2 += A[r][k] * A[r][k];
+        const double c0 = A[k][k];
+        if (tail2 == 0.0) continue;
+        double beta = sqrt(c0 * c0 + tail2);
+        if (c0 >= 0) beta = -beta;
+        double v[4] = {0, 0, 0, 0};
+        for (int r = k + 1; r < 4; ++r) v[r] = A[r][k] / (c0 - beta);
+        v[k] = 1.0;
+        const double tau = (beta - c0) / beta;
+        for (int c = k; c < 4; ++c) {
+            double s = 0;
+            for (int r = k; r < 4; ++r) s += v[r] * A[r][c];
+            s *= tau;
+            for (int r = k; r < 4; ++r) A[r][c] -= s * v[r];
+        }
+        double s = 0;
+        for (int r = k; r < 4; ++r) s += v[r] * b[r];
+        s *= tau;
+        for (int r = k; r < 4; ++r) b[r] -= s * v[r];
+    }
+    for (int k = 3; k >= 0; --k) {
+        double s = b[k];
+        for (int c = k + 1; c < 4; ++c) s -= A[k][c] * x[c];
+        x[k] = s / A[k][k];
+    }
+}
+
+// k_lift_solve — one block.  mode 0: bundle lift: G = Z^T Z from the 5 appended rows Z^T = Y^T L^-T
+// (so G = Y^T Sigma_sub^-1 Y = [M^T W M, M^T W obs; ...], EqFMatrices.cpp:239-242), 4x4 QR solve,
+// DeltaU = DUF + KPara x (:243), then the SE(3) x R^3 part of the lift and X <- Delta X, bias update:
+//   discrete   liftTotalSpaceInnovationDiscrete EqFMatrices.cpp:254-259
+//   continuous VIOExp(liftTotalSpaceInnovation)  EqFMatrices.cpp:69-78, VIOGroup.cpp:245-248
+// mode 1 (useInnovationLift = false): VIOExp(liftInnovation(gamma, xi0)) EqFMatrices.cpp:35-48.
+// Then VIOFilter.cpp:295-296 and the pose record.
+__global__ void __launch_bounds__(256) k_lift_solve(BaseState* st, StepScratch* sc, const double* gamma, const double* Aug,
+                                                    int lda, int p, int use_lift, int discrete, double stamp,
+                                                    double* Gamma_out, int apply) {
+    __shared__ double part[15][256];
+    __shared__ double G[15];
+    const int tid = threadIdx.x;
+    if (use_lift) {
+        double acc[15];
+#pragma unroll
+        for (int k = 0; k < 15; ++k) acc[k] = 0.0;
+        for (int col = tid; col < p; col += 256) {
+            double z[5];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) z[c] = Aug[(p + c) + (size_t)lda * col];
+            int k = 0;
+#pragma unroll
+            for (int a = 0; a < 5; ++a)
+#pragma unroll
+                for (int b = a; b < 5; ++b) acc[k++] += z[a] * z[b];
+        }
+#pragma unroll
+        for (int k = 0; k < 15; ++k) part[k][tid] = acc[k];
+        __syncthreads();
+        if (tid < 15) {
+            double s = 0.0;
+            for (int j = 0; j < 256; ++j) s += part[tid][j];
+            G[tid] = s;
+        }
+        __syncthreads();
+    }
+    if (tid != 0) return;
+    double DU[6];
+    V3 Dw;
+    const double* g = gamma + 6;
+    if (use_lift) {
+        double A[4][4], b[4], x[4];
+        int k = 0;
+        double Gf[5][5];
+        for (int a = 0; a < 5; ++a)
+            for (int c = a; c < 5; ++c) { Gf[a][c] = G[k]; Gf[c][a] = G[k]; ++k; }
+        for (int a = 0; a < 4; ++a) { for (int c = 0; c < 4; ++c) A[a][c] = Gf[a][c]; b[a] = Gf[a][4]; }
+        qr_solve4(A, b, x);
+        for (int r = 0; r < 6; ++r) {
+            double s = 0.0;
+            for (int c = 0; c < 4; ++c) s += sc->KPara[r][c] * x[c];
+            DU[r] = sc->DUF[r] + s;
+        }
+        if (Gamma_out)
+            for (int r = 0; r < 6; ++r) Gamma_out[r] = DU[r];
+        const V3 gv = v3(g[2], g[3], g[4]);
+        if (discrete) {
+            sc->DeltaA = se3_exp(v3(DU[0], DU[1], DU[2]), v3(DU[3], DU[4], DU[5]));
+            Dw = st->vel0 - rotate(sc->DeltaA.R, st->vel0 + gv);
+        } else {
+            sc->DeltaA = se3_exp(v3(DU[0], DU[1], DU[2]), v3(DU[3], DU[4], DU[5]));
+            Dw = -gv - skew(v3(DU[0], DU[1], DU[2])) * st->vel0;
+        }
+    } else {
+        int sing = 0;
+        const V3 eta0 = rotate_inv(st->pose0.R, v3(0, 0, 1));
+        M32 D = stereo_sphere_chart_inv_diff(0.0, 0.0, eta0, &sing);
+        V3 t = v3(D.m[0][0] * g[0] + D.m[0][1] * g[1], D.m[1][0] * g[0] + D.m[1][1] * g[1], D.m[2][0] * g[0] + D.m[2][1] * g[1]);
+        V3 Om = -(skew(eta0) * t);
+        sc->DeltaA = se3_exp(Om, v3(0, 0, 0));
+        Dw = -v3(g[2], g[3], g[4]) - skew(Om) * st->vel0;
+        if (sing) atomicOr(&st->flags, FLAG_SINGULAR);
+    }
+    if (!apply) return;  // kernel-level bundle-lift entry point only wants Gamma[0:6]
+    sc->Deltaw = Dw;
+    for (int k = 0; k < 6; ++k) st->bias[k] += gamma[k];                       // VIOFilter.cpp:295
+    st->Xw = Dw + rotate(sc->DeltaA.R, st->Xw);                               // VIOGroup.cpp:96
+    st->XA = sc->DeltaA * st->XA;                                             // VIOGroup.cpp:95
+    const Se3 P = st->pose0 * st->XA;
+    st->pose_record[0] = stamp;
+    st->pose_record[1] = P.x.x; st->pose_record[2] = P.x.y; st->pose_record[3] = P.x.z;
+    st->pose_record[4] = P.R.w; st->pose_record[5] = P.R.x; st->pose_record[6] = P.R.y; st->pose_record[7] = P.R.z;
+}
+
+// k_lift_apply — thread per feature: Q_i <- DeltaQ_i * Q_i (VIOGroup.cpp:104-107) with
+//   discrete: DeltaQ_i from q0 + Gamma_qi (EqFMatrices.cpp:264-270)
+//   continuous: SOT3Exp(W_i), W_i = (-q0 x g / |q0|^2, -q0.g / |q0|^2) (EqFMatrices.cpp:50-63 / 80-93)
+__global__ void __launch_bounds__(128) k_lift_apply(BaseState* st, Landmarks L, int N, const double* gamma, int discrete) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int sing = 0;
+    const V3 q0 = load_q0(L, i);
+    const double* gq = gamma + 11 + 3 * i;
+    const V3 gv = v3(gq[0], gq[1], gq[2]);
+    Sot3 dQ;
+    if (discrete) {
+        const V3 q1 = q0 + gv;
+        dQ.R = so3_from_vectors(normalized(q1), normalized(q0), &sing);
+        dQ.a = norm(q0) / norm(q1);
+    } else {
+        const double n2 = dot(q0, q0);
+        dQ = sot3_exp(-cross(q0, gv) / n2, -dot(q0, gv) / n2);
+    }
+    store_Q(L, i, dQ * load_Q(L, i));
+    if (sing) atomicOr(&st->flags, FLAG_SINGULAR);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blocked Cholesky panels (stand-in for the reference's explicit inverses, VIOFilter.cpp:277 and
+// EqFMatrices.cpp:239).  The augmented buffer holds the SPD matrix (k x k, lower triangle used) with
+// r extra rows below it; after the sweep the extra rows hold R L^-T.
+// ------------------------------------------------------------------------------------------------
+// k_potrf_diag: one CTA factors the nb x nb (nb <= 64) diagonal block at (j, j) in shared memory.
+__global__ void __launch_bounds__(256) k_potrf_diag(double* A, int lda, int j, int nb, int* flags) {
+    __shared__ double a[64][65];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < nb * nb; e += 256) {
+        const int r = e % nb, c = e / nb;
+        a[r][c] = A[(j + r) + (size_t)lda * (j + c)];
+    }
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+        if (tid == 0) {
+            double d = a[k][k];
+            if (!(d > 0.0)) { atomicOr(flags, FLAG_NOT_SPD); d = fabs(d) + 1e-300; }
+            a[k][k] = sqrt(d);
+        }
+        __syncthreads();
+        const double dk = a[k][k];
+        for (int r = k + 1 + tid; r < nb; r += 256) a[r][k] /= dk;
+        __syncthreads();
+        const int rem = nb - k - 1;
+        for (int e = tid; e < rem * rem; e += 256) {
+            const int r = k + 1 + e % rem, c = k + 1 + e / rem;
+            if (c <= r) a[r][c] -= a[r][k] * a[c][k];
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nb * nb; e += 256) {
+        const int r = e % nb, c = e / nb;
+        if (c <= r) A[(j + r) + (size_t)lda * (j + c)] = a[r][c];
+    }
+}
+
+// k_trsm_rows: rows [row0, row1) of the panel columns [j, j+nb):  X <- X L_jj^-T, one thread per row.
+__global__ void __launch_bounds__(128) k_trsm_rows(double* A, int lda, int j, int nb, int row0, int row1) {
+    __shared__ double l[64][65];
+    for (int e = threadIdx.x; e < nb * nb; e += 128) {
+        const int r = e % nb, c = e / nb;
+        l[r][c] = A[(j + r) + (size_t)lda * (j + c)];
+    }
+    __syncthreads();
+    const int row = row0 + blockIdx.x * 128 + threadIdx.x;
+    if (row >= row1) return;
+    double x[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) x[c] = c < nb ? A[row + (size_t)lda * (j + c)] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+        if (c < nb) {
+            double s = x[c];
+#pragma unroll
+            for (int q = 0; q < c; ++q) s -= x[q] * l[c][q];
+            x[c] = s / l[c][c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 64; ++c)
+        if (c < nb) A[row + (size_t)lda * (j + c)] = x[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+__global__ void k_copy_block(const double* src, int lds, double* dst, int ldd, int rows, int cols) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r < rows && c < cols) dst[r + (size_t)ldd * c] = src[r + (size_t)lds * c];
+}
+__global__ void k_set_identity_rows(double* A, int lda, int row0, int n) {
+    // A[row0 + i, c] = (i == c), i, c in [0, n)
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r < n && c < n) A[(row0 + r) + (size_t)lda * c] = (r == c) ? 1.0 : 0.0;
+}
+__global__ void k_add_diag_const(double* A, int lda, int n, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[i + (size_t)lda * i] += v;
+}
+__global__ void k_set_diag_one(double* A, int lda, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[i + (size_t)lda * i] = 1.0;
+}
+
+// removeOutliers test, VIOFilter.cpp:429-443: flag_i = |y_i - normalise(q_hat_i)| > threshold
+__global__ void k_outlier_flags(Landmarks L, int N, const double* bearings, double thr, int* flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const V3 qh = inverse(load_Q(L, i)) * load_q0(L, i);
+    const V3 yh = normalized(qh);
+    const V3 d = v3(bearings[3 * i], bearings[3 * i + 1], bearings[3 * i + 2]) - yh;
+    flags[i] = norm(d) > thr ? 1 : 0;
+}
+
+// removeRows / removeCols (VIOFilter.cpp:29-47) as one gather: dst[r,c] = src[map[r], map[c]]
+__global__ void k_gather_sigma(const double* src, double* dst, int ld, const int* map, int n_new) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r < n_new && c < n_new) dst[r + (size_t)ld * c] = src[map[r] + (size_t)ld * map[c]];
+}
+// landmark arrays: dst field f, slot i = src field f, slot keep[i]
+__global__ void k_gather_landmarks(const double* src, double* dst, int cap, const int* keep, int n_new) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.y;
+    if (i < n_new) dst[(size_t)f * cap + i] = src[(size_t)f * cap + keep[i]];
+}
+__global__ void k_gather_bearings(const double* src, double* dst, const int* idx, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int s = idx[i];
+        dst[3 * i] = src[3 * s]; dst[3 * i + 1] = src[3 * s + 1]; dst[3 * i + 2] = src[3 * s + 2];
+    }
+}
+
+// addNewLandmarks, VIOFilter.cpp:345-391.  One block.  Median: element of rank oldN/2 of the squared
+// depths (what nth_element at size/2 leaves there), then q0 = y * depth, Q = identity.
+__global__ void __launch_bounds__(1024) k_add_landmarks(Landmarks L, int oldN, int newN, const double* bearings,
+                                                        double initialSceneDepth, double* scratch) {
+    __shared__ double s_depth;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_depth = initialSceneDepth;
+    for (int i = tid; i < oldN; i += blockDim.x) {
+        const V3 qh = inverse(load_Q(L, i)) * load_q0(L, i);
+        scratch[i] = dot(qh, qh);
+    }
+    __syncthreads();
+    const int target = oldN / 2;
+    for (int i = tid; i < oldN; i += blockDim.x) {
+        const double v = scratch[i];
+        int rank = 0;
+        for (int j = 0; j < oldN; ++j) {
+            const double u = scratch[j];
+            rank += (u < v) || (u == v && j < i);
+        }
+        if (rank == target) s_depth = pow(v, 0.5);
+    }
+    __syncthreads();
+    const double depth = s_depth;
+    for (int k = tid; k < newN; k += blockDim.x) {
+        const int i = oldN + k;
+        L.q0(0)[i] = bearings[3 * i] * depth;
+        L.q0(1)[i] = bearings[3 * i + 1] * depth;
+        L.q0(2)[i] = bearings[3 * i + 2] * depth;
+        L.Q(0)[i] = 1.0; L.Q(1)[i] = 0.0; L.Q(2)[i] = 0.0; L.Q(3)[i] = 0.0; L.Q(4)[i] = 1.0;
+    }
+}
+// Sigma growth: rows/cols [n0, n1) zero, diagonal = initialPointVariance (VIOFilter.cpp:384-390)
+__global__ void k_grow_sigma(double* S, int ld, int n0, int n1, double var) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= n1 || c >= n1) return;
+    if (r < n0 && c < n0) return;
+    S[r + (size_t)ld * c] = (r == c) ? var : 0.0;
+}
+
+// setInertialPoints, VIOFilter.cpp:93-118 (points in the world frame -> camera frame of xi0)
+__global__ void k_set_inertial_points(const BaseState* st, Landmarks L, int N, const double* points) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const Se3 inv = inverse(st->pose0 * st->cam);
+    const V3 q = inv * v3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+    L.q0(0)[i] = q.x; L.q0(1)[i] = q.y; L.q0(2)[i] = q.z;
+    L.Q(0)[i] = 1.0; L.Q(1)[i] = 0.0; L.Q(2)[i] = 0.0; L.Q(3)[i] = 0.0; L.Q(4)[i] = 1.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+void launch_step_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const ImuArgs& a, const RiccatiOut& ro) {
+    k_step_prepare<<<1, 32, 0, s>>>(st, sc, a, ro);
+}
+void launch_feature_step(cudaStream_t s, BaseState* st, const StepScratch* sc, Landmarks L, int N, int do_riccati,
+                         int discrete, const RiccatiOut& ro) {
+    if (N > 0) k_feature_step<<<cdiv(N, 8), 256, 0, s>>>(st, sc, L, N, do_riccati, discrete, ro);
+}
+void launch_build_C_delta(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* bearings, double* C, int ldc,
+                          double* delta) {
+    if (N > 0) k_build_C_delta<<<cdiv(N, 8), 256, 0, s>>>(st, L, N, bearings, C, ldc, delta);
+}
+void launch_gemv(cudaStream_t s, const double* K, int ldk, int n, int m, const double* x, double* y) {
+    k_gemv<<<cdiv(n, 32), 256, 0, s>>>(K, ldk, n, m, x, y);
+}
+void launch_lift_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma) {
+    k_lift_prepare<<<1, 32, 0, s>>>(st, sc, gamma);
+}
+void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, int N, const double* gamma, double* Aug,
+                          int lda, int p) {
+    k_lift_features<<<cdiv(N > 5 ? N : 5, 128), 128, 0, s>>>(sc, L, N, gamma, Aug, lda, p);
+}
+void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
+                       int use_lift, int discrete, double stamp, double* Gamma_out, int apply) {
+    k_lift_solve<<<1, 256, 0, s>>>(st, sc, gamma, Aug, lda, p, use_lift, discrete, stamp, Gamma_out, apply);
+}
+void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete) {
+    if (N > 0) k_lift_apply<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, gamma, discrete);
+}
+void launch_potrf_diag(cudaStream_t s, double* A, int lda, int j, int nb, int* flags) {
+    k_potrf_diag<<<1, 256, 0, s>>>(A, lda, j, nb, flags);
+}
+void launch_trsm_rows(cudaStream_t s, double* A, int lda, int j, int nb, int row0, int row1) {
+    if (row1 > row0) k_trsm_rows<<<cdiv(row1 - row0, 128), 128, 0, s>>>(A, lda, j, nb, row0, row1);
+}
+void launch_copy_block(cudaStream_t s, const double* src, int lds, double* dst, int ldd, int rows, int cols) {
+    if (rows > 0 && cols > 0) k_copy_block<<<dim3(cdiv(rows, 256), cols), 256, 0, s>>>(src, lds, dst, ldd, rows, cols);
+}
+void launch_set_identity_rows(cudaStream_t s, double* A, int lda, int row0, int n) {
+    if (n > 0) k_set_identity_rows<<<dim3(cdiv(n, 256), n), 256, 0, s>>>(A, lda, row0, n);
+}
+void launch_add_diag_const(cudaStream_t s, double* A, int lda, int n, double v) {
+    if (n > 0) k_add_diag_const<<<cdiv(n, 256), 256, 0, s>>>(A, lda, n, v);
+}
+void launch_set_diag_one(cudaStream_t s, double* A, int lda, int n) {
+    if (n > 0) k_set_diag_one<<<cdiv(n, 256), 256, 0, s>>>(A, lda, n);
+}
+void launch_outlier_flags(cudaStream_t s, Landmarks L, int N, const double* bearings, double thr, int* flags) {
+    if (N > 0) k_outlier_flags<<<cdiv(N, 128), 128, 0, s>>>(L, N, bearings, thr, flags);
+}
+void launch_gather_sigma(cudaStream_t s, const double* src, double* dst, int ld, const int* map, int n_new) {
+    if (n_new > 0) k_gather_sigma<<<dim3(cdiv(n_new, 256), n_new), 256, 0, s>>>(src, dst, ld, map, n_new);
+}
+void launch_gather_landmarks(cudaStream_t s, const double* src, double* dst, int cap, const int* keep, int n_new) {
+    if (n_new > 0) k_gather_landmarks<<<dim3(cdiv(n_new, 128), LM_FIELDS), 128, 0, s>>>(src, dst, cap, keep, n_new);
+}
+void launch_gather_bearings(cudaStream_t s, const double* src, double* dst, const int* idx, int n) {
+    if (n > 0) k_gather_bearings<<<cdiv(n, 128), 128, 0, s>>>(src, dst, idx, n);
+}
+void launch_add_landmarks(cudaStream_t s, Landmarks L, int oldN, int newN, const double* bearings, double depth0,
+                          double* scratch) {
+    k_add_landmarks<<<1, 1024, 0, s>>>(L, oldN, newN, bearings, depth0, scratch);
+}
+void launch_grow_sigma(cudaStream_t s, double* S, int ld, int n0, int n1, double var) {
+    k_grow_sigma<<<dim3(cdiv(n1, 256), n1), 256, 0, s>>>(S, ld, n0, n1, var);
+}
+void launch_set_inertial_points(cudaStream_t s, const BaseState* st, Landmarks L, int N, const double* points) {
+    if (N > 0) k_set_inertial_points<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, points);
+}
+
+}  // namespace eqvio

@@ -1,0 +1,32 @@
+// kernels_api.cuh — host-callable launchers of the kernels in filter_kernels.cu.
+#pragma once
+#include "filter_kernels.cuh"
+
+namespace eqvio {
+void launch_step_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const ImuArgs& a, const RiccatiOut& ro);
+void launch_feature_step(cudaStream_t s, BaseState* st, const StepScratch* sc, Landmarks L, int N, int do_riccati,
+                         int discrete, const RiccatiOut& ro);
+void launch_build_C_delta(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* bearings, double* C, int ldc,
+                          double* delta);
+void launch_gemv(cudaStream_t s, const double* K, int ldk, int n, int m, const double* x, double* y);
+void launch_lift_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma);
+void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, int N, const double* gamma, double* Aug,
+                          int lda, int p);
+void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
+                       int use_lift, int discrete, double stamp, double* Gamma_out, int apply);
+void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete);
+void launch_potrf_diag(cudaStream_t s, double* A, int lda, int j, int nb, int* flags);
+void launch_trsm_rows(cudaStream_t s, double* A, int lda, int j, int nb, int row0, int row1);
+void launch_copy_block(cudaStream_t s, const double* src, int lds, double* dst, int ldd, int rows, int cols);
+void launch_set_identity_rows(cudaStream_t s, double* A, int lda, int row0, int n);
+void launch_add_diag_const(cudaStream_t s, double* A, int lda, int n, double v);
+void launch_set_diag_one(cudaStream_t s, double* A, int lda, int n);
+void launch_outlier_flags(cudaStream_t s, Landmarks L, int N, const double* bearings, double thr, int* flags);
+void launch_gather_sigma(cudaStream_t s, const double* src, double* dst, int ld, const int* map, int n_new);
+void launch_gather_landmarks(cudaStream_t s, const double* src, double* dst, int cap, const int* keep, int n_new);
+void launch_gather_bearings(cudaStream_t s, const double* src, double* dst, const int* idx, int n);
+void launch_add_landmarks(cudaStream_t s, Landmarks L, int oldN, int newN, const double* bearings, double depth0,
+                          double* scratch);
+void launch_grow_sigma(cudaStream_t s, double* S, int ld, int n0, int n1, double var);
+void launch_set_inertial_points(cudaStream_t s, const BaseState* st, Landmarks L, int N, const double* points);
+}  // namespace eqvio

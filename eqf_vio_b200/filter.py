@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference's `class VIOFilter` (eqf_vio/include/eqf_vio/VIOFilter.h:41-88)
+over the C ABI: same method names, argument meaning and silent-skip behaviour; every call lands in
+csrc/libeqvio_b200.so (hand-written sm_100a kernels).  Status codes the reference expresses by silently
+returning are returned as small positive ints (abi.SKIPPED_DT ...); errors raise EqvioError."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import abi
+from .settings import Settings
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _vec(a, n=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} values, got {a.size}")
+    return a
+
+
+@dataclass
+class VIOStateEstimate:
+    """VIOState (eqf_vio/include/eqf_vio/VIOState.h:51-60) as plain arrays; poses are x y z qw qx qy qz."""
+
+    pose: np.ndarray
+    velocity: np.ndarray
+    cameraOffset: np.ndarray
+    ids: np.ndarray
+    bodyLandmarks: np.ndarray
+
+
+class VIOFilter:
+    def __init__(self, settings: Settings, device: int = 0):
+        self._L = abi.lib()
+        self.settings = settings.copy()
+        self._h = C.c_void_p()
+        abi.check(self._L.eqvio_create(C.byref(self.settings), int(device), C.byref(self._h)), "eqvio_create")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.eqvio_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs (VIOFilter.h:74-81) ----
+    def reset(self):
+        abi.check(self._L.eqvio_reset(self._h), "eqvio_reset")
+
+    def processIMUData(self, stamp, omega, accel) -> int:
+        o, a = _vec(omega, 3), _vec(accel, 3)
+        return abi.check(self._L.eqvio_process_imu(self._h, float(stamp), _p(o), _p(a)), "eqvio_process_imu")
+
+    def processVisionData(self, stamp, ids, bearings) -> int:
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        y = _vec(bearings, 3 * ids.size)
+        return abi.check(
+            self._L.eqvio_process_vision(self._h, float(stamp), int(ids.size), ids.ctypes.data_as(C.POINTER(C.c_int)), _p(y)),
+            "eqvio_process_vision",
+        )
+
+    def processVisionDataDevice(self, stamp, ids, bearings_dev_ptr: int) -> int:
+        """Bearings already resident in device memory (3n doubles at `bearings_dev_ptr`)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        return abi.check(
+            self._L.eqvio_process_vision_dev(self._h, float(stamp), int(ids.size), ids.ctypes.data_as(C.POINTER(C.c_int)), C.c_void_p(bearings_dev_ptr)),
+            "eqvio_process_vision_dev",
+        )
+
+    def setInertialPoints(self, ids, points):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        p = _vec(points, 3 * ids.size)
+        abi.check(self._L.eqvio_set_inertial_points(self._h, int(ids.size), ids.ctypes.data_as(C.POINTER(C.c_int)), _p(p)), "eqvio_set_inertial_points")
+
+    # ---- outputs (VIOFilter.h:84-86) ----
+    def getTime(self) -> float:
+        t = C.c_double()
+        abi.check(self._L.eqvio_get_time(self._h, C.byref(t)), "eqvio_get_time")
+        return t.value
+
+    @property
+    def numLandmarks(self) -> int:
+        n = C.c_int()
+        abi.check(self._L.eqvio_get_num_landmarks(self._h, C.byref(n)), "eqvio_get_num_landmarks")
+        return n.value
+
+    def stateEstimate(self) -> VIOStateEstimate:
+        N = self.numLandmarks
+        pose, vel, cam = np.zeros(7), np.zeros(3), np.zeros(7)
+        ids = np.zeros(max(N, 1), dtype=np.int32)
+        lm = np.zeros(3 * max(N, 1))
+        n = C.c_int()
+        abi.check(
+            self._L.eqvio_get_state(self._h, _p(pose), _p(vel), _p(cam), C.byref(n), N, ids.ctypes.data_as(C.POINTER(C.c_int)), _p(lm)),
+            "eqvio_get_state",
+        )
+        return VIOStateEstimate(pose, vel, cam, ids[:N].copy(), lm[: 3 * N].reshape(N, 3).copy())
+
+    def poseRecord(self) -> np.ndarray:
+        rec = np.zeros(8)
+        abi.check(self._L.eqvio_get_pose_record(self._h, _p(rec)), "eqvio_get_pose_record")
+        return rec
+
+    def poseRecordDevicePtr(self) -> int:
+        p = C.c_void_p()
+        abi.check(self._L.eqvio_pose_record_dev(self._h, C.byref(p)), "eqvio_pose_record_dev")
+        return p.value
+
+    def stateCovariance(self) -> np.ndarray:
+        n = 11 + 3 * self.numLandmarks
+        S = np.zeros((n, n), order="F")
+        abi.check(self._L.eqvio_get_covariance(self._h, _p(S), n), "eqvio_get_covariance")
+        return S
+
+    def inputBias(self) -> np.ndarray:
+        b = np.zeros(6)
+        abi.check(self._L.eqvio_get_bias(self._h, _p(b)), "eqvio_get_bias")
+        return b
+
+    # ---- snapshot / restore ----
+    def get_snapshot(self) -> np.ndarray:
+        d = np.zeros(self._L.eqvio_snapshot_size(self.numLandmarks))
+        abi.check(self._L.eqvio_get_snapshot(self._h, _p(d), d.size), "eqvio_get_snapshot")
+        return d
+
+    def set_snapshot(self, d):
+        d = _vec(d)
+        abi.check(self._L.eqvio_set_snapshot(self._h, _p(d), d.size), "eqvio_set_snapshot")
+
+    # ---- kernel-level entry points ----
+    def build_FB(self, T, omega):
+        n = 11 + 3 * self.numLandmarks
+        F = np.zeros((n, n), order="F")
+        Bb = np.zeros((n, 6), order="F")
+        abi.check(self._L.eqvio_build_FB(self._h, float(T), _p(_vec(omega, 3)), _p(F), _p(Bb)), "eqvio_build_FB")
+        return F, Bb
+
+    def riccati_propagate(self, T, omega):
+        abi.check(self._L.eqvio_riccati_propagate(self._h, float(T), _p(_vec(omega, 3))), "eqvio_riccati_propagate")
+
+    def build_C_delta(self, bearings):
+        N = self.numLandmarks
+        Cm = np.zeros((2 * N, 11 + 3 * N), order="F")
+        d = np.zeros(2 * N)
+        abi.check(self._L.eqvio_build_C_delta(self._h, _p(_vec(bearings, 3 * N)), _p(Cm), _p(d)), "eqvio_build_C_delta")
+        return Cm, d
+
+    def gain_update(self, bearings):
+        N = self.numLandmarks
+        n = 11 + 3 * N
+        K = np.zeros((n, 2 * N), order="F")
+        g = np.zeros(n)
+        abi.check(self._L.eqvio_gain_update(self._h, _p(_vec(bearings, 3 * N)), _p(K), _p(g)), "eqvio_gain_update")
+        return K, g
+
+    def bundle_lift(self, gamma_eqf):
+        N = self.numLandmarks
+        G = np.zeros(9 + 3 * N)
+        abi.check(self._L.eqvio_bundle_lift(self._h, _p(_vec(gamma_eqf, 5 + 3 * N)), _p(G)), "eqvio_bundle_lift")
+        return G
+
+    # ---- instrumentation ----
+    def synchronize(self):
+        abi.check(self._L.eqvio_synchronize(self._h), "eqvio_synchronize")
+
+    def launch_count(self, reset=False) -> int:
+        c = C.c_longlong()
+        abi.check(self._L.eqvio_launch_count(self._h, C.byref(c), int(reset)), "eqvio_launch_count")
+        return c.value
+
+    def profile_enable(self, on=True):
+        abi.check(self._L.eqvio_profile_enable(self._h, int(on)), "eqvio_profile_enable")
+
+    def profile_read(self, reset=True):
+        n = C.c_longlong()
+        ms, fl = C.c_double(), C.c_double()
+        abi.check(self._L.eqvio_profile_read(self._h, C.byref(n), C.byref(ms), C.byref(fl), int(reset)), "eqvio_profile_read")
+        return n.value, ms.value, fl.value
+
+    def stream_ptr(self) -> int:
+        p = C.c_void_p()
+        abi.check(self._L.eqvio_stream(self._h, C.byref(p)), "eqvio_stream")
+        return p.value or 0
+
+
+def dgemm(A, B, transB=False, alpha=1.0, beta=0.0, Cin=None, device=0, reps=1):
+    """C = alpha * A @ op(B) + beta * Cin on the library's DMMA kernel (host arrays).  Returns (C, ms)."""
+    L = abi.lib()
+    A = np.asfortranarray(A, dtype=np.float64)
+    B = np.asfortranarray(B, dtype=np.float64)
+    M, K = A.shape
+    N = B.shape[0] if transB else B.shape[1]
+    assert (B.shape[1] if transB else B.shape[0]) == K
+    Cm = np.zeros((M, N), order="F") if Cin is None else np.asfortranarray(Cin, dtype=np.float64).copy(order="F")
+    ms = C.c_float()
+    abi.check(
+        L.eqvio_dgemm(int(device), int(transB), M, N, K, float(alpha), _p(A), max(A.shape[0], 1), _p(B), max(B.shape[0], 1), float(beta), _p(Cm), max(M, 1), int(reps), C.byref(ms)),
+        "eqvio_dgemm",
+    )
+    return Cm, ms.value

@@ -1,0 +1,122 @@
+"""POD mirror of VIOFilter::Settings (reference: eqf_vio/include/eqf_vio/VIOFilterSettings.h:28-50)
+as a ctypes structure laid out exactly like `eqvio_settings_t` in include/eqvio.h, plus the two
+configurations the reference ships: the struct defaults and EQVIO_config_template.yaml."""
+from __future__ import annotations
+
+import ctypes as C
+
+_DOUBLE_FIELDS = [
+    "biasOmegaProcessVariance",
+    "biasAccelProcessVariance",
+    "gravityProcessVariance",
+    "velocityProcessVariance",
+    "pointProcessVariance",
+    "velOmegaVariance",
+    "velAccelVariance",
+    "measurementVariance",
+    "initialGravityVariance",
+    "initialVelocityVariance",
+    "initialPointVariance",
+    "initialBiasOmegaVariance",
+    "initialBiasAccelVariance",
+    "initialSceneDepth",
+    "outlierThreshold",
+]
+_BOOL_FIELDS = ["useInnovationLift", "useDiscreteInnovationLift", "useDiscreteVelocityLift", "fastRiccati"]
+
+
+class Settings(C.Structure):
+    _fields_ = (
+        [(n, C.c_double) for n in _DOUBLE_FIELDS]
+        + [(n, C.c_int) for n in _BOOL_FIELDS]
+        + [("initialAccelBias", C.c_double * 3), ("initialOmegaBias", C.c_double * 3), ("cameraOffset", C.c_double * 7)]
+    )
+
+    def as_dict(self) -> dict:
+        d = {n: getattr(self, n) for n in _DOUBLE_FIELDS}
+        d.update({n: bool(getattr(self, n)) for n in _BOOL_FIELDS})
+        d["initialAccelBias"] = tuple(self.initialAccelBias)
+        d["initialOmegaBias"] = tuple(self.initialOmegaBias)
+        d["cameraOffset"] = tuple(self.cameraOffset)
+        return d
+
+    def copy(self) -> "Settings":
+        s = Settings()
+        C.memmove(C.byref(s), C.byref(self), C.sizeof(Settings))
+        return s
+
+
+def default_settings() -> Settings:
+    """Struct defaults, VIOFilterSettings.h:29-50."""
+    s = Settings()
+    for n in ("biasOmegaProcessVariance", "biasAccelProcessVariance", "gravityProcessVariance", "velocityProcessVariance", "pointProcessVariance"):
+        setattr(s, n, 0.001)
+    s.velOmegaVariance = s.velAccelVariance = s.measurementVariance = 0.1
+    s.initialGravityVariance = s.initialVelocityVariance = s.initialPointVariance = 1.0
+    s.initialBiasOmegaVariance = s.initialBiasAccelVariance = 1.0
+    s.initialSceneDepth = 1.0
+    s.outlierThreshold = 0.01
+    s.useInnovationLift = s.useDiscreteInnovationLift = s.useDiscreteVelocityLift = 1
+    s.fastRiccati = 0
+    s.cameraOffset[:] = (0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0)
+    return s
+
+
+# `eqf:` section of eqf_vio/EQVIO_config_template.yaml:1-29
+TEMPLATE_EQF = {
+    "initialGravityVariance": 1.0,
+    "initialVelocityVariance": 1.0,
+    "initialPointVariance": 5000.0,
+    "biasOmegaProcessVariance": 0.0001,
+    "biasAccelProcessVariance": 0.0001,
+    "gravityProcessVariance": 0.01,
+    "velocityProcessVariance": 0.1,
+    "pointProcessVariance": 0.001,
+    "measurementVariance": 0.003,
+    "velOmegaVariance": 0.0001,
+    "velAccelVariance": 0.0001,
+    "initialBiasOmegaVariance": 1.0,
+    "initialBiasAccelVariance": 1.0,
+    "initialSceneDepth": 1.0,
+    "outlierThreshold": 0.01,
+    "fastRiccati": False,
+    "useInnovationLift": True,
+    "useDiscreteInnovationLift": True,
+    "useDiscreteVelocityLift": True,
+    "cameraOffset": ["xw", -0.0216401454975, -0.064676986768, 0.00981073058949, 0.7123014606690344, -0.007707179755538301, 0.010499323370588468, 0.7017528002920512],
+}
+
+
+def settings_from_eqf_node(node: dict) -> Settings:
+    """Same key handling as VIOFilter::Settings::Settings(const YAML::Node&)
+    (VIOFilterSettings.h:56-109): absent keys keep the struct default (safeConfig, common.h:22-29);
+    cameraOffset is ["xw", x, y, z, qw, qx, qy, qz]."""
+    s = default_settings()
+    for n in _DOUBLE_FIELDS:
+        if n in node:
+            setattr(s, n, float(node[n]))
+    for n in _BOOL_FIELDS:
+        if n in node:
+            setattr(s, n, int(bool(node[n])))
+    for n in ("initialAccelBias", "initialOmegaBias"):
+        if n in node:
+            getattr(s, n)[:] = [float(v) for v in node[n][:3]]
+    if "cameraOffset" in node:
+        co = node["cameraOffset"]
+        if co[0] != "xw":
+            raise ValueError('cameraOffset[0] must be "xw"')
+        s.cameraOffset[:] = [float(v) for v in co[1:8]]
+    return s
+
+
+def template_settings(**overrides) -> Settings:
+    node = dict(TEMPLATE_EQF)
+    node.update(overrides)
+    return settings_from_eqf_node(node)
+
+
+def settings_from_yaml(path: str) -> Settings:
+    import yaml
+
+    with open(path) as f:
+        return settings_from_eqf_node(yaml.safe_load(f)["eqf"])

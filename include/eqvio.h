@@ -1,0 +1,190 @@
+/*
+ * eqvio.h — C ABI of the B200-native EqF-VIO filter hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer; its boundary is the
+ * public surface of `class VIOFilter` (reference: eqf_vio/include/eqf_vio/VIOFilter.h:64-88).  Every
+ * entry point below names the reference member it replaces.  All types are POD, every function
+ * returns an `int` status (0 = OK), no exception crosses this boundary, output buffers are
+ * caller-owned.  One handle = one CUDA device + one CUDA stream; a handle is not thread-safe but
+ * distinct handles are independent (one filter session per GPU for the multi-session configuration).
+ *
+ * Conventions (identical to the reference):
+ *   - Sigma is n x n, n = 11 + 3N, column-major (Eigen default), index map
+ *     [0,3) gyro bias, [3,6) accel bias, [6,8) gravity chart, [8,11) body velocity,
+ *     [11+3i, 14+3i) landmark i          (eqf_vio/src/VIOFilter.cpp:54-57,163-167)
+ *   - rotations are unit quaternions in (w, x, y, z) order; poses are (x, y, z, qw, qx, qy, qz),
+ *     the "xw" order of the YAML `cameraOffset` key (eqf_vio/include/eqf_vio/VIOFilterSettings.h:95-108)
+ *   - bearings are unit 3-vectors in the camera frame, sorted by ascending id
+ *     (eqf_vio/src/VIOFilter.cpp:239-240)
+ */
+#ifndef EQVIO_H
+#define EQVIO_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EQVIO_SIGMA_BASE_SIZE 11 /* eqf_vio/include/eqf_vio/VIOFilter.h:28 */
+#define EQVIO_GRAVITY_CONSTANT 9.81 /* eqf_vio/include/eqf_vio/IMUVelocity.h:22 */
+
+/* Field-for-field mirror of VIOFilter::Settings (VIOFilterSettings.h:28-50), same defaults via
+ * eqvio_settings_default().  bools are ints. */
+typedef struct eqvio_settings {
+    double biasOmegaProcessVariance;
+    double biasAccelProcessVariance;
+    double gravityProcessVariance;
+    double velocityProcessVariance;
+    double pointProcessVariance;
+    double velOmegaVariance;
+    double velAccelVariance;
+    double measurementVariance;
+    double initialGravityVariance;
+    double initialVelocityVariance;
+    double initialPointVariance;
+    double initialBiasOmegaVariance;
+    double initialBiasAccelVariance;
+    double initialSceneDepth;
+    double outlierThreshold;
+    int useInnovationLift;
+    int useDiscreteInnovationLift;
+    int useDiscreteVelocityLift;
+    int fastRiccati;
+    double initialAccelBias[3];
+    double initialOmegaBias[3];
+    double cameraOffset[7]; /* x y z qw qx qy qz */
+} eqvio_settings_t;
+
+typedef struct eqvio_filter* eqvio_handle_t;
+
+/* Status codes.  The reference returns void and signals these conditions by silently returning
+ * (VIOFilter.cpp:147-152, 235-236, 258-259), by assert (:190,205,299-300) or by throwing
+ * std::domain_error (libs/core/src/SO3.cpp:160-161). */
+enum {
+    EQVIO_OK = 0,
+    EQVIO_SKIPPED_DT = 1,       /* dt <= 0 or no previous stamp: nothing integrated (VIOFilter.cpp:147-152) */
+    EQVIO_NOT_INITIALISED = 2,  /* vision before the first IMU sample (VIOFilter.cpp:235) */
+    EQVIO_EMPTY_MEASUREMENT = 3,/* no bearings left after bookkeeping (VIOFilter.cpp:258-259) */
+    EQVIO_ERR_ARG = -1,
+    EQVIO_ERR_CUDA = -2,
+    EQVIO_ERR_NAN = -3,            /* NaN in Sigma or X (the reference's asserts) */
+    EQVIO_ERR_SINGULAR_CHART = -4, /* SO3FromVectors on opposing vectors (SO3.cpp:160) */
+    EQVIO_ERR_NOT_SPD = -5,        /* Cholesky of S or Sigma failed */
+    EQVIO_ERR_NO_DEVICE = -6,
+    EQVIO_ERR_UNSORTED = -7        /* bearings not sorted by ascending id (VIOFilter.cpp:239-240) */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Struct defaults of VIOFilter::Settings (VIOFilterSettings.h:29-50). */
+int eqvio_settings_default(eqvio_settings_t* s);
+
+/* VIOFilter::VIOFilter(const Settings&) (VIOFilter.cpp:60-73).  `device` is the CUDA ordinal. */
+int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* out);
+int eqvio_destroy(eqvio_handle_t h);
+/* VIOFilter::reset() (VIOFilter.cpp:84-91) */
+int eqvio_reset(eqvio_handle_t h);
+
+/* ---- inputs -------------------------------------------------------------------------------- */
+
+/* VIOFilter::processIMUData (VIOFilter.cpp:120-131).  Asynchronous: enqueues on the handle's stream
+ * and returns; the 7 doubles travel as kernel arguments.  Returns EQVIO_SKIPPED_DT when nothing was
+ * integrated (first sample, dt <= 0) — the velocity/time latch still happens, as in the reference. */
+int eqvio_process_imu(eqvio_handle_t h, double stamp, const double omega[3], const double accel[3]);
+
+/* VIOFilter::processVisionData (VIOFilter.cpp:232-302).  `ids` (n ints) ascending, `bearings`
+ * 3n doubles (x,y,z per bearing, unit norm), both HOST pointers. */
+int eqvio_process_vision(eqvio_handle_t h, double stamp, int n, const int* ids, const double* bearings);
+
+/* Same call with the bearings already resident in device memory (ids stay on the host: landmark
+ * bookkeeping is host-side index work).  Used for the HBM-resident throughput figure. */
+int eqvio_process_vision_dev(eqvio_handle_t h, double stamp, int n, const int* ids,
+                             const double* bearings_dev);
+
+/* VIOFilter::setInertialPoints (VIOFilter.cpp:93-118): n points (id, world xyz). */
+int eqvio_set_inertial_points(eqvio_handle_t h, int n, const int* ids, const double* points);
+
+/* ---- outputs (synchronise the handle's stream) ---------------------------------------------- */
+
+/* VIOFilter::getTime (VIOFilter.cpp:343) */
+int eqvio_get_time(eqvio_handle_t h, double* t);
+/* Current number of landmarks N (n = 11 + 3N). */
+int eqvio_get_num_landmarks(eqvio_handle_t h, int* n);
+/* VIOFilter::stateEstimate (VIOFilter.cpp:304) = stateGroupAction(X, xi0) (VIOGroup.cpp:23).
+ * pose/cam_offset: x y z qw qx qy qz; ids/landmarks may be NULL; *n receives N.  cap = capacity of
+ * ids/landmarks in landmarks. */
+int eqvio_get_state(eqvio_handle_t h, double pose[7], double velocity[3], double cam_offset[7],
+                    int* n, int cap, int* ids, double* landmarks);
+/* Pose only (x y z qw qx qy qz) + stamp: the 8-double record gathered across sessions. */
+int eqvio_get_pose_record(eqvio_handle_t h, double rec[8]);
+/* Device pointer to the 8-double pose record refreshed by every vision update (t x y z qw qx qy qz);
+ * valid for the lifetime of the handle; stream-ordered after the update. */
+int eqvio_pose_record_dev(eqvio_handle_t h, double** dev_ptr);
+/* VIOFilter::stateCovariance (VIOFilter.cpp:306-309): n x n column-major into dst with leading
+ * dimension ld >= n. */
+int eqvio_get_covariance(eqvio_handle_t h, double* dst, int ld);
+/* inputBias (VIOFilter.h:46): omega bias [0,3), accel bias [3,6). */
+int eqvio_get_bias(eqvio_handle_t h, double bias[6]);
+
+/* ---- snapshot / restore (lossless; the reference only has the write-only CSV dump
+ *      operator<< at VIOFilter.cpp:311-341) --------------------------------------------------
+ * Layout (doubles):  [0] N  [1] currentTime  [2] initialisedFlag  [3] accumulatedTime
+ *   [4,10) inputBias  [10,16) currentVelocity (omega, accel)  [16,22) accumulatedVelocity
+ *   [22,29) xi0.pose (qw qx qy qz x y z)  [29,32) xi0.velocity  [32,39) xi0.cameraOffset (q, x)
+ *   [39,46) X.A (q, x)  [46,49) X.w
+ *   then N records of 9: id, q0 xyz, Q quaternion wxyz, Q scale a
+ *   then Sigma, n x n column-major.
+ */
+#define EQVIO_SNAPSHOT_HEADER 49
+#define EQVIO_SNAPSHOT_PER_LANDMARK 9
+size_t eqvio_snapshot_size(int n_landmarks); /* in doubles */
+int eqvio_get_snapshot(eqvio_handle_t h, double* dst, size_t cap);
+int eqvio_set_snapshot(eqvio_handle_t h, const double* src, size_t len);
+
+/* ---- kernel-level entry points (unit parity + ncu).  They act on the handle's current
+ *      (xi0, X, Sigma); outputs are HOST buffers. ------------------------------------------- */
+
+/* EqFStateMatrixA_euclid_impl + EqFInputMatrixB_euclid_impl + biased assembly
+ * (EqFMatrices.cpp:277-317,346-382; VIOFilter.cpp:177-185).  Writes F = I + T*[[0,0],[-Bt,A0t]]
+ * (n x n, col-major, ld = n) and B_b = [0;Bt] (n x 6) for mean angular velocity `omega`. */
+int eqvio_build_FB(eqvio_handle_t h, double T, const double omega[3], double* F, double* Bb);
+/* Riccati step Sigma <- T (P + B_b R B_b^T) + F Sigma F^T (VIOFilter.cpp:162-189) on the handle's
+ * Sigma, with A/B evaluated at the current state.  Does not propagate X. */
+int eqvio_riccati_propagate(eqvio_handle_t h, double T, const double omega[3]);
+/* delta = outputCoordinateChart(outputGroupAction(X^-1, y), measureSystemState(xi0)) and
+ * C = [0, C0] (VIOFilter.cpp:264-273; EqFMatrices.cpp:319-344).  bearings: 3N host doubles aligned
+ * with the state.  C is m x n col-major (ld = m), delta has m = 2N entries; either may be NULL. */
+int eqvio_build_C_delta(eqvio_handle_t h, const double* bearings, double* C, double* delta);
+/* S, K, gamma = K delta, Sigma <- Sigma - K C Sigma (VIOFilter.cpp:276-279,297).  Outputs optional:
+ * K (n x m col-major), gamma (n).  Does not lift / touch X. */
+int eqvio_gain_update(eqvio_handle_t h, const double* bearings, double* K, double* gamma);
+/* bundleLift (EqFMatrices.cpp:173-252) of a base innovation gamma_eqf (5+3N) with the handle's
+ * current Sigma[6:,6:]; Gamma out has 9+3N entries. */
+int eqvio_bundle_lift(eqvio_handle_t h, const double* gamma_eqf, double* Gamma);
+
+/* Plain fp64 GEMM on the library's DMMA kernel, host buffers, column-major:
+ * C <- alpha * A * op(B) + beta * C,  A is M x K, op(B) is K x N (transB: B stored N x K).
+ * `reps` > 1 repeats the launch and *ms receives the mean CUDA-event time per launch (may be NULL). */
+int eqvio_dgemm(int device, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+                const double* B, int ldb, double beta, double* C, int ldc, int reps, float* ms);
+
+/* ---- instrumentation ----------------------------------------------------------------------- */
+
+int eqvio_synchronize(eqvio_handle_t h);
+/* Number of kernel launches issued by this handle since creation / last reset of the counter. */
+int eqvio_launch_count(eqvio_handle_t h, long long* count, int reset);
+/* When enabled, every Sigma-contraction (GEMM) launch is bracketed by CUDA events on the handle's
+ * stream; eqvio_profile_read synchronises and returns launches, total ms and executed flops. */
+int eqvio_profile_enable(eqvio_handle_t h, int on);
+int eqvio_profile_read(eqvio_handle_t h, long long* gemm_launches, double* gemm_ms, double* gemm_flops,
+                       int reset);
+/* The handle's CUDA stream (cudaStream_t as void*), for callers that order their own work after it. */
+int eqvio_stream(eqvio_handle_t h, void** stream);
+const char* eqvio_status_string(int status);
+const char* eqvio_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQVIO_H */
