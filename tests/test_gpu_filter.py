@@ -1,0 +1,258 @@
+"""Parity of the CUDA filter path (through the C ABI, eqf_vio_b200/filter.py -> libeqvio_b200.so)
+against the CPU oracle and the committed golden vectors.
+
+Tolerances (fp64 throughout, stated per north_star):
+  * one step from an identical state: rel-Frobenius(Sigma) < 1e-9, lifted state < 1e-8 absolute
+    (the reference's formulation loses ~5 digits in K = Sigma C^T S^-1);
+  * free-running sequences: rel-Frobenius(Sigma) < 2e-8 and state < 1e-4 — the same spread the two CPU
+    restatements show against each other (tests/test_oracle_cross.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from eqf_vio_b200 import abi
+from eqf_vio_b200.settings import template_settings
+from eqf_vio_b200.synthetic import period_sequence
+from helpers import feed, rel, run, split_snapshot
+from oracle.c_oracle import COracleFilter
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STEP_SIGMA_TOL, STEP_STATE_TOL = 1e-9, 1e-8
+SEQ_SIGMA_TOL, SEQ_STATE_TOL = 2e-8, 1e-4
+
+
+def gpu_filter(s):
+    from eqf_vio_b200.filter import VIOFilter
+
+    return VIOFilter(s)
+
+
+def test_golden_pieces():
+    z = np.load(os.path.join(GOLDEN, "pieces_N8.npz"))
+    s = template_settings(outlierThreshold=1e9)
+    f = gpu_filter(s)
+    f.set_snapshot(z["snapshot"])
+    assert np.array_equal(f.get_snapshot(), z["snapshot"])  # lossless snapshot / restore
+    F, Bb = f.build_FB(float(z["T"]), z["omega"])
+    assert np.abs(F - z["F"]).max() < 1e-13 and np.abs(Bb - z["Bb"]).max() < 1e-13
+    assert np.array_equal(f.get_snapshot(), z["snapshot"])  # kernel-level entry point leaves the state alone
+    C, d = f.build_C_delta(z["bearings"])
+    assert np.abs(C - z["C"]).max() < 1e-13 and np.abs(d - z["delta"]).max() < 1e-13
+    G = f.bundle_lift(z["gamma_eqf"])
+    assert np.abs(G - z["Gamma"]).max() < 1e-9 * max(1.0, np.abs(z["Gamma"]).max())
+    f.riccati_propagate(float(z["T"]), z["omega"])
+    assert rel(f.stateCovariance(), z["Sigma_prop"]) < 1e-14
+    f.set_snapshot(z["snapshot"])
+    K, g = f.gain_update(z["bearings"])
+    assert rel(K, z["K"]) < 1e-9 and rel(g, z["gamma"]) < 1e-9
+    assert rel(f.stateCovariance(), z["Sigma_upd"]) < STEP_SIGMA_TOL
+
+
+def _overrides(z):
+    return dict(eval(str(z["overrides"])))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "seq_*.npz"))), ids=os.path.basename)
+def test_golden_sequences(path):
+    """Free-running against the committed vectors, all Settings modes (discrete / continuous lifts,
+    fastRiccati, no innovation lift)."""
+    z = np.load(path)
+    f = gpu_filter(template_settings(**_overrides(z)))
+    imu, vs, ids, y = z["imu"], z["vision_stamps"], z["ids"], z["bearings"]
+    i = j = k = 0
+    while i < len(imu) or j < len(vs):
+        if i < len(imu) and (j >= len(vs) or imu[i, 0] < vs[j]):
+            r = f.processIMUData(imu[i, 0], imu[i, 1:4], imu[i, 4:7])
+            i += 1
+        else:
+            r = f.processVisionData(vs[j], ids, y[j])
+            hg, Sg = split_snapshot(z[f"snap{j}"])
+            h, S = split_snapshot(f.get_snapshot())
+            assert rel(S, Sg) < SEQ_SIGMA_TOL and np.abs(h - hg).max() < SEQ_STATE_TOL, (j, rel(S, Sg), np.abs(h - hg).max())
+            j += 1
+        assert r == int(z["status"][k])
+        k += 1
+
+
+@pytest.mark.parametrize("N,periods", [(5, 3), (64, 3), (100, 2)])
+def test_every_step_from_identical_state(N, periods):
+    """The step map itself: before each event the GPU filter is re-seeded with the oracle's state, both
+    take the event, results compared at the north_star tolerance.  N = 100 also crosses the initial
+    buffer capacity (reallocation path)."""
+    s = template_settings(outlierThreshold=1e9)
+    seq = period_sequence(N, periods, camera_offset=tuple(s.cameraOffset))
+    f, o = gpu_filter(s), COracleFilter(s)
+    worst_s = worst_h = 0.0
+    for kind, i in seq.events():
+        f.set_snapshot(o.get_snapshot())
+        r1, r2 = feed(f, seq, kind, i), feed(o, seq, kind, i)
+        assert r1 == r2
+        if kind == "vision" or i % 3 == 0:
+            h1, S1 = split_snapshot(f.get_snapshot())
+            h2, S2 = split_snapshot(o.get_snapshot())
+            worst_s, worst_h = max(worst_s, rel(S1, S2)), max(worst_h, np.abs(h1 - h2).max())
+    assert worst_s < STEP_SIGMA_TOL and worst_h < STEP_STATE_TOL, (worst_s, worst_h)
+
+
+def test_free_running_sequence_N64():
+    s = template_settings(outlierThreshold=1e9)
+    seq = period_sequence(64, 6, camera_offset=tuple(s.cameraOffset))
+    f, o = gpu_filter(s), COracleFilter(s)
+    for kind, i in seq.events():
+        assert feed(f, seq, kind, i) == feed(o, seq, kind, i)
+        if kind == "vision":
+            h1, S1 = split_snapshot(f.get_snapshot())
+            h2, S2 = split_snapshot(o.get_snapshot())
+            assert rel(S1, S2) < SEQ_SIGMA_TOL and np.abs(h1 - h2).max() < SEQ_STATE_TOL
+    e, oe = f.stateEstimate(), o.stateEstimate()
+    assert np.abs(e.pose - oe["pose"]).max() < SEQ_STATE_TOL and np.abs(e.bodyLandmarks - oe["landmarks"]).max() < SEQ_STATE_TOL
+    assert np.abs(f.inputBias() - o.bias()).max() < 1e-8
+    assert np.array_equal(e.ids, oe["ids"])
+
+
+def test_bookkeeping_landmarks_come_and_go():
+    """removeOldLandmarks / matchMeasurementsToState / removeOutliers / addNewLandmarks
+    (VIOFilter.cpp:211-230, 345-443) with the template outlier threshold and ragged id sets."""
+    rng = np.random.default_rng(3)
+    s = template_settings()
+    seq = period_sequence(12, 8, camera_offset=tuple(s.cameraOffset))
+    f, o = gpu_filter(s), COracleFilter(s)
+    for kind, i in seq.events():
+        if kind == "imu":
+            feed(f, seq, kind, i), feed(o, seq, kind, i)
+            continue
+        sel = np.sort(rng.choice(12, size=int(rng.integers(3, 12)), replace=False)) if i > 0 else np.arange(8)
+        assert feed(f, seq, kind, i, sel=sel) == feed(o, seq, kind, i, sel=sel)
+        a, b = f.get_snapshot(), o.get_snapshot()
+        assert a.size == b.size
+        h1, S1 = split_snapshot(a)
+        h2, S2 = split_snapshot(b)
+        assert np.array_equal(h1[49::9], h2[49::9])  # same ids in the same order
+        assert rel(S1, S2) < SEQ_SIGMA_TOL and np.abs(h1 - h2).max() < SEQ_STATE_TOL
+
+
+def test_outliers_removed_like_reference():
+    s = template_settings(outlierThreshold=0.05)
+    seq = period_sequence(10, 3, camera_offset=tuple(s.cameraOffset))
+    f, o = gpu_filter(s), COracleFilter(s)
+    for kind, i in seq.events():
+        if kind == "vision" and i == 2:
+            y = seq.bearings[i].copy()
+            y[3] = -y[3]  # gross outlier
+            y[7] = np.array([0.0, 0.6, 0.8])
+            r1 = f.processVisionData(seq.vision_stamps[i], seq.ids, y)
+            r2 = o.processVisionData(seq.vision_stamps[i], seq.ids, y)
+            assert r1 == r2
+        else:
+            feed(f, seq, kind, i), feed(o, seq, kind, i)
+    assert f.numLandmarks == o.N
+    h1, S1 = split_snapshot(f.get_snapshot())
+    h2, S2 = split_snapshot(o.get_snapshot())
+    assert np.array_equal(h1[49::9], h2[49::9]) and rel(S1, S2) < SEQ_SIGMA_TOL
+
+
+def test_silent_skips_and_errors():
+    s = template_settings()
+    f = gpu_filter(s)
+    y = np.array([[0.0, 0.6, 0.8]])
+    assert f.processVisionData(0.5, [0], y) == abi.SKIPPED_DT        # no IMU yet (VIOFilter.cpp:147-148, 235)
+    assert f.processIMUData(1.0, [0, 0, 0], [0.1, 0.2, 9.8]) == abi.SKIPPED_DT  # first sample only initialises
+    assert f.processIMUData(1.0, [0, 0, 0], [0.1, 0.2, 9.8]) == abi.SKIPPED_DT  # dt <= 0
+    assert f.processVisionData(0.9, [0], y) == abi.SKIPPED_DT        # stale frame dropped entirely
+    assert f.numLandmarks == 0
+    assert f.processIMUData(1.005, [0, 0, 0], [0.1, 0.2, 9.8]) == abi.OK
+    assert f.processVisionData(1.0075, [0], y) == abi.OK
+    assert f.getTime() == 1.0075 and f.numLandmarks == 1
+    with pytest.raises(abi.EqvioError) as e:
+        f.processVisionData(1.06, [3, 1], np.array([[0, 0.6, 0.8], [0.6, 0, 0.8]]))
+    assert e.value.status == abi.ERR_UNSORTED
+    assert f.processVisionData(1.07, [], np.zeros((0, 3))) == abi.EMPTY_MEASUREMENT
+    assert f.numLandmarks == 0
+
+
+def test_set_inertial_points():
+    s = template_settings(outlierThreshold=1e9)
+    f, o = gpu_filter(s), COracleFilter(s)
+    for flt in (f, o):
+        flt.processIMUData(0.0, [0, 0, 0], [0.3, -0.2, 9.7])
+    pts = np.random.default_rng(5).uniform(-5, 5, (7, 3)) + np.array([0, 0, 8.0])
+    ids = np.arange(7)
+    f.setInertialPoints(ids, pts)
+    o.setInertialPoints(ids, pts)
+    a, b = f.get_snapshot(), o.get_snapshot()
+    assert np.abs(a - b).max() < 1e-12
+
+
+def test_device_resident_bearings_match_host_path():
+    import torch
+
+    s = template_settings(outlierThreshold=1e9)
+    seq = period_sequence(32, 3, camera_offset=tuple(s.cameraOffset))
+    f1, f2 = gpu_filter(s), gpu_filter(s)
+    ydev = torch.tensor(seq.bearings, dtype=torch.float64, device="cuda").contiguous()
+    torch.cuda.synchronize()
+    for kind, i in seq.events():
+        if kind == "imu":
+            feed(f1, seq, kind, i), feed(f2, seq, kind, i)
+        else:
+            f1.processVisionData(seq.vision_stamps[i], seq.ids, seq.bearings[i])
+            f2.processVisionDataDevice(seq.vision_stamps[i], seq.ids, ydev[i].data_ptr())
+    assert np.array_equal(f1.get_snapshot(), f2.get_snapshot())
+    assert f1.launch_count() > 0
+
+
+def test_single_step_parity_N256():
+    """BASELINE config 3 size (n = 779): one Riccati step and one update from an oracle state."""
+    s = template_settings(outlierThreshold=1e9)
+    seq = period_sequence(256, 1, camera_offset=tuple(s.cameraOffset))
+    f, o = gpu_filter(s), COracleFilter(s)
+    run(o, seq, ("vision", 1))
+    f.set_snapshot(o.get_snapshot())
+    i = int(np.searchsorted(seq.imu[:, 0], seq.vision_stamps[1])) - 1
+    om = seq.imu[i, 1:4]
+    f.riccati_propagate(0.005, om)
+    o.riccati_propagate(0.005, om)
+    assert rel(f.stateCovariance(), o.stateCovariance()) < 1e-13
+    f.set_snapshot(o.get_snapshot())
+    r1 = f.processVisionData(seq.vision_stamps[1], seq.ids, seq.bearings[1])
+    r2 = o.processVisionData(seq.vision_stamps[1], seq.ids, seq.bearings[1])
+    assert r1 == r2 == 0
+    h1, S1 = split_snapshot(f.get_snapshot())
+    h2, S2 = split_snapshot(o.get_snapshot())
+    assert rel(S1, S2) < STEP_SIGMA_TOL and np.abs(h1 - h2).max() < STEP_STATE_TOL, (rel(S1, S2), np.abs(h1 - h2).max())
+
+
+def test_full_size_properties_N512():
+    """N = 512 (the headline size): properties that need no oracle.  Sigma stays finite and symmetric to
+    round-off, the update contracts it (trace drops), an update with zero innovation leaves X alone, and
+    the Riccati step is linear in Sigma."""
+    s = template_settings(outlierThreshold=1e9)
+    seq = period_sequence(512, 1, camera_offset=tuple(s.cameraOffset))
+    f = gpu_filter(s)
+    run(f, seq, ("vision", 1))
+    S0 = f.stateCovariance()
+    assert np.isfinite(S0).all() and rel(S0, S0.T) < 1e-11
+    snap = f.get_snapshot()
+    om = np.array([0.1, 0.05, -0.02])
+    f.riccati_propagate(0.005, om)
+    S1 = f.stateCovariance()
+    # linearity: propagate(2 Sigma) - propagate(Sigma) == F Sigma F^T == propagate(Sigma) - T (P + B R B^T)
+    snap2 = snap.copy()
+    hn = 49 + 9 * 512
+    snap2[hn:] *= 2.0
+    f.set_snapshot(snap2)
+    f.riccati_propagate(0.005, om)
+    S2 = f.stateCovariance()
+    f.set_snapshot(snap)
+    F, Bb = f.build_FB(0.005, om)
+    assert rel(S2 - S1, F @ S0 @ F.T) < 1e-12
+    tr0 = np.trace(S1)
+    f.set_snapshot(snap)
+    assert f.processVisionData(seq.vision_stamps[1], seq.ids, seq.bearings[1]) == 0
+    S3 = f.stateCovariance()
+    assert np.isfinite(S3).all() and rel(S3, S3.T) < 1e-9
+    assert np.trace(S3) < tr0
+    assert np.min(np.diag(S3)) > 0
