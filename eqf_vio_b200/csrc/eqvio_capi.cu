@@ -9,9 +9,9 @@
 //
 // Dense products follow the reference's association (eqf_vio/src/VIOFilter.cpp:188-189, 276-277, 297):
 //   (F Sigma) F^T, (C Sigma) C^T, (Sigma C^T) S^-1, (K C) Sigma.
-// The two explicit inverses are replaced by a blocked Cholesky sweep on an augmented buffer:
-//   S^-1 = X X^T with X = L^-T carried as appended identity rows; bundleLift needs only
-//   Y^T Sigma_sub^-1 Y for five vectors, obtained as Z^T Z with Z^T = Y^T L^-T appended the same way.
+// The two explicit inverses are blocked Schur eliminations by unpivoted LU (no symmetry assumed, like
+// Eigen's PartialPivLU inverse): [[S, I], [I, 0]] -> bottom-right = -S^-1, and bundleLift needs only
+// Y^T Sigma_sub^-1 Y for five vectors: [[Sigma_sub, Y], [Y^T, 0]] -> bottom-right = -Y^T Sigma_sub^-1 Y.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -57,6 +57,7 @@ struct eqvio_filter {
     // device state
     BaseState* st = nullptr;
     StepScratch* sc = nullptr;
+    double *Linv = nullptr, *Uinv = nullptr;  // 64 x 64 triangular inverses of the current pivot block
     Landmarks L{nullptr, 0}, L2{nullptr, 0};
     double *Sigma = nullptr, *Sigma2 = nullptr, *F = nullptr, *W = nullptr, *Bb = nullptr, *Aug = nullptr;
     double *C = nullptr, *CS = nullptr, *SCt = nullptr, *K = nullptr, *Saug = nullptr, *Sinv = nullptr;
@@ -119,7 +120,7 @@ static int ensure_capacity(Filter* f, int needN) {
     CU_TRY(dalloc(&Bb, (size_t)ld * 8));
     CU_TRY(dalloc(&C, (size_t)ldm * (ld + 32))); CU_TRY(dalloc(&CS, (size_t)ldm * (ld + 32)));
     CU_TRY(dalloc(&SCt, (size_t)ld * (ldm + 32))); CU_TRY(dalloc(&K, (size_t)ld * (ldm + 32)));
-    CU_TRY(dalloc(&Saug, (size_t)ld2m * (ldm + 32))); CU_TRY(dalloc(&Sinv, (size_t)ldm * (ldm + 32)));
+    CU_TRY(dalloc(&Saug, (size_t)ld2m * (ld2m + 32))); CU_TRY(dalloc(&Sinv, (size_t)ldm * (ldm + 32)));
     CU_TRY(dalloc(&delta, (size_t)ldm)); CU_TRY(dalloc(&gamma, (size_t)ld)); CU_TRY(dalloc(&Gamma, (size_t)ld));
     CU_TRY(dalloc(&y_in, (size_t)3 * cap + 8)); CU_TRY(dalloc(&y, (size_t)3 * cap + 8)); CU_TRY(dalloc(&scratch, (size_t)cap + 8));
     CU_TRY(dalloc(&d_flags, (size_t)cap + 8)); CU_TRY(dalloc(&d_map, (size_t)ld + 8));
@@ -128,7 +129,7 @@ static int ensure_capacity(Filter* f, int needN) {
     CU_TRY(cudaMemsetAsync(Aug, 0, nn * 8, s));
     CU_TRY(cudaMemsetAsync(CS, 0, (size_t)ldm * (ld + 32) * 8, s));
     CU_TRY(cudaMemsetAsync(SCt, 0, (size_t)ld * (ldm + 32) * 8, s)); CU_TRY(cudaMemsetAsync(K, 0, (size_t)ld * (ldm + 32) * 8, s));
-    CU_TRY(cudaMemsetAsync(Saug, 0, (size_t)ld2m * (ldm + 32) * 8, s)); CU_TRY(cudaMemsetAsync(Sinv, 0, (size_t)ldm * (ldm + 32) * 8, s));
+    CU_TRY(cudaMemsetAsync(Saug, 0, (size_t)ld2m * (ld2m + 32) * 8, s)); CU_TRY(cudaMemsetAsync(Sinv, 0, (size_t)ldm * (ldm + 32) * 8, s));
     CU_TRY(cudaMemsetAsync(L.base, 0, (size_t)LM_FIELDS * cap * 8, s)); CU_TRY(cudaMemsetAsync(L2.base, 0, (size_t)LM_FIELDS * cap * 8, s));
     CU_TRY(cudaMemsetAsync(gamma, 0, (size_t)ld * 8, s)); CU_TRY(cudaMemsetAsync(delta, 0, (size_t)ldm * 8, s));
     if (o.Sigma) {
@@ -181,7 +182,9 @@ static int prepare_layout(Filter* f) {
 // GEMM wrapper with launch counting and optional event bracketing
 // ------------------------------------------------------------------------------------------------
 static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
-                double beta, const double* Cin, int ldcin, double* D, int ldd, int riccati_diag = 0, double T = 0.0) {
+                double beta, const double* Cin, int ldcin, double* D, int ldd, int riccati_diag = 0, double T = 0.0,
+                int force_config = -1) {
+    if (M <= 0 || N <= 0) return EQVIO_OK;
     GemmProblem g;
     g.M = M; g.N = N; g.K = K;
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.transB = transB;
@@ -199,25 +202,29 @@ static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const 
         pe.flops = 2.0 * M * N * K;
         cudaEventRecord(pe.a, f->stream);
     }
-    CU_TRY(dgemm_launch(g, f->stream));
+    CU_TRY(dgemm_launch(g, f->stream, force_config));
     if (f->profiling) { cudaEventRecord(pe.b, f->stream); f->prof.push_back(pe); }
     f->launches += 1;
     return EQVIO_OK;
 }
 
-// Blocked Cholesky of the k x k SPD matrix at the top of Aug with r appended rows (-> R L^-T).
-static int chol_augmented(Filter* f, double* Aug, int lda, int k, int r) {
+// Blocked Schur elimination of the leading k x k block (k a multiple of 16, identity-padded by
+// k_schur_setup) of the (k + r) x (k + c) matrix Aug by unpivoted LU: on return the bottom-right r x c
+// block holds Z - R A^-1 Cc.
+static int schur_lu(Filter* f, double* Aug, int lda, int k, int r, int c) {
     for (int j = 0; j < k; j += 64) {
         const int nb = std::min(64, k - j);
-        launch_potrf_diag(f->stream, Aug, lda, j, nb, &f->st->flags);
-        launch_trsm_rows(f->stream, Aug, lda, j, nb, j + nb, k + r);
-        f->launches += 2;
-        if (j + nb < k) {
-            double* P = Aug + (j + nb) + (size_t)lda * j;
-            double* T22 = Aug + (j + nb) + (size_t)lda * (j + nb);
-            int st = gemm(f, 1, k + r - (j + nb), k - (j + nb), nb, -1.0, P, lda, P, lda, 1.0, T22, lda, T22, lda);
-            if (st) return st;
-        }
+        const int rows = k + r - (j + nb), cols = k + c - (j + nb);
+        CU_TRY(launch_getrf_diag_inv(f->stream, Aug, lda, j, nb, f->Linv, f->Uinv, &f->st->flags));
+        f->launches += 1;
+        double* Lp = Aug + (j + nb) + (size_t)lda * j;         // rows x nb, below the diagonal block
+        double* Up = Aug + j + (size_t)lda * (j + nb);         // nb x cols, right of it
+        double* T22 = Aug + (j + nb) + (size_t)lda * (j + nb);
+        int st;
+        // panel solves as GEMMs with the triangular inverses, in place (one 64-wide tile owns its rows / columns)
+        if ((st = gemm(f, 0, rows, nb, nb, 1.0, Lp, lda, f->Uinv, 64, 0.0, nullptr, 0, Lp, lda, 0, 0.0, 2))) return st;   // X U = B
+        if ((st = gemm(f, 0, nb, cols, nb, 1.0, f->Linv, 64, Up, lda, 0.0, nullptr, 0, Up, lda, 0, 0.0, 2))) return st;   // L X = B
+        if ((st = gemm(f, 0, rows, cols, nb, -1.0, Lp, lda, Up, lda, 1.0, T22, lda, T22, lda))) return st;
     }
     return EQVIO_OK;
 }
@@ -304,7 +311,7 @@ static int compact(Filter* f, const std::vector<int>& keep) {
 // The measurement update, VIOFilter.cpp:264-297, on matched bearings f->y (3N, device).
 // want_lift = 0 stops after gamma / Sigma update (kernel-level entry point).
 static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
-    const int N = f->N, n = n_of(N), m = 2 * N, p = 5 + 3 * N, ld = f->ld, ldm = f->ldm;
+    const int N = f->N, n = n_of(N), m = 2 * N, p = 5 + 3 * N, pb = round_up(p, 16), ld = f->ld, ldm = f->ldm;
     int st = prepare_layout(f);
     if (st) return st;
     cudaStream_t s = f->stream;
@@ -314,15 +321,15 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
     if ((st = gemm(f, 0, m, n, n, 1.0, f->C, ldm, f->Sigma, ld, 0.0, nullptr, 0, f->CS, ldm))) return st;
     if ((st = gemm(f, 1, m, m, n, 1.0, f->CS, ldm, f->C, ldm, 0.0, nullptr, 0, f->Saug, f->ld2m))) return st;
     launch_add_diag_const(s, f->Saug, f->ld2m, m, f->s.measurementVariance);
-    // S^-1 = X X^T, X = L^-T from the augmented Cholesky sweep       (S.inverse(), :277)
-    launch_set_identity_rows(s, f->Saug, f->ld2m, m, m);
+    // S.inverse() (:277): eliminate S from [[S, I], [I, 0]]; the bottom-right block becomes -S^-1
+    const int mp = round_up(m, 16);
+    launch_schur_setup(s, f->Saug, f->ld2m, m, mp, m, m, 1);
     f->launches += 2;
-    if ((st = chol_augmented(f, f->Saug, f->ld2m, m, m))) return st;
-    const double* X = f->Saug + m;
-    if ((st = gemm(f, 1, m, m, m, 1.0, X, f->ld2m, X, f->ld2m, 0.0, nullptr, 0, f->Sinv, ldm))) return st;
+    if ((st = schur_lu(f, f->Saug, f->ld2m, mp, m, m))) return st;
+    const double* negSinv = f->Saug + mp + (size_t)f->ld2m * mp;
     // K = (Sigma C^T) S^-1                                           :277
     if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
-    if ((st = gemm(f, 0, n, m, m, 1.0, f->SCt, ld, f->Sinv, ldm, 0.0, nullptr, 0, f->K, ld))) return st;
+    if ((st = gemm(f, 0, n, m, m, -1.0, f->SCt, ld, negSinv, f->ld2m, 0.0, nullptr, 0, f->K, ld))) return st;
     launch_gemv(s, f->K, ld, n, m, f->delta, f->gamma);  // :279
     f->launches += 1;
     if (do_lift) {
@@ -331,11 +338,12 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
             // bundleLift with the PRIOR Sigma block (:285 precedes :297)
             launch_lift_prepare(s, f->st, f->sc, f->gamma);
             launch_copy_block(s, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
-            launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, p);
-            f->launches += 3;
-            if ((st = chol_augmented(f, f->Aug, ld, p, 5))) return st;
+            launch_schur_setup(s, f->Aug, ld, p, pb, 5, 5, 0);
+            launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb);
+            f->launches += 4;
+            if ((st = schur_lu(f, f->Aug, ld, pb, 5, 5))) return st;
         }
-        launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, p, use_lift, discrete, stamp, nullptr, 1);
+        launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, use_lift, discrete, stamp, nullptr, 1);
         launch_lift_apply(s, f->st, f->L, N, f->gamma, use_lift ? discrete : 0);
         f->launches += 2;
     }
@@ -424,6 +432,10 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     CU_TRY(cudaEventRecord(f->stage_free, f->stream));
     CU_TRY(dalloc(&f->st, 1));
     CU_TRY(dalloc(&f->sc, 1));
+    CU_TRY(dalloc(&f->Linv, 64 * 80));
+    CU_TRY(dalloc(&f->Uinv, 64 * 80));
+    CU_TRY(cudaMemset(f->Linv, 0, 64 * 80 * 8));
+    CU_TRY(cudaMemset(f->Uinv, 0, 64 * 80 * 8));
     int st = ensure_capacity(f, 64);
     if (st) return st;
     st = init_state(f);
@@ -438,7 +450,7 @@ int eqvio_destroy(eqvio_handle_t f) {
     cudaStreamSynchronize(f->stream);
     for (auto& e : f->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     free_device(f);
-    cudaFree(f->st); cudaFree(f->sc);
+    cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
     cudaEventDestroy(f->stage_free);
@@ -853,11 +865,13 @@ int eqvio_bundle_lift(eqvio_handle_t f, const double* gamma_eqf, double* Gamma) 
     cudaStream_t s = f->stream;
     launch_lift_prepare(s, f->st, f->sc, f->gamma);
     launch_copy_block(s, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
-    launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, p);
-    f->launches += 3;
-    int st = chol_augmented(f, f->Aug, ld, p, 5);
+    const int pb = round_up(p, 16);
+    launch_schur_setup(s, f->Aug, ld, p, pb, 5, 5, 0);
+    launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb);
+    f->launches += 4;
+    int st = schur_lu(f, f->Aug, ld, pb, 5, 5);
     if (st) return st;
-    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, p, 1, 1, f->currentTime, f->Gamma, 0);
+    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, 1, 1, f->currentTime, f->Gamma, 0);
     f->launches += 1;
     CU_TRY(cudaStreamSynchronize(s));
     CU_TRY(cudaMemcpy(Gamma, f->Gamma, 48, cudaMemcpyDeviceToHost));

@@ -4,7 +4,7 @@
 //   k_build_C_delta     one warp per feature: 2x3 C block + innovation delta_i
 //   k_gemv              gamma = K delta
 //   k_lift_prepare / k_lift_features / k_lift_solve / k_lift_apply   bundleLift + discrete lift + X <- Delta X
-//   k_potrf_diag / k_trsm_rows   panel kernels of the blocked Cholesky used for S^-1 and Sigma_sub^-1
+//   k_getrf_diag_inv   diagonal-block LU + triangular inverses of the blocked Schur elimination (S^-1, Sigma_sub^-1)
 //   bookkeeping: outlier flags, Sigma / landmark compaction, median depth + landmark append
 #include "filter_kernels.cuh"
 #include "kernels_api.cuh"
@@ -282,13 +282,18 @@ __global__ void k_lift_prepare(BaseState* st, StepScratch* sc, const double* gam
 
 // k_lift_features: per feature, Y_i = D_i [M_i | obs_i] (3 x 5) with (EqFMatrices.cpp:218-236)
 //   M_i = [-[p_i]x, I] Ad(P0) KPara,  obs_i = -R_C Q_i^-1 gamma_qi - [-[p_i]x, I] Ad(P0) DUF,  D_i = Qhat_i R_C^T.
-// Written transposed as the 5 appended rows of the augmented Cholesky buffer:
-//   Aug[p + c, 5 + 3i + r] = Y_i[r][c]   (first five columns of the appended rows are zero).
+// Written as the border of the Schur problem [[Sigma_sub, Y], [Y^T, 0]]:
+//   Aug[p + c, 5 + 3i + r] = Aug[5 + 3i + r, p + c] = Y_i[r][c]; the first five rows of Y are zero.
 __global__ void __launch_bounds__(128) k_lift_features(const StepScratch* sc, Landmarks L, int N, const double* gamma,
                                                        double* Aug, int lda, int p) {
+    // p here is the border offset (Sigma_sub's size rounded up to 16, identity-padded by k_schur_setup)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 5)
-        for (int c = 0; c < 5; ++c) Aug[(p + c) + (size_t)lda * i] = 0.0;
+        for (int c = 0; c < 5; ++c) {
+            Aug[(p + c) + (size_t)lda * i] = 0.0;
+            Aug[i + (size_t)lda * (p + c)] = 0.0;
+            Aug[(p + i) + (size_t)lda * (p + c)] = 0.0;
+        }
     if (i >= N) return;
     const Sot3 Q = load_Q(L, i);
     const V3 q0 = load_q0(L, i);
@@ -323,8 +328,11 @@ __global__ void __launch_bounds__(128) k_lift_features(const StepScratch* sc, La
 #pragma unroll
     for (int c = 0; c < 5; ++c)
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
-            Aug[(p + c) + (size_t)lda * (5 + 3 * i + r)] = Dm.m[r][0] * MO[0][c] + Dm.m[r][1] * MO[1][c] + Dm.m[r][2] * MO[2][c];
+        for (int r = 0; r < 3; ++r) {
+            const double yv = Dm.m[r][0] * MO[0][c] + Dm.m[r][1] * MO[1][c] + Dm.m[r][2] * MO[2][c];
+            Aug[(p + c) + (size_t)lda * (5 + 3 * i + r)] = yv;
+            Aug[(5 + 3 * i + r) + (size_t)lda * (p + c)] = yv;
+        }
 }
 
 // 4x4 Householder QR solve (EqFMatrices.cpp:240-242)
@@ -358,54 +366,29 @@ __device__ void qr_solve4(double A[4][4], double b[4], double x[4]) {
     }
 }
 
-// k_lift_solve — one block.  mode 0: bundle lift: G = Z^T Z from the 5 appended rows Z^T = Y^T L^-T
-// (so G = Y^T Sigma_sub^-1 Y = [M^T W M, M^T W obs; ...], EqFMatrices.cpp:239-242), 4x4 QR solve,
-// DeltaU = DUF + KPara x (:243), then the SE(3) x R^3 part of the lift and X <- Delta X, bias update:
+// k_lift_solve — single thread.  mode use_lift: G = Y^T Sigma_sub^-1 Y is the negated bottom-right 5 x 5
+// block left by the Schur elimination (G[0:4,0:4] = M^T W M, G[0:4,4] = M^T W obs with
+// W = D^T Sigma_sub^-1 D, EqFMatrices.cpp:239-242), 4x4 QR solve, DeltaU = DUF + KPara x (:243), then
+// the SE(3) x R^3 part of the lift and X <- Delta X, bias update:
 //   discrete   liftTotalSpaceInnovationDiscrete EqFMatrices.cpp:254-259
 //   continuous VIOExp(liftTotalSpaceInnovation)  EqFMatrices.cpp:69-78, VIOGroup.cpp:245-248
-// mode 1 (useInnovationLift = false): VIOExp(liftInnovation(gamma, xi0)) EqFMatrices.cpp:35-48.
+// use_lift = 0 (useInnovationLift = false): VIOExp(liftInnovation(gamma, xi0)) EqFMatrices.cpp:35-48.
 // Then VIOFilter.cpp:295-296 and the pose record.
-__global__ void __launch_bounds__(256) k_lift_solve(BaseState* st, StepScratch* sc, const double* gamma, const double* Aug,
-                                                    int lda, int p, int use_lift, int discrete, double stamp,
-                                                    double* Gamma_out, int apply) {
-    __shared__ double part[15][256];
-    __shared__ double G[15];
+__global__ void k_lift_solve(BaseState* st, StepScratch* sc, const double* gamma, const double* Aug,
+                             int lda, int p, int use_lift, int discrete, double stamp,
+                             double* Gamma_out, int apply) {
     const int tid = threadIdx.x;
-    if (use_lift) {
-        double acc[15];
-#pragma unroll
-        for (int k = 0; k < 15; ++k) acc[k] = 0.0;
-        for (int col = tid; col < p; col += 256) {
-            double z[5];
-#pragma unroll
-            for (int c = 0; c < 5; ++c) z[c] = Aug[(p + c) + (size_t)lda * col];
-            int k = 0;
-#pragma unroll
-            for (int a = 0; a < 5; ++a)
-#pragma unroll
-                for (int b = a; b < 5; ++b) acc[k++] += z[a] * z[b];
-        }
-#pragma unroll
-        for (int k = 0; k < 15; ++k) part[k][tid] = acc[k];
-        __syncthreads();
-        if (tid < 15) {
-            double s = 0.0;
-            for (int j = 0; j < 256; ++j) s += part[tid][j];
-            G[tid] = s;
-        }
-        __syncthreads();
-    }
+    double G[5][5];
+    if (use_lift && tid == 0)
+        for (int a = 0; a < 5; ++a)
+            for (int b = 0; b < 5; ++b) G[a][b] = -Aug[(p + a) + (size_t)lda * (p + b)];
     if (tid != 0) return;
     double DU[6];
     V3 Dw;
     const double* g = gamma + 6;
     if (use_lift) {
         double A[4][4], b[4], x[4];
-        int k = 0;
-        double Gf[5][5];
-        for (int a = 0; a < 5; ++a)
-            for (int c = a; c < 5; ++c) { Gf[a][c] = G[k]; Gf[c][a] = G[k]; ++k; }
-        for (int a = 0; a < 4; ++a) { for (int c = 0; c < 4; ++c) A[a][c] = Gf[a][c]; b[a] = Gf[a][4]; }
+        for (int a = 0; a < 4; ++a) { for (int c = 0; c < 4; ++c) A[a][c] = G[a][c]; b[a] = G[a][4]; }
         qr_solve4(A, b, x);
         for (int r = 0; r < 6; ++r) {
             double s = 0.0;
@@ -467,67 +450,93 @@ __global__ void __launch_bounds__(128) k_lift_apply(BaseState* st, Landmarks L, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Blocked Cholesky panels (stand-in for the reference's explicit inverses, VIOFilter.cpp:277 and
-// EqFMatrices.cpp:239).  The augmented buffer holds the SPD matrix (k x k, lower triangle used) with
-// r extra rows below it; after the sweep the extra rows hold R L^-T.
+// Blocked Schur elimination by UNPIVOTED LU (stand-in for the reference's explicit inverses,
+// VIOFilter.cpp:277 `S.inverse()` and EqFMatrices.cpp:239 `Sigma.inverse()`, which Eigen evaluates with
+// PartialPivLU on the matrices AS THEY ARE, i.e. including their round-off-level asymmetry).
+// The augmented buffer is [[A, Cc], [R, Z]] with A k x k; eliminating A leaves Z - R A^-1 Cc in the
+// bottom-right block.  A is symmetric positive definite up to rounding, so no pivoting is needed;
+// nothing here assumes symmetry (a Cholesky sweep would, and measurably departs from the reference:
+// the asymmetry of S is ~1e-11 relative because C annihilates the large radial variance — see
+// DESIGN.md "Numerical conditioning").
 // ------------------------------------------------------------------------------------------------
-// k_potrf_diag: one CTA factors the nb x nb (nb <= 64) diagonal block at (j, j) in shared memory.
-__global__ void __launch_bounds__(256) k_potrf_diag(double* A, int lda, int j, int nb, int* flags) {
-    __shared__ double a[64][65];
-    const int tid = threadIdx.x;
-    for (int e = tid; e < nb * nb; e += 256) {
-        const int r = e % nb, c = e / nb;
-        a[r][c] = A[(j + r) + (size_t)lda * (j + c)];
+// k_getrf_diag_inv: one CTA factors the nb x nb (nb <= 64) diagonal block at (j, j) in shared memory
+// (unit-lower L below the diagonal, U on and above it, written back in place) and also forms the two
+// triangular inverses L^-1, U^-1 (64 x 64, column-major, identity-padded) so that the panel solves
+// X U = B and L X = B become small GEMMs on the DMMA kernel instead of per-row substitutions.
+// 1024 threads = 64 rows x 16 column groups; one barrier per elimination step.
+__global__ void __launch_bounds__(1024) k_getrf_diag_inv(double* A, int lda, int j, int nb, double* Linv, double* Uinv,
+                                                         int* flags) {
+    extern __shared__ double sm_lu[];
+    double(*a)[65] = reinterpret_cast<double(*)[65]>(sm_lu);
+    double(*e)[65] = reinterpret_cast<double(*)[65]>(sm_lu + 64 * 65);
+    double(*x)[65] = reinterpret_cast<double(*)[65]>(sm_lu + 2 * 64 * 65);
+    const int tid = threadIdx.x, r = tid & 63, cg = tid >> 6;  // 64 rows x 16 column groups, 4 columns each
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = cg + 16 * i;
+        a[r][c] = (r < nb && c < nb) ? A[(j + r) + (size_t)lda * (j + c)] : (r == c ? 1.0 : 0.0);
+        e[r][c] = (r == c) ? 1.0 : 0.0;
+        x[r][c] = (r == c) ? 1.0 : 0.0;
     }
     __syncthreads();
-    for (int k = 0; k < nb; ++k) {
-        if (tid == 0) {
-            double d = a[k][k];
-            if (!(d > 0.0)) { atomicOr(flags, FLAG_NOT_SPD); d = fabs(d) + 1e-300; }
-            a[k][k] = sqrt(d);
-        }
-        __syncthreads();
-        const double dk = a[k][k];
-        for (int r = k + 1 + tid; r < nb; r += 256) a[r][k] /= dk;
-        __syncthreads();
-        const int rem = nb - k - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int r = k + 1 + e % rem, c = k + 1 + e / rem;
-            if (c <= r) a[r][c] -= a[r][k] * a[c][k];
+    // forward elimination on [A | I]: the row operations turn I into L^-1.  In step k a column c > k
+    // belongs to the trailing block of A, a column c <= k to the already non-trivial part of L^-1.
+    for (int k = 0; k < 63; ++k) {
+        const double piv = a[k][k];
+        if (tid == 0 && !(fabs(piv) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
+        if (r > k) {
+            const double l = a[r][k] / piv;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = cg + 16 * i;
+                if (c > k) a[r][c] -= l * a[k][c];
+                else e[r][c] -= l * e[k][c];
+            }
         }
         __syncthreads();
     }
-    for (int e = tid; e < nb * nb; e += 256) {
-        const int r = e % nb, c = e / nb;
-        if (c <= r) A[(j + r) + (size_t)lda * (j + c)] = a[r][c];
+    // U X = I by backward rank-1 updates; rows stay unscaled until the end
+    for (int q = 63; q > 0; --q) {
+        if (r < q) {
+            const double f = a[r][q] / a[q][q];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = cg + 16 * i;
+                if (c >= q) x[r][c] -= f * x[q][c];
+            }
+        }
+        __syncthreads();
+    }
+    const double dr = a[r][r];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = cg + 16 * i;
+        Uinv[r + 64 * c] = (c >= r) ? x[r][c] / dr : 0.0;
+        Linv[r + 64 * c] = (c <= r) ? e[r][c] : 0.0;
+        if (r < nb && c < nb) A[(j + r) + (size_t)lda * (j + c)] = (c >= r) ? a[r][c] : a[r][c] / a[c][c];
     }
 }
 
-// k_trsm_rows: rows [row0, row1) of the panel columns [j, j+nb):  X <- X L_jj^-T, one thread per row.
-__global__ void __launch_bounds__(128) k_trsm_rows(double* A, int lda, int j, int nb, int row0, int row1) {
-    __shared__ double l[64][65];
-    for (int e = threadIdx.x; e < nb * nb; e += 128) {
-        const int r = e % nb, c = e / nb;
-        l[r][c] = A[(j + r) + (size_t)lda * (j + c)];
+// Everything of the Schur problem except the leading k x k block A and (when !identity_border) the
+// border entries written elsewhere.  Layout: A in [0,k)^2, identity padding on [k,kpad), border rows /
+// columns at offset kpad:  [[A, 0, Cc], [0, I, 0], [R, 0, 0]].  identity_border: R = Cc = I (k x k).
+__global__ void k_schur_setup(double* A, int lda, int k, int kpad, int r, int c, int identity_border) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x, col = blockIdx.y;
+    if (row >= kpad + r || col >= kpad + c) return;
+    if (row < k && col < k) return;
+    double v;
+    if (row < kpad && col < kpad) v = (row == col) ? 1.0 : 0.0;          // padding block
+    else if (row >= kpad && col >= kpad) v = 0.0;                         // bottom-right
+    else if (row < kpad) {                                                // top-right border
+        if (row >= k) v = 0.0;
+        else if (identity_border) v = (row == col - kpad) ? 1.0 : 0.0;
+        else return;
+    } else {                                                              // bottom-left border
+        if (col >= k) v = 0.0;
+        else if (identity_border) v = (row - kpad == col) ? 1.0 : 0.0;
+        else return;
     }
-    __syncthreads();
-    const int row = row0 + blockIdx.x * 128 + threadIdx.x;
-    if (row >= row1) return;
-    double x[64];
-#pragma unroll
-    for (int c = 0; c < 64; ++c) x[c] = c < nb ? A[row + (size_t)lda * (j + c)] : 0.0;
-#pragma unroll
-    for (int c = 0; c < 64; ++c) {
-        if (c < nb) {
-            double s = x[c];
-#pragma unroll
-            for (int q = 0; q < c; ++q) s -= x[q] * l[c][q];
-            x[c] = s / l[c][c];
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 64; ++c)
-        if (c < nb) A[row + (size_t)lda * (j + c)] = x[c];
+    A[row + (size_t)lda * col] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -657,16 +666,24 @@ void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, in
 }
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
                        int use_lift, int discrete, double stamp, double* Gamma_out, int apply) {
-    k_lift_solve<<<1, 256, 0, s>>>(st, sc, gamma, Aug, lda, p, use_lift, discrete, stamp, Gamma_out, apply);
+    k_lift_solve<<<1, 32, 0, s>>>(st, sc, gamma, Aug, lda, p, use_lift, discrete, stamp, Gamma_out, apply);
 }
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete) {
     if (N > 0) k_lift_apply<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, gamma, discrete);
 }
-void launch_potrf_diag(cudaStream_t s, double* A, int lda, int j, int nb, int* flags) {
-    k_potrf_diag<<<1, 256, 0, s>>>(A, lda, j, nb, flags);
+cudaError_t launch_getrf_diag_inv(cudaStream_t s, double* A, int lda, int j, int nb, double* Linv, double* Uinv, int* flags) {
+    static bool attr_set = false;
+    const int smem = 3 * 64 * 65 * (int)sizeof(double);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_getrf_diag_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_getrf_diag_inv<<<1, 1024, smem, s>>>(A, lda, j, nb, Linv, Uinv, flags);
+    return cudaGetLastError();
 }
-void launch_trsm_rows(cudaStream_t s, double* A, int lda, int j, int nb, int row0, int row1) {
-    if (row1 > row0) k_trsm_rows<<<cdiv(row1 - row0, 128), 128, 0, s>>>(A, lda, j, nb, row0, row1);
+void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border) {
+    k_schur_setup<<<dim3(cdiv(kpad + r, 256), kpad + c), 256, 0, s>>>(A, lda, k, kpad, r, c, identity_border);
 }
 void launch_copy_block(cudaStream_t s, const double* src, int lds, double* dst, int ldd, int rows, int cols) {
     if (rows > 0 && cols > 0) k_copy_block<<<dim3(cdiv(rows, 256), cols), 256, 0, s>>>(src, lds, dst, ldd, rows, cols);

@@ -15,8 +15,8 @@ void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, in
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
                        int use_lift, int discrete, double stamp, double* Gamma_out, int apply);
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete);
-void launch_potrf_diag(cudaStream_t s, double* A, int lda, int j, int nb, int* flags);
-void launch_trsm_rows(cudaStream_t s, double* A, int lda, int j, int nb, int row0, int row1);
+cudaError_t launch_getrf_diag_inv(cudaStream_t s, double* A, int lda, int j, int nb, double* Linv, double* Uinv, int* flags);
+void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border);
 void launch_copy_block(cudaStream_t s, const double* src, int lds, double* dst, int ldd, int rows, int cols);
 void launch_set_identity_rows(cudaStream_t s, double* A, int lda, int row0, int n);
 void launch_add_diag_const(cudaStream_t s, double* A, int lda, int n, double v);

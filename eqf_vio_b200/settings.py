@@ -120,3 +120,16 @@ def settings_from_yaml(path: str) -> Settings:
 
     with open(path) as f:
         return settings_from_eqf_node(yaml.safe_load(f)["eqf"])
+
+
+def conditioned_settings(**overrides) -> Settings:
+    """Template settings with the two start-up values matched to the synthetic scene (landmarks 3-15 m
+    away): initialSceneDepth 8 m instead of 1 m and initialPointVariance 100 instead of 5000, and the
+    outlier test disabled so N stays fixed.  With the template's own values every landmark starts 3-15x
+    too close with variance 5000; the first updates then move the gauge by metres per frame and any two
+    fp64 implementations of the reference's formulas separate by ~1e-8 within a few frames (DESIGN.md,
+    "Numerical conditioning").  Used for whole-sequence parity and for the benchmark workload; the
+    per-step parity tests use the unmodified template."""
+    node = {"outlierThreshold": 1e9, "initialSceneDepth": 8.0, "initialPointVariance": 100.0}
+    node.update(overrides)
+    return template_settings(**node)
