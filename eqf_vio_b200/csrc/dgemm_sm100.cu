@@ -17,6 +17,7 @@
 
 #include <cudaTypedefs.h>  // PFN_cuTensorMapEncodeTiled
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace eqvio {
 
@@ -87,6 +88,7 @@ struct KernelParams {
     int ldcin;
     double alpha, beta;
     int add_diag;  // D[m][m] += T * Pd(class of m)
+    int no_edge_skip;  // debug A/B switch: treat partial tiles like full ones
     double T;
     double Pd[5];
 };
@@ -125,7 +127,21 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t* empty = full + STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    // 1-D grid, full tiles first and the partial edge tiles last: in an edge tile the warps whose
+    // sub-tile is entirely outside the matrix do no MMAs, so it is cheap, and cheap work dispatched last
+    // fills the tail of the last wave (n = 11 + 3N is never a multiple of the tile size).
+    int tile_m, tile_n;
+    {
+        const int Tm = (p.M + BM - 1) / BM, Tn = (p.N + BN - 1) / BN, Fm = p.M / BM, Fn = p.N / BN;
+        const int id = blockIdx.x, interior = Fm * Fn;
+        if (id < interior) { tile_m = id % Fm; tile_n = id / Fm; }
+        else {
+            const int e = id - interior;
+            if (Tn > Fn && e < Fm) { tile_m = e; tile_n = Fn; }          // partial last tile column
+            else { tile_m = Fm; tile_n = e - (Tn > Fn ? Fm : 0); }       // partial last tile row (incl. corner)
+        }
+        (void)Tm;
+    }
     const int KT = (p.K + 15) >> 4;
 
     if (threadIdx.x == 0) {
@@ -176,6 +192,14 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // K-major: row n (n&7 == g), chunk (k>>1)^g
     const uint32_t km_off0 = (uint32_t)(g * 128 + ((((k0 >> 1) ^ g) & 7) << 4) + (k0 & 1) * 8);
 
+    // valid 8-row / 8-column blocks of this warp's sub-tile (edge tiles only compute these)
+    const int m_rem = p.M - (tile_m * BM + wm * WM), n_rem = p.N - (tile_n * BN + wn * WN);
+    const int mbv = m_rem <= 0 ? 0 : (m_rem >= WM ? MB : (m_rem + 7) >> 3);
+    const int nbv = n_rem <= 0 ? 0 : (n_rem >= WN ? NB : (n_rem + 7) >> 3);
+    // warp-granular skipping only: a warp whose whole sub-tile lies outside the matrix just keeps the
+    // barriers moving; per-block predication of mma.sync costs a convergence barrier per DMMA (measured: slower)
+    const bool idle = ((mbv == 0) || (nbv == 0)) && !p.no_edge_skip;
+
     const uint32_t a_warp = (uint32_t)((wm * WM / 16) * 2048);
     const uint32_t b_warp = TRANSB ? (uint32_t)((wn * WN / 16) * 2048) : (uint32_t)(wn * WN * 128);
     // note: for TRANSB with WN % 16 == 8 the warp's first 8-column block may start mid-atom
@@ -187,34 +211,36 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         mbar_wait(&full[s], ph);
         const uint32_t sa = base + s * Cfg::STAGE_BYTES + a_warp;
         const uint32_t sb = base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + b_warp;
+        if (!idle) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int j1 = j >> 1, j0 = j & 1;
-            // XOR constants move k by (j1<<3 | j0): k*128 bits [7,10], chunk bit j0 for MN-major;
-            // chunk bit (j1<<2) and half bit j0 for K-major
-            const uint32_t mn_x = (uint32_t)((((j1 << 3) | j0) << 7) | (j0 << 4));
-            const uint32_t km_x = (uint32_t)((j1 << 6) | (j0 << 3));
-            double af[MB], bf[NB];
+            for (int j = 0; j < 4; ++j) {
+                const int j1 = j >> 1, j0 = j & 1;
+                // XOR constants move k by (j1<<3 | j0): k*128 bits [7,10], chunk bit j0 for MN-major;
+                // chunk bit (j1<<2) and half bit j0 for K-major
+                const uint32_t mn_x = (uint32_t)((((j1 << 3) | j0) << 7) | (j0 << 4));
+                const uint32_t km_x = (uint32_t)((j1 << 6) | (j0 << 3));
+                double af[MB], bf[NB];
 #pragma unroll
-            for (int i = 0; i < MB; ++i) {
-                const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((i & 1) << 6)) + (uint32_t)((i >> 1) * 2048);
-                af[i] = lds_f64(sa + off);
-            }
-#pragma unroll
-            for (int i = 0; i < NB; ++i) {
-                if (TRANSB) {
-                    const int blk = i + b_half;
-                    const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((blk & 1) << 6)) + (uint32_t)((blk >> 1) * 2048);
-                    bf[i] = lds_f64(sb + off);
-                } else {
-                    const uint32_t off = (km_off0 ^ km_x) + (uint32_t)(i * 1024);
-                    bf[i] = lds_f64(sb + off);
+                for (int i = 0; i < MB; ++i) {
+                    const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((i & 1) << 6)) + (uint32_t)((i >> 1) * 2048);
+                    af[i] = lds_f64(sa + off);
                 }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    if (TRANSB) {
+                        const int blk = i + b_half;
+                        const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((blk & 1) << 6)) + (uint32_t)((blk >> 1) * 2048);
+                        bf[i] = lds_f64(sb + off);
+                    } else {
+                        const uint32_t off = (km_off0 ^ km_x) + (uint32_t)(i * 1024);
+                        bf[i] = lds_f64(sb + off);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < MB; ++i)
+#pragma unroll
+                    for (int jn = 0; jn < NB; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i], bf[jn]);
             }
-#pragma unroll
-            for (int i = 0; i < MB; ++i)
-#pragma unroll
-                for (int jn = 0; jn < NB; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i], bf[jn]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -249,6 +275,10 @@ using Cfg128x128 = TileCfg<128, 128, 64, 32, 4, 1>;
 using Cfg128x64 = TileCfg<128, 64, 32, 32, 4, 2>;
 using Cfg64x64 = TileCfg<64, 64, 32, 32, 4, 3>;
 using Cfg32x32 = TileCfg<32, 32, 16, 16, 4, 4>;
+using Cfg32x64 = TileCfg<32, 64, 16, 32, 4, 4>;
+using Cfg64x32 = TileCfg<64, 32, 32, 16, 4, 4>;
+using Cfg32x32s6 = TileCfg<32, 32, 16, 16, 6, 5>;
+using Cfg48x48 = TileCfg<48, 48, 16, 48, 4, 4>;
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -300,53 +330,60 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     p.alpha = g.epi.alpha;
     p.beta = g.epi.Cin ? g.epi.beta : 0.0;
     p.add_diag = g.epilogue == EPI_RICCATI;
+    {
+        static int noedge = -1;
+        if (noedge < 0) { const char* e = getenv("EQVIO_GEMM_NOEDGE"); noedge = (e && e[0] == '1') ? 1 : 0; }
+        p.no_edge_skip = noedge;
+    }
     p.T = g.epi.T;
     for (int i = 0; i < 5; ++i) p.Pd[i] = g.epi.Pd[i];
-    dim3 grid((g.M + Cfg::BM - 1) / Cfg::BM, (g.N + Cfg::BN - 1) / Cfg::BN);
+    dim3 grid(((g.M + Cfg::BM - 1) / Cfg::BM) * ((g.N + Cfg::BN - 1) / Cfg::BN));
     cudaError_t e;
+    static bool attr_done[2] = {false, false};  // per template instantiation (function-local static)
     if (g.transB) {
         auto k = dgemm_dmma_tma_kernel<Cfg, true>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
+        if (!attr_done[1]) {
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            attr_done[1] = true;
+        }
         k<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
     } else {
         auto k = dgemm_dmma_tma_kernel<Cfg, false>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
+        if (!attr_done[0]) {
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            attr_done[0] = true;
+        }
         k<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
     }
     return cudaGetLastError();
 }
 
-int dgemm_num_configs() { return 4; }
+int dgemm_num_configs() { return 8; }
 const char* dgemm_config_name(int cfg) {
     switch (cfg) {
         case 0: return "128x128x16 (8 DMMA warps 64x32, 4 stages)";
         case 1: return "128x64x16 (8 DMMA warps 32x32, 4 stages)";
         case 2: return "64x64x16 (4 DMMA warps 32x32, 4 stages)";
         case 3: return "32x32x16 (4 DMMA warps 16x16, 4 stages)";
+        case 4: return "32x64x16 (4 DMMA warps 16x32, 4 stages)";
+        case 5: return "64x32x16 (4 DMMA warps 32x16, 4 stages)";
+        case 6: return "32x32x16 (4 DMMA warps 16x16, 6 stages, 5 CTA/SM)";
+        case 7: return "48x48x16 (3 DMMA warps 16x48, 4 stages)";
     }
     return "?";
 }
 
-// Pick the tile shape that minimises waves * per-wave time on 148 SMs.  An SM retires 64 fp64
-// FMA/clk (measured, profiles/r01_dmma_microbench.md) however many CTAs share it, so the model is
-// time ~ ceil(tiles / (148*occ)) * occ * BM*BN / eff.
+// Tile-shape choice, from measurement on B200 (profiles/r01_gemm_tiles.md): an SM retires 64 fp64 FMA/clk
+// however many CTAs share it and fp64 needs so little operand bandwidth that the smallest tile wins at
+// every filter size (n = 203 ... 3083) — many small CTAs per SM balance the 148 SMs best (n = 11 + 3N is
+// never a multiple of a big tile) and the DMMA pipe stays ~87% busy either way.  Larger tiles stay
+// selectable (EQVIO_GEMM_CONFIG / force_config) for experiments.
 int dgemm_pick_config(int M, int N, int K) {
     (void)K;
-    static const int bm[4] = {128, 128, 64, 32}, bn[4] = {128, 64, 64, 32}, occ[4] = {1, 2, 3, 4};
-    static const double eff[4] = {1.0, 0.97, 0.92, 0.70};
-    int best = 0;
-    double best_t = 1e300;
-    for (int c = 0; c < 4; ++c) {
-        long tiles = (long)((M + bm[c] - 1) / bm[c]) * ((N + bn[c] - 1) / bn[c]);
-        long slots = 148L * occ[c];
-        long waves = (tiles + slots - 1) / slots;
-        long resident = tiles < slots ? (tiles + 147) / 148 : occ[c];  // CTAs sharing an SM in a wave
-        double t = (double)waves * (double)resident * bm[c] * bn[c] / eff[c];
-        if (t < best_t) { best_t = t; best = c; }
-    }
-    return best;
+    const long tiles32 = (long)((M + 31) / 32) * ((N + 31) / 32);
+    return tiles32 <= 148 ? 6 : 3;  // tiny problems: deeper pipeline, 5 CTAs/SM (latency-bound)
 }
 
 cudaError_t dgemm_launch(const GemmProblem& g, cudaStream_t stream, int force_config) {
@@ -356,6 +393,10 @@ cudaError_t dgemm_launch(const GemmProblem& g, cudaStream_t stream, int force_co
         case 0: return launch_cfg<Cfg128x128>(g, stream);
         case 1: return launch_cfg<Cfg128x64>(g, stream);
         case 2: return launch_cfg<Cfg64x64>(g, stream);
+        case 4: return launch_cfg<Cfg32x64>(g, stream);
+        case 5: return launch_cfg<Cfg64x32>(g, stream);
+        case 6: return launch_cfg<Cfg32x32s6>(g, stream);
+        case 7: return launch_cfg<Cfg48x48>(g, stream);
         default: return launch_cfg<Cfg32x32>(g, stream);
     }
 }

@@ -463,34 +463,49 @@ __global__ void __launch_bounds__(128) k_lift_apply(BaseState* st, Landmarks L, 
 // (unit-lower L below the diagonal, U on and above it, written back in place) and also forms the two
 // triangular inverses L^-1, U^-1 (64 x 64, column-major, identity-padded) so that the panel solves
 // X U = B and L X = B become small GEMMs on the DMMA kernel instead of per-row substitutions.
-// 1024 threads = 64 rows x 16 column groups; one barrier per elimination step.
-__global__ void __launch_bounds__(1024) k_getrf_diag_inv(double* A, int lda, int j, int nb, double* Linv, double* Uinv,
-                                                         int* flags) {
+// 512 threads = 64 rows x 8 column groups; one barrier per elimination step; multipliers use the
+// reciprocal of the pivot (1 ulp-level difference from a division, far inside the parity tolerance).
+__global__ void __launch_bounds__(512) k_getrf_diag_inv(double* A, int lda, int j, int nb, double* Linv, double* Uinv,
+                                                        int* flags) {
     extern __shared__ double sm_lu[];
     double(*a)[65] = reinterpret_cast<double(*)[65]>(sm_lu);
     double(*e)[65] = reinterpret_cast<double(*)[65]>(sm_lu + 64 * 65);
     double(*x)[65] = reinterpret_cast<double(*)[65]>(sm_lu + 2 * 64 * 65);
-    const int tid = threadIdx.x, r = tid & 63, cg = tid >> 6;  // 64 rows x 16 column groups, 4 columns each
+    double* rp = sm_lu + 3 * 64 * 65;  // reciprocals of the pivots
+    const int tid = threadIdx.x, r = tid & 63, cg = tid >> 6;  // 64 rows x 8 column groups, 8 columns each
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = cg + 16 * i;
+    for (int i = 0; i < 8; ++i) {
+        const int c = cg + 8 * i;
         a[r][c] = (r < nb && c < nb) ? A[(j + r) + (size_t)lda * (j + c)] : (r == c ? 1.0 : 0.0);
         e[r][c] = (r == c) ? 1.0 : 0.0;
         x[r][c] = (r == c) ? 1.0 : 0.0;
     }
     __syncthreads();
+    if (tid == 0) {
+        if (!(fabs(a[0][0]) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
+        rp[0] = 1.0 / a[0][0];
+    }
+    __syncthreads();
     // forward elimination on [A | I]: the row operations turn I into L^-1.  In step k a column c > k
     // belongs to the trailing block of A, a column c <= k to the already non-trivial part of L^-1.
+    // The thread that finalises the next pivot a[k+1][k+1] also stores its reciprocal, so no thread
+    // divides on the per-step critical path except that one.
     for (int k = 0; k < 63; ++k) {
-        const double piv = a[k][k];
-        if (tid == 0 && !(fabs(piv) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
         if (r > k) {
-            const double l = a[r][k] / piv;
+            const double l = a[r][k] * rp[k];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = cg + 16 * i;
-                if (c > k) a[r][c] -= l * a[k][c];
-                else e[r][c] -= l * e[k][c];
+            for (int i = 0; i < 8; ++i) {
+                const int c = cg + 8 * i;
+                if (c > k) {
+                    const double v = a[r][c] - l * a[k][c];
+                    a[r][c] = v;
+                    if (r == k + 1 && c == k + 1) {
+                        if (!(fabs(v) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
+                        rp[k + 1] = 1.0 / v;
+                    }
+                } else {
+                    e[r][c] -= l * e[k][c];
+                }
             }
         }
         __syncthreads();
@@ -498,22 +513,22 @@ __global__ void __launch_bounds__(1024) k_getrf_diag_inv(double* A, int lda, int
     // U X = I by backward rank-1 updates; rows stay unscaled until the end
     for (int q = 63; q > 0; --q) {
         if (r < q) {
-            const double f = a[r][q] / a[q][q];
+            const double f = a[r][q] * rp[q];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = cg + 16 * i;
+            for (int i = 0; i < 8; ++i) {
+                const int c = cg + 8 * i;
                 if (c >= q) x[r][c] -= f * x[q][c];
             }
         }
         __syncthreads();
     }
-    const double dr = a[r][r];
+    const double dr = rp[r];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = cg + 16 * i;
-        Uinv[r + 64 * c] = (c >= r) ? x[r][c] / dr : 0.0;
+    for (int i = 0; i < 8; ++i) {
+        const int c = cg + 8 * i;
+        Uinv[r + 64 * c] = (c >= r) ? x[r][c] * dr : 0.0;
         Linv[r + 64 * c] = (c <= r) ? e[r][c] : 0.0;
-        if (r < nb && c < nb) A[(j + r) + (size_t)lda * (j + c)] = (c >= r) ? a[r][c] : a[r][c] / a[c][c];
+        if (r < nb && c < nb) A[(j + r) + (size_t)lda * (j + c)] = (c >= r) ? a[r][c] : a[r][c] * rp[c];
     }
 }
 
@@ -673,13 +688,13 @@ void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const 
 }
 cudaError_t launch_getrf_diag_inv(cudaStream_t s, double* A, int lda, int j, int nb, double* Linv, double* Uinv, int* flags) {
     static bool attr_set = false;
-    const int smem = 3 * 64 * 65 * (int)sizeof(double);
+    const int smem = (3 * 64 * 65 + 64) * (int)sizeof(double);
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_getrf_diag_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_getrf_diag_inv<<<1, 1024, smem, s>>>(A, lda, j, nb, Linv, Uinv, flags);
+    k_getrf_diag_inv<<<1, 512, smem, s>>>(A, lda, j, nb, Linv, Uinv, flags);
     return cudaGetLastError();
 }
 void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border) {
