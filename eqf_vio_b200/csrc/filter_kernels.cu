@@ -467,58 +467,87 @@ __global__ void __launch_bounds__(128) k_lift_apply(BaseState* st, Landmarks L, 
 // reciprocal of the pivot (1 ulp-level difference from a division, far inside the parity tolerance).
 __global__ void __launch_bounds__(512) k_getrf_diag_inv(double* A, int lda, int j, int nb, double* Linv, double* Uinv,
                                                         int* flags) {
-    extern __shared__ double sm_lu[];
-    double(*a)[65] = reinterpret_cast<double(*)[65]>(sm_lu);
-    double(*e)[65] = reinterpret_cast<double(*)[65]>(sm_lu + 64 * 65);
-    double(*x)[65] = reinterpret_cast<double(*)[65]>(sm_lu + 2 * 64 * 65);
-    double* rp = sm_lu + 3 * 64 * 65;  // reciprocals of the pivots
-    const int tid = threadIdx.x, r = tid & 63, cg = tid >> 6;  // 64 rows x 8 column groups, 8 columns each
+    // Register-resident elimination: thread (r, cg) keeps its 8 entries of row r of A, of L^-1 (e) and of
+    // the unscaled U^-1 (x) in registers; per step only the pivot row, the multiplier column and the
+    // pivot reciprocal travel through shared memory (double-buffered, one barrier per step).  The first
+    // version kept [A | I] in shared memory and was bound by the ~98 KB of shared traffic per step.
+    __shared__ double rowbuf[2][64];
+    __shared__ double colbuf[2][64];
+    __shared__ double rp[64];
+    __shared__ double usm[64][65];  // U for the backward pass
+    const int tid = threadIdx.x, r = tid & 63, cg = tid >> 6;  // 64 rows x 8 column groups; column c = cg + 8 i
+    double a[8], e[8], x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cg + 8 * i;
-        a[r][c] = (r < nb && c < nb) ? A[(j + r) + (size_t)lda * (j + c)] : (r == c ? 1.0 : 0.0);
-        e[r][c] = (r == c) ? 1.0 : 0.0;
-        x[r][c] = (r == c) ? 1.0 : 0.0;
+        a[i] = (r < nb && c < nb) ? A[(j + r) + (size_t)lda * (j + c)] : (r == c ? 1.0 : 0.0);
+        e[i] = (r == c) ? 1.0 : 0.0;
+        x[i] = (r == c) ? 1.0 : 0.0;
     }
-    __syncthreads();
-    if (tid == 0) {
-        if (!(fabs(a[0][0]) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
-        rp[0] = 1.0 / a[0][0];
+    // publish pivot row 0, multiplier column 0, reciprocal of pivot 0
+    if (r == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rowbuf[0][cg + 8 * i] = (cg + 8 * i > 0) ? a[i] : e[i];
+        if (cg == 0) {
+            if (!(fabs(a[0]) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
+            rp[0] = 1.0 / a[0];
+        }
     }
+    if (cg == 0) colbuf[0][r] = a[0];
     __syncthreads();
-    // forward elimination on [A | I]: the row operations turn I into L^-1.  In step k a column c > k
-    // belongs to the trailing block of A, a column c <= k to the already non-trivial part of L^-1.
-    // The thread that finalises the next pivot a[k+1][k+1] also stores its reciprocal, so no thread
-    // divides on the per-step critical path except that one.
+    // forward elimination on [A | I]: row operations turn I into L^-1.  In step k a column c > k belongs
+    // to the trailing block of A, a column c <= k to the non-trivial part of L^-1 (row k of it is final).
+#pragma unroll
     for (int k = 0; k < 63; ++k) {
+        const int b = k & 1;
         if (r > k) {
-            const double l = a[r][k] * rp[k];
+            const double l = colbuf[b][r] * rp[k];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = cg + 8 * i;
-                if (c > k) {
-                    const double v = a[r][c] - l * a[k][c];
-                    a[r][c] = v;
-                    if (r == k + 1 && c == k + 1) {
-                        if (!(fabs(v) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
-                        rp[k + 1] = 1.0 / v;
-                    }
-                } else {
-                    e[r][c] -= l * e[k][c];
-                }
+                if (c > k) a[i] -= l * rowbuf[b][c];
+                else e[i] -= l * rowbuf[b][c];
             }
         }
-        __syncthreads();
-    }
-    // U X = I by backward rank-1 updates; rows stay unscaled until the end
-    for (int q = 63; q > 0; --q) {
-        if (r < q) {
-            const double f = a[r][q] * rp[q];
+        // publish row k+1 (A part for c > k+1, L^-1 part for c <= k+1), column k+1 and 1 / pivot k+1
+        if (r == k + 1) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int c = cg + 8 * i;
-                if (c >= q) x[r][c] -= f * x[q][c];
+                rowbuf[b ^ 1][c] = (c > k + 1) ? a[i] : e[i];
             }
+            if (cg == ((k + 1) & 7)) {
+                const double piv = a[(k + 1) >> 3];
+                if (!(fabs(piv) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
+                rp[k + 1] = 1.0 / piv;
+            }
+        }
+        if (cg == ((k + 1) & 7)) colbuf[b ^ 1][r] = a[(k + 1) >> 3];
+        __syncthreads();
+    }
+    // a[] now holds U (c >= r) and the un-divided multipliers (c < r); park U in shared memory
+#pragma unroll
+    for (int i = 0; i < 8; ++i) usm[r][cg + 8 * i] = a[i];
+    // U X = I by backward rank-1 updates on unscaled rows: x[r][:] -= (U[r][q] / U[q][q]) x[q][:], q = 63..1
+    if (r == 63) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rowbuf[1][cg + 8 * i] = x[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 63; q > 0; --q) {
+        const int b = q & 1;
+        if (r < q) {
+            const double f = usm[r][q] * rp[q];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = cg + 8 * i;
+                if (c >= q) x[i] -= f * rowbuf[b][c];
+            }
+        }
+        if (r == q - 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rowbuf[b ^ 1][cg + 8 * i] = x[i];
         }
         __syncthreads();
     }
@@ -526,9 +555,9 @@ __global__ void __launch_bounds__(512) k_getrf_diag_inv(double* A, int lda, int 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cg + 8 * i;
-        Uinv[r + 64 * c] = (c >= r) ? x[r][c] * dr : 0.0;
-        Linv[r + 64 * c] = (c <= r) ? e[r][c] : 0.0;
-        if (r < nb && c < nb) A[(j + r) + (size_t)lda * (j + c)] = (c >= r) ? a[r][c] : a[r][c] * rp[c];
+        Uinv[r + 64 * c] = (c >= r) ? x[i] * dr : 0.0;
+        Linv[r + 64 * c] = (c <= r) ? e[i] : 0.0;
+        if (r < nb && c < nb) A[(j + r) + (size_t)lda * (j + c)] = (c >= r) ? a[i] : a[i] * rp[c];
     }
 }
 
@@ -687,14 +716,7 @@ void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const 
     if (N > 0) k_lift_apply<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, gamma, discrete);
 }
 cudaError_t launch_getrf_diag_inv(cudaStream_t s, double* A, int lda, int j, int nb, double* Linv, double* Uinv, int* flags) {
-    static bool attr_set = false;
-    const int smem = (3 * 64 * 65 + 64) * (int)sizeof(double);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_getrf_diag_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    k_getrf_diag_inv<<<1, 512, smem, s>>>(A, lda, j, nb, Linv, Uinv, flags);
+    k_getrf_diag_inv<<<1, 512, 0, s>>>(A, lda, j, nb, Linv, Uinv, flags);
     return cudaGetLastError();
 }
 void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border) {
