@@ -308,6 +308,7 @@ def main():
     f.profile_read(reset=True)
     for _ in range(K):
         run_period_resident(next(it))
+    classes = f.profile_read_classes(reset=False)
     g_launches, g_ms, g_flops = f.profile_read(reset=True)
     f.profile_enable(False)
 
@@ -360,6 +361,8 @@ def main():
                 "flops_per_launch_avg": g_flops / g_launches if g_launches else None,
                 "peak_source": "measured live: torch.matmul fp64 8192^3 (cuBLAS DGEMM), best of 5, same GPU; MEASURED_PEAKS.json holds no fp64 figure. DMMA pipe ceiling measured at 37.1 TFLOP/s (profiles/r01_dmma_microbench.md)",
                 "gemm_share_of_step": g_ms / (dev_ms / world) if dev_ms else None,
+                "by_class": {k: {"launches": v["launches"], "ms_per_period": v["ms"] / K, "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0)}
+                             for k, v in classes.items()},
             },
             "gflops_dense_equiv": fm["period"] * K * world / (dev_ms * 1e-3) / 1e9,
             "flop_model_period_gflop": fm["period"] / 1e9,

@@ -49,6 +49,7 @@ SIGNATURES = {
     "eqvio_launch_count": (C.c_int, [_h, C.POINTER(C.c_longlong), C.c_int]),
     "eqvio_profile_enable": (C.c_int, [_h, C.c_int]),
     "eqvio_profile_read": (C.c_int, [_h, C.POINTER(C.c_longlong), _dp, _dp, C.c_int]),
+    "eqvio_profile_read_class": (C.c_int, [_h, C.c_int, C.POINTER(C.c_longlong), _dp, _dp, C.c_int]),
     "eqvio_stream": (C.c_int, [_h, C.POINTER(C.c_void_p)]),
     "eqvio_status_string": (C.c_char_p, [C.c_int]),
     "eqvio_version": (C.c_char_p, []),

@@ -40,7 +40,8 @@ static void set_error(cudaError_t e, const char* what, int line) {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-struct ProfEvent { cudaEvent_t a, b; double flops; };
+struct ProfEvent { cudaEvent_t a, b; double flops; int cls; };
+enum { PROF_RICCATI = 0, PROF_UPDATE = 1, PROF_SCHUR_GEMM = 2, PROF_SCHUR_DIAG = 3, PROF_CLASSES = 4 };
 
 struct eqvio_filter {
     int device = 0;
@@ -75,6 +76,9 @@ struct eqvio_filter {
     std::vector<ProfEvent> prof;
     long long prof_launches = 0;
     double prof_ms = 0, prof_flops = 0;
+    long long cls_launches[PROF_CLASSES] = {0, 0, 0, 0};
+    double cls_ms[PROF_CLASSES] = {0, 0, 0, 0}, cls_flops[PROF_CLASSES] = {0, 0, 0, 0};
+    int prof_cls = PROF_UPDATE;  // class tag applied to the launches that follow
 };
 
 typedef eqvio_filter Filter;
@@ -200,6 +204,7 @@ static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const 
     if (f->profiling) {
         cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
         pe.flops = 2.0 * M * N * K;
+        pe.cls = f->prof_cls;
         cudaEventRecord(pe.a, f->stream);
     }
     CU_TRY(dgemm_launch(g, f->stream, force_config));
@@ -212,10 +217,19 @@ static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const 
 // k_schur_setup) of the (k + r) x (k + c) matrix Aug by unpivoted LU: on return the bottom-right r x c
 // block holds Z - R A^-1 Cc.
 static int schur_lu(Filter* f, double* Aug, int lda, int k, int r, int c) {
+    struct ClsGuard { Filter* f; ~ClsGuard() { f->prof_cls = PROF_UPDATE; } } guard{f};
+    f->prof_cls = PROF_SCHUR_GEMM;
     for (int j = 0; j < k; j += 64) {
         const int nb = std::min(64, k - j);
         const int rows = k + r - (j + nb), cols = k + c - (j + nb);
+        ProfEvent pe;
+        if (f->profiling) {
+            cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
+            pe.flops = 0.0; pe.cls = PROF_SCHUR_DIAG;
+            cudaEventRecord(pe.a, f->stream);
+        }
         CU_TRY(launch_getrf_diag_inv(f->stream, Aug, lda, j, nb, f->Linv, f->Uinv, &f->st->flags));
+        if (f->profiling) { cudaEventRecord(pe.b, f->stream); f->prof.push_back(pe); }
         f->launches += 1;
         double* Lp = Aug + (j + nb) + (size_t)lda * j;         // rows x nb, below the diagonal block
         double* Up = Aug + j + (size_t)lda * (j + nb);         // nb x cols, right of it
@@ -241,10 +255,13 @@ static RiccatiOut riccati_out(Filter* f) {
 // The two Sigma GEMMs of the Riccati step (VIOFilter.cpp:188-189); F, B_b already built.
 static int riccati_gemms(Filter* f, double T) {
     const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld;
+    f->prof_cls = PROF_RICCATI;
     int st = gemm(f, 0, n, n, n, 1.0, f->F, ld, f->Sigma, ld, 0.0, nullptr, 0, f->W, ld);  // W = F Sigma
     if (st) return st;
     // Sigma = [W | T B_b R] [F | B_b]^T + T P      (K runs over n16 + 6 columns; [n, n16) are zero)
-    return gemm(f, 1, n, n, n16 + 6, 1.0, f->W, ld, f->F, ld, 0.0, nullptr, 0, f->Sigma, ld, 1, T);
+    st = gemm(f, 1, n, n, n16 + 6, 1.0, f->W, ld, f->F, ld, 0.0, nullptr, 0, f->Sigma, ld, 1, T);
+    f->prof_cls = PROF_UPDATE;
+    return st;
 }
 
 // integrateUpToTime, VIOFilter.cpp:146-209.  Returns 1 integrated, 0 skipped, <0 error.
@@ -949,7 +966,8 @@ int eqvio_profile_read(eqvio_handle_t f, long long* gemm_launches, double* gemm_
     for (auto& e : f->prof) {
         float t = 0;
         cudaEventElapsedTime(&t, e.a, e.b);
-        f->prof_ms += t; f->prof_flops += e.flops; f->prof_launches += 1;
+        f->cls_ms[e.cls] += t; f->cls_flops[e.cls] += e.flops; f->cls_launches[e.cls] += 1;
+        if (e.cls != PROF_SCHUR_DIAG) { f->prof_ms += t; f->prof_flops += e.flops; f->prof_launches += 1; }
         cudaEventDestroy(e.a); cudaEventDestroy(e.b);
     }
     f->prof.clear();
@@ -957,6 +975,16 @@ int eqvio_profile_read(eqvio_handle_t f, long long* gemm_launches, double* gemm_
     if (gemm_ms) *gemm_ms = f->prof_ms;
     if (gemm_flops) *gemm_flops = f->prof_flops;
     if (reset) { f->prof_launches = 0; f->prof_ms = 0; f->prof_flops = 0; }
+    return EQVIO_OK;
+}
+int eqvio_profile_read_class(eqvio_handle_t f, int cls, long long* launches, double* ms, double* flops, int reset) {
+    if (!f || cls < 0 || cls >= PROF_CLASSES) return EQVIO_ERR_ARG;
+    int st = eqvio_profile_read(f, nullptr, nullptr, nullptr, 0);
+    if (st) return st;
+    if (launches) *launches = f->cls_launches[cls];
+    if (ms) *ms = f->cls_ms[cls];
+    if (flops) *flops = f->cls_flops[cls];
+    if (reset) { f->cls_launches[cls] = 0; f->cls_ms[cls] = 0; f->cls_flops[cls] = 0; }
     return EQVIO_OK;
 }
 int eqvio_stream(eqvio_handle_t f, void** stream) {

@@ -188,6 +188,17 @@ class VIOFilter:
         abi.check(self._L.eqvio_profile_read(self._h, C.byref(n), C.byref(ms), C.byref(fl), int(reset)), "eqvio_profile_read")
         return n.value, ms.value, fl.value
 
+    PROFILE_CLASSES = ("riccati_gemm", "update_gemm", "schur_gemm", "schur_diag_lu")
+
+    def profile_read_classes(self, reset=True) -> dict:
+        out = {}
+        for cls, name in enumerate(self.PROFILE_CLASSES):
+            n = C.c_longlong()
+            ms, fl = C.c_double(), C.c_double()
+            abi.check(self._L.eqvio_profile_read_class(self._h, cls, C.byref(n), C.byref(ms), C.byref(fl), int(reset)), "eqvio_profile_read_class")
+            out[name] = {"launches": n.value, "ms": ms.value, "flops": fl.value}
+        return out
+
     def stream_ptr(self) -> int:
         p = C.c_void_p()
         abi.check(self._L.eqvio_stream(self._h, C.byref(p)), "eqvio_stream")

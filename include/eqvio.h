@@ -179,6 +179,10 @@ int eqvio_launch_count(eqvio_handle_t h, long long* count, int reset);
 int eqvio_profile_enable(eqvio_handle_t h, int on);
 int eqvio_profile_read(eqvio_handle_t h, long long* gemm_launches, double* gemm_ms, double* gemm_flops,
                        int reset);
+/* Same, per class of launch: 0 = Riccati GEMMs (F Sigma, W F^T), 1 = update GEMMs (C Sigma, S, Sigma C^T,
+ * K, K C, Sigma - K C Sigma), 2 = GEMMs inside the blocked Schur eliminations (S^-1, Sigma_sub^-1),
+ * 3 = the diagonal-block LU kernels of those eliminations (flops reported as 0). */
+int eqvio_profile_read_class(eqvio_handle_t h, int cls, long long* launches, double* ms, double* flops, int reset);
 /* The handle's CUDA stream (cudaStream_t as void*), for callers that order their own work after it. */
 int eqvio_stream(eqvio_handle_t h, void** stream);
 const char* eqvio_status_string(int status);
