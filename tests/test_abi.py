@@ -74,3 +74,20 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, fn)
+
+
+def test_cpp_facade_compiles_and_runs(tmp_path):
+    """include/eqvio/VIOFilter.hpp (the reference's class surface on POD types) builds against the C ABI;
+    the example exits 0 both with a GPU (runs the filter) and without (reports EQVIO_ERR_NO_DEVICE)."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "replay_minimal")
+    csrc = os.path.join(ROOT, "eqf_vio_b200", "csrc")
+    subprocess.check_call([gxx, "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "replay_minimal.cpp"),
+                           "-L", csrc, "-leqvio_b200", "-Wl,-rpath," + csrc, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr

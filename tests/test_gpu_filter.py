@@ -15,11 +15,10 @@ import pytest
 from eqf_vio_b200 import abi
 from eqf_vio_b200.settings import template_settings
 from eqf_vio_b200.synthetic import period_sequence
-from helpers import feed, rel, run, split_snapshot
+from helpers import feed, golden_paths, golden_settings, golden_tolerances, rel, replay_golden, run, split_snapshot
 from oracle.c_oracle import COracleFilter
 
 pytestmark = pytest.mark.gpu
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STEP_SIGMA_TOL, STEP_STATE_TOL = 1e-9, 1e-8
 SEQ_SIGMA_TOL, SEQ_STATE_TOL = 2e-8, 1e-4
 
@@ -30,51 +29,56 @@ def gpu_filter(s):
     return VIOFilter(s)
 
 
-def test_golden_pieces():
-    z = np.load(os.path.join(GOLDEN, "pieces_N8.npz"))
-    s = template_settings(outlierThreshold=1e9)
+@pytest.mark.parametrize("path", golden_paths("steps_"), ids=os.path.basename)
+def test_golden_steps(path):
+    """Kernel-level entry points and single steps against vectors recorded from the reference's sources."""
+    z = np.load(path)
+    s = golden_settings(z)
+    N = int(z["N"])
+    n = 11 + 3 * N
     f = gpu_filter(s)
     f.set_snapshot(z["snapshot"])
     assert np.array_equal(f.get_snapshot(), z["snapshot"])  # lossless snapshot / restore
-    F, Bb = f.build_FB(float(z["T"]), z["omega"])
-    assert np.abs(F - z["F"]).max() < 1e-13 and np.abs(Bb - z["Bb"]).max() < 1e-13
+    # F = I + T [[0,0],[-Bt,A0t]], B_b = [0;Bt]  (VIOFilter.cpp:177-185) from the reference's A0t, Bt
+    T = 0.005
+    F, Bb = f.build_FB(T, z["omega"])
+    Fref = np.eye(n)
+    Fref[6:, 6:] += T * z["A0"]
+    Fref[6:, :6] += -T * z["Bt"]
+    assert np.abs(F - Fref).max() < 1e-13 and np.abs(Bb[6:] - z["Bt"]).max() < 1e-13 and np.abs(Bb[:6]).max() == 0.0
     assert np.array_equal(f.get_snapshot(), z["snapshot"])  # kernel-level entry point leaves the state alone
     C, d = f.build_C_delta(z["bearings"])
-    assert np.abs(C - z["C"]).max() < 1e-13 and np.abs(d - z["delta"]).max() < 1e-13
+    assert np.abs(C[:, 6:] - z["C0"]).max() < 1e-13 and np.abs(C[:, :6]).max() == 0.0 and np.abs(d - z["delta"]).max() < 1e-13
     G = f.bundle_lift(z["gamma_eqf"])
     assert np.abs(G - z["Gamma"]).max() < 1e-9 * max(1.0, np.abs(z["Gamma"]).max())
-    f.riccati_propagate(float(z["T"]), z["omega"])
-    assert rel(f.stateCovariance(), z["Sigma_prop"]) < 1e-14
-    f.set_snapshot(z["snapshot"])
-    K, g = f.gain_update(z["bearings"])
-    assert rel(K, z["K"]) < 1e-9 and rel(g, z["gamma"]) < 1e-9
-    assert rel(f.stateCovariance(), z["Sigma_upd"]) < STEP_SIGMA_TOL
+    row = z["imu_row"]
+    assert f.processIMUData(row[0], row[1:4], row[4:7]) == 0
+    h, S = split_snapshot(f.get_snapshot())
+    hg, Sg = split_snapshot(z["snap_after_imu"])
+    assert rel(S, Sg) < 1e-13 and np.abs(h - hg).max() < 1e-12
+    assert f.processVisionData(float(z["vision_stamp"]), z["ids"], z["bearings"]) == 0
+    h, S = split_snapshot(f.get_snapshot())
+    hg, Sg = split_snapshot(z["snap_after_vision"])
+    assert rel(S, Sg) < STEP_SIGMA_TOL and np.abs(h - hg).max() < STEP_STATE_TOL, (rel(S, Sg), np.abs(h - hg).max())
 
 
-def _overrides(z):
-    return dict(eval(str(z["overrides"])))
-
-
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "seq_*.npz"))), ids=os.path.basename)
+@pytest.mark.parametrize("path", golden_paths("seq_"), ids=os.path.basename)
 def test_golden_sequences(path):
-    """Free-running against the committed vectors, all Settings modes (discrete / continuous lifts,
-    fastRiccati, no innovation lift)."""
+    """Free-running against the reference-recorded vectors: every Settings mode (discrete / continuous
+    lifts, fastRiccati, no innovation lift) and the landmark bookkeeping case."""
     z = np.load(path)
-    f = gpu_filter(template_settings(**_overrides(z)))
-    imu, vs, ids, y = z["imu"], z["vision_stamps"], z["ids"], z["bearings"]
-    i = j = k = 0
-    while i < len(imu) or j < len(vs):
-        if i < len(imu) and (j >= len(vs) or imu[i, 0] < vs[j]):
-            r = f.processIMUData(imu[i, 0], imu[i, 1:4], imu[i, 4:7])
-            i += 1
-        else:
-            r = f.processVisionData(vs[j], ids, y[j])
-            hg, Sg = split_snapshot(z[f"snap{j}"])
-            h, S = split_snapshot(f.get_snapshot())
-            assert rel(S, Sg) < SEQ_SIGMA_TOL and np.abs(h - hg).max() < SEQ_STATE_TOL, (j, rel(S, Sg), np.abs(h - hg).max())
-            j += 1
-        assert r == int(z["status"][k])
-        k += 1
+    f = gpu_filter(golden_settings(z))
+    tol_s, tol_h = golden_tolerances(z)
+
+    def check(j, gold):
+        snap = f.get_snapshot()
+        assert snap.size == gold.size, (j, snap[0], gold[0])
+        hg, Sg = split_snapshot(gold)
+        h, S = split_snapshot(snap)
+        assert np.array_equal(h[49::9], hg[49::9])
+        assert rel(S, Sg) < tol_s and np.abs(h - hg).max() < tol_h, (j, rel(S, Sg), np.abs(h - hg).max())
+
+    replay_golden(z, f, check)
 
 
 @pytest.mark.parametrize("N,periods", [(5, 3), (64, 3), (100, 2)])

@@ -11,15 +11,10 @@ import pytest
 
 from eqf_vio_b200.settings import template_settings
 from eqf_vio_b200.synthetic import period_sequence
-from helpers import feed, np_settings, rel, run, split_snapshot
+from helpers import feed, golden_paths, golden_settings, golden_tolerances, np_settings, rel, replay_golden, run, split_snapshot
 from oracle import c_oracle, eqvio_numpy as onp
 from oracle.c_oracle import COracleFilter
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-
-
-def _overrides(z):
-    return dict(eval(str(z["overrides"])))
 
 
 def test_dense_helpers():
@@ -104,47 +99,54 @@ def test_bookkeeping_c_vs_numpy():
             assert rel(S1, S2) < 5e-9
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "seq_*.npz"))), ids=os.path.basename)
-def test_golden_sequences(path):
+@pytest.mark.parametrize("path", golden_paths("seq_"), ids=os.path.basename)
+@pytest.mark.parametrize("which", ["c", "numpy"])
+def test_golden_sequences(path, which):
+    """Both restatements against the vectors recorded from the reference's own sources."""
     z = np.load(path)
-    s = template_settings(**_overrides(z))
+    s = golden_settings(z)
+    f = COracleFilter(s) if which == "c" else onp.VIOFilter(np_settings(s))
+    tol_s, tol_h = golden_tolerances(z)
+
+    def check(j, gold):
+        snap = f.get_snapshot()
+        assert snap.size == gold.size, (j, snap[0], gold[0])  # same landmark count
+        hg, Sg = split_snapshot(gold)
+        h, S = split_snapshot(snap)
+        assert np.array_equal(h[49::9], hg[49::9])  # same ids, same order
+        assert rel(S, Sg) < tol_s and np.abs(h - hg).max() < tol_h, (j, rel(S, Sg), np.abs(h - hg).max())
+
+    replay_golden(z, f, check)
+
+
+@pytest.mark.parametrize("path", golden_paths("steps_"), ids=os.path.basename)
+def test_golden_steps(path):
+    """The reference's free functions (A0, Bt, C0, delta, bundleLift) and one IMU / one vision step from
+    a recorded state: per-step, so the tolerance is tight for both start-ups."""
+    z = np.load(path)
+    s = golden_settings(z)
+    N = int(z["N"])
     fc, fn = COracleFilter(s), onp.VIOFilter(np_settings(s))
-    imu, vs, ids, y = z["imu"], z["vision_stamps"], z["ids"], z["bearings"]
-    i = j = k = 0
-    while i < len(imu) or j < len(vs):
-        if i < len(imu) and (j >= len(vs) or imu[i, 0] < vs[j]):
-            r = fc.processIMUData(imu[i, 0], imu[i, 1:4], imu[i, 4:7])
-            fn.processIMUData(imu[i, 0], imu[i, 1:4], imu[i, 4:7])
-            i += 1
-        else:
-            r = fc.processVisionData(vs[j], ids, y[j])
-            fn.processVisionData(vs[j], ids, y[j])
-            gold = z[f"snap{j}"]
-            hg, Sg = split_snapshot(gold)
-            hc, Sc = split_snapshot(fc.get_snapshot())
-            hn, Sn = split_snapshot(fn.get_snapshot())
-            assert rel(Sc, Sg) < 1e-12 and np.abs(hc - hg).max() < 1e-12  # C oracle reproduces its own vectors
-            assert rel(Sn, Sg) < 5e-9 and np.abs(hn - hg).max() < 1e-6    # independent restatement
-            j += 1
-        assert r == int(z["status"][k])
-        k += 1
-
-
-def test_golden_pieces():
-    z = np.load(os.path.join(GOLDEN, "pieces_N8.npz"))
-    s = template_settings(outlierThreshold=1e9)
-    fc = COracleFilter(s)
     fc.set_snapshot(z["snapshot"])
-    F, Bb = fc.build_FB(float(z["T"]), z["omega"])
-    assert np.abs(F - z["F"]).max() < 1e-14 and np.abs(Bb - z["Bb"]).max() < 1e-14
-    C, d = fc.build_C_delta(z["bearings"])
-    assert np.abs(C - z["C"]).max() < 1e-14 and np.abs(d - z["delta"]).max() < 1e-14
-    assert np.abs(fc.bundle_lift(z["gamma_eqf"]) - z["Gamma"]).max() < 1e-12
-    fc.riccati_propagate(float(z["T"]), z["omega"])
-    assert rel(fc.stateCovariance(), z["Sigma_prop"]) < 1e-14
-    fc.set_snapshot(z["snapshot"])
-    K, g = fc.gain_update(z["bearings"])
-    assert rel(K, z["K"]) < 1e-12 and rel(fc.stateCovariance(), z["Sigma_upd"]) < 1e-12
+    fn.set_snapshot(z["snapshot"])
+    xi0m = onp.project_to_manifold(fn.xi0)
+    for A0, Bt, C0 in ((fc.state_matrix_A(z["omega"]), fc.input_matrix_B(), fc.output_matrix_C()),
+                       (onp.state_matrix_A(fn.X, xi0m, z["omega"]), onp.input_matrix_B(fn.X, xi0m), onp.output_matrix_C(xi0m))):
+        assert np.abs(A0 - z["A0"]).max() < 1e-12 and np.abs(Bt - z["Bt"]).max() < 1e-12 and np.abs(C0 - z["C0"]).max() < 1e-13
+    assert np.abs(fc.build_C_delta(z["bearings"])[1] - z["delta"]).max() < 1e-14
+    assert np.abs(fn.build_C_delta(z["bearings"].reshape(N, 3))[1] - z["delta"]).max() < 1e-14
+    assert np.abs(fc.bundle_lift(z["gamma_eqf"]) - z["Gamma"]).max() < 1e-10
+    assert np.abs(onp.bundle_lift(z["gamma_eqf"], fn.xi0, fn.X, fn.Sigma[6:, 6:]) - z["Gamma"]).max() < 1e-9
+    row = z["imu_row"]
+    for f in (fc, fn):
+        f.processIMUData(row[0], row[1:4], row[4:7])
+        h, S = split_snapshot(f.get_snapshot())
+        hg, Sg = split_snapshot(z["snap_after_imu"])
+        assert rel(S, Sg) < 1e-13 and np.abs(h - hg).max() < 1e-12
+        f.processVisionData(float(z["vision_stamp"]), z["ids"], z["bearings"])
+        h, S = split_snapshot(f.get_snapshot())
+        hg, Sg = split_snapshot(z["snap_after_vision"])
+        assert rel(S, Sg) < 1e-9 and np.abs(h - hg).max() < 1e-8, (rel(S, Sg), np.abs(h - hg).max())
 
 
 def test_silent_skips():
