@@ -12,7 +12,7 @@ int main() {
     try {
         eqvio::VIOFilter filter(s);
         eqvio::IMUVelocity imu;
-        imu.accel = {0.0, 0.0, 9.81};
+        imu.accel = {0.3, -0.2, 9.7};  // not exactly +z: the gravity chart pole (reference VIOState.cpp:243) is singular for a perfectly level start
         for (int k = 0; k < 22; ++k) {
             imu.stamp = 0.005 * k;
             filter.processIMUData(imu);
