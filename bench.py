@@ -47,8 +47,8 @@ def flop_model(N):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--features", type=int, default=512)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -57,47 +57,80 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons sampled every 20 ms through NVML while the timed region runs
+    (the B200_PROFILING.md clocks line; falls back to polling nvidia-smi if pynvml is unavailable)."""
 
-    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.samples, self._stop, self.t, self.proc = index, [], threading.Event(), None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active", "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self):
+        if self.nv is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            sm = [s[0] for s in self.samples]
+            busy = [c for c in sm if c > 0.5 * max(sm)] if sm else []
+            reasons = set()
+            for _, _, rs in self.samples:
+                for name, bit in self.REASONS.items():
+                    if rs & bit:
+                        reasons.add(name)
+            return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": self.sm_max,
+                    "power_w_max": max((s[1] for s in self.samples), default=None), "samples": len(sm), "reasons": sorted(reasons),
+                    "how": "NVML, 20 ms period, over warm-up + timed region of the device-timed pass"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
         self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
+        out = self.proc.communicate(timeout=2)[0]
+        sm, mx, rs = [], [], set()
+        for line in out.splitlines():
+            c = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+                sm.append(float(c[0])); mx.append(float(c[1]))
+                v = int(c[3], 16)
+                for name, bit in self.REASONS.items():
+                    if v & bit:
+                        rs.add(name)
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        busy = [c for c in sm if c > 0.5 * max(sm)] if sm else []
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(rs), "how": "nvidia-smi -lms 100"}
 
 
 def run_reference(args, rank, world):
@@ -262,12 +295,12 @@ def main():
 
     it = iter(periods)
     # ---------------- pass 1: inputs resident in HBM, device-timed (value) ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(W):
         run_period_resident(next(it))
-    sampler = ClockSampler(local_rank)
     barrier()
     f.launch_count(reset=True)
-    sampler.start()
     pairs = []
     for _ in range(K):
         flush_l2()
