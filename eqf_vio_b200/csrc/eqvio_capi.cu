@@ -46,6 +46,9 @@ enum { PROF_RICCATI = 0, PROF_UPDATE = 1, PROF_SCHUR_GEMM = 2, PROF_SCHUR_DIAG =
 struct eqvio_filter {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;   // second stream: dense GEMMs that overlap the latency-bound Schur eliminations
+    cudaStream_t cur = nullptr;    // stream the next gemm() goes to (main unless forked)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     eqvio_settings_t s;
     // host-side scalars of the reference class (VIOFilter.h:49-55)
     bool initialised = false;
@@ -205,13 +208,27 @@ static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const 
         cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
         pe.flops = 2.0 * M * N * K;
         pe.cls = f->prof_cls;
-        cudaEventRecord(pe.a, f->stream);
+        cudaEventRecord(pe.a, f->cur);
     }
-    CU_TRY(dgemm_launch(g, f->stream, force_config));
-    if (f->profiling) { cudaEventRecord(pe.b, f->stream); f->prof.push_back(pe); }
+    CU_TRY(dgemm_launch(g, f->cur, force_config));
+    if (f->profiling) { cudaEventRecord(pe.b, f->cur); f->prof.push_back(pe); }
     f->launches += 1;
     return EQVIO_OK;
 }
+
+// fork / join of the side stream around work that may overlap the main stream
+static int fork_side(Filter* f) {
+    CU_TRY(cudaEventRecord(f->ev_fork, f->stream));
+    CU_TRY(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
+    f->cur = f->side;
+    return EQVIO_OK;
+}
+static int end_side(Filter* f) {  // side work issued; following launches go to the main stream again
+    CU_TRY(cudaEventRecord(f->ev_join, f->side));
+    f->cur = f->stream;
+    return EQVIO_OK;
+}
+static int join_side(Filter* f) { CU_TRY(cudaStreamWaitEvent(f->stream, f->ev_join, 0)); return EQVIO_OK; }
 
 // Blocked Schur elimination of the leading k x k block (k a multiple of 16, identity-padded by
 // k_schur_setup) of the (k + r) x (k + c) matrix Aug by unpivoted LU: on return the bottom-right r x c
@@ -342,13 +359,27 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
     const int mp = round_up(m, 16);
     launch_schur_setup(s, f->Saug, f->ld2m, m, mp, m, m, 1);
     f->launches += 2;
+    // Sigma C^T does not depend on S^-1: it runs on the side stream under the (latency-bound) elimination
+    if ((st = fork_side(f))) return st;
+    if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
+    if ((st = end_side(f))) return st;
     if ((st = schur_lu(f, f->Saug, f->ld2m, mp, m, m))) return st;
     const double* negSinv = f->Saug + mp + (size_t)f->ld2m * mp;
+    if ((st = join_side(f))) return st;
     // K = (Sigma C^T) S^-1                                           :277
-    if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
     if ((st = gemm(f, 0, n, m, m, -1.0, f->SCt, ld, negSinv, f->ld2m, 0.0, nullptr, 0, f->K, ld))) return st;
     launch_gemv(s, f->K, ld, n, m, f->delta, f->gamma);  // :279
     f->launches += 1;
+    // Sigma <- Sigma - (K C) Sigma (:297) reads the PRIOR Sigma, K and C and writes the twin buffer; the lift
+    // (:285-296) reads the prior Sigma and gamma and writes X.  Independent: the two GEMMs go to the side
+    // stream and run under the lift's Schur elimination.
+    if (do_sigma) {
+        if ((st = fork_side(f))) return st;
+        if ((st = gemm(f, 0, n, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, f->W, ld))) return st;
+        if ((st = gemm(f, 0, n, n, n, -1.0, f->W, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld))) return st;
+        if ((st = end_side(f))) return st;
+        // W's columns [0, n) now hold K C; the Riccati step rewrites them (W = F Sigma) before use.
+    }
     if (do_lift) {
         const int use_lift = f->s.useInnovationLift, discrete = f->s.useDiscreteInnovationLift;
         if (use_lift) {
@@ -365,11 +396,8 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
         f->launches += 2;
     }
     if (do_sigma) {
-        // Sigma <- Sigma - (K C) Sigma                                :297
-        if ((st = gemm(f, 0, n, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, f->W, ld))) return st;
-        if ((st = gemm(f, 0, n, n, n, -1.0, f->W, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld))) return st;
+        if ((st = join_side(f))) return st;
         std::swap(f->Sigma, f->Sigma2);
-        // W's columns [0, n) now hold K C; the Riccati step rewrites them (W = F Sigma) before use.
     }
     return EQVIO_OK;
 }
@@ -444,7 +472,17 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     Filter* f = new Filter();
     f->device = device;
     f->s = *settings;
-    CU_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    {
+        // the main stream carries the latency-bound chains (Schur pivots): highest priority, so its small kernels
+        // get SM slots as soon as CTAs of the big side-stream GEMMs retire
+        int lo = 0, hi = 0;
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU_TRY(cudaStreamCreateWithPriority(&f->stream, cudaStreamNonBlocking, hi));
+        CU_TRY(cudaStreamCreateWithPriority(&f->side, cudaStreamNonBlocking, lo));
+    }
+    f->cur = f->stream;
+    CU_TRY(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&f->stage_free, cudaEventDisableTiming));
     CU_TRY(cudaEventRecord(f->stage_free, f->stream));
     CU_TRY(dalloc(&f->st, 1));
@@ -465,12 +503,15 @@ int eqvio_destroy(eqvio_handle_t f) {
     if (!f) return EQVIO_ERR_ARG;
     cudaSetDevice(f->device);
     cudaStreamSynchronize(f->stream);
+    cudaStreamSynchronize(f->side);
     for (auto& e : f->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     free_device(f);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
     cudaEventDestroy(f->stage_free);
+    cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join);
+    cudaStreamDestroy(f->side);
     cudaStreamDestroy(f->stream);
     delete f;
     return EQVIO_OK;
