@@ -47,6 +47,8 @@ struct eqvio_filter {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;   // second stream: dense GEMMs that overlap the latency-bound Schur eliminations
+    cudaStream_t lift = nullptr;   // third stream: the Sigma_sub elimination of bundleLift, concurrent with the S / K / gamma chain
+    cudaEvent_t ev_lift_fork = nullptr, ev_lift_done = nullptr;
     cudaStream_t cur = nullptr;    // stream the next gemm() goes to (main unless forked)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     eqvio_settings_t s;
@@ -61,7 +63,9 @@ struct eqvio_filter {
     // device state
     BaseState* st = nullptr;
     StepScratch* sc = nullptr;
-    double *Linv = nullptr, *Uinv = nullptr;  // 64 x 64 triangular inverses of the current pivot block
+    double *Linv = nullptr, *Uinv = nullptr;  // 64 x 64 triangular inverses of the current pivot block (S chain)
+    double *LinvL = nullptr, *UinvL = nullptr;  // lift chain: every block's L_jj^-1 is kept (forward substitution), U_jj^-1 scratch
+    double *yo = nullptr, *b4 = nullptr;       // D obs (p) and M^T W obs (4)
     Landmarks L{nullptr, 0}, L2{nullptr, 0};
     double *Sigma = nullptr, *Sigma2 = nullptr, *F = nullptr, *W = nullptr, *Bb = nullptr, *Aug = nullptr;
     double *C = nullptr, *CS = nullptr, *SCt = nullptr, *K = nullptr, *Saug = nullptr, *Sinv = nullptr;
@@ -99,7 +103,8 @@ static void free_device(Filter* f) {
     cudaFree(f->Sigma); cudaFree(f->Sigma2); cudaFree(f->F); cudaFree(f->W); cudaFree(f->Bb); cudaFree(f->Aug);
     cudaFree(f->C); cudaFree(f->CS); cudaFree(f->SCt); cudaFree(f->K); cudaFree(f->Saug); cudaFree(f->Sinv);
     cudaFree(f->delta); cudaFree(f->gamma); cudaFree(f->y_in); cudaFree(f->y); cudaFree(f->scratch); cudaFree(f->Gamma);
-    cudaFree(f->d_flags); cudaFree(f->d_map);
+    cudaFree(f->d_flags); cudaFree(f->d_map); cudaFree(f->LinvL); cudaFree(f->yo);
+    f->LinvL = f->yo = nullptr;
     f->L.base = f->L2.base = nullptr;
     f->Sigma = f->Sigma2 = f->F = f->W = f->Bb = f->Aug = f->C = f->CS = f->SCt = f->K = f->Saug = f->Sinv = nullptr;
     f->delta = f->gamma = f->y_in = f->y = f->scratch = f->Gamma = nullptr;
@@ -120,6 +125,9 @@ static int ensure_capacity(Filter* f, int needN) {
     Landmarks L{nullptr, cap}, L2{nullptr, cap};
     double *Sigma, *Sigma2, *F, *W, *Bb, *Aug, *C, *CS, *SCt, *K, *Saug, *Sinv, *delta, *gamma, *y_in, *y, *scratch, *Gamma;
     int *d_flags, *d_map;
+    double *LinvL, *yo;
+    CU_TRY(dalloc(&LinvL, (size_t)(ld / 64 + 2) * 4096 + 1024));
+    CU_TRY(dalloc(&yo, (size_t)ld + 64));
     CU_TRY(dalloc(&L.base, (size_t)LM_FIELDS * cap));
     CU_TRY(dalloc(&L2.base, (size_t)LM_FIELDS * cap));
     CU_TRY(dalloc(&Sigma, nn)); CU_TRY(dalloc(&Sigma2, nn)); CU_TRY(dalloc(&F, nn)); CU_TRY(dalloc(&W, nn));
@@ -139,6 +147,7 @@ static int ensure_capacity(Filter* f, int needN) {
     CU_TRY(cudaMemsetAsync(Saug, 0, (size_t)ld2m * (ld2m + 32) * 8, s)); CU_TRY(cudaMemsetAsync(Sinv, 0, (size_t)ldm * (ldm + 32) * 8, s));
     CU_TRY(cudaMemsetAsync(L.base, 0, (size_t)LM_FIELDS * cap * 8, s)); CU_TRY(cudaMemsetAsync(L2.base, 0, (size_t)LM_FIELDS * cap * 8, s));
     CU_TRY(cudaMemsetAsync(gamma, 0, (size_t)ld * 8, s)); CU_TRY(cudaMemsetAsync(delta, 0, (size_t)ldm * 8, s));
+    CU_TRY(cudaMemsetAsync(LinvL, 0, ((size_t)(ld / 64 + 2) * 4096 + 1024) * 8, s)); CU_TRY(cudaMemsetAsync(yo, 0, ((size_t)ld + 64) * 8, s));
     if (o.Sigma) {
         const int n = n_of(f->N);
         CU_TRY(cudaMemcpy2DAsync(Sigma, (size_t)ld * 8, o.Sigma, (size_t)o.ld * 8, (size_t)n * 8, n, cudaMemcpyDeviceToDevice, s));
@@ -153,6 +162,7 @@ static int ensure_capacity(Filter* f, int needN) {
     f->C = C; f->CS = CS; f->SCt = SCt; f->K = K; f->Saug = Saug; f->Sinv = Sinv;
     f->delta = delta; f->gamma = gamma; f->y_in = y_in; f->y = y; f->scratch = scratch; f->Gamma = Gamma;
     f->d_flags = d_flags; f->d_map = d_map;
+    f->LinvL = LinvL; f->yo = yo;
     f->layoutN = -1;
     // pinned staging sized for the capacity
     size_t need_d = (size_t)LM_FIELDS * cap + 3 * (size_t)cap + 256, need_i = (size_t)ld + cap + 64;
@@ -233,28 +243,32 @@ static int join_side(Filter* f) { CU_TRY(cudaStreamWaitEvent(f->stream, f->ev_jo
 // Blocked Schur elimination of the leading k x k block (k a multiple of 16, identity-padded by
 // k_schur_setup) of the (k + r) x (k + c) matrix Aug by unpivoted LU: on return the bottom-right r x c
 // block holds Z - R A^-1 Cc.
-static int schur_lu(Filter* f, double* Aug, int lda, int k, int r, int c) {
-    struct ClsGuard { Filter* f; ~ClsGuard() { f->prof_cls = PROF_UPDATE; } } guard{f};
+static int schur_lu(Filter* f, cudaStream_t s, double* Aug, int lda, int k, int r, int c, double* LinvWs, double* UinvWs,
+                    bool keep_linv) {
+    struct Guard { Filter* f; cudaStream_t prev; ~Guard() { f->prof_cls = PROF_UPDATE; f->cur = prev; } } guard{f, f->cur};
     f->prof_cls = PROF_SCHUR_GEMM;
+    f->cur = s;
     for (int j = 0; j < k; j += 64) {
         const int nb = std::min(64, k - j);
         const int rows = k + r - (j + nb), cols = k + c - (j + nb);
+        double* Linv = keep_linv ? LinvWs + (size_t)(j / 64) * 4096 : LinvWs;
+        double* Uinv = UinvWs;
         ProfEvent pe;
         if (f->profiling) {
             cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
             pe.flops = 0.0; pe.cls = PROF_SCHUR_DIAG;
-            cudaEventRecord(pe.a, f->stream);
+            cudaEventRecord(pe.a, s);
         }
-        CU_TRY(launch_getrf_diag_inv(f->stream, Aug, lda, j, nb, f->Linv, f->Uinv, &f->st->flags));
-        if (f->profiling) { cudaEventRecord(pe.b, f->stream); f->prof.push_back(pe); }
+        CU_TRY(launch_getrf_diag_inv(s, Aug, lda, j, nb, Linv, Uinv, &f->st->flags));
+        if (f->profiling) { cudaEventRecord(pe.b, s); f->prof.push_back(pe); }
         f->launches += 1;
         double* Lp = Aug + (j + nb) + (size_t)lda * j;         // rows x nb, below the diagonal block
         double* Up = Aug + j + (size_t)lda * (j + nb);         // nb x cols, right of it
         double* T22 = Aug + (j + nb) + (size_t)lda * (j + nb);
         int st;
         // panel solves as GEMMs with the triangular inverses, in place (one 64-wide tile owns its rows / columns)
-        if ((st = gemm(f, 0, rows, nb, nb, 1.0, Lp, lda, f->Uinv, 64, 0.0, nullptr, 0, Lp, lda, 0, 0.0, 2))) return st;   // X U = B
-        if ((st = gemm(f, 0, nb, cols, nb, 1.0, f->Linv, 64, Up, lda, 0.0, nullptr, 0, Up, lda, 0, 0.0, 2))) return st;   // L X = B
+        if ((st = gemm(f, 0, rows, nb, nb, 1.0, Lp, lda, Uinv, 64, 0.0, nullptr, 0, Lp, lda, 0, 0.0, 2))) return st;   // X U = B
+        if ((st = gemm(f, 0, nb, cols, nb, 1.0, Linv, 64, Up, lda, 0.0, nullptr, 0, Up, lda, 0, 0.0, 2))) return st;   // L X = B
         if ((st = gemm(f, 0, rows, cols, nb, -1.0, Lp, lda, Up, lda, 1.0, T22, lda, T22, lda))) return st;
     }
     return EQVIO_OK;
@@ -349,6 +363,21 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
     int st = prepare_layout(f);
     if (st) return st;
     cudaStream_t s = f->stream;
+    const bool lift_chain = do_lift && f->s.useInnovationLift;
+    if (lift_chain) {
+        // bundleLift's elimination of Sigma_sub (the PRIOR Sigma block, :285 precedes :297) does not depend on
+        // the innovation except through one border column, so it runs on its own stream while the main stream
+        // goes through S, S^-1, K and gamma; the gamma-dependent column is folded in afterwards (k_lift_fwdsub).
+        CU_TRY(cudaEventRecord(f->ev_lift_fork, s));
+        CU_TRY(cudaStreamWaitEvent(f->lift, f->ev_lift_fork, 0));
+        launch_lift_prepare(f->lift, f->st, f->sc, nullptr);
+        launch_copy_block(f->lift, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
+        launch_schur_setup(f->lift, f->Aug, ld, p, pb, 4, 4, 0);
+        launch_lift_features(f->lift, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
+        f->launches += 4;
+        if ((st = schur_lu(f, f->lift, f->Aug, ld, pb, 4, 4, f->LinvL, f->UinvL, true))) return st;
+        CU_TRY(cudaEventRecord(f->ev_lift_done, f->lift));
+    }
     launch_build_C_delta(s, f->st, f->L, N, f->y, f->C, ldm, f->delta);
     f->launches += 1;
     // S = (C Sigma) C^T + Q                                        VIOFilter.cpp:276
@@ -363,7 +392,7 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
     if ((st = fork_side(f))) return st;
     if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
     if ((st = end_side(f))) return st;
-    if ((st = schur_lu(f, f->Saug, f->ld2m, mp, m, m))) return st;
+    if ((st = schur_lu(f, f->stream, f->Saug, f->ld2m, mp, m, m, f->Linv, f->Uinv, false))) return st;
     const double* negSinv = f->Saug + mp + (size_t)f->ld2m * mp;
     if ((st = join_side(f))) return st;
     // K = (Sigma C^T) S^-1                                           :277
@@ -383,15 +412,13 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
     if (do_lift) {
         const int use_lift = f->s.useInnovationLift, discrete = f->s.useDiscreteInnovationLift;
         if (use_lift) {
-            // bundleLift with the PRIOR Sigma block (:285 precedes :297)
+            CU_TRY(cudaStreamWaitEvent(s, f->ev_lift_done, 0));
             launch_lift_prepare(s, f->st, f->sc, f->gamma);
-            launch_copy_block(s, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
-            launch_schur_setup(s, f->Aug, ld, p, pb, 5, 5, 0);
-            launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb);
-            f->launches += 4;
-            if ((st = schur_lu(f, f->Aug, ld, pb, 5, 5))) return st;
+            launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb, f->yo);
+            launch_lift_fwdsub(s, f->Aug, ld, pb, f->LinvL, f->yo, f->b4);
+            f->launches += 3;
         }
-        launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, use_lift, discrete, stamp, nullptr, 1);
+        launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->b4, use_lift, discrete, stamp, nullptr, 1);
         launch_lift_apply(s, f->st, f->L, N, f->gamma, use_lift ? discrete : 0);
         f->launches += 2;
     }
@@ -479,6 +506,9 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
         CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU_TRY(cudaStreamCreateWithPriority(&f->stream, cudaStreamNonBlocking, hi));
         CU_TRY(cudaStreamCreateWithPriority(&f->side, cudaStreamNonBlocking, lo));
+        CU_TRY(cudaStreamCreateWithPriority(&f->lift, cudaStreamNonBlocking, hi));
+        CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_fork, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_done, cudaEventDisableTiming));
     }
     f->cur = f->stream;
     CU_TRY(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
@@ -489,6 +519,9 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     CU_TRY(dalloc(&f->sc, 1));
     CU_TRY(dalloc(&f->Linv, 64 * 80));
     CU_TRY(dalloc(&f->Uinv, 64 * 80));
+    CU_TRY(dalloc(&f->UinvL, 64 * 80));
+    CU_TRY(cudaMemset(f->UinvL, 0, 64 * 80 * 8));
+    CU_TRY(dalloc(&f->b4, 8));
     CU_TRY(cudaMemset(f->Linv, 0, 64 * 80 * 8));
     CU_TRY(cudaMemset(f->Uinv, 0, 64 * 80 * 8));
     int st = ensure_capacity(f, 64);
@@ -504,14 +537,15 @@ int eqvio_destroy(eqvio_handle_t f) {
     cudaSetDevice(f->device);
     cudaStreamSynchronize(f->stream);
     cudaStreamSynchronize(f->side);
+    cudaStreamSynchronize(f->lift);
     for (auto& e : f->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     free_device(f);
-    cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv);
+    cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL); cudaFree(f->b4);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
     cudaEventDestroy(f->stage_free);
-    cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join);
-    cudaStreamDestroy(f->side);
+    cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join); cudaEventDestroy(f->ev_lift_fork); cudaEventDestroy(f->ev_lift_done);
+    cudaStreamDestroy(f->side); cudaStreamDestroy(f->lift);
     cudaStreamDestroy(f->stream);
     delete f;
     return EQVIO_OK;
@@ -921,15 +955,19 @@ int eqvio_bundle_lift(eqvio_handle_t f, const double* gamma_eqf, double* Gamma) 
     memcpy(g.data() + 6, gamma_eqf, (size_t)p * 8);
     CU_TRY(cudaMemcpy(f->gamma, g.data(), g.size() * 8, cudaMemcpyHostToDevice));
     cudaStream_t s = f->stream;
-    launch_lift_prepare(s, f->st, f->sc, f->gamma);
-    launch_copy_block(s, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
     const int pb = round_up(p, 16);
-    launch_schur_setup(s, f->Aug, ld, p, pb, 5, 5, 0);
-    launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb);
+    launch_lift_prepare(s, f->st, f->sc, nullptr);
+    launch_copy_block(s, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
+    launch_schur_setup(s, f->Aug, ld, p, pb, 4, 4, 0);
+    launch_lift_features(s, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
     f->launches += 4;
-    int st = schur_lu(f, f->Aug, ld, pb, 5, 5);
+    int st = schur_lu(f, s, f->Aug, ld, pb, 4, 4, f->LinvL, f->UinvL, true);
     if (st) return st;
-    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, 1, 1, f->currentTime, f->Gamma, 0);
+    launch_lift_prepare(s, f->st, f->sc, f->gamma);
+    launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb, f->yo);
+    launch_lift_fwdsub(s, f->Aug, ld, pb, f->LinvL, f->yo, f->b4);
+    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->b4, 1, 1, f->currentTime, f->Gamma, 0);
+    f->launches += 3;
     f->launches += 1;
     CU_TRY(cudaStreamSynchronize(s));
     CU_TRY(cudaMemcpy(Gamma, f->Gamma, 48, cudaMemcpyDeviceToHost));

@@ -250,10 +250,31 @@ __global__ void __launch_bounds__(256) k_gemv(const double* K, int ldk, int n, i
 //   R_C, Ad(P0), P_hat T_IC.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_lift_prepare(BaseState* st, StepScratch* sc, const double* gamma) {
+    // gamma == nullptr: the parts that do not depend on the innovation (they ride on the Sigma_sub
+    // elimination, which runs concurrently with the S / K / gamma chain); gamma != nullptr: DUF only.
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int sing = 0;
-    const V3 eta0 = normalized(rotate_inv(st->pose0.R, v3(0, 0, 1)));
-    sc->eta0n = eta0;
+    if (gamma == nullptr) {
+        const V3 eta0 = normalized(rotate_inv(st->pose0.R, v3(0, 0, 1)));
+        sc->eta0n = eta0;
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 4; ++c) sc->KPara[r][c] = 0.0;
+        sc->KPara[0][0] = eta0.x; sc->KPara[1][0] = eta0.y; sc->KPara[2][0] = eta0.z;
+        sc->KPara[3][1] = sc->KPara[4][2] = sc->KPara[5][3] = 1.0;
+        const Se3 Phat = st->pose0 * st->XA;
+        sc->RC = Phat.R * st->cam.R;
+        sc->RCt = to_matrix(q_inverse(sc->RC));
+        sc->PT = Phat * st->cam;
+        // Ad(P0), SE3.cpp:95-103
+        M3 R = to_matrix(st->pose0.R), sxR = skew(st->pose0.x) * R;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                sc->AdP0[r][c] = R.m[r][c]; sc->AdP0[r][3 + c] = 0.0;
+                sc->AdP0[3 + r][c] = sxR.m[r][c]; sc->AdP0[3 + r][3 + c] = R.m[r][c];
+            }
+        return;
+    }
+    const V3 eta0 = sc->eta0n;
     const double* g = gamma + 6;
     M32 D = stereo_sphere_chart_inv_diff(0.0, 0.0, eta0, &sing);
     V3 t = v3(D.m[0][0] * g[0] + D.m[0][1] * g[1], D.m[1][0] * g[0] + D.m[1][1] * g[1], D.m[2][0] * g[0] + D.m[2][1] * g[1]);
@@ -262,45 +283,34 @@ __global__ void k_lift_prepare(BaseState* st, StepScratch* sc, const double* gam
     M3 P = m3_identity() + outer(eta0, eta0) * -1.0;
     V3 duf = P * Om;
     sc->DUF[0] = duf.x; sc->DUF[1] = duf.y; sc->DUF[2] = duf.z; sc->DUF[3] = sc->DUF[4] = sc->DUF[5] = 0.0;
-    for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 4; ++c) sc->KPara[r][c] = 0.0;
-    sc->KPara[0][0] = eta0.x; sc->KPara[1][0] = eta0.y; sc->KPara[2][0] = eta0.z;
-    sc->KPara[3][1] = sc->KPara[4][2] = sc->KPara[5][3] = 1.0;
-    const Se3 Phat = st->pose0 * st->XA;
-    sc->RC = Phat.R * st->cam.R;
-    sc->RCt = to_matrix(q_inverse(sc->RC));
-    sc->PT = Phat * st->cam;
-    // Ad(P0), SE3.cpp:95-103
-    M3 R = to_matrix(st->pose0.R), sxR = skew(st->pose0.x) * R;
-    for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) {
-            sc->AdP0[r][c] = R.m[r][c]; sc->AdP0[r][3 + c] = 0.0;
-            sc->AdP0[3 + r][c] = sxR.m[r][c]; sc->AdP0[3 + r][3 + c] = R.m[r][c];
-        }
     if (sing) atomicOr(&st->flags, FLAG_SINGULAR);
 }
 
-// k_lift_features: per feature, Y_i = D_i [M_i | obs_i] (3 x 5) with (EqFMatrices.cpp:218-236)
+// k_lift_features: per feature (EqFMatrices.cpp:218-236)
 //   M_i = [-[p_i]x, I] Ad(P0) KPara,  obs_i = -R_C Q_i^-1 gamma_qi - [-[p_i]x, I] Ad(P0) DUF,  D_i = Qhat_i R_C^T.
-// Written as the border of the Schur problem [[Sigma_sub, Y], [Y^T, 0]]:
-//   Aug[p + c, 5 + 3i + r] = Aug[5 + 3i + r, p + c] = Y_i[r][c]; the first five rows of Y are zero.
+// gamma == nullptr (innovation-independent part): Ym = D M (p x 4) as the border of the Schur problem
+//   [[Sigma_sub, Ym], [Ym^T, 0]]:  Aug[pb + c, 5 + 3i + r] = Aug[5 + 3i + r, pb + c] = (D_i M_i)[r][c];
+//   the first five rows of Ym are zero.
+// gamma != nullptr: yo = D obs (p entries, yo[0:5] = 0) into `yo`.
 __global__ void __launch_bounds__(128) k_lift_features(const StepScratch* sc, Landmarks L, int N, const double* gamma,
-                                                       double* Aug, int lda, int p) {
-    // p here is the border offset (Sigma_sub's size rounded up to 16, identity-padded by k_schur_setup)
+                                                       double* Aug, int lda, int pb, double* yo) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 5)
-        for (int c = 0; c < 5; ++c) {
-            Aug[(p + c) + (size_t)lda * i] = 0.0;
-            Aug[i + (size_t)lda * (p + c)] = 0.0;
-            Aug[(p + i) + (size_t)lda * (p + c)] = 0.0;
-        }
+    if (gamma == nullptr) {
+        if (i < 5)
+            for (int c = 0; c < 4; ++c) {
+                Aug[(pb + c) + (size_t)lda * i] = 0.0;
+                Aug[i + (size_t)lda * (pb + c)] = 0.0;
+                if (i < 4) Aug[(pb + i) + (size_t)lda * (pb + c)] = 0.0;
+            }
+    } else {
+        if (i < 5) yo[i] = 0.0;
+        if (i < 16 && 5 + 3 * N + i < pb) yo[5 + 3 * N + i] = 0.0;  // identity-padded tail of the Schur problem
+    }
     if (i >= N) return;
     const Sot3 Q = load_Q(L, i);
     const V3 q0 = load_q0(L, i);
     const V3 qh = inverse(Q) * q0;
     const V3 pH = sc->PT * qh;
-    const double* gq = gamma + 11 + 3 * i;
-    const V3 alpha = -rotate(sc->RC, inverse(Q) * v3(gq[0], gq[1], gq[2]));
     // pHatMat * AdP0 (3 x 6)
     M3 nsp = skew(pH) * -1.0;
     double pmAd[3][6];
@@ -309,30 +319,86 @@ __global__ void __launch_bounds__(128) k_lift_features(const StepScratch* sc, La
 #pragma unroll
         for (int c = 0; c < 6; ++c)
             pmAd[r][c] = nsp.m[r][0] * sc->AdP0[0][c] + nsp.m[r][1] * sc->AdP0[1][c] + nsp.m[r][2] * sc->AdP0[2][c] + sc->AdP0[3 + r][c];
-    double MO[3][5];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s += pmAd[r][k] * sc->DUF[k];
-        MO[r][4] = v3_get(alpha, r) - s;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            double m = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) m += pmAd[r][k] * sc->KPara[k][c];
-            MO[r][c] = m;
-        }
-    }
     const M3 Dm = as_matrix3(Q) * sc->RCt;
+    if (gamma == nullptr) {
+        double Mi[3][4];
 #pragma unroll
-    for (int c = 0; c < 5; ++c)
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                double m = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) m += pmAd[r][k] * sc->KPara[k][c];
+                Mi[r][c] = m;
+            }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double yv = Dm.m[r][0] * Mi[0][c] + Dm.m[r][1] * Mi[1][c] + Dm.m[r][2] * Mi[2][c];
+                Aug[(pb + c) + (size_t)lda * (5 + 3 * i + r)] = yv;
+                Aug[(5 + 3 * i + r) + (size_t)lda * (pb + c)] = yv;
+            }
+    } else {
+        const double* gq = gamma + 11 + 3 * i;
+        const V3 alpha = -rotate(sc->RC, inverse(Q) * v3(gq[0], gq[1], gq[2]));
+        double ob[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const double yv = Dm.m[r][0] * MO[0][c] + Dm.m[r][1] * MO[1][c] + Dm.m[r][2] * MO[2][c];
-            Aug[(p + c) + (size_t)lda * (5 + 3 * i + r)] = yv;
-            Aug[(5 + 3 * i + r) + (size_t)lda * (p + c)] = yv;
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sacc += pmAd[r][k] * sc->DUF[k];
+            ob[r] = v3_get(alpha, r) - sacc;
         }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) yo[5 + 3 * i + r] = Dm.m[r][0] * ob[0] + Dm.m[r][1] * ob[1] + Dm.m[r][2] * ob[2];
+    }
+}
+
+// k_lift_fwdsub — one CTA.  z = L^-1 yo by blocked forward substitution with the unit-lower factor the
+// Schur elimination left in Aug (sub-diagonal blocks) and the per-block L_jj^-1 it stored, then
+// b4 = (Ym^T U^-1) z, the four entries M^T W obs of the normal equations (EqFMatrices.cpp:240-242):
+// Ym^T U^-1 is what the elimination leaves in the border rows pb..pb+3.  yo[p..pb) must be zero.
+__global__ void __launch_bounds__(1024) k_lift_fwdsub(const double* Aug, int lda, int pb, const double* LinvBlocks, double* yo,
+                                                      double* b4) {
+    __shared__ double zj[64];
+    __shared__ double red[4][32];
+    const int tid = threadIdx.x;
+    for (int j0 = 0; j0 < pb; j0 += 64) {
+        const int nb = min(64, pb - j0);
+        const double* Li = LinvBlocks + (size_t)(j0 >> 6) * 4096;
+        {   // z_j = L_jj^-1 y_j : 16 lanes per row
+            const int row = tid >> 4, part = tid & 15;
+            double sacc = 0.0;
+            if (row < nb)
+                for (int q = part; q <= row; q += 16) sacc += Li[row + 64 * q] * yo[j0 + q];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o, 16);
+            __syncthreads();  // everyone has read y_j
+            if (part == 0 && row < nb) { zj[row] = sacc; yo[j0 + row] = sacc; }
+        }
+        __syncthreads();
+        for (int r = j0 + nb + tid; r < pb; r += 1024) {
+            double acc0 = 0.0, acc1 = 0.0;
+            const double* a = Aug + r + (size_t)lda * j0;
+            for (int q = 0; q < nb; q += 2) { acc0 += a[(size_t)lda * q] * zj[q]; acc1 += a[(size_t)lda * (q + 1)] * zj[q + 1]; }
+            yo[r] -= acc0 + acc1;
+        }
+        __syncthreads();
+    }
+    // b4[a] = sum_col Aug[pb + a, col] * z[col]
+    const int a = tid >> 8, i = tid & 255;
+    double sacc = 0.0;
+    for (int col = i; col < pb; col += 256) sacc += Aug[(pb + a) + (size_t)lda * col] * yo[col];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+    if ((tid & 31) == 0) red[a][(tid & 255) >> 5] = sacc;
+    __syncthreads();
+    if (tid < 4) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[tid][k];
+        b4[tid] = t;
+    }
 }
 
 // 4x4 Householder QR solve (EqFMatrices.cpp:240-242)
@@ -366,22 +432,24 @@ __device__ void qr_solve4(double A[4][4], double b[4], double x[4]) {
     }
 }
 
-// k_lift_solve — single thread.  mode use_lift: G = Y^T Sigma_sub^-1 Y is the negated bottom-right 5 x 5
-// block left by the Schur elimination (G[0:4,0:4] = M^T W M, G[0:4,4] = M^T W obs with
-// W = D^T Sigma_sub^-1 D, EqFMatrices.cpp:239-242), 4x4 QR solve, DeltaU = DUF + KPara x (:243), then
+// k_lift_solve — single thread.  mode use_lift: M^T W M (W = D^T Sigma_sub^-1 D, EqFMatrices.cpp:239-242)
+// is the negated bottom-right 4 x 4 block left by the Schur elimination, M^T W obs comes from
+// k_lift_fwdsub; 4x4 QR solve, DeltaU = DUF + KPara x (:243), then
 // the SE(3) x R^3 part of the lift and X <- Delta X, bias update:
 //   discrete   liftTotalSpaceInnovationDiscrete EqFMatrices.cpp:254-259
 //   continuous VIOExp(liftTotalSpaceInnovation)  EqFMatrices.cpp:69-78, VIOGroup.cpp:245-248
 // use_lift = 0 (useInnovationLift = false): VIOExp(liftInnovation(gamma, xi0)) EqFMatrices.cpp:35-48.
 // Then VIOFilter.cpp:295-296 and the pose record.
 __global__ void k_lift_solve(BaseState* st, StepScratch* sc, const double* gamma, const double* Aug,
-                             int lda, int p, int use_lift, int discrete, double stamp,
+                             int lda, int p, const double* b4, int use_lift, int discrete, double stamp,
                              double* Gamma_out, int apply) {
     const int tid = threadIdx.x;
-    double G[5][5];
+    double G[4][5];
     if (use_lift && tid == 0)
-        for (int a = 0; a < 5; ++a)
-            for (int b = 0; b < 5; ++b) G[a][b] = -Aug[(p + a) + (size_t)lda * (p + b)];
+        for (int a = 0; a < 4; ++a) {
+            for (int b = 0; b < 4; ++b) G[a][b] = -Aug[(p + a) + (size_t)lda * (p + b)];
+            G[a][4] = b4[a];
+        }
     if (tid != 0) return;
     double DU[6];
     V3 Dw;
@@ -853,12 +921,15 @@ void launch_lift_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const d
     k_lift_prepare<<<1, 32, 0, s>>>(st, sc, gamma);
 }
 void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, int N, const double* gamma, double* Aug,
-                          int lda, int p) {
-    k_lift_features<<<cdiv(N > 5 ? N : 5, 128), 128, 0, s>>>(sc, L, N, gamma, Aug, lda, p);
+                          int lda, int pb, double* yo) {
+    k_lift_features<<<cdiv(N > 16 ? N : 16, 128), 128, 0, s>>>(sc, L, N, gamma, Aug, lda, pb, yo);
+}
+void launch_lift_fwdsub(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* yo, double* b4) {
+    k_lift_fwdsub<<<1, 1024, 0, s>>>(Aug, lda, pb, LinvBlocks, yo, b4);
 }
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
-                       int use_lift, int discrete, double stamp, double* Gamma_out, int apply) {
-    k_lift_solve<<<1, 32, 0, s>>>(st, sc, gamma, Aug, lda, p, use_lift, discrete, stamp, Gamma_out, apply);
+                       const double* b4, int use_lift, int discrete, double stamp, double* Gamma_out, int apply) {
+    k_lift_solve<<<1, 32, 0, s>>>(st, sc, gamma, Aug, lda, p, b4, use_lift, discrete, stamp, Gamma_out, apply);
 }
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete) {
     if (N > 0) k_lift_apply<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, gamma, discrete);

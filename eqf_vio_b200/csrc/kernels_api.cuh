@@ -11,9 +11,10 @@ void launch_build_C_delta(cudaStream_t s, BaseState* st, Landmarks L, int N, con
 void launch_gemv(cudaStream_t s, const double* K, int ldk, int n, int m, const double* x, double* y);
 void launch_lift_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma);
 void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, int N, const double* gamma, double* Aug,
-                          int lda, int p);
+                          int lda, int pb, double* yo);
+void launch_lift_fwdsub(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* yo, double* b4);
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
-                       int use_lift, int discrete, double stamp, double* Gamma_out, int apply);
+                       const double* b4, int use_lift, int discrete, double stamp, double* Gamma_out, int apply);
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete);
 cudaError_t launch_getrf_diag_inv(cudaStream_t s, double* A, int lda, int j, int nb, double* Linv, double* Uinv, int* flags);
 void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border);
