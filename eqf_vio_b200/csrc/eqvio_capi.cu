@@ -47,6 +47,9 @@ struct eqvio_filter {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;   // second stream: dense GEMMs that overlap the latency-bound Schur eliminations
+    cudaStream_t main_h = nullptr, lift_h = nullptr;  // helper streams of the two Schur chains (look-ahead)
+    cudaEvent_t ev_sa = nullptr, ev_sb = nullptr, ev_la = nullptr, ev_lb = nullptr;
+    double *cornerS = nullptr, *cornerL = nullptr;
     cudaStream_t lift = nullptr;   // third stream: the Sigma_sub elimination of bundleLift, concurrent with the S / K / gamma chain
     cudaEvent_t ev_lift_fork = nullptr, ev_lift_done = nullptr;
     cudaStream_t cur = nullptr;    // stream the next gemm() goes to (main unless forked)
@@ -89,6 +92,14 @@ struct eqvio_filter {
 };
 
 typedef eqvio_filter Filter;
+
+// One blocked Schur elimination = a chain stream, a helper stream for the look-ahead, two events and its workspaces.
+struct SchurChain {
+    cudaStream_t s, h;
+    cudaEvent_t ev_a, ev_b;
+    double *Linv, *Uinv, *corner;  // corner: 64 x 64 scratch with the next diagonal block already updated
+    bool keep_linv;
+};
 
 static int n_of(int N) { return EQVIO_SIGMA_BASE_SIZE + 3 * N; }
 
@@ -241,36 +252,67 @@ static int end_side(Filter* f) {  // side work issued; following launches go to 
 static int join_side(Filter* f) { CU_TRY(cudaStreamWaitEvent(f->stream, f->ev_join, 0)); return EQVIO_OK; }
 
 // Blocked Schur elimination of the leading k x k block (k a multiple of 16, identity-padded by
-// k_schur_setup) of the (k + r) x (k + c) matrix Aug by unpivoted LU: on return the bottom-right r x c
-// block holds Z - R A^-1 Cc.
-static int schur_lu(Filter* f, cudaStream_t s, double* Aug, int lda, int k, int r, int c, double* LinvWs, double* UinvWs,
-                    bool keep_linv) {
+// k_schur_setup) of the (k + r) x (k + c) matrix Aug by unpivoted LU: on return (in stream ch.s) the
+// bottom-right r x c block holds Z - R A^-1 Cc, the sub-diagonal blocks hold L and, with keep_linv, every
+// L_jj^-1 is kept.  Per 64-wide step, with look-ahead so that the sequential pivot chain does not wait for the
+// trailing update:
+//   ch.s: LU + triangular inverses of the diagonal block (read from the look-ahead scratch after step 0)
+//   ch.s: column panel  X U = B  as GEMM with U^-1      |  ch.h: row panel  L X = B  as GEMM with L^-1
+//   ch.s: the NEXT diagonal block only, into the scratch   (64 x 64 x 64)
+//   ch.h: the full trailing update                          (overlaps the next step's diagonal LU)
+// The diagonal blocks of Aug itself are left stale (nothing reads them again).
+static int schur_lu(Filter* f, const SchurChain& ch, double* Aug, int lda, int k, int r, int c) {
     struct Guard { Filter* f; cudaStream_t prev; ~Guard() { f->prof_cls = PROF_UPDATE; f->cur = prev; } } guard{f, f->cur};
     f->prof_cls = PROF_SCHUR_GEMM;
-    f->cur = s;
+    int st;
+    // the helper stream starts behind everything already queued on the chain stream
+    CU_TRY(cudaEventRecord(ch.ev_a, ch.s));
+    CU_TRY(cudaStreamWaitEvent(ch.h, ch.ev_a, 0));
     for (int j = 0; j < k; j += 64) {
         const int nb = std::min(64, k - j);
         const int rows = k + r - (j + nb), cols = k + c - (j + nb);
-        double* Linv = keep_linv ? LinvWs + (size_t)(j / 64) * 4096 : LinvWs;
-        double* Uinv = UinvWs;
+        double* Linv = ch.keep_linv ? ch.Linv + (size_t)(j / 64) * 4096 : ch.Linv;
+        double* Uinv = ch.Uinv;
         ProfEvent pe;
         if (f->profiling) {
             cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
             pe.flops = 0.0; pe.cls = PROF_SCHUR_DIAG;
-            cudaEventRecord(pe.a, s);
+            cudaEventRecord(pe.a, ch.s);
         }
-        CU_TRY(launch_getrf_diag_inv(s, Aug, lda, j, nb, Linv, Uinv, &f->st->flags));
-        if (f->profiling) { cudaEventRecord(pe.b, s); f->prof.push_back(pe); }
+        if (j == 0) CU_TRY(launch_getrf_diag_inv(ch.s, Aug, lda, nullptr, 0, nb, Linv, Uinv, &f->st->flags));
+        else CU_TRY(launch_getrf_diag_inv(ch.s, ch.corner, 64, nullptr, 0, nb, Linv, Uinv, &f->st->flags));
+        if (f->profiling) { cudaEventRecord(pe.b, ch.s); f->prof.push_back(pe); }
         f->launches += 1;
         double* Lp = Aug + (j + nb) + (size_t)lda * j;         // rows x nb, below the diagonal block
         double* Up = Aug + j + (size_t)lda * (j + nb);         // nb x cols, right of it
         double* T22 = Aug + (j + nb) + (size_t)lda * (j + nb);
-        int st;
-        // panel solves as GEMMs with the triangular inverses, in place (one 64-wide tile owns its rows / columns)
-        if ((st = gemm(f, 0, rows, nb, nb, 1.0, Lp, lda, Uinv, 64, 0.0, nullptr, 0, Lp, lda, 0, 0.0, 2))) return st;   // X U = B
+        // panel solves as GEMMs with the triangular inverses, in place (one 64-wide tile owns its rows / columns).
+        // Both wait for the previous trailing update (queued on ch.h): the row panel by stream order, the column
+        // panel through ev_b.
+        CU_TRY(cudaEventRecord(ch.ev_a, ch.s));                // diagonal block done
+        CU_TRY(cudaStreamWaitEvent(ch.h, ch.ev_a, 0));
+        if (j > 0) CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_b, 0));   // ev_b still = previous trailing update: the column panel needs it
+        f->cur = ch.h;
         if ((st = gemm(f, 0, nb, cols, nb, 1.0, Linv, 64, Up, lda, 0.0, nullptr, 0, Up, lda, 0, 0.0, 2))) return st;   // L X = B
+        CU_TRY(cudaEventRecord(ch.ev_b, ch.h));                // now ev_b = row panel of this step
+        f->cur = ch.s;
+        if ((st = gemm(f, 0, rows, nb, nb, 1.0, Lp, lda, Uinv, 64, 0.0, nullptr, 0, Lp, lda, 0, 0.0, 2))) return st;   // X U = B
+        CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_b, 0));         // the corner and the trailing update need both panels
+        const int nb2 = std::min(64, k - (j + nb));
+        if (nb2 > 0) {
+            // look-ahead: next diagonal block = its current value - L_panel[0:nb2, :] U_panel[:, 0:nb2]
+            if ((st = gemm(f, 0, nb2, nb2, nb, -1.0, Lp, lda, Up, lda, 1.0, T22, lda, ch.corner, 64, 0, 0.0, 2))) return st;
+        }
+        // full trailing update on the helper stream (needs both panels: ev_a2 after the column panel / corner)
+        CU_TRY(cudaEventRecord(ch.ev_a, ch.s));
+        CU_TRY(cudaStreamWaitEvent(ch.h, ch.ev_a, 0));
+        f->cur = ch.h;
         if ((st = gemm(f, 0, rows, cols, nb, -1.0, Lp, lda, Up, lda, 1.0, T22, lda, T22, lda))) return st;
+        CU_TRY(cudaEventRecord(ch.ev_b, ch.h));
+        f->cur = ch.s;
     }
+    // the chain stream's consumers need the last trailing update
+    CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_b, 0));
     return EQVIO_OK;
 }
 
@@ -375,7 +417,7 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
         launch_schur_setup(f->lift, f->Aug, ld, p, pb, 4, 4, 0);
         launch_lift_features(f->lift, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
         f->launches += 4;
-        if ((st = schur_lu(f, f->lift, f->Aug, ld, pb, 4, 4, f->LinvL, f->UinvL, true))) return st;
+        if ((st = schur_lu(f, SchurChain{f->lift, f->lift_h, f->ev_la, f->ev_lb, f->LinvL, f->UinvL, f->cornerL, true}, f->Aug, ld, pb, 4, 4))) return st;
         CU_TRY(cudaEventRecord(f->ev_lift_done, f->lift));
     }
     launch_build_C_delta(s, f->st, f->L, N, f->y, f->C, ldm, f->delta);
@@ -392,7 +434,7 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
     if ((st = fork_side(f))) return st;
     if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
     if ((st = end_side(f))) return st;
-    if ((st = schur_lu(f, f->stream, f->Saug, f->ld2m, mp, m, m, f->Linv, f->Uinv, false))) return st;
+    if ((st = schur_lu(f, SchurChain{f->stream, f->main_h, f->ev_sa, f->ev_sb, f->Linv, f->Uinv, f->cornerS, false}, f->Saug, f->ld2m, mp, m, m))) return st;
     const double* negSinv = f->Saug + mp + (size_t)f->ld2m * mp;
     if ((st = join_side(f))) return st;
     // K = (Sigma C^T) S^-1                                           :277
@@ -507,6 +549,9 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
         CU_TRY(cudaStreamCreateWithPriority(&f->stream, cudaStreamNonBlocking, hi));
         CU_TRY(cudaStreamCreateWithPriority(&f->side, cudaStreamNonBlocking, lo));
         CU_TRY(cudaStreamCreateWithPriority(&f->lift, cudaStreamNonBlocking, hi));
+        CU_TRY(cudaStreamCreateWithPriority(&f->main_h, cudaStreamNonBlocking, hi));
+        CU_TRY(cudaStreamCreateWithPriority(&f->lift_h, cudaStreamNonBlocking, hi));
+        for (cudaEvent_t* e : {&f->ev_sa, &f->ev_sb, &f->ev_la, &f->ev_lb}) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_fork, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_done, cudaEventDisableTiming));
     }
@@ -522,6 +567,10 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     CU_TRY(dalloc(&f->UinvL, 64 * 80));
     CU_TRY(cudaMemset(f->UinvL, 0, 64 * 80 * 8));
     CU_TRY(dalloc(&f->b4, 8));
+    CU_TRY(dalloc(&f->cornerS, 64 * 80));
+    CU_TRY(dalloc(&f->cornerL, 64 * 80));
+    CU_TRY(cudaMemset(f->cornerS, 0, 64 * 80 * 8));
+    CU_TRY(cudaMemset(f->cornerL, 0, 64 * 80 * 8));
     CU_TRY(cudaMemset(f->Linv, 0, 64 * 80 * 8));
     CU_TRY(cudaMemset(f->Uinv, 0, 64 * 80 * 8));
     int st = ensure_capacity(f, 64);
@@ -538,6 +587,8 @@ int eqvio_destroy(eqvio_handle_t f) {
     cudaStreamSynchronize(f->stream);
     cudaStreamSynchronize(f->side);
     cudaStreamSynchronize(f->lift);
+    cudaStreamSynchronize(f->main_h);
+    cudaStreamSynchronize(f->lift_h);
     for (auto& e : f->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     free_device(f);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL); cudaFree(f->b4);
@@ -545,7 +596,9 @@ int eqvio_destroy(eqvio_handle_t f) {
     if (f->h_istage) cudaFreeHost(f->h_istage);
     cudaEventDestroy(f->stage_free);
     cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join); cudaEventDestroy(f->ev_lift_fork); cudaEventDestroy(f->ev_lift_done);
-    cudaStreamDestroy(f->side); cudaStreamDestroy(f->lift);
+    cudaStreamDestroy(f->side); cudaStreamDestroy(f->lift); cudaStreamDestroy(f->main_h); cudaStreamDestroy(f->lift_h);
+    for (cudaEvent_t e : {f->ev_sa, f->ev_sb, f->ev_la, f->ev_lb}) cudaEventDestroy(e);
+    cudaFree(f->cornerS); cudaFree(f->cornerL);
     cudaStreamDestroy(f->stream);
     delete f;
     return EQVIO_OK;
@@ -961,7 +1014,7 @@ int eqvio_bundle_lift(eqvio_handle_t f, const double* gamma_eqf, double* Gamma) 
     launch_schur_setup(s, f->Aug, ld, p, pb, 4, 4, 0);
     launch_lift_features(s, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
     f->launches += 4;
-    int st = schur_lu(f, s, f->Aug, ld, pb, 4, 4, f->LinvL, f->UinvL, true);
+    int st = schur_lu(f, SchurChain{s, f->main_h, f->ev_sa, f->ev_sb, f->LinvL, f->UinvL, f->cornerL, true}, f->Aug, ld, pb, 4, 4);
     if (st) return st;
     launch_lift_prepare(s, f->st, f->sc, f->gamma);
     launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb, f->yo);

@@ -661,8 +661,11 @@ __device__ void lu32(double (*S)[65], double (*LI)[65], double (*UI)[65], Lu32Sc
 // solves and the Schur update as 32^3 products by all 512 threads, lu32 on the trailing block, and the
 // off-diagonal blocks of the inverses as two more triple products.  The pivot chain (the sequential
 // part) therefore runs on 4 warps with a 128-thread barrier per step instead of 16 warps.
-__global__ void __launch_bounds__(512) k_getrf_diag_inv(double* A, int lda, int j, int nb, double* Linv, double* Uinv,
-                                                        int* flags) {
+// `Ain` (leading dimension ldin) is where the block is read from — the matrix itself, or a 64 x 64 scratch
+// holding the already-updated block when the trailing update of the previous step is still in flight
+// (look-ahead); `Aout` (may be null) receives the factors.
+__global__ void __launch_bounds__(512) k_getrf_diag_inv(const double* Ain, int ldin, double* Aout, int ldout, int nb, double* Linv,
+                                                        double* Uinv, int* flags) {
     extern __shared__ double sm_lu[];
     double(*S)[65] = reinterpret_cast<double(*)[65]>(sm_lu);
     double(*LI)[65] = reinterpret_cast<double(*)[65]>(sm_lu + 64 * 65);
@@ -674,7 +677,7 @@ __global__ void __launch_bounds__(512) k_getrf_diag_inv(double* A, int lda, int 
     DBG_CLK(0);
     for (int idx = tid; idx < 64 * 64; idx += 512) {
         const int r = idx & 63, c = idx >> 6;
-        S[r][c] = (r < nb && c < nb) ? A[(j + r) + (size_t)lda * (j + c)] : (r == c ? 1.0 : 0.0);
+        S[r][c] = (r < nb && c < nb) ? Ain[r + (size_t)ldin * c] : (r == c ? 1.0 : 0.0);
         LI[r][c] = 0.0;
         UI[r][c] = 0.0;
     }
@@ -769,7 +772,7 @@ __global__ void __launch_bounds__(512) k_getrf_diag_inv(double* A, int lda, int 
         const int r = idx & 63, c = idx >> 6;
         Linv[r + 64 * c] = LI[r][c];
         Uinv[r + 64 * c] = UI[r][c];
-        if (r < nb && c < nb) A[(j + r) + (size_t)lda * (j + c)] = S[r][c];
+        if (Aout != nullptr && r < nb && c < nb) Aout[r + (size_t)ldout * c] = S[r][c];
     }
     DBG_CLK(6);
 }
@@ -934,7 +937,8 @@ void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const dou
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete) {
     if (N > 0) k_lift_apply<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, gamma, discrete);
 }
-cudaError_t launch_getrf_diag_inv(cudaStream_t s, double* A, int lda, int j, int nb, double* Linv, double* Uinv, int* flags) {
+cudaError_t launch_getrf_diag_inv(cudaStream_t s, const double* Ain, int ldin, double* Aout, int ldout, int nb, double* Linv,
+                                  double* Uinv, int* flags) {
     static bool attr_set = false;
     const int smem = (3 * 64 * 65 + 2 * 32 * 33) * (int)sizeof(double) + (int)sizeof(Lu32Scratch) + 16;
     if (!attr_set) {
@@ -942,7 +946,7 @@ cudaError_t launch_getrf_diag_inv(cudaStream_t s, double* A, int lda, int j, int
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_getrf_diag_inv<<<1, 512, smem, s>>>(A, lda, j, nb, Linv, Uinv, flags);
+    k_getrf_diag_inv<<<1, 512, smem, s>>>(Ain, ldin, Aout, ldout, nb, Linv, Uinv, flags);
     return cudaGetLastError();
 }
 void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border) {

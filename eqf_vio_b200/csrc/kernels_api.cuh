@@ -16,7 +16,8 @@ void launch_lift_fwdsub(cudaStream_t s, const double* Aug, int lda, int pb, cons
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
                        const double* b4, int use_lift, int discrete, double stamp, double* Gamma_out, int apply);
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete);
-cudaError_t launch_getrf_diag_inv(cudaStream_t s, double* A, int lda, int j, int nb, double* Linv, double* Uinv, int* flags);
+cudaError_t launch_getrf_diag_inv(cudaStream_t s, const double* Ain, int ldin, double* Aout, int ldout, int nb, double* Linv,
+                                  double* Uinv, int* flags);
 void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border);
 void launch_copy_block(cudaStream_t s, const double* src, int lds, double* dst, int ldd, int rows, int cols);
 void launch_set_identity_rows(cudaStream_t s, double* A, int lda, int row0, int n);

@@ -1,0 +1,25 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): every kernel of the path
+at two sizes, landmark churn included."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from eqf_vio_b200.filter import VIOFilter, dgemm
+from eqf_vio_b200.settings import template_settings, conditioned_settings
+from eqf_vio_b200.synthetic import period_sequence
+
+rng = np.random.default_rng(0)
+for N, s in ((9, template_settings()), (70, conditioned_settings())):
+    seq = period_sequence(N, 3, camera_offset=tuple(s.cameraOffset))
+    f = VIOFilter(s)
+    for kind, i in seq.events():
+        if kind == "imu":
+            f.processIMUData(seq.imu[i, 0], seq.imu[i, 1:4], seq.imu[i, 4:7])
+        else:
+            sel = np.sort(rng.choice(N, size=max(3, N - 2), replace=False)) if i > 0 else np.arange(N - 1)
+            f.processVisionData(seq.vision_stamps[i], seq.ids[sel], seq.bearings[i][sel])
+    e = f.stateEstimate()
+    S = f.stateCovariance()
+    print("N", N, "landmarks", f.numLandmarks, "finite", np.isfinite(S).all(), "launches", f.launch_count())
+A = rng.standard_normal((45, 37)); B = rng.standard_normal((37, 50))
+C, _ = dgemm(A, B)
+print("gemm", np.abs(C - A @ B).max())
