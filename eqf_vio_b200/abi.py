@@ -45,11 +45,15 @@ SIGNATURES = {
     "eqvio_gain_update": (C.c_int, [_h, _dp, _dp, _dp]),
     "eqvio_bundle_lift": (C.c_int, [_h, _dp, _dp]),
     "eqvio_dgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp, C.c_int, _dp, C.c_int, C.c_double, _dp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "eqvio_getrf_block": (C.c_int, [C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_float)]),
     "eqvio_synchronize": (C.c_int, [_h]),
     "eqvio_launch_count": (C.c_int, [_h, C.POINTER(C.c_longlong), C.c_int]),
+    "eqvio_set_graphs": (C.c_int, [_h, C.c_int]),
+    "eqvio_graph_stats": (C.c_int, [_h, C.POINTER(C.c_longlong), _ip]),
     "eqvio_profile_enable": (C.c_int, [_h, C.c_int]),
     "eqvio_profile_read": (C.c_int, [_h, C.POINTER(C.c_longlong), _dp, _dp, C.c_int]),
     "eqvio_profile_read_class": (C.c_int, [_h, C.c_int, C.POINTER(C.c_longlong), _dp, _dp, C.c_int]),
+    "eqvio_profile_timeline": (C.c_int, [_h, _dp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "eqvio_stream": (C.c_int, [_h, C.POINTER(C.c_void_p)]),
     "eqvio_status_string": (C.c_char_p, [C.c_int]),
     "eqvio_version": (C.c_char_p, []),

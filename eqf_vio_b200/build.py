@@ -34,21 +34,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), lib: str = LIB) -> str:
+    """`extra_flags` / `lib` build an instrumented variant next to the product library (tools/ only)."""
+    if lib == LIB and not force and not needs_build():
         return LIB
+    tag = "" if lib == LIB else "." + os.path.basename(lib).replace(".so", "")
     objs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", tag + ".o"))
+        cmd = [nvcc(), *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [nvcc(), "-shared", "-o", lib, *objs, "-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -89,7 +89,9 @@ struct KernelParams {
     double alpha, beta;
     int add_diag;  // D[m][m] += T * Pd(class of m)
     int no_edge_skip;  // debug A/B switch: treat partial tiles like full ones
+    int skip_m, skip_n;  // output box [0, skip_m) x [0, skip_n) is not written
     double T;
+    const double* T_dev;  // non-null: T is read from device memory
     double Pd[5];
 };
 
@@ -143,6 +145,7 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         (void)Tm;
     }
     const int KT = (p.K + 15) >> 4;
+    if ((tile_m + 1) * BM <= p.skip_m && (tile_n + 1) * BN <= p.skip_n) return;  // whole tile inside the skipped box
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -247,6 +250,7 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
 
     // ===== epilogue: registers -> global =====
+    const double Tstep = (p.add_diag && p.T_dev != nullptr) ? *p.T_dev : p.T;
     const int m_base = tile_m * BM + wm * WM + g;
     const int n_base = tile_n * BN + wn * WN + 2 * t;
 #pragma unroll
@@ -259,9 +263,10 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int i = 0; i < MB; ++i) {
                 const int m = m_base + i * 8;
                 if (m >= p.M) continue;
+                if (m < p.skip_m && n < p.skip_n) continue;
                 double v = p.alpha * acc[i][jn][c];
                 if (p.beta != 0.0) v += p.beta * p.Cin[(size_t)m + (size_t)p.ldcin * n];
-                if (p.add_diag && m == n) v += p.T * process_diag(p, m);
+                if (p.add_diag && m == n) v += Tstep * process_diag(p, m);
                 p.D[(size_t)m + (size_t)p.ldd * n] = v;
             }
         }
@@ -336,6 +341,8 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
         p.no_edge_skip = noedge;
     }
     p.T = g.epi.T;
+    p.skip_m = g.skip_m; p.skip_n = g.skip_n;
+    p.T_dev = g.epi.T_dev;
     for (int i = 0; i < 5; ++i) p.Pd[i] = g.epi.Pd[i];
     dim3 grid(((g.M + Cfg::BM - 1) / Cfg::BM) * ((g.N + Cfg::BN - 1) / Cfg::BN));
     cudaError_t e;

@@ -30,6 +30,7 @@ struct GemmEpilogueArgs {
     int ldcin;
     // Riccati epilogue
     double T;
+    const double* T_dev;  // when non-null the step length is read from device memory (lets a CUDA graph replay the launch)
     const double* Bb;  // n x 6 column-major, leading dimension ldbb
     int ldbb;
     double Rd[6];      // diag(velOmegaVariance x3, velAccelVariance x3)
@@ -43,6 +44,9 @@ struct GemmProblem {
     double* D; int ldd;
     int epilogue;
     GemmEpilogueArgs epi;
+    // Output elements with m < skip_m and n < skip_n are left untouched (tiles entirely inside the box exit at
+    // once): the trailing update of a Schur step leaves the next diagonal block to the chain kernel.
+    int skip_m = 0, skip_n = 0;
 };
 
 // Host API.  All pointers are device pointers; A, B must be 16-byte aligned with even lda/ldb and

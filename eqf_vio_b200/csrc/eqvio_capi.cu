@@ -14,7 +14,9 @@
 // Y^T Sigma_sub^-1 Y for five vectors: [[Sigma_sub, Y], [Y^T, 0]] -> bottom-right = -Y^T Sigma_sub^-1 Y.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <unordered_map>
 #include <vector>
 
@@ -40,16 +42,22 @@ static void set_error(cudaError_t e, const char* what, int line) {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-struct ProfEvent { cudaEvent_t a, b; double flops; int cls; };
-enum { PROF_RICCATI = 0, PROF_UPDATE = 1, PROF_SCHUR_GEMM = 2, PROF_SCHUR_DIAG = 3, PROF_CLASSES = 4 };
+struct ProfEvent { cudaEvent_t a, b; double flops; int cls; int lane; };
+enum { PROF_RICCATI = 0, PROF_UPDATE = 1, PROF_SCHUR_GEMM = 2, PROF_SCHUR_DIAG = 3, PROF_MISC = 4, PROF_CLASSES = 5 };
+struct TimelineEntry { double cls, lane, t0, t1, flops; };
+
+struct GraphKey { int kind, N, flags; const double *Sigma, *Lbase; };  // the Sigma and landmark buffers ping-pong independently
+struct CachedGraph { GraphKey key; cudaGraphExec_t exec; long long launches; long long last_use; bool broken; };
 
 struct eqvio_filter {
     int device = 0;
+    bool use_graphs = true;            // EQVIO_GRAPHS=0 disables
+    std::vector<CachedGraph> graphs;
+    long long graph_clock = 0, graph_launches = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;   // second stream: dense GEMMs that overlap the latency-bound Schur eliminations
     cudaStream_t main_h = nullptr, lift_h = nullptr;  // helper streams of the two Schur chains (look-ahead)
-    cudaEvent_t ev_sa = nullptr, ev_sb = nullptr, ev_la = nullptr, ev_lb = nullptr;
-    double *cornerS = nullptr, *cornerL = nullptr;
+    cudaEvent_t ev_sa = nullptr, ev_sb = nullptr, ev_st = nullptr, ev_la = nullptr, ev_lb = nullptr, ev_lt = nullptr;
     cudaStream_t lift = nullptr;   // third stream: the Sigma_sub elimination of bundleLift, concurrent with the S / K / gamma chain
     cudaEvent_t ev_lift_fork = nullptr, ev_lift_done = nullptr;
     cudaStream_t cur = nullptr;    // stream the next gemm() goes to (main unless forked)
@@ -86,18 +94,85 @@ struct eqvio_filter {
     std::vector<ProfEvent> prof;
     long long prof_launches = 0;
     double prof_ms = 0, prof_flops = 0;
-    long long cls_launches[PROF_CLASSES] = {0, 0, 0, 0};
-    double cls_ms[PROF_CLASSES] = {0, 0, 0, 0}, cls_flops[PROF_CLASSES] = {0, 0, 0, 0};
+    long long cls_launches[PROF_CLASSES] = {0, 0, 0, 0, 0};
+    double cls_ms[PROF_CLASSES] = {0, 0, 0, 0, 0}, cls_flops[PROF_CLASSES] = {0, 0, 0, 0, 0};
+    cudaEvent_t prof_base = nullptr;          // time origin of the timeline (recorded by eqvio_profile_enable)
+    std::vector<TimelineEntry> timeline;      // filled by eqvio_profile_read while profiling is on
     int prof_cls = PROF_UPDATE;  // class tag applied to the launches that follow
 };
 
 typedef eqvio_filter Filter;
 
+// ------------------------------------------------------------------------------------------------
+// CUDA graphs.  A vision update is ~200 stream-ordered launches on five streams and an IMU tick three
+// launches behind k_step_prepare; issued one by one the host (launch + tensor-map encode per GEMM)
+// is slower than the GPU for every N the filter is used at.  Both launch sequences depend only on
+// (N, which of the two Sigma buffers is current, mode flags): the second time a key is seen its
+// sequence is stream-captured (fork / join events included) into a graph, afterwards it is replayed
+// with one cudaGraphLaunch.  Per-step scalars (T, stamp) are read from device memory written by
+// k_step_prepare, so nothing in a captured node changes between replays.
+// ------------------------------------------------------------------------------------------------
+enum { GRAPH_RICCATI = 1, GRAPH_UPDATE = 2 };
+static void drop_graphs(Filter* f) {
+    for (auto& g : f->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    f->graphs.clear();
+}
+static int run_graphed(Filter* f, int kind, int flags, const std::function<int()>& body) {
+    if (!f->use_graphs || f->profiling) return body();
+    const GraphKey key{kind, f->N, flags, f->Sigma, f->L.base};
+    CachedGraph* e = nullptr;
+    for (auto& g : f->graphs)
+        if (g.key.kind == key.kind && g.key.N == key.N && g.key.flags == key.flags && g.key.Sigma == key.Sigma && g.key.Lbase == key.Lbase) { e = &g; break; }
+    ++f->graph_clock;
+    if (!e) {
+        // first sight of this key: launch directly (this also performs the one-off cudaFuncSetAttribute calls)
+        if (f->graphs.size() >= 16) {
+            size_t old = 0;
+            for (size_t i = 1; i < f->graphs.size(); ++i)
+                if (f->graphs[i].last_use < f->graphs[old].last_use) old = i;
+            if (f->graphs[old].exec) cudaGraphExecDestroy(f->graphs[old].exec);
+            f->graphs.erase(f->graphs.begin() + old);
+        }
+        f->graphs.push_back(CachedGraph{key, nullptr, 0, f->graph_clock, false});
+        return body();
+    }
+    e->last_use = f->graph_clock;
+    if (e->broken) return body();
+    if (!e->exec) {
+        const long long before = f->launches;
+        if (cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            e->broken = true;
+            return body();
+        }
+        const int st = body();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
+        const long long captured = f->launches - before;
+        f->launches = before;
+        if (st != EQVIO_OK || ce != cudaSuccess || !graph ||
+            cudaGraphInstantiate(&e->exec, graph, 0) != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            e->exec = nullptr;
+            e->broken = true;   // nothing ran during the capture: issue the launches directly
+            return body();
+        }
+        cudaGraphDestroy(graph);
+        e->launches = captured;
+    }
+    CU_TRY(cudaGraphLaunch(e->exec, f->stream));
+    f->launches += e->launches;
+    f->graph_launches += 1;
+    return EQVIO_OK;
+}
+
 // One blocked Schur elimination = a chain stream, a helper stream for the look-ahead, two events and its workspaces.
 struct SchurChain {
     cudaStream_t s, h;
-    cudaEvent_t ev_a, ev_b;
-    double *Linv, *Uinv, *corner;  // corner: 64 x 64 scratch with the next diagonal block already updated
+    cudaEvent_t ev_a, ev_b, ev_t;
+    double *Linv, *Uinv;
     bool keep_linv;
 };
 
@@ -132,6 +207,7 @@ static int ensure_capacity(Filter* f, int needN) {
     const int ldm = round_up(2 * cap, 16) + 16;
     const int ld2m = round_up(4 * cap, 16) + 32;
     const size_t nn = (size_t)ld * (ld + 32);
+    drop_graphs(f);  // captured launches hold the old buffers
     Filter o = *f;  // old pointers
     Landmarks L{nullptr, cap}, L2{nullptr, cap};
     double *Sigma, *Sigma2, *F, *W, *Bb, *Aug, *C, *CS, *SCt, *K, *Saug, *Sinv, *delta, *gamma, *y_in, *y, *scratch, *Gamma;
@@ -209,30 +285,48 @@ static int prepare_layout(Filter* f) {
 // ------------------------------------------------------------------------------------------------
 // GEMM wrapper with launch counting and optional event bracketing
 // ------------------------------------------------------------------------------------------------
+static int lane_of(const Filter* f, cudaStream_t s) {
+    return s == f->stream ? 0 : s == f->side ? 1 : s == f->lift ? 2 : s == f->main_h ? 3 : s == f->lift_h ? 4 : 5;
+}
+// Event bracket around the launches that follow on stream `s` (only while profiling is enabled).
+static void prof_begin(Filter* f, ProfEvent& pe, cudaStream_t s, int cls, double flops) {
+    if (!f->profiling) return;
+    cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
+    pe.flops = flops; pe.cls = cls; pe.lane = lane_of(f, s);
+    cudaEventRecord(pe.a, s);
+}
+static void prof_end(Filter* f, ProfEvent& pe, cudaStream_t s) {
+    if (!f->profiling) return;
+    cudaEventRecord(pe.b, s);
+    f->prof.push_back(pe);
+}
+
+struct ProfScope {  // brackets the launches of a block: { ProfScope ps(f, stream, cls); launch...; }
+    Filter* f; cudaStream_t s; ProfEvent pe;
+    ProfScope(Filter* f_, cudaStream_t s_, int cls) : f(f_), s(s_) { prof_begin(f, pe, s, cls, 0.0); }
+    ~ProfScope() { prof_end(f, pe, s); }
+};
+
 static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
                 double beta, const double* Cin, int ldcin, double* D, int ldd, int riccati_diag = 0, double T = 0.0,
-                int force_config = -1) {
+                int force_config = -1, int skip = 0) {
     if (M <= 0 || N <= 0) return EQVIO_OK;
     GemmProblem g;
     g.M = M; g.N = N; g.K = K;
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.transB = transB;
     g.D = D; g.ldd = ldd;
+    g.skip_m = g.skip_n = skip;
     g.epilogue = riccati_diag ? EPI_RICCATI : EPI_AXPBY;
     g.epi.alpha = alpha; g.epi.beta = beta; g.epi.Cin = Cin; g.epi.ldcin = ldcin;
-    g.epi.T = T; g.epi.Bb = nullptr; g.epi.ldbb = 0;
+    g.epi.T = T; g.epi.T_dev = riccati_diag ? &f->sc->T : nullptr; g.epi.Bb = nullptr; g.epi.ldbb = 0;
     for (int i = 0; i < 6; ++i) g.epi.Rd[i] = 0;
     g.epi.Pd[0] = f->s.biasOmegaProcessVariance; g.epi.Pd[1] = f->s.biasAccelProcessVariance;
     g.epi.Pd[2] = f->s.gravityProcessVariance; g.epi.Pd[3] = f->s.velocityProcessVariance;
     g.epi.Pd[4] = f->s.pointProcessVariance;
     ProfEvent pe;
-    if (f->profiling) {
-        cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
-        pe.flops = 2.0 * M * N * K;
-        pe.cls = f->prof_cls;
-        cudaEventRecord(pe.a, f->cur);
-    }
+    prof_begin(f, pe, f->cur, f->prof_cls, 2.0 * M * N * K);
     CU_TRY(dgemm_launch(g, f->cur, force_config));
-    if (f->profiling) { cudaEventRecord(pe.b, f->cur); f->prof.push_back(pe); }
+    prof_end(f, pe, f->cur);
     f->launches += 1;
     return EQVIO_OK;
 }
@@ -254,13 +348,13 @@ static int join_side(Filter* f) { CU_TRY(cudaStreamWaitEvent(f->stream, f->ev_jo
 // Blocked Schur elimination of the leading k x k block (k a multiple of 16, identity-padded by
 // k_schur_setup) of the (k + r) x (k + c) matrix Aug by unpivoted LU: on return (in stream ch.s) the
 // bottom-right r x c block holds Z - R A^-1 Cc, the sub-diagonal blocks hold L and, with keep_linv, every
-// L_jj^-1 is kept.  Per 64-wide step, with look-ahead so that the sequential pivot chain does not wait for the
-// trailing update:
-//   ch.s: LU + triangular inverses of the diagonal block (read from the look-ahead scratch after step 0)
+// L_jj^-1 is kept.  Per 64-wide step j, with look-ahead so that the sequential chain never waits for a trailing
+// update:
+//   ch.s: k_chain_block: D_j = A[j,j] - L[j,j-1] U[j-1,j] (the update the previous trailing GEMM skipped), LU of
+//         D_j, L_jj^-1, U_jj^-1                                  needs only the two panels of step j-1
 //   ch.s: column panel  X U = B  as GEMM with U^-1      |  ch.h: row panel  L X = B  as GEMM with L^-1
-//   ch.s: the NEXT diagonal block only, into the scratch   (64 x 64 x 64)
-//   ch.h: the full trailing update                          (overlaps the next step's diagonal LU)
-// The diagonal blocks of Aug itself are left stale (nothing reads them again).
+//   ch.h: trailing update, minus the next diagonal block        (overlaps the next chain kernel)
+// The chain is kernel -> panel -> kernel; the diagonal blocks of Aug itself are left stale (nothing reads them).
 static int schur_lu(Filter* f, const SchurChain& ch, double* Aug, int lda, int k, int r, int c) {
     struct Guard { Filter* f; cudaStream_t prev; ~Guard() { f->prof_cls = PROF_UPDATE; f->cur = prev; } } guard{f, f->cur};
     f->prof_cls = PROF_SCHUR_GEMM;
@@ -273,46 +367,37 @@ static int schur_lu(Filter* f, const SchurChain& ch, double* Aug, int lda, int k
         const int rows = k + r - (j + nb), cols = k + c - (j + nb);
         double* Linv = ch.keep_linv ? ch.Linv + (size_t)(j / 64) * 4096 : ch.Linv;
         double* Uinv = ch.Uinv;
-        ProfEvent pe;
-        if (f->profiling) {
-            cudaEventCreate(&pe.a); cudaEventCreate(&pe.b);
-            pe.flops = 0.0; pe.cls = PROF_SCHUR_DIAG;
-            cudaEventRecord(pe.a, ch.s);
+        if (j > 0) CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_b, 0));    // row panel of step j-1 (its column panel is in stream order)
+        {
+            ProfScope ps(f, ch.s, PROF_SCHUR_DIAG);
+            CU_TRY(launch_chain_block(ch.s, Aug, lda, j, nb, j > 0 ? 64 : 0, nullptr, 0, nullptr, 0, Linv, Uinv, &f->st->flags));
         }
-        if (j == 0) CU_TRY(launch_getrf_diag_inv(ch.s, Aug, lda, nullptr, 0, nb, Linv, Uinv, &f->st->flags));
-        else CU_TRY(launch_getrf_diag_inv(ch.s, ch.corner, 64, nullptr, 0, nb, Linv, Uinv, &f->st->flags));
-        if (f->profiling) { cudaEventRecord(pe.b, ch.s); f->prof.push_back(pe); }
         f->launches += 1;
         double* Lp = Aug + (j + nb) + (size_t)lda * j;         // rows x nb, below the diagonal block
         double* Up = Aug + j + (size_t)lda * (j + nb);         // nb x cols, right of it
         double* T22 = Aug + (j + nb) + (size_t)lda * (j + nb);
-        // panel solves as GEMMs with the triangular inverses, in place (one 64-wide tile owns its rows / columns).
-        // Both wait for the previous trailing update (queued on ch.h): the row panel by stream order, the column
-        // panel through ev_b.
-        CU_TRY(cudaEventRecord(ch.ev_a, ch.s));                // diagonal block done
+        // panel solves as GEMMs with the triangular inverses, in place (one 64-wide tile owns its rows / columns);
+        // both need the previous trailing update (queued on ch.h): the row panel by stream order, the column panel
+        // through ev_t
+        CU_TRY(cudaEventRecord(ch.ev_a, ch.s));                // chain kernel done
         CU_TRY(cudaStreamWaitEvent(ch.h, ch.ev_a, 0));
-        if (j > 0) CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_b, 0));   // ev_b still = previous trailing update: the column panel needs it
+        if (j > 0) CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_t, 0));
         f->cur = ch.h;
         if ((st = gemm(f, 0, nb, cols, nb, 1.0, Linv, 64, Up, lda, 0.0, nullptr, 0, Up, lda, 0, 0.0, 2))) return st;   // L X = B
-        CU_TRY(cudaEventRecord(ch.ev_b, ch.h));                // now ev_b = row panel of this step
+        CU_TRY(cudaEventRecord(ch.ev_b, ch.h));
         f->cur = ch.s;
         if ((st = gemm(f, 0, rows, nb, nb, 1.0, Lp, lda, Uinv, 64, 0.0, nullptr, 0, Lp, lda, 0, 0.0, 2))) return st;   // X U = B
-        CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_b, 0));         // the corner and the trailing update need both panels
-        const int nb2 = std::min(64, k - (j + nb));
-        if (nb2 > 0) {
-            // look-ahead: next diagonal block = its current value - L_panel[0:nb2, :] U_panel[:, 0:nb2]
-            if ((st = gemm(f, 0, nb2, nb2, nb, -1.0, Lp, lda, Up, lda, 1.0, T22, lda, ch.corner, 64, 0, 0.0, 2))) return st;
-        }
-        // full trailing update on the helper stream (needs both panels: ev_a2 after the column panel / corner)
+        // trailing update on the helper stream; the next diagonal block is the next chain kernel's
         CU_TRY(cudaEventRecord(ch.ev_a, ch.s));
         CU_TRY(cudaStreamWaitEvent(ch.h, ch.ev_a, 0));
+        const int nb2 = std::min(64, k - (j + nb));
         f->cur = ch.h;
-        if ((st = gemm(f, 0, rows, cols, nb, -1.0, Lp, lda, Up, lda, 1.0, T22, lda, T22, lda))) return st;
-        CU_TRY(cudaEventRecord(ch.ev_b, ch.h));
+        if ((st = gemm(f, 0, rows, cols, nb, -1.0, Lp, lda, Up, lda, 1.0, T22, lda, T22, lda, 0, 0.0, -1, std::max(nb2, 0)))) return st;
+        CU_TRY(cudaEventRecord(ch.ev_t, ch.h));
         f->cur = ch.s;
     }
     // the chain stream's consumers need the last trailing update
-    CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_b, 0));
+    CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_t, 0));
     return EQVIO_OK;
 }
 
@@ -360,15 +445,24 @@ static int integrate(Filter* f, double newTime, bool doRiccati, const double* om
     if (!a.do_init && !a.do_integrate && !a.do_latch) return 0;
     if (a.do_riccati) { int st = prepare_layout(f); if (st) return st; }
     RiccatiOut ro = riccati_out(f);
-    launch_step_prepare(f->stream, f->st, f->sc, a, ro);
-    f->launches += 1;
+    {
+        ProfScope ps(f, f->stream, PROF_MISC);
+        launch_step_prepare(f->stream, f->st, f->sc, a, ro);   // the sample, dt and T travel as kernel arguments
+        f->launches += 1;
+    }
     if (a.do_integrate) {
-        if (f->N > 0) { launch_feature_step(f->stream, f->st, f->sc, f->L, f->N, a.do_riccati, a.discrete_lift, ro); f->launches += 1; }
-        if (a.do_riccati) {
-            int st = riccati_gemms(f, a.T);
-            if (st) return st;
-            f->accTime = 0.0;
-        }
+        // everything behind k_step_prepare reads its scalars (T, dt, stamp) from device memory: replayable
+        auto tail = [&]() -> int {
+            if (f->N > 0) {
+                ProfScope ps(f, f->stream, PROF_MISC);
+                launch_feature_step(f->stream, f->st, f->sc, f->L, f->N, a.do_riccati, a.discrete_lift, ro);
+                f->launches += 1;
+            }
+            return a.do_riccati ? riccati_gemms(f, a.T) : EQVIO_OK;
+        };
+        const int st = a.do_riccati ? run_graphed(f, GRAPH_RICCATI, a.discrete_lift, tail) : tail();
+        if (st) return st;
+        if (a.do_riccati) f->accTime = 0.0;
         f->currentTime = newTime;
     }
     return integrated;
@@ -400,10 +494,9 @@ static int compact(Filter* f, const std::vector<int>& keep) {
 
 // The measurement update, VIOFilter.cpp:264-297, on matched bearings f->y (3N, device).
 // want_lift = 0 stops after gamma / Sigma update (kernel-level entry point).
-static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
+static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     const int N = f->N, n = n_of(N), m = 2 * N, p = 5 + 3 * N, pb = round_up(p, 16), ld = f->ld, ldm = f->ldm;
-    int st = prepare_layout(f);
-    if (st) return st;
+    int st;
     cudaStream_t s = f->stream;
     const bool lift_chain = do_lift && f->s.useInnovationLift;
     if (lift_chain) {
@@ -412,34 +505,49 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
         // goes through S, S^-1, K and gamma; the gamma-dependent column is folded in afterwards (k_lift_fwdsub).
         CU_TRY(cudaEventRecord(f->ev_lift_fork, s));
         CU_TRY(cudaStreamWaitEvent(f->lift, f->ev_lift_fork, 0));
-        launch_lift_prepare(f->lift, f->st, f->sc, nullptr);
-        launch_copy_block(f->lift, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
-        launch_schur_setup(f->lift, f->Aug, ld, p, pb, 4, 4, 0);
-        launch_lift_features(f->lift, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
+        {
+            ProfScope ps(f, f->lift, PROF_MISC);
+            launch_lift_prepare(f->lift, f->st, f->sc, nullptr);
+            launch_copy_block(f->lift, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
+            launch_schur_setup(f->lift, f->Aug, ld, p, pb, 4, 4, 0);
+            launch_lift_features(f->lift, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
+        }
         f->launches += 4;
-        if ((st = schur_lu(f, SchurChain{f->lift, f->lift_h, f->ev_la, f->ev_lb, f->LinvL, f->UinvL, f->cornerL, true}, f->Aug, ld, pb, 4, 4))) return st;
+        if ((st = schur_lu(f, SchurChain{f->lift, f->lift_h, f->ev_la, f->ev_lb, f->ev_lt, f->LinvL, f->UinvL, true}, f->Aug, ld, pb, 4, 4))) return st;
         CU_TRY(cudaEventRecord(f->ev_lift_done, f->lift));
     }
-    launch_build_C_delta(s, f->st, f->L, N, f->y, f->C, ldm, f->delta);
+    {
+        ProfScope ps(f, s, PROF_MISC);
+        launch_build_C_delta(s, f->st, f->L, N, f->y, f->C, ldm, f->delta);
+    }
     f->launches += 1;
     // S = (C Sigma) C^T + Q                                        VIOFilter.cpp:276
     if ((st = gemm(f, 0, m, n, n, 1.0, f->C, ldm, f->Sigma, ld, 0.0, nullptr, 0, f->CS, ldm))) return st;
     if ((st = gemm(f, 1, m, m, n, 1.0, f->CS, ldm, f->C, ldm, 0.0, nullptr, 0, f->Saug, f->ld2m))) return st;
-    launch_add_diag_const(s, f->Saug, f->ld2m, m, f->s.measurementVariance);
+    {
+        ProfScope ps(f, s, PROF_MISC);
+        launch_add_diag_const(s, f->Saug, f->ld2m, m, f->s.measurementVariance);
+    }
     // S.inverse() (:277): eliminate S from [[S, I], [I, 0]]; the bottom-right block becomes -S^-1
     const int mp = round_up(m, 16);
-    launch_schur_setup(s, f->Saug, f->ld2m, m, mp, m, m, 1);
+    {
+        ProfScope ps(f, s, PROF_MISC);
+        launch_schur_setup(s, f->Saug, f->ld2m, m, mp, m, m, 1);
+    }
     f->launches += 2;
     // Sigma C^T does not depend on S^-1: it runs on the side stream under the (latency-bound) elimination
     if ((st = fork_side(f))) return st;
     if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
     if ((st = end_side(f))) return st;
-    if ((st = schur_lu(f, SchurChain{f->stream, f->main_h, f->ev_sa, f->ev_sb, f->Linv, f->Uinv, f->cornerS, false}, f->Saug, f->ld2m, mp, m, m))) return st;
+    if ((st = schur_lu(f, SchurChain{f->stream, f->main_h, f->ev_sa, f->ev_sb, f->ev_st, f->Linv, f->Uinv, false}, f->Saug, f->ld2m, mp, m, m))) return st;
     const double* negSinv = f->Saug + mp + (size_t)f->ld2m * mp;
     if ((st = join_side(f))) return st;
     // K = (Sigma C^T) S^-1                                           :277
     if ((st = gemm(f, 0, n, m, m, -1.0, f->SCt, ld, negSinv, f->ld2m, 0.0, nullptr, 0, f->K, ld))) return st;
-    launch_gemv(s, f->K, ld, n, m, f->delta, f->gamma);  // :279
+    {
+        ProfScope ps(f, s, PROF_MISC);
+        launch_gemv(s, f->K, ld, n, m, f->delta, f->gamma);  // :279
+    }
     f->launches += 1;
     // Sigma <- Sigma - (K C) Sigma (:297) reads the PRIOR Sigma, K and C and writes the twin buffer; the lift
     // (:285-296) reads the prior Sigma and gamma and writes X.  Independent: the two GEMMs go to the side
@@ -455,19 +563,31 @@ static int update(Filter* f, double stamp, bool do_lift, bool do_sigma) {
         const int use_lift = f->s.useInnovationLift, discrete = f->s.useDiscreteInnovationLift;
         if (use_lift) {
             CU_TRY(cudaStreamWaitEvent(s, f->ev_lift_done, 0));
-            launch_lift_prepare(s, f->st, f->sc, f->gamma);
-            launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb, f->yo);
-            launch_lift_fwdsub(s, f->Aug, ld, pb, f->LinvL, f->yo, f->b4);
+            {
+                ProfScope ps(f, s, PROF_MISC);
+                launch_lift_prepare(s, f->st, f->sc, f->gamma);
+                launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb, f->yo);
+                launch_lift_fwdsub(s, f->Aug, ld, pb, f->LinvL, f->yo, f->b4);
+            }
             f->launches += 3;
         }
-        launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->b4, use_lift, discrete, stamp, nullptr, 1);
-        launch_lift_apply(s, f->st, f->L, N, f->gamma, use_lift ? discrete : 0);
+        {
+            ProfScope ps(f, s, PROF_MISC);
+            launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->b4, use_lift, discrete, nullptr, 1);
+            launch_lift_apply(s, f->st, f->L, N, f->gamma, use_lift ? discrete : 0);
+        }
         f->launches += 2;
     }
-    if (do_sigma) {
-        if ((st = join_side(f))) return st;
-        std::swap(f->Sigma, f->Sigma2);
-    }
+    if (do_sigma && (st = join_side(f))) return st;
+    return EQVIO_OK;
+}
+
+static int update(Filter* f, bool do_lift, bool do_sigma) {
+    int st = prepare_layout(f);
+    if (st) return st;
+    const int flags = (do_lift ? 1 : 0) | (do_sigma ? 2 : 0);
+    if ((st = run_graphed(f, GRAPH_UPDATE, flags, [&]() { return update_launches(f, do_lift, do_sigma); }))) return st;
+    if (do_sigma) std::swap(f->Sigma, f->Sigma2);   // the update wrote the twin buffer
     return EQVIO_OK;
 }
 
@@ -551,11 +671,12 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
         CU_TRY(cudaStreamCreateWithPriority(&f->lift, cudaStreamNonBlocking, hi));
         CU_TRY(cudaStreamCreateWithPriority(&f->main_h, cudaStreamNonBlocking, hi));
         CU_TRY(cudaStreamCreateWithPriority(&f->lift_h, cudaStreamNonBlocking, hi));
-        for (cudaEvent_t* e : {&f->ev_sa, &f->ev_sb, &f->ev_la, &f->ev_lb}) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t* e : {&f->ev_sa, &f->ev_sb, &f->ev_st, &f->ev_la, &f->ev_lb, &f->ev_lt}) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_fork, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_done, cudaEventDisableTiming));
     }
     f->cur = f->stream;
+    if (const char* e = getenv("EQVIO_GRAPHS")) f->use_graphs = !(e[0] == '0');
     CU_TRY(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&f->stage_free, cudaEventDisableTiming));
@@ -567,10 +688,6 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     CU_TRY(dalloc(&f->UinvL, 64 * 80));
     CU_TRY(cudaMemset(f->UinvL, 0, 64 * 80 * 8));
     CU_TRY(dalloc(&f->b4, 8));
-    CU_TRY(dalloc(&f->cornerS, 64 * 80));
-    CU_TRY(dalloc(&f->cornerL, 64 * 80));
-    CU_TRY(cudaMemset(f->cornerS, 0, 64 * 80 * 8));
-    CU_TRY(cudaMemset(f->cornerL, 0, 64 * 80 * 8));
     CU_TRY(cudaMemset(f->Linv, 0, 64 * 80 * 8));
     CU_TRY(cudaMemset(f->Uinv, 0, 64 * 80 * 8));
     int st = ensure_capacity(f, 64);
@@ -590,6 +707,8 @@ int eqvio_destroy(eqvio_handle_t f) {
     cudaStreamSynchronize(f->main_h);
     cudaStreamSynchronize(f->lift_h);
     for (auto& e : f->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (f->prof_base) cudaEventDestroy(f->prof_base);
+    drop_graphs(f);
     free_device(f);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL); cudaFree(f->b4);
     if (f->h_stage) cudaFreeHost(f->h_stage);
@@ -597,8 +716,7 @@ int eqvio_destroy(eqvio_handle_t f) {
     cudaEventDestroy(f->stage_free);
     cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join); cudaEventDestroy(f->ev_lift_fork); cudaEventDestroy(f->ev_lift_done);
     cudaStreamDestroy(f->side); cudaStreamDestroy(f->lift); cudaStreamDestroy(f->main_h); cudaStreamDestroy(f->lift_h);
-    for (cudaEvent_t e : {f->ev_sa, f->ev_sb, f->ev_la, f->ev_lb}) cudaEventDestroy(e);
-    cudaFree(f->cornerS); cudaFree(f->cornerL);
+    for (cudaEvent_t e : {f->ev_sa, f->ev_sb, f->ev_st, f->ev_la, f->ev_lb, f->ev_lt}) cudaEventDestroy(e);
     cudaStreamDestroy(f->stream);
     delete f;
     return EQVIO_OK;
@@ -716,7 +834,7 @@ static int process_vision_impl(Filter* f, double stamp, int nmeas, const int* mi
         f->N = nmeas;
     }
     if (nmeas == 0) return EQVIO_EMPTY_MEASUREMENT;
-    return update(f, stamp, true, true);
+    return update(f, true, true);
 }
 
 int eqvio_process_vision(eqvio_handle_t f, double stamp, int n, const int* ids, const double* bearings) {
@@ -990,7 +1108,7 @@ int eqvio_gain_update(eqvio_handle_t f, const double* bearings, double* K, doubl
     CU_TRY(cudaSetDevice(f->device));
     int st = upload_bearings(f, bearings);
     if (st) return st;
-    if ((st = update(f, f->currentTime, false, true))) return st;
+    if ((st = update(f, false, true))) return st;
     const int n = n_of(f->N), m = 2 * f->N;
     CU_TRY(cudaStreamSynchronize(f->stream));
     if (K) CU_TRY(cudaMemcpy2D(K, (size_t)n * 8, f->K, (size_t)f->ld * 8, (size_t)n * 8, m, cudaMemcpyDeviceToHost));
@@ -1014,12 +1132,12 @@ int eqvio_bundle_lift(eqvio_handle_t f, const double* gamma_eqf, double* Gamma) 
     launch_schur_setup(s, f->Aug, ld, p, pb, 4, 4, 0);
     launch_lift_features(s, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
     f->launches += 4;
-    int st = schur_lu(f, SchurChain{s, f->main_h, f->ev_sa, f->ev_sb, f->LinvL, f->UinvL, f->cornerL, true}, f->Aug, ld, pb, 4, 4);
+    int st = schur_lu(f, SchurChain{s, f->main_h, f->ev_sa, f->ev_sb, f->ev_st, f->LinvL, f->UinvL, true}, f->Aug, ld, pb, 4, 4);
     if (st) return st;
     launch_lift_prepare(s, f->st, f->sc, f->gamma);
     launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb, f->yo);
     launch_lift_fwdsub(s, f->Aug, ld, pb, f->LinvL, f->yo, f->b4);
-    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->b4, 1, 1, f->currentTime, f->Gamma, 0);
+    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->b4, 1, 1, f->Gamma, 0);
     f->launches += 3;
     f->launches += 1;
     CU_TRY(cudaStreamSynchronize(s));
@@ -1071,6 +1189,42 @@ int eqvio_dgemm(int device, int transB, int M, int N, int K, double alpha, const
     return EQVIO_OK;
 }
 
+// One diagonal block of the Schur eliminations on its own (unit parity + timing): unpivoted LU of the nb x nb
+// block A (nb <= 64) and the two 64 x 64 identity-padded triangular inverses.
+int eqvio_getrf_block(int device, int nb, const double* A, int lda, double* LU, double* Linv, double* Uinv, int reps, float* us) {
+    if (nb < 1 || nb > 64 || !A || lda < nb) return EQVIO_ERR_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return EQVIO_ERR_NO_DEVICE;
+    CU_TRY(cudaSetDevice(device));
+    double *dA, *dLU, *dL, *dU;
+    int* dflags;
+    CU_TRY(dalloc(&dA, 64 * 64)); CU_TRY(dalloc(&dLU, 64 * 64)); CU_TRY(dalloc(&dL, 64 * 64)); CU_TRY(dalloc(&dU, 64 * 64));
+    CU_TRY(dalloc(&dflags, 1));
+    CU_TRY(cudaMemset(dA, 0, 64 * 64 * 8)); CU_TRY(cudaMemset(dLU, 0, 64 * 64 * 8)); CU_TRY(cudaMemset(dflags, 0, 4));
+    CU_TRY(cudaMemcpy2D(dA, 64 * 8, A, (size_t)lda * 8, (size_t)nb * 8, nb, cudaMemcpyHostToDevice));
+    CU_TRY(launch_chain_block(0, nullptr, 0, 0, nb, 0, dA, 64, dLU, 64, dL, dU, dflags));
+    CU_TRY(cudaDeviceSynchronize());
+    if (reps > 1 && us) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < reps; ++i) CU_TRY(launch_chain_block(0, nullptr, 0, 0, nb, 0, dA, 64, dLU, 64, dL, dU, dflags));
+        cudaEventRecord(e1, 0);
+        CU_TRY(cudaEventSynchronize(e1));
+        float t;
+        cudaEventElapsedTime(&t, e0, e1);
+        *us = 1000.f * t / reps;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    } else if (us) *us = 0;
+    if (LU) CU_TRY(cudaMemcpy2D(LU, (size_t)nb * 8, dLU, 64 * 8, (size_t)nb * 8, nb, cudaMemcpyDeviceToHost));
+    if (Linv) CU_TRY(cudaMemcpy(Linv, dL, 64 * 64 * 8, cudaMemcpyDeviceToHost));
+    if (Uinv) CU_TRY(cudaMemcpy(Uinv, dU, 64 * 64 * 8, cudaMemcpyDeviceToHost));
+    int flags = 0;
+    CU_TRY(cudaMemcpy(&flags, dflags, 4, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dLU); cudaFree(dL); cudaFree(dU); cudaFree(dflags);
+    return flags_to_status(flags);
+}
+
 // ---- instrumentation ----
 int eqvio_synchronize(eqvio_handle_t f) {
     if (!f) return EQVIO_ERR_ARG;
@@ -1086,9 +1240,30 @@ int eqvio_launch_count(eqvio_handle_t f, long long* count, int reset) {
     if (reset) f->launches = 0;
     return EQVIO_OK;
 }
+int eqvio_graph_stats(eqvio_handle_t f, long long* graph_launches, int* cached_graphs) {
+    if (!f) return EQVIO_ERR_ARG;
+    if (graph_launches) *graph_launches = f->graph_launches;
+    if (cached_graphs) {
+        int c = 0;
+        for (auto& g : f->graphs) c += g.exec != nullptr;
+        *cached_graphs = c;
+    }
+    return EQVIO_OK;
+}
+int eqvio_set_graphs(eqvio_handle_t f, int on) {
+    if (!f) return EQVIO_ERR_ARG;
+    f->use_graphs = on != 0;
+    return EQVIO_OK;
+}
 int eqvio_profile_enable(eqvio_handle_t f, int on) {
     if (!f) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
     f->profiling = on != 0;
+    if (on) {
+        if (!f->prof_base) CU_TRY(cudaEventCreate(&f->prof_base));
+        CU_TRY(cudaEventRecord(f->prof_base, f->stream));
+        f->timeline.clear();
+    }
     return EQVIO_OK;
 }
 int eqvio_profile_read(eqvio_handle_t f, long long* gemm_launches, double* gemm_ms, double* gemm_flops, int reset) {
@@ -1098,8 +1273,13 @@ int eqvio_profile_read(eqvio_handle_t f, long long* gemm_launches, double* gemm_
     for (auto& e : f->prof) {
         float t = 0;
         cudaEventElapsedTime(&t, e.a, e.b);
+        if (f->prof_base && f->timeline.size() < (size_t)1 << 20) {
+            float t0 = 0;
+            cudaEventElapsedTime(&t0, f->prof_base, e.a);
+            f->timeline.push_back(TimelineEntry{(double)e.cls, (double)e.lane, (double)t0, (double)t0 + t, e.flops});
+        }
         f->cls_ms[e.cls] += t; f->cls_flops[e.cls] += e.flops; f->cls_launches[e.cls] += 1;
-        if (e.cls != PROF_SCHUR_DIAG) { f->prof_ms += t; f->prof_flops += e.flops; f->prof_launches += 1; }
+        if (e.cls != PROF_SCHUR_DIAG && e.cls != PROF_MISC) { f->prof_ms += t; f->prof_flops += e.flops; f->prof_launches += 1; }
         cudaEventDestroy(e.a); cudaEventDestroy(e.b);
     }
     f->prof.clear();
@@ -1117,6 +1297,17 @@ int eqvio_profile_read_class(eqvio_handle_t f, int cls, long long* launches, dou
     if (ms) *ms = f->cls_ms[cls];
     if (flops) *flops = f->cls_flops[cls];
     if (reset) { f->cls_launches[cls] = 0; f->cls_ms[cls] = 0; f->cls_flops[cls] = 0; }
+    return EQVIO_OK;
+}
+int eqvio_profile_timeline(eqvio_handle_t f, double* out, size_t cap_entries, size_t* count) {
+    if (!f || !count) return EQVIO_ERR_ARG;
+    int st = eqvio_profile_read(f, nullptr, nullptr, nullptr, 0);
+    if (st) return st;
+    *count = f->timeline.size();
+    if (out) {
+        const size_t k = std::min(cap_entries, f->timeline.size());
+        memcpy(out, f->timeline.data(), k * sizeof(TimelineEntry));
+    }
     return EQVIO_OK;
 }
 int eqvio_stream(eqvio_handle_t f, void** stream) {

@@ -35,6 +35,7 @@ __device__ __forceinline__ V3 load_q0(const Landmarks& L, int i) { return v3(L.q
 __global__ void k_step_prepare(BaseState* st, StepScratch* sc, ImuArgs a, RiccatiOut ro) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int sing = 0;
+    sc->stamp = a.stamp;
     V3 uo = v3(a.omega[0] - st->bias[0], a.omega[1] - st->bias[1], a.omega[2] - st->bias[2]);
     V3 ua = v3(a.accel[0] - st->bias[3], a.accel[1] - st->bias[4], a.accel[2] - st->bias[5]);
     if (a.do_init) {  // initialiseFromIMUData, VIOFilter.cpp:133-144
@@ -441,8 +442,8 @@ __device__ void qr_solve4(double A[4][4], double b[4], double x[4]) {
 // use_lift = 0 (useInnovationLift = false): VIOExp(liftInnovation(gamma, xi0)) EqFMatrices.cpp:35-48.
 // Then VIOFilter.cpp:295-296 and the pose record.
 __global__ void k_lift_solve(BaseState* st, StepScratch* sc, const double* gamma, const double* Aug,
-                             int lda, int p, const double* b4, int use_lift, int discrete, double stamp,
-                             double* Gamma_out, int apply) {
+                             int lda, int p, const double* b4, int use_lift, int discrete, double* Gamma_out,
+                             int apply) {
     const int tid = threadIdx.x;
     double G[4][5];
     if (use_lift && tid == 0)
@@ -489,7 +490,7 @@ __global__ void k_lift_solve(BaseState* st, StepScratch* sc, const double* gamma
     st->Xw = Dw + rotate(sc->DeltaA.R, st->Xw);                               // VIOGroup.cpp:96
     st->XA = sc->DeltaA * st->XA;                                             // VIOGroup.cpp:95
     const Se3 P = st->pose0 * st->XA;
-    st->pose_record[0] = stamp;
+    st->pose_record[0] = sc->stamp;  // written by k_step_prepare of this frame's integrateUpToTime
     st->pose_record[1] = P.x.x; st->pose_record[2] = P.x.y; st->pose_record[3] = P.x.z;
     st->pose_record[4] = P.R.w; st->pose_record[5] = P.R.x; st->pose_record[6] = P.R.y; st->pose_record[7] = P.R.z;
 }
@@ -780,6 +781,234 @@ __global__ void __launch_bounds__(512) k_getrf_diag_inv(const double* Ain, int l
 extern "C" int eqvio_debug_clocks(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_dbg_clk, sizeof(long long) * 16); }
 #endif
 
+// ------------------------------------------------------------------------------------------------
+// k_chain_block — the sequential link of the blocked Schur eliminations, one CTA of 16 warps per 64-wide
+// diagonal block.  Everything that is a product runs on DMMA.8x8x4 from shared memory; only the 64 pivots
+// themselves are scalar.
+//   prologue (block j > 0): D_j = A[j,j] - L[j,j-1] U[j-1,j]  (the look-ahead "corner": the trailing update of
+//             step j-1 skips this block, so the diagonal block never waits for that GEMM)
+//   LU:       eight 8-wide sub-steps: LU of the 8 x 8 diagonal block (one thread, registers), its two
+//             triangular inverses by substitution (16 threads), the 8-wide row / column panels as products
+//             with those inverses, rank-8 trailing update
+//   inverses: L^-1, U^-1 (64 x 64) by recursive doubling over the 8 x 8 diagonal inverses:
+//             X21 = -L22^-1 (L21 L11^-1),  X12 = -U11^-1 (U12 U22^-1)   for block sizes 8, 16, 32
+// Shared-memory matrices are column-major with leading dimension 68 (= 4 mod 16 doubles): every DMMA fragment
+// load (A: row g, k t;  B: k t, column g) hits 16 distinct 8-byte slots per half-warp, and the global <-> shared
+// copies are coalesced and conflict-free.
+// ------------------------------------------------------------------------------------------------
+constexpr int LDW = 68;
+constexpr int CHAIN_WARPS = 16;
+
+// Reciprocal to ~1 ulp without leaving the fp64 pipe: MUFU.RCP64H seed, one cubic and one quadratic Newton
+// step (the sequence nvcc's own division uses, minus its range fix-ups: pivots are variances, far from the
+// ends of the exponent range; a zero / non-finite pivot is caught by the caller's check).
+__device__ __forceinline__ double pivot_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+__device__ __forceinline__ void dmma_f64(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// One 8 x 8 output block by one warp:  C = (ACC ? C : 0) + sign * A (8 x K) B (K x 8); operands column-major in
+// shared memory with leading dimension LDW; A points at (row0, k = 0), B at (k = 0, col0), C at (row0, col0).
+// C may alias A or B (in-place panel products): every fragment is read before anything is written.
+template <int K, bool ACC>
+__device__ __forceinline__ void blk8(double* C, const double* A, const double* B, double sign, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double c0 = 0.0, c1 = 0.0;
+    if (ACC) { c0 = C[g + (2 * t) * LDW]; c1 = C[g + (2 * t + 1) * LDW]; }
+    double a[K / 4], b[K / 4];
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) { a[q] = sign * A[g + (4 * q + t) * LDW]; b[q] = B[(4 * q + t) + g * LDW]; }
+#pragma unroll
+    for (int q = 0; q < K / 4; ++q) dmma_f64(c0, c1, a[q], b[q]);
+    __syncwarp();
+    C[g + (2 * t) * LDW] = c0;
+    C[g + (2 * t + 1) * LDW] = c1;
+}
+
+// C (8 MB x 8 NB blocks) = (ACC ? C : 0) + sign * A B with the MB * NB (<= 64) output blocks dealt round-robin to
+// the 16 warps; all shapes are compile-time, so the block -> (row, column) maps cost nothing.
+template <int MB, int NB, int K, bool ACC>
+__device__ __forceinline__ void mm_smem(double* C, const double* A, const double* B, double sign, int warp, int lane) {
+    static_assert(MB * NB <= 4 * CHAIN_WARPS, "at most four blocks per warp");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int b = warp + CHAIN_WARPS * i;
+        if (i * CHAIN_WARPS < MB * NB && b < MB * NB) {
+            const int r0 = 8 * (b % MB), c0 = 8 * (b / MB);
+            blk8<K, ACC>(C + r0 + c0 * LDW, A + r0, B + c0 * LDW, sign, lane);
+        }
+    }
+}
+
+// Sub-step PB of the 64 x 64 LU: 8 x 8 diagonal LU + its triangular inverses (warp 0), 8-wide panels, rank-8 update.
+template <int PB>
+__device__ __forceinline__ void lu_substep(double* S, double* LI, double* UI, double* rp, int warp, int lane, int& bad) {
+    constexpr int c0 = 8 * PB, REM = 7 - PB;   // REM: 8-blocks right of / below the diagonal block
+    double* Sd = S + c0 + c0 * LDW;
+    if (warp == 0) {
+        // LU of the diagonal block: lane r (< 8; the other lanes mirror) keeps row r in registers, the pivot row
+        // travels by shuffle, every lane forms the pivot reciprocal itself
+        const int r = lane & 7;
+        double a[8], rk[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[c] = Sd[r + c * LDW];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double piv = __shfl_sync(0xffffffffu, a[k], k);
+            bad |= !(fabs(piv) > 0.0);
+            rk[k] = pivot_rcp(piv);
+            const double l = (r > k) ? a[k] * rk[k] : 0.0;
+#pragma unroll
+            for (int c = k + 1; c < 8; ++c) {
+                const double u = __shfl_sync(0xffffffffu, a[c], k);
+                a[c] = fma(-l, u, a[c]);
+            }
+            if (r > k) a[k] = l;
+        }
+        if (lane < 8) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) Sd[r + c * LDW] = a[c];
+        }
+        __syncwarp();
+        // both triangular inverses by one substitution code path: lanes 0..7 column `cc` of L8^-1 (unit lower,
+        // forward), lanes 8..15 column of U8^-1 on the index-reversed block (upper -> lower, diagonal 1 / pivot)
+        if (lane < 16) {
+            const bool up = lane >= 8;
+            const int cc = lane & 7;
+            double x[8], sacc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sacc[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double d = up ? rk[7 - i] : 1.0;
+                x[i] = (i < cc) ? 0.0 : (i == cc ? d : -(d * sacc[i]));
+#pragma unroll
+                for (int q = i + 1; q < 8; ++q) {
+                    const double mqi = up ? Sd[(7 - q) + (7 - i) * LDW] : Sd[q + i * LDW];
+                    sacc[q] = fma(mqi, x[i], sacc[q]);
+                }
+            }
+            double* XI = up ? UI : LI;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int ri = up ? 7 - i : i, ci = up ? 7 - cc : cc;
+                XI[(c0 + ri) + (c0 + ci) * LDW] = x[i];
+            }
+        }
+    }
+    (void)rp;
+    __syncthreads();
+    if (REM > 0) {
+        // panels, in place: L[c0+8.., c0..c0+8) = A U8^-1 (warps 0..REM-1), U[c0..c0+8, c0+8..) = L8^-1 A (warps 8..8+REM-1)
+        if (warp < REM) {
+            double* blk = S + (c0 + 8 + 8 * warp) + c0 * LDW;
+            blk8<8, false>(blk, blk, UI + c0 + c0 * LDW, 1.0, lane);
+        } else if (warp >= 8 && warp < 8 + REM) {
+            double* blk = S + c0 + (c0 + 8 + 8 * (warp - 8)) * LDW;
+            blk8<8, false>(blk, LI + c0 + c0 * LDW, blk, 1.0, lane);
+        }
+        __syncthreads();
+        mm_smem<(REM > 0 ? REM : 1), (REM > 0 ? REM : 1), 8, true>(S + (c0 + 8) + (c0 + 8) * LDW, S + (c0 + 8) + c0 * LDW,
+                                                                  S + c0 + (c0 + 8) * LDW, -1.0, warp, lane);
+        __syncthreads();
+    }
+}
+
+// One level of the recursive doubling for L^-1 and U^-1: diagonal blocks of size SZ are inverted, the blocks that
+// couple consecutive pairs follow as  X21 = -L22^-1 (L21 L11^-1),  X12 = -U11^-1 (U12 U22^-1).
+template <int SZ>
+__device__ __forceinline__ void inv_level(const double* S, double* LI, double* UI, double* TMP, int warp, int lane) {
+    constexpr int SB = SZ / 8, PER = SB * SB, NBLK = (64 / (2 * SZ)) * 2 * PER;   // 8, 16, 32 output blocks
+#pragma unroll
+    for (int phase = 0; phase < 2; ++phase) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int b = warp + CHAIN_WARPS * i;
+            if (i * CHAIN_WARPS < NBLK && b < NBLK) {
+                const int pair = b / (2 * PER), rm = b % (2 * PER), isU = rm / PER, bb = rm % PER, bi = bb % SB, bj = bb / SB;
+                const int o = 2 * SZ * pair;
+                // L: rows [o+SZ, o+2SZ), cols [o, o+SZ);  U: rows [o, o+SZ), cols [o+SZ, o+2SZ)
+                const int R0 = (isU ? o : o + SZ) + 8 * bi, C0 = (isU ? o + SZ : o) + 8 * bj;
+                if (phase == 0) {      // TMP = L21 L11^-1   |   TMP = U12 U22^-1
+                    blk8<SZ, false>(TMP + R0 + C0 * LDW, S + R0 + (isU ? o + SZ : o) * LDW,
+                                    (isU ? UI + (o + SZ) : LI + o) + C0 * LDW, 1.0, lane);
+                } else {               // X21 = -L22^-1 TMP  |   X12 = -U11^-1 TMP
+                    blk8<SZ, false>((isU ? UI : LI) + R0 + C0 * LDW, isU ? UI + R0 + o * LDW : LI + R0 + (o + SZ) * LDW,
+                                    TMP + (isU ? o : o + SZ) + C0 * LDW, -1.0, lane);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(512) k_chain_block(double* A, int lda, int j, int nb, int prev_nb, const double* Din, int ldin,
+                                                     double* LUout, int ldout, double* Linv, double* Uinv, int* flags) {
+    extern __shared__ double sm_ch[];
+    double* S = sm_ch;                  // work matrix -> L (strictly lower, multipliers) and U
+    double* LI = sm_ch + 64 * LDW;      // L^-1 (prologue: the L panel block)
+    double* UI = sm_ch + 2 * 64 * LDW;  // U^-1 (prologue: the U panel block)
+    double* TMP = sm_ch + 3 * 64 * LDW;
+    double* rp = sm_ch + 4 * 64 * LDW;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    DBG_CLK(0);
+    // ---- load: the diagonal block (identity-padded to 64), and for j > 0 the two panel blocks next to it ----
+    const double* D = Din ? Din : A + j + (size_t)lda * j;
+    const int ldd = Din ? ldin : lda;
+    for (int idx = tid; idx < 64 * 64; idx += 512) {
+        const int r = idx & 63, c = idx >> 6;
+        S[r + c * LDW] = (r < nb && c < nb) ? D[r + (size_t)ldd * c] : (r == c ? 1.0 : 0.0);
+        if (prev_nb > 0) {
+            // L[j, j-1] (nb x prev_nb) sits left of the block, U[j-1, j] (prev_nb x nb) above it
+            LI[r + c * LDW] = (r < nb && c < prev_nb) ? A[(j + r) + (size_t)lda * (j - prev_nb + c)] : 0.0;
+            UI[r + c * LDW] = (r < prev_nb && c < nb) ? A[(j - prev_nb + r) + (size_t)lda * (j + c)] : 0.0;
+        }
+    }
+    __syncthreads();
+    if (prev_nb > 0) {
+        mm_smem<8, 8, 64, true>(S, LI, UI, -1.0, warp, lane);
+        __syncthreads();
+    }
+    for (int idx = tid; idx < 64 * 64; idx += 512) {
+        const int r = idx & 63, c = idx >> 6;
+        LI[r + c * LDW] = 0.0;
+        UI[r + c * LDW] = 0.0;
+    }
+    __syncthreads();
+    DBG_CLK(1);
+    int bad = 0;
+    lu_substep<0>(S, LI, UI, rp, warp, lane, bad);
+    lu_substep<1>(S, LI, UI, rp, warp, lane, bad);
+    lu_substep<2>(S, LI, UI, rp, warp, lane, bad);
+    lu_substep<3>(S, LI, UI, rp, warp, lane, bad);
+    lu_substep<4>(S, LI, UI, rp, warp, lane, bad);
+    lu_substep<5>(S, LI, UI, rp, warp, lane, bad);
+    lu_substep<6>(S, LI, UI, rp, warp, lane, bad);
+    lu_substep<7>(S, LI, UI, rp, warp, lane, bad);
+    if (bad && tid == 0) atomicOr(flags, FLAG_NOT_SPD);
+    DBG_CLK(2);
+    inv_level<8>(S, LI, UI, TMP, warp, lane);
+    inv_level<16>(S, LI, UI, TMP, warp, lane);
+    inv_level<32>(S, LI, UI, TMP, warp, lane);
+    DBG_CLK(3);
+    for (int idx = tid; idx < 64 * 64; idx += 512) {
+        const int r = idx & 63, c = idx >> 6;
+        Linv[r + 64 * c] = LI[r + c * LDW];
+        Uinv[r + 64 * c] = UI[r + c * LDW];
+        if (LUout != nullptr && r < nb && c < nb) LUout[r + (size_t)ldout * c] = S[r + c * LDW];
+    }
+    DBG_CLK(4);
+}
+
 // Everything of the Schur problem except the leading k x k block A and (when !identity_border) the
 // border entries written elsewhere.  Layout: A in [0,k)^2, identity padding on [k,kpad), border rows /
 // columns at offset kpad:  [[A, 0, Cc], [0, I, 0], [R, 0, 0]].  identity_border: R = Cc = I (k x k).
@@ -931,8 +1160,8 @@ void launch_lift_fwdsub(cudaStream_t s, const double* Aug, int lda, int pb, cons
     k_lift_fwdsub<<<1, 1024, 0, s>>>(Aug, lda, pb, LinvBlocks, yo, b4);
 }
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
-                       const double* b4, int use_lift, int discrete, double stamp, double* Gamma_out, int apply) {
-    k_lift_solve<<<1, 32, 0, s>>>(st, sc, gamma, Aug, lda, p, b4, use_lift, discrete, stamp, Gamma_out, apply);
+                       const double* b4, int use_lift, int discrete, double* Gamma_out, int apply) {
+    k_lift_solve<<<1, 32, 0, s>>>(st, sc, gamma, Aug, lda, p, b4, use_lift, discrete, Gamma_out, apply);
 }
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete) {
     if (N > 0) k_lift_apply<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, gamma, discrete);
@@ -947,6 +1176,18 @@ cudaError_t launch_getrf_diag_inv(cudaStream_t s, const double* Ain, int ldin, d
         attr_set = true;
     }
     k_getrf_diag_inv<<<1, 512, smem, s>>>(Ain, ldin, Aout, ldout, nb, Linv, Uinv, flags);
+    return cudaGetLastError();
+}
+cudaError_t launch_chain_block(cudaStream_t s, double* A, int lda, int j, int nb, int prev_nb, const double* Din, int ldin,
+                               double* LUout, int ldout, double* Linv, double* Uinv, int* flags) {
+    static bool attr_done = false;
+    const int smem = (4 * 64 * LDW + 16) * (int)sizeof(double);
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_chain_block, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    k_chain_block<<<1, 512, smem, s>>>(A, lda, j, nb, prev_nb, Din, ldin, LUout, ldout, Linv, Uinv, flags);
     return cudaGetLastError();
 }
 void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border) {

@@ -40,7 +40,8 @@ struct StepScratch {
     M3 RT_IC;      // R_IC^-1 as a matrix                  (EqFMatrices.cpp:371)
     M3 RT_IC_sx;   // R_IC^-1 [x_IC]x                      (EqFMatrices.cpp:376)
     V3 vC;         // camera-frame linear velocity, mean omega (EqFMatrices.cpp:302-304)
-    double T;      // accumulated time of this Riccati step
+    double T;      // accumulated time of this Riccati step (also read by the Riccati GEMM epilogue)
+    double stamp;  // stamp of the step being processed (pose record of the vision update)
     double Rd[6];
     // state propagate
     Se3 camInv;    // SE3Exp(-dt U_C)                      (VIOGroup.cpp:229-230)

@@ -179,6 +179,15 @@ class VIOFilter:
         abi.check(self._L.eqvio_launch_count(self._h, C.byref(c), int(reset)), "eqvio_launch_count")
         return c.value
 
+    def set_graphs(self, on=True):
+        abi.check(self._L.eqvio_set_graphs(self._h, int(on)), "eqvio_set_graphs")
+
+    def graph_stats(self):
+        """(graph replays so far, instantiated graphs held)."""
+        n, c = C.c_longlong(), C.c_int()
+        abi.check(self._L.eqvio_graph_stats(self._h, C.byref(n), C.byref(c)), "eqvio_graph_stats")
+        return n.value, c.value
+
     def profile_enable(self, on=True):
         abi.check(self._L.eqvio_profile_enable(self._h, int(on)), "eqvio_profile_enable")
 
@@ -188,7 +197,17 @@ class VIOFilter:
         abi.check(self._L.eqvio_profile_read(self._h, C.byref(n), C.byref(ms), C.byref(fl), int(reset)), "eqvio_profile_read")
         return n.value, ms.value, fl.value
 
-    PROFILE_CLASSES = ("riccati_gemm", "update_gemm", "schur_gemm", "schur_diag_lu")
+    PROFILE_CLASSES = ("riccati_gemm", "update_gemm", "schur_gemm", "schur_diag_lu", "small_kernels")
+    PROFILE_LANES = ("main", "side", "lift", "main_helper", "lift_helper", "other")
+
+    def profile_timeline(self) -> np.ndarray:
+        """(k, 5) array: class, stream lane, start ms, end ms, flops of every bracketed launch since profile_enable."""
+        cnt = C.c_size_t()
+        abi.check(self._L.eqvio_profile_timeline(self._h, None, 0, C.byref(cnt)), "eqvio_profile_timeline")
+        out = np.zeros((cnt.value, 5))
+        if cnt.value:
+            abi.check(self._L.eqvio_profile_timeline(self._h, _p(out), cnt.value, C.byref(cnt)), "eqvio_profile_timeline")
+        return out
 
     def profile_read_classes(self, reset=True) -> dict:
         out = {}
@@ -203,6 +222,19 @@ class VIOFilter:
         p = C.c_void_p()
         abi.check(self._L.eqvio_stream(self._h, C.byref(p)), "eqvio_stream")
         return p.value or 0
+
+
+def getrf_block(A, device=0, reps=1):
+    """Unpivoted LU of an nb x nb block (nb <= 64) and the 64 x 64 identity-padded triangular inverses on the
+    library's diagonal-block kernel.  Returns (LU, Linv, Uinv, microseconds per launch)."""
+    L = abi.lib()
+    A = np.asfortranarray(A, dtype=np.float64)
+    nb = A.shape[0]
+    LU = np.zeros((nb, nb), order="F")
+    Li, Ui = np.zeros((64, 64), order="F"), np.zeros((64, 64), order="F")
+    us = C.c_float()
+    abi.check(L.eqvio_getrf_block(int(device), nb, _p(A), nb, _p(LU), _p(Li), _p(Ui), int(reps), C.byref(us)), "eqvio_getrf_block")
+    return LU, Li, Ui, us.value
 
 
 def dgemm(A, B, transB=False, alpha=1.0, beta=0.0, Cin=None, device=0, reps=1):

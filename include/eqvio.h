@@ -169,11 +169,26 @@ int eqvio_bundle_lift(eqvio_handle_t h, const double* gamma_eqf, double* Gamma);
 int eqvio_dgemm(int device, int transB, int M, int N, int K, double alpha, const double* A, int lda,
                 const double* B, int ldb, double beta, double* C, int ldc, int reps, float* ms);
 
+/* One diagonal block of the blocked Schur eliminations that stand in for `S.inverse()` (VIOFilter.cpp:277)
+ * and `Sigma.inverse()` (EqFMatrices.cpp:239): unpivoted LU of the nb x nb block A (nb <= 64, col-major,
+ * host) and the triangular inverses L^-1, U^-1 as 64 x 64 identity-padded col-major matrices.  LU (nb x nb,
+ * ld = nb: unit-lower multipliers below the diagonal, U on and above), Linv, Uinv may be NULL.
+ * `reps` > 1 repeats the launch and *us receives the mean CUDA-event time per launch in microseconds. */
+int eqvio_getrf_block(int device, int nb, const double* A, int lda, double* LU, double* Linv, double* Uinv,
+                      int reps, float* us);
+
 /* ---- instrumentation ----------------------------------------------------------------------- */
 
 int eqvio_synchronize(eqvio_handle_t h);
 /* Number of kernel launches issued by this handle since creation / last reset of the counter. */
 int eqvio_launch_count(eqvio_handle_t h, long long* count, int reset);
+/* CUDA graphs: the launch sequence of a vision update (and of the Riccati step behind k_step_prepare) depends
+ * only on the landmark count, on which of the two Sigma buffers is current and on mode flags; the second time
+ * such a key is seen the sequence is stream-captured and from then on replayed with one cudaGraphLaunch.
+ * eqvio_set_graphs(h, 0) issues every launch directly (also: environment EQVIO_GRAPHS=0 at eqvio_create);
+ * eqvio_graph_stats reports graph replays so far and instantiated graphs held. */
+int eqvio_set_graphs(eqvio_handle_t h, int on);
+int eqvio_graph_stats(eqvio_handle_t h, long long* graph_launches, int* cached_graphs);
 /* When enabled, every Sigma-contraction (GEMM) launch is bracketed by CUDA events on the handle's
  * stream; eqvio_profile_read synchronises and returns launches, total ms and executed flops. */
 int eqvio_profile_enable(eqvio_handle_t h, int on);
@@ -183,6 +198,11 @@ int eqvio_profile_read(eqvio_handle_t h, long long* gemm_launches, double* gemm_
  * K, K C, Sigma - K C Sigma), 2 = GEMMs inside the blocked Schur eliminations (S^-1, Sigma_sub^-1),
  * 3 = the diagonal-block LU kernels of those eliminations (flops reported as 0). */
 int eqvio_profile_read_class(eqvio_handle_t h, int cls, long long* launches, double* ms, double* flops, int reset);
+/* Timeline of every bracketed launch since profiling was enabled: 5 doubles per entry — class (0-3 as
+ * above, 4 = the O(N) / O(n m) kernels), stream lane (0 main, 1 side, 2 lift chain, 3 / 4 the chains' helper
+ * streams), start ms, end ms (relative to eqvio_profile_enable), flops.  *count receives the number of
+ * entries available; at most cap_entries are copied to out (may be NULL). */
+int eqvio_profile_timeline(eqvio_handle_t h, double* out, size_t cap_entries, size_t* count);
 /* The handle's CUDA stream (cudaStream_t as void*), for callers that order their own work after it. */
 int eqvio_stream(eqvio_handle_t h, void** stream);
 const char* eqvio_status_string(int status);

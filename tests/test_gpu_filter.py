@@ -282,3 +282,44 @@ def test_full_size_properties_N512():
     assert np.isfinite(S3).all() and rel(S3, S3.T) < 1e-9
     assert np.trace(S3) < tr0
     assert np.min(np.diag(S3)) > 0
+
+
+@pytest.mark.parametrize("fast", [0, 1], ids=["riccati_every_tick", "fastRiccati"])
+def test_graph_replay_is_bit_identical(fast):
+    """The CUDA-graph replay of the update / Riccati launch sequences (eqvio_set_graphs) runs the same kernels on
+    the same data as direct launches: Sigma and the state must agree bit for bit, and the graph path must be taken."""
+    from eqf_vio_b200.settings import conditioned_settings
+
+    s = conditioned_settings(outlierThreshold=1e9, fastRiccati=fast)
+    seq = period_sequence(40, 7, camera_offset=tuple(s.cameraOffset))
+    a, b = gpu_filter(s), gpu_filter(s)
+    b.set_graphs(False)
+    for kind, i in seq.events():
+        feed(a, seq, kind, i)
+        feed(b, seq, kind, i)
+    replays, held = a.graph_stats()
+    assert replays > 0 and held >= 2, (replays, held)   # both Sigma-buffer parities of the update were captured
+    assert b.graph_stats()[0] == 0
+    assert np.array_equal(a.get_snapshot(), b.get_snapshot())
+    assert a.launch_count() == b.launch_count()
+
+
+def test_graph_cache_follows_landmark_churn():
+    """Landmark count changes every frame (features dropped and re-added): keys change, graphs are only built for
+    keys seen twice, results stay those of the direct path."""
+    from eqf_vio_b200.settings import conditioned_settings
+
+    s = conditioned_settings(outlierThreshold=1e9)
+    seq = period_sequence(24, 8, camera_offset=tuple(s.cameraOffset))
+    a, b = gpu_filter(s), gpu_filter(s)
+    b.set_graphs(False)
+    for kind, i in seq.events():
+        sel = None
+        if kind == "vision":
+            keep = np.ones(24, dtype=bool)
+            keep[(3 * i) % 24] = False          # a different feature missing in each frame
+            keep[(7 * i + 1) % 24] = i % 3 != 0
+            sel = np.nonzero(keep)[0]
+        feed(a, seq, kind, i, sel=sel)
+        feed(b, seq, kind, i, sel=sel)
+    assert np.array_equal(a.get_snapshot(), b.get_snapshot())
