@@ -52,6 +52,8 @@ struct CachedGraph { GraphKey key; cudaGraphExec_t exec; long long launches; lon
 struct eqvio_filter {
     int device = 0;
     bool use_graphs = true;            // EQVIO_GRAPHS=0 disables
+    int trail_delay = 2;               // EQVIO_TRAIL_DELAY: empty kernels in front of each trailing update (see schur_lu)
+    unsigned long long* stamps = nullptr;   // EQVIO_STAMPS=1: %globaltimer marks inside the update (64 slots)
     std::vector<CachedGraph> graphs;
     long long graph_clock = 0, graph_launches = 0;
     cudaStream_t stream = nullptr;
@@ -76,7 +78,8 @@ struct eqvio_filter {
     StepScratch* sc = nullptr;
     double *Linv = nullptr, *Uinv = nullptr;  // 64 x 64 triangular inverses of the current pivot block (S chain)
     double *LinvL = nullptr, *UinvL = nullptr;  // lift chain: every block's L_jj^-1 is kept (forward substitution), U_jj^-1 scratch
-    double *yo = nullptr, *b4 = nullptr;       // D obs (p) and M^T W obs (4)
+    double *yo = nullptr, *Rt = nullptr;       // D obs (p) and Ym^T Sigma_sub^-1 (4 x pb, row-major)
+    int* wave = nullptr;                        // per-block ready flags of k_lift_rsolve
     Landmarks L{nullptr, 0}, L2{nullptr, 0};
     double *Sigma = nullptr, *Sigma2 = nullptr, *F = nullptr, *W = nullptr, *Bb = nullptr, *Aug = nullptr;
     double *C = nullptr, *CS = nullptr, *SCt = nullptr, *K = nullptr, *Saug = nullptr, *Sinv = nullptr;
@@ -189,8 +192,8 @@ static void free_device(Filter* f) {
     cudaFree(f->Sigma); cudaFree(f->Sigma2); cudaFree(f->F); cudaFree(f->W); cudaFree(f->Bb); cudaFree(f->Aug);
     cudaFree(f->C); cudaFree(f->CS); cudaFree(f->SCt); cudaFree(f->K); cudaFree(f->Saug); cudaFree(f->Sinv);
     cudaFree(f->delta); cudaFree(f->gamma); cudaFree(f->y_in); cudaFree(f->y); cudaFree(f->scratch); cudaFree(f->Gamma);
-    cudaFree(f->d_flags); cudaFree(f->d_map); cudaFree(f->LinvL); cudaFree(f->yo);
-    f->LinvL = f->yo = nullptr;
+    cudaFree(f->d_flags); cudaFree(f->d_map); cudaFree(f->LinvL); cudaFree(f->yo); cudaFree(f->Rt); cudaFree(f->wave);
+    f->LinvL = f->yo = f->Rt = nullptr; f->wave = nullptr;
     f->L.base = f->L2.base = nullptr;
     f->Sigma = f->Sigma2 = f->F = f->W = f->Bb = f->Aug = f->C = f->CS = f->SCt = f->K = f->Saug = f->Sinv = nullptr;
     f->delta = f->gamma = f->y_in = f->y = f->scratch = f->Gamma = nullptr;
@@ -212,7 +215,10 @@ static int ensure_capacity(Filter* f, int needN) {
     Landmarks L{nullptr, cap}, L2{nullptr, cap};
     double *Sigma, *Sigma2, *F, *W, *Bb, *Aug, *C, *CS, *SCt, *K, *Saug, *Sinv, *delta, *gamma, *y_in, *y, *scratch, *Gamma;
     int *d_flags, *d_map;
-    double *LinvL, *yo;
+    double *LinvL, *yo, *Rt;
+    int* wave;
+    CU_TRY(dalloc(&Rt, (size_t)4 * (ld + 64) + 64));
+    CU_TRY(dalloc(&wave, (size_t)ld / 64 + 8));
     CU_TRY(dalloc(&LinvL, (size_t)(ld / 64 + 2) * 4096 + 1024));
     CU_TRY(dalloc(&yo, (size_t)ld + 64));
     CU_TRY(dalloc(&L.base, (size_t)LM_FIELDS * cap));
@@ -249,7 +255,7 @@ static int ensure_capacity(Filter* f, int needN) {
     f->C = C; f->CS = CS; f->SCt = SCt; f->K = K; f->Saug = Saug; f->Sinv = Sinv;
     f->delta = delta; f->gamma = gamma; f->y_in = y_in; f->y = y; f->scratch = scratch; f->Gamma = Gamma;
     f->d_flags = d_flags; f->d_map = d_map;
-    f->LinvL = LinvL; f->yo = yo;
+    f->LinvL = LinvL; f->yo = yo; f->Rt = Rt; f->wave = wave;
     f->layoutN = -1;
     // pinned staging sized for the capacity
     size_t need_d = (size_t)LM_FIELDS * cap + 3 * (size_t)cap + 256, need_i = (size_t)ld + cap + 64;
@@ -301,6 +307,11 @@ static void prof_end(Filter* f, ProfEvent& pe, cudaStream_t s) {
     f->prof.push_back(pe);
 }
 
+enum { ST_BEGIN = 0, ST_LIFT_SETUP, ST_LIFT_CHAIN, ST_LIFT_RSOLVE, ST_C_DELTA, ST_S_FORMED, ST_S_CHAIN, ST_K, ST_GAMMA,
+       ST_SIDE1_DONE, ST_LIFT_JOIN, ST_LIFT_FEATURES, ST_LIFT_APPLIED, ST_SIDE2_DONE, ST_END, ST_COUNT };
+static void stamp(Filter* f, cudaStream_t s, int idx) {
+    if (f->stamps) { launch_stamp(s, f->stamps + idx); f->launches += 1; }
+}
 struct ProfScope {  // brackets the launches of a block: { ProfScope ps(f, stream, cls); launch...; }
     Filter* f; cudaStream_t s; ProfEvent pe;
     ProfScope(Filter* f_, cudaStream_t s_, int cls) : f(f_), s(s_) { prof_begin(f, pe, s, cls, 0.0); }
@@ -373,6 +384,8 @@ static int schur_lu(Filter* f, const SchurChain& ch, double* Aug, int lda, int k
             CU_TRY(launch_chain_block(ch.s, Aug, lda, j, nb, j > 0 ? 64 : 0, nullptr, 0, nullptr, 0, Linv, Uinv, &f->st->flags));
         }
         f->launches += 1;
+        const int sbase = (ch.keep_linv ? 32 : 272) + 3 * (j / 64);   // debug stamps: chain kernel / column panel / trailing update
+        if (sbase + 2 < 512) stamp(f, ch.s, sbase);
         double* Lp = Aug + (j + nb) + (size_t)lda * j;         // rows x nb, below the diagonal block
         double* Up = Aug + j + (size_t)lda * (j + nb);         // nb x cols, right of it
         double* T22 = Aug + (j + nb) + (size_t)lda * (j + nb);
@@ -387,12 +400,19 @@ static int schur_lu(Filter* f, const SchurChain& ch, double* Aug, int lda, int k
         CU_TRY(cudaEventRecord(ch.ev_b, ch.h));
         f->cur = ch.s;
         if ((st = gemm(f, 0, rows, nb, nb, 1.0, Lp, lda, Uinv, 64, 0.0, nullptr, 0, Lp, lda, 0, 0.0, 2))) return st;   // X U = B
+        if (sbase + 2 < 512) stamp(f, ch.s, sbase + 1);
         // trailing update on the helper stream; the next diagonal block is the next chain kernel's
         CU_TRY(cudaEventRecord(ch.ev_a, ch.s));
         CU_TRY(cudaStreamWaitEvent(ch.h, ch.ev_a, 0));
         const int nb2 = std::min(64, k - (j + nb));
         f->cur = ch.h;
+        // The next chain kernel and this trailing update become ready together.  If the update's CTAs are dispatched
+        // first they fill every SM and the chain kernel (one CTA, 139 KB of shared memory) waits for the whole GEMM to
+        // drain; a couple of empty kernels in front of the update let the chain kernel get its SM first.
+        if (nb2 > 0)
+            for (int d = 0; d < f->trail_delay; ++d) { launch_nop(ch.h); f->launches += 1; }
         if ((st = gemm(f, 0, rows, cols, nb, -1.0, Lp, lda, Up, lda, 1.0, T22, lda, T22, lda, 0, 0.0, -1, std::max(nb2, 0)))) return st;
+        if (sbase + 2 < 512) stamp(f, ch.h, sbase + 2);
         CU_TRY(cudaEventRecord(ch.ev_t, ch.h));
         f->cur = ch.s;
     }
@@ -499,10 +519,11 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     int st;
     cudaStream_t s = f->stream;
     const bool lift_chain = do_lift && f->s.useInnovationLift;
+    stamp(f, s, ST_BEGIN);
     if (lift_chain) {
         // bundleLift's elimination of Sigma_sub (the PRIOR Sigma block, :285 precedes :297) does not depend on
         // the innovation except through one border column, so it runs on its own stream while the main stream
-        // goes through S, S^-1, K and gamma; the gamma-dependent column is folded in afterwards (k_lift_fwdsub).
+        // goes through S, S^-1, K and gamma; the gamma-independent factor Ym^T Sigma_sub^-1 follows it there (k_lift_rsolve).
         CU_TRY(cudaEventRecord(f->ev_lift_fork, s));
         CU_TRY(cudaStreamWaitEvent(f->lift, f->ev_lift_fork, 0));
         {
@@ -513,7 +534,15 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
             launch_lift_features(f->lift, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
         }
         f->launches += 4;
+        stamp(f, f->lift, ST_LIFT_SETUP);
         if ((st = schur_lu(f, SchurChain{f->lift, f->lift_h, f->ev_la, f->ev_lb, f->ev_lt, f->LinvL, f->UinvL, true}, f->Aug, ld, pb, 4, 4))) return st;
+        stamp(f, f->lift, ST_LIFT_CHAIN);
+        {
+            ProfScope ps(f, f->lift, PROF_MISC);
+            launch_lift_rsolve(f->lift, f->Aug, ld, pb, f->LinvL, f->Rt, f->wave);
+        }
+        f->launches += 1;
+        stamp(f, f->lift, ST_LIFT_RSOLVE);
         CU_TRY(cudaEventRecord(f->ev_lift_done, f->lift));
     }
     {
@@ -521,6 +550,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
         launch_build_C_delta(s, f->st, f->L, N, f->y, f->C, ldm, f->delta);
     }
     f->launches += 1;
+    stamp(f, s, ST_C_DELTA);
     // S = (C Sigma) C^T + Q                                        VIOFilter.cpp:276
     if ((st = gemm(f, 0, m, n, n, 1.0, f->C, ldm, f->Sigma, ld, 0.0, nullptr, 0, f->CS, ldm))) return st;
     if ((st = gemm(f, 1, m, m, n, 1.0, f->CS, ldm, f->C, ldm, 0.0, nullptr, 0, f->Saug, f->ld2m))) return st;
@@ -535,20 +565,25 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
         launch_schur_setup(s, f->Saug, f->ld2m, m, mp, m, m, 1);
     }
     f->launches += 2;
+    stamp(f, s, ST_S_FORMED);
     // Sigma C^T does not depend on S^-1: it runs on the side stream under the (latency-bound) elimination
     if ((st = fork_side(f))) return st;
     if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
+    stamp(f, f->side, ST_SIDE1_DONE);
     if ((st = end_side(f))) return st;
     if ((st = schur_lu(f, SchurChain{f->stream, f->main_h, f->ev_sa, f->ev_sb, f->ev_st, f->Linv, f->Uinv, false}, f->Saug, f->ld2m, mp, m, m))) return st;
     const double* negSinv = f->Saug + mp + (size_t)f->ld2m * mp;
+    stamp(f, s, ST_S_CHAIN);
     if ((st = join_side(f))) return st;
     // K = (Sigma C^T) S^-1                                           :277
     if ((st = gemm(f, 0, n, m, m, -1.0, f->SCt, ld, negSinv, f->ld2m, 0.0, nullptr, 0, f->K, ld))) return st;
+    stamp(f, s, ST_K);
     {
         ProfScope ps(f, s, PROF_MISC);
         launch_gemv(s, f->K, ld, n, m, f->delta, f->gamma);  // :279
     }
     f->launches += 1;
+    stamp(f, s, ST_GAMMA);
     // Sigma <- Sigma - (K C) Sigma (:297) reads the PRIOR Sigma, K and C and writes the twin buffer; the lift
     // (:285-296) reads the prior Sigma and gamma and writes X.  Independent: the two GEMMs go to the side
     // stream and run under the lift's Schur elimination.
@@ -556,6 +591,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
         if ((st = fork_side(f))) return st;
         if ((st = gemm(f, 0, n, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, f->W, ld))) return st;
         if ((st = gemm(f, 0, n, n, n, -1.0, f->W, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld))) return st;
+        stamp(f, f->side, ST_SIDE2_DONE);
         if ((st = end_side(f))) return st;
         // W's columns [0, n) now hold K C; the Riccati step rewrites them (W = F Sigma) before use.
     }
@@ -563,22 +599,25 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
         const int use_lift = f->s.useInnovationLift, discrete = f->s.useDiscreteInnovationLift;
         if (use_lift) {
             CU_TRY(cudaStreamWaitEvent(s, f->ev_lift_done, 0));
+            stamp(f, s, ST_LIFT_JOIN);
             {
                 ProfScope ps(f, s, PROF_MISC);
                 launch_lift_prepare(s, f->st, f->sc, f->gamma);
                 launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb, f->yo);
-                launch_lift_fwdsub(s, f->Aug, ld, pb, f->LinvL, f->yo, f->b4);
             }
-            f->launches += 3;
+            f->launches += 2;
+            stamp(f, s, ST_LIFT_FEATURES);
         }
         {
             ProfScope ps(f, s, PROF_MISC);
-            launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->b4, use_lift, discrete, nullptr, 1);
+            launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->Rt, f->yo, use_lift, discrete, nullptr, 1);
             launch_lift_apply(s, f->st, f->L, N, f->gamma, use_lift ? discrete : 0);
         }
         f->launches += 2;
+        stamp(f, s, ST_LIFT_APPLIED);
     }
     if (do_sigma && (st = join_side(f))) return st;
+    stamp(f, s, ST_END);
     return EQVIO_OK;
 }
 
@@ -677,6 +716,9 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     }
     f->cur = f->stream;
     if (const char* e = getenv("EQVIO_GRAPHS")) f->use_graphs = !(e[0] == '0');
+    if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
+    if (const char* e = getenv("EQVIO_STAMPS"))
+        if (e[0] == '1') { CU_TRY(dalloc(&f->stamps, 512)); CU_TRY(cudaMemset(f->stamps, 0, 512 * 8)); }
     CU_TRY(cudaEventCreateWithFlags(&f->ev_fork, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&f->ev_join, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&f->stage_free, cudaEventDisableTiming));
@@ -687,7 +729,6 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     CU_TRY(dalloc(&f->Uinv, 64 * 80));
     CU_TRY(dalloc(&f->UinvL, 64 * 80));
     CU_TRY(cudaMemset(f->UinvL, 0, 64 * 80 * 8));
-    CU_TRY(dalloc(&f->b4, 8));
     CU_TRY(cudaMemset(f->Linv, 0, 64 * 80 * 8));
     CU_TRY(cudaMemset(f->Uinv, 0, 64 * 80 * 8));
     int st = ensure_capacity(f, 64);
@@ -710,7 +751,8 @@ int eqvio_destroy(eqvio_handle_t f) {
     if (f->prof_base) cudaEventDestroy(f->prof_base);
     drop_graphs(f);
     free_device(f);
-    cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL); cudaFree(f->b4);
+    cudaFree(f->stamps);
+    cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
     cudaEventDestroy(f->stage_free);
@@ -1134,12 +1176,11 @@ int eqvio_bundle_lift(eqvio_handle_t f, const double* gamma_eqf, double* Gamma) 
     f->launches += 4;
     int st = schur_lu(f, SchurChain{s, f->main_h, f->ev_sa, f->ev_sb, f->ev_st, f->LinvL, f->UinvL, true}, f->Aug, ld, pb, 4, 4);
     if (st) return st;
+    launch_lift_rsolve(s, f->Aug, ld, pb, f->LinvL, f->Rt, f->wave);
     launch_lift_prepare(s, f->st, f->sc, f->gamma);
     launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb, f->yo);
-    launch_lift_fwdsub(s, f->Aug, ld, pb, f->LinvL, f->yo, f->b4);
-    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->b4, 1, 1, f->Gamma, 0);
-    f->launches += 3;
-    f->launches += 1;
+    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->Rt, f->yo, 1, 1, f->Gamma, 0);
+    f->launches += 4;
     CU_TRY(cudaStreamSynchronize(s));
     CU_TRY(cudaMemcpy(Gamma, f->Gamma, 48, cudaMemcpyDeviceToHost));
     memcpy(Gamma + 6, gamma_eqf + 2, (size_t)(3 + 3 * N) * 8);  // EqFMatrices.cpp:246-249
@@ -1238,6 +1279,13 @@ int eqvio_launch_count(eqvio_handle_t f, long long* count, int reset) {
     if (!f || !count) return EQVIO_ERR_ARG;
     *count = f->launches;
     if (reset) f->launches = 0;
+    return EQVIO_OK;
+}
+int eqvio_debug_stamps(eqvio_handle_t f, unsigned long long* out, int n) {
+    if (!f || !out || !f->stamps || n > 512) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    CU_TRY(cudaMemcpy(out, f->stamps, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return EQVIO_OK;
 }
 int eqvio_graph_stats(eqvio_handle_t f, long long* graph_launches, int* cached_graphs) {

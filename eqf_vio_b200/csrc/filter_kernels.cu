@@ -6,6 +6,7 @@
 //   k_lift_prepare / k_lift_features / k_lift_solve / k_lift_apply   bundleLift + discrete lift + X <- Delta X
 //   k_getrf_diag_inv   diagonal-block LU + triangular inverses of the blocked Schur elimination (S^-1, Sigma_sub^-1)
 //   bookkeeping: outlier flags, Sigma / landmark compaction, median depth + landmark append
+#include <cstdlib>
 #include "filter_kernels.cuh"
 #include "kernels_api.cuh"
 
@@ -356,50 +357,76 @@ __global__ void __launch_bounds__(128) k_lift_features(const StepScratch* sc, La
     }
 }
 
-// k_lift_fwdsub — one CTA.  z = L^-1 yo by blocked forward substitution with the unit-lower factor the
-// Schur elimination left in Aug (sub-diagonal blocks) and the per-block L_jj^-1 it stored, then
-// b4 = (Ym^T U^-1) z, the four entries M^T W obs of the normal equations (EqFMatrices.cpp:240-242):
-// Ym^T U^-1 is what the elimination leaves in the border rows pb..pb+3.  yo[p..pb) must be zero.
-__global__ void __launch_bounds__(1024) k_lift_fwdsub(const double* Aug, int lda, int pb, const double* LinvBlocks, double* yo,
-                                                      double* b4) {
-    __shared__ double zj[64];
-    __shared__ double red[4][32];
-    const int tid = threadIdx.x;
-    for (int j0 = 0; j0 < pb; j0 += 64) {
-        const int nb = min(64, pb - j0);
-        const double* Li = LinvBlocks + (size_t)(j0 >> 6) * 4096;
-        {   // z_j = L_jj^-1 y_j : 16 lanes per row
-            const int row = tid >> 4, part = tid & 15;
-            double sacc = 0.0;
-            if (row < nb)
-                for (int q = part; q <= row; q += 16) sacc += Li[row + 64 * q] * yo[j0 + q];
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o, 16);
-            __syncthreads();  // everyone has read y_j
-            if (part == 0 && row < nb) { zj[row] = sacc; yo[j0 + row] = sacc; }
+// k_lift_rsolve — R^T = Ym^T Sigma_sub^-1 (4 x pb), the gamma-INDEPENDENT factor of the normal equations'
+// right-hand side M^T W obs = (Ym^T Sigma_sub^-1) (D obs)  (EqFMatrices.cpp:239-242).  The Schur elimination
+// leaves G = Ym^T U^-1 in the border rows pb..pb+3 and the unit-lower factor L in the sub-diagonal blocks of
+// Aug (with every L_jj^-1 kept), so R^T = G L^-1 is a block back-substitution from the right:
+//     R_j = (G_j - sum_{i > j} R_i L_ij) L_jj^-1,      j = last block ... 0.
+// One CTA per 64-wide block, all launched together: CTA c owns block j = nblk-1-c, streams its L_ij tiles through
+// shared memory and consumes R_i in the order they are published (release / acquire flag per block), so the
+// only serial part is one 4 x 64 x 64 product per link instead of a whole single-CTA sweep.  CTAs only wait on
+// lower-numbered CTAs, which the hardware dispatches first: no co-residency requirement.
+// Runs on the lift stream behind the elimination, before the innovation exists; once gamma is known
+// M^T W obs = R^T yo is four dot products (k_lift_solve).
+__global__ void __launch_bounds__(256) k_lift_rsolve(const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt,
+                                                     int* ready) {
+    extern __shared__ double sm_rs[];
+    double* tiles = sm_rs;                    // two L_ij buffers, 64 x 64, ld 65: the next tile loads while the flag is awaited
+    double* linv = sm_rs + 2 * 64 * 65;       // L_jj^-1, loaded once up front
+    double(*Ri)[64] = reinterpret_cast<double(*)[64]>(sm_rs + 3 * 64 * 65);
+    const int nblk = (pb + 63) >> 6, j = nblk - 1 - (int)blockIdx.x, j0 = j << 6, nbj = min(64, pb - j0);
+    const int tid = threadIdx.x, a = tid >> 6, c = tid & 63;   // thread (a, c): entry (a, j0 + c) of R^T
+    double acc = (c < nbj) ? Aug[(pb + a) + (size_t)lda * (j0 + c)] : 0.0;
+    auto load_tile = [&](int i, double* dst) {
+        const int i0 = i << 6, nbi = min(64, pb - i0);
+        for (int idx = tid; idx < 64 * 64; idx += 256) {
+            const int r = idx & 63, cc = idx >> 6;
+            dst[r + 65 * cc] = (r < nbi && cc < nbj) ? Aug[(i0 + r) + (size_t)lda * (j0 + cc)] : 0.0;
         }
-        __syncthreads();
-        for (int r = j0 + nb + tid; r < pb; r += 1024) {
-            double acc0 = 0.0, acc1 = 0.0;
-            const double* a = Aug + r + (size_t)lda * j0;
-            for (int q = 0; q < nb; q += 2) { acc0 += a[(size_t)lda * q] * zj[q]; acc1 += a[(size_t)lda * (q + 1)] * zj[q + 1]; }
-            yo[r] -= acc0 + acc1;
-        }
-        __syncthreads();
+    };
+    {
+        const double* Li = LinvBlocks + (size_t)j * 4096;
+        for (int idx = tid; idx < 64 * 64; idx += 256) linv[(idx & 63) + 65 * (idx >> 6)] = Li[idx];
     }
-    // b4[a] = sum_col Aug[pb + a, col] * z[col]
-    const int a = tid >> 8, i = tid & 255;
-    double sacc = 0.0;
-    for (int col = i; col < pb; col += 256) sacc += Aug[(pb + a) + (size_t)lda * col] * yo[col];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-    if ((tid & 31) == 0) red[a][(tid & 255) >> 5] = sacc;
+    if (nblk - 1 > j) load_tile(nblk - 1, tiles);
+    for (int i = nblk - 1; i > j; --i) {
+        const int i0 = i << 6, nbi = min(64, pb - i0);
+        const double* tile = tiles + ((nblk - 1 - i) & 1) * 64 * 65;
+        __syncthreads();   // the other buffer and R_i of the previous iteration are consumed
+        if (i - 1 > j) load_tile(i - 1, tiles + ((nblk - i) & 1) * 64 * 65);
+        if (tid == 0) {
+            int v;
+            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready + i) : "memory"); } while (v == 0);
+        }
+        __syncthreads();
+        Ri[a][c] = (c < nbi) ? __ldcg(Rt + (size_t)a * pb + i0 + c) : 0.0;
+        __syncthreads();
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll 4
+        for (int q = 0; q < 64; q += 4) {
+            p0 = fma(Ri[a][q], tile[q + 65 * c], p0);
+            p1 = fma(Ri[a][q + 1], tile[q + 1 + 65 * c], p1);
+            p2 = fma(Ri[a][q + 2], tile[q + 2 + 65 * c], p2);
+            p3 = fma(Ri[a][q + 3], tile[q + 3 + 65 * c], p3);
+        }
+        acc -= (p0 + p1) + (p2 + p3);
+    }
     __syncthreads();
-    if (tid < 4) {
-        double t = 0.0;
-        for (int k = 0; k < 8; ++k) t += red[tid][k];
-        b4[tid] = t;
+    // R_j = acc * L_jj^-1 (64 x 64, identity-padded)
+    Ri[a][c] = acc;
+    __syncthreads();
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < 64; q += 4) {
+        p0 = fma(Ri[a][q], linv[q + 65 * c], p0);
+        p1 = fma(Ri[a][q + 1], linv[q + 1 + 65 * c], p1);
+        p2 = fma(Ri[a][q + 2], linv[q + 2 + 65 * c], p2);
+        p3 = fma(Ri[a][q + 3], linv[q + 3 + 65 * c], p3);
     }
+    if (c < nbj) __stcg(Rt + (size_t)a * pb + j0 + c, (p0 + p1) + (p2 + p3));
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready + j), "r"(1) : "memory");
 }
 
 // 4x4 Householder QR solve (EqFMatrices.cpp:240-242)
@@ -435,16 +462,26 @@ __device__ void qr_solve4(double A[4][4], double b[4], double x[4]) {
 
 // k_lift_solve — single thread.  mode use_lift: M^T W M (W = D^T Sigma_sub^-1 D, EqFMatrices.cpp:239-242)
 // is the negated bottom-right 4 x 4 block left by the Schur elimination, M^T W obs comes from
-// k_lift_fwdsub; 4x4 QR solve, DeltaU = DUF + KPara x (:243), then
+// R^T yo with R^T from k_lift_rsolve; 4x4 QR solve, DeltaU = DUF + KPara x (:243), then
 // the SE(3) x R^3 part of the lift and X <- Delta X, bias update:
 //   discrete   liftTotalSpaceInnovationDiscrete EqFMatrices.cpp:254-259
 //   continuous VIOExp(liftTotalSpaceInnovation)  EqFMatrices.cpp:69-78, VIOGroup.cpp:245-248
 // use_lift = 0 (useInnovationLift = false): VIOExp(liftInnovation(gamma, xi0)) EqFMatrices.cpp:35-48.
 // Then VIOFilter.cpp:295-296 and the pose record.
-__global__ void k_lift_solve(BaseState* st, StepScratch* sc, const double* gamma, const double* Aug,
-                             int lda, int p, const double* b4, int use_lift, int discrete, double* Gamma_out,
-                             int apply) {
+__global__ void __launch_bounds__(128) k_lift_solve(BaseState* st, StepScratch* sc, const double* gamma, const double* Aug,
+                                                    int lda, int p, const double* Rt, const double* yo, int use_lift,
+                                                    int discrete, double* Gamma_out, int apply) {
+    __shared__ double b4[4];
     const int tid = threadIdx.x;
+    if (use_lift) {   // M^T W obs = R^T yo: warp a forms entry a
+        const int a = tid >> 5;
+        double sacc = 0.0;
+        for (int col = tid & 31; col < p; col += 32) sacc = fma(Rt[(size_t)a * p + col], yo[col], sacc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if ((tid & 31) == 0) b4[a] = sacc;
+    }
+    __syncthreads();
     double G[4][5];
     if (use_lift && tid == 0)
         for (int a = 0; a < 4; ++a) {
@@ -834,26 +871,23 @@ __device__ __forceinline__ void blk8(double* C, const double* A, const double* B
     C[g + (2 * t + 1) * LDW] = c1;
 }
 
-// C (8 MB x 8 NB blocks) = (ACC ? C : 0) + sign * A B with the MB * NB (<= 64) output blocks dealt round-robin to
-// the 16 warps; all shapes are compile-time, so the block -> (row, column) maps cost nothing.
-template <int MB, int NB, int K, bool ACC>
-__device__ __forceinline__ void mm_smem(double* C, const double* A, const double* B, double sign, int warp, int lane) {
-    static_assert(MB * NB <= 4 * CHAIN_WARPS, "at most four blocks per warp");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int b = warp + CHAIN_WARPS * i;
-        if (i * CHAIN_WARPS < MB * NB && b < MB * NB) {
-            const int r0 = 8 * (b % MB), c0 = 8 * (b / MB);
-            blk8<K, ACC>(C + r0 + c0 * LDW, A + r0, B + c0 * LDW, sign, lane);
-        }
-    }
+// C (8 mb x 8 nb blocks, mb, nb <= 8) = (ACC ? C : 0) + sign * A B: the output blocks are dealt to the 16 warps as a
+// 4 x 4 grid (no divisions, at most four blocks per warp).  The kernel's code is executed once per launch, so
+// instruction fetch is part of the critical path: loops stay rolled wherever a register array does not force
+// unrolling.
+template <int K, bool ACC>
+__device__ __forceinline__ void mm_smem(double* C, const double* A, const double* B, int mb, int nb, double sign, int warp, int lane) {
+#pragma unroll 1
+    for (int bj = warp >> 2; bj < nb; bj += 4)
+#pragma unroll 1
+        for (int bi = warp & 3; bi < mb; bi += 4) blk8<K, ACC>(C + 8 * bi + 8 * bj * LDW, A + 8 * bi, B + 8 * bj * LDW, sign, lane);
 }
 
-// Sub-step PB of the 64 x 64 LU: 8 x 8 diagonal LU + its triangular inverses (warp 0), 8-wide panels, rank-8 update.
-template <int PB>
-__device__ __forceinline__ void lu_substep(double* S, double* LI, double* UI, double* rp, int warp, int lane, int& bad) {
-    constexpr int c0 = 8 * PB, REM = 7 - PB;   // REM: 8-blocks right of / below the diagonal block
+// Sub-step pb of the 64 x 64 LU: 8 x 8 diagonal LU + its triangular inverses (warp 0), 8-wide panels, rank-8 update.
+__device__ __forceinline__ void lu_substep(int pb, double* S, double* LI, double* UI, int warp, int lane, int& bad) {
+    const int c0 = 8 * pb, rem = 7 - pb;   // rem: 8-blocks right of / below the diagonal block
     double* Sd = S + c0 + c0 * LDW;
+    if (pb == 0) DBG_CLK(5);
     if (warp == 0) {
         // LU of the diagonal block: lane r (< 8; the other lanes mirror) keeps row r in registers, the pivot row
         // travels by shuffle, every lane forms the pivot reciprocal itself
@@ -879,6 +913,7 @@ __device__ __forceinline__ void lu_substep(double* S, double* LI, double* UI, do
             for (int c = 0; c < 8; ++c) Sd[r + c * LDW] = a[c];
         }
         __syncwarp();
+        if (pb == 0) DBG_CLK(6);
         // both triangular inverses by one substitution code path: lanes 0..7 column `cc` of L8^-1 (unit lower,
         // forward), lanes 8..15 column of U8^-1 on the index-reversed block (upper -> lower, diagonal 1 / pivot)
         if (lane < 16) {
@@ -905,21 +940,23 @@ __device__ __forceinline__ void lu_substep(double* S, double* LI, double* UI, do
             }
         }
     }
-    (void)rp;
+    if (pb == 0) DBG_CLK(7);
     __syncthreads();
-    if (REM > 0) {
-        // panels, in place: L[c0+8.., c0..c0+8) = A U8^-1 (warps 0..REM-1), U[c0..c0+8, c0+8..) = L8^-1 A (warps 8..8+REM-1)
-        if (warp < REM) {
-            double* blk = S + (c0 + 8 + 8 * warp) + c0 * LDW;
-            blk8<8, false>(blk, blk, UI + c0 + c0 * LDW, 1.0, lane);
-        } else if (warp >= 8 && warp < 8 + REM) {
-            double* blk = S + c0 + (c0 + 8 + 8 * (warp - 8)) * LDW;
-            blk8<8, false>(blk, LI + c0 + c0 * LDW, blk, 1.0, lane);
+    if (pb == 0) DBG_CLK(8);
+    if (rem > 0) {
+        // panels, in place: L[c0+8.., c0..c0+8) = A U8^-1 (warps 0..rem-1), U[c0..c0+8, c0+8..) = L8^-1 A (warps 8..8+rem-1)
+        if ((warp & 7) < rem) {
+            const bool isU = warp >= 8;
+            double* blk = isU ? S + c0 + (c0 + 8 + 8 * (warp - 8)) * LDW : S + (c0 + 8 + 8 * warp) + c0 * LDW;
+            blk8<8, false>(blk, isU ? LI + c0 + c0 * LDW : blk, isU ? blk : UI + c0 + c0 * LDW, 1.0, lane);
         }
+        if (pb == 0) DBG_CLK(9);
         __syncthreads();
-        mm_smem<(REM > 0 ? REM : 1), (REM > 0 ? REM : 1), 8, true>(S + (c0 + 8) + (c0 + 8) * LDW, S + (c0 + 8) + c0 * LDW,
-                                                                  S + c0 + (c0 + 8) * LDW, -1.0, warp, lane);
+        if (pb == 0) DBG_CLK(10);
+        mm_smem<8, true>(S + (c0 + 8) + (c0 + 8) * LDW, S + (c0 + 8) + c0 * LDW, S + c0 + (c0 + 8) * LDW, rem, rem, -1.0, warp, lane);
+        if (pb == 0) DBG_CLK(11);
         __syncthreads();
+        if (pb == 0) DBG_CLK(12);
     }
 }
 
@@ -958,7 +995,6 @@ __global__ void __launch_bounds__(512) k_chain_block(double* A, int lda, int j, 
     double* LI = sm_ch + 64 * LDW;      // L^-1 (prologue: the L panel block)
     double* UI = sm_ch + 2 * 64 * LDW;  // U^-1 (prologue: the U panel block)
     double* TMP = sm_ch + 3 * 64 * LDW;
-    double* rp = sm_ch + 4 * 64 * LDW;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     DBG_CLK(0);
     // ---- load: the diagonal block (identity-padded to 64), and for j > 0 the two panel blocks next to it ----
@@ -975,7 +1011,7 @@ __global__ void __launch_bounds__(512) k_chain_block(double* A, int lda, int j, 
     }
     __syncthreads();
     if (prev_nb > 0) {
-        mm_smem<8, 8, 64, true>(S, LI, UI, -1.0, warp, lane);
+        mm_smem<64, true>(S, LI, UI, 8, 8, -1.0, warp, lane);
         __syncthreads();
     }
     for (int idx = tid; idx < 64 * 64; idx += 512) {
@@ -986,14 +1022,8 @@ __global__ void __launch_bounds__(512) k_chain_block(double* A, int lda, int j, 
     __syncthreads();
     DBG_CLK(1);
     int bad = 0;
-    lu_substep<0>(S, LI, UI, rp, warp, lane, bad);
-    lu_substep<1>(S, LI, UI, rp, warp, lane, bad);
-    lu_substep<2>(S, LI, UI, rp, warp, lane, bad);
-    lu_substep<3>(S, LI, UI, rp, warp, lane, bad);
-    lu_substep<4>(S, LI, UI, rp, warp, lane, bad);
-    lu_substep<5>(S, LI, UI, rp, warp, lane, bad);
-    lu_substep<6>(S, LI, UI, rp, warp, lane, bad);
-    lu_substep<7>(S, LI, UI, rp, warp, lane, bad);
+#pragma unroll 1
+    for (int pb = 0; pb < 8; ++pb) lu_substep(pb, S, LI, UI, warp, lane, bad);
     if (bad && tid == 0) atomicOr(flags, FLAG_NOT_SPD);
     DBG_CLK(2);
     inv_level<8>(S, LI, UI, TMP, warp, lane);
@@ -1034,6 +1064,16 @@ __global__ void k_schur_setup(double* A, int lda, int k, int kpad, int r, int c,
 // ------------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------------
+// %globaltimer stamp (ns): the only way to time points INSIDE a replayed CUDA graph (tools/graph_stamps.py)
+__global__ void k_stamp(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+void launch_stamp(cudaStream_t s, unsigned long long* slot) { k_stamp<<<1, 1, 0, s>>>(slot); }
+__global__ void k_nop() {}
+void launch_nop(cudaStream_t s) { k_nop<<<1, 32, 0, s>>>(); }
+
 __global__ void k_copy_block(const double* src, int lds, double* dst, int ldd, int rows, int cols) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
     if (r < rows && c < cols) dst[r + (size_t)ldd * c] = src[r + (size_t)lds * c];
@@ -1156,12 +1196,17 @@ void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, in
                           int lda, int pb, double* yo) {
     k_lift_features<<<cdiv(N > 16 ? N : 16, 128), 128, 0, s>>>(sc, L, N, gamma, Aug, lda, pb, yo);
 }
-void launch_lift_fwdsub(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* yo, double* b4) {
-    k_lift_fwdsub<<<1, 1024, 0, s>>>(Aug, lda, pb, LinvBlocks, yo, b4);
+void launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt, int* ready) {
+    const int nblk = (pb + 63) / 64;
+    const int smem = (3 * 64 * 65 + 4 * 64) * (int)sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(k_lift_rsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_done = true; }
+    cudaMemsetAsync(ready, 0, (size_t)nblk * sizeof(int), s);
+    k_lift_rsolve<<<nblk, 256, smem, s>>>(Aug, lda, pb, LinvBlocks, Rt, ready);
 }
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
-                       const double* b4, int use_lift, int discrete, double* Gamma_out, int apply) {
-    k_lift_solve<<<1, 32, 0, s>>>(st, sc, gamma, Aug, lda, p, b4, use_lift, discrete, Gamma_out, apply);
+                       const double* Rt, const double* yo, int use_lift, int discrete, double* Gamma_out, int apply) {
+    k_lift_solve<<<1, 128, 0, s>>>(st, sc, gamma, Aug, lda, p, Rt, yo, use_lift, discrete, Gamma_out, apply);
 }
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete) {
     if (N > 0) k_lift_apply<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, gamma, discrete);
@@ -1181,7 +1226,8 @@ cudaError_t launch_getrf_diag_inv(cudaStream_t s, const double* Ain, int ldin, d
 cudaError_t launch_chain_block(cudaStream_t s, double* A, int lda, int j, int nb, int prev_nb, const double* Din, int ldin,
                                double* LUout, int ldout, double* Linv, double* Uinv, int* flags) {
     static bool attr_done = false;
-    const int smem = (4 * 64 * LDW + 16) * (int)sizeof(double);
+    static int smem = 0;
+    if (!smem) { const char* e = getenv("EQVIO_CHAIN_SMEM_KB"); smem = e ? atoi(e) * 1024 : (4 * 64 * LDW + 16) * (int)sizeof(double); }
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_chain_block, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;

@@ -12,9 +12,9 @@ void launch_gemv(cudaStream_t s, const double* K, int ldk, int n, int m, const d
 void launch_lift_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma);
 void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, int N, const double* gamma, double* Aug,
                           int lda, int pb, double* yo);
-void launch_lift_fwdsub(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* yo, double* b4);
+void launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt, int* ready);
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
-                       const double* b4, int use_lift, int discrete, double* Gamma_out, int apply);
+                       const double* Rt, const double* yo, int use_lift, int discrete, double* Gamma_out, int apply);
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete);
 cudaError_t launch_getrf_diag_inv(cudaStream_t s, const double* Ain, int ldin, double* Aout, int ldout, int nb, double* Linv,
                                   double* Uinv, int* flags);
@@ -23,6 +23,8 @@ cudaError_t launch_getrf_diag_inv(cudaStream_t s, const double* Ain, int ldin, d
 // writes L^-1, U^-1 (64 x 64, identity-padded) and optionally the factors.
 cudaError_t launch_chain_block(cudaStream_t s, double* A, int lda, int j, int nb, int prev_nb, const double* Din, int ldin,
                                double* LUout, int ldout, double* Linv, double* Uinv, int* flags);
+void launch_stamp(cudaStream_t s, unsigned long long* slot);
+void launch_nop(cudaStream_t s);   // empty kernel: a few microseconds of stream-ordered delay
 void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border);
 void launch_copy_block(cudaStream_t s, const double* src, int lds, double* dst, int ldd, int rows, int cols);
 void launch_set_identity_rows(cudaStream_t s, double* A, int lda, int row0, int n);
