@@ -52,6 +52,7 @@ struct CachedGraph { GraphKey key; cudaGraphExec_t exec; long long launches; lon
 struct eqvio_filter {
     int device = 0;
     bool use_graphs = true;            // EQVIO_GRAPHS=0 disables
+    int sigma_after_lift = -1;         // EQVIO_SIGMA_AFTER_LIFT: 0 / 1 / -1 = only for n >= 1024
     int trail_delay = 2;               // EQVIO_TRAIL_DELAY: empty kernels in front of each trailing update (see schur_lu)
     unsigned long long* stamps = nullptr;   // EQVIO_STAMPS=1: %globaltimer marks inside the update (64 slots)
     std::vector<CachedGraph> graphs;
@@ -61,7 +62,7 @@ struct eqvio_filter {
     cudaStream_t main_h = nullptr, lift_h = nullptr;  // helper streams of the two Schur chains (look-ahead)
     cudaEvent_t ev_sa = nullptr, ev_sb = nullptr, ev_st = nullptr, ev_la = nullptr, ev_lb = nullptr, ev_lt = nullptr;
     cudaStream_t lift = nullptr;   // third stream: the Sigma_sub elimination of bundleLift, concurrent with the S / K / gamma chain
-    cudaEvent_t ev_lift_fork = nullptr, ev_lift_done = nullptr;
+    cudaEvent_t ev_lift_fork = nullptr, ev_lift_done = nullptr, ev_lift_elim = nullptr;
     cudaStream_t cur = nullptr;    // stream the next gemm() goes to (main unless forked)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     eqvio_settings_t s;
@@ -537,6 +538,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
         stamp(f, f->lift, ST_LIFT_SETUP);
         if ((st = schur_lu(f, SchurChain{f->lift, f->lift_h, f->ev_la, f->ev_lb, f->ev_lt, f->LinvL, f->UinvL, true}, f->Aug, ld, pb, 4, 4))) return st;
         stamp(f, f->lift, ST_LIFT_CHAIN);
+        CU_TRY(cudaEventRecord(f->ev_lift_elim, f->lift));
         {
             ProfScope ps(f, f->lift, PROF_MISC);
             launch_lift_rsolve(f->lift, f->Aug, ld, pb, f->LinvL, f->Rt, f->wave);
@@ -568,6 +570,9 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     stamp(f, s, ST_S_FORMED);
     // Sigma C^T does not depend on S^-1: it runs on the side stream under the (latency-bound) elimination
     if ((st = fork_side(f))) return st;
+    // (a few empty kernels first: the S chain's first kernel becomes ready at the same moment and must get its SM
+    // before this GEMM's 2400 CTAs occupy every slot for the next 170 us)
+    for (int d = 0; d < f->trail_delay; ++d) { launch_nop(f->side); f->launches += 1; }
     if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
     stamp(f, f->side, ST_SIDE1_DONE);
     if ((st = end_side(f))) return st;
@@ -589,6 +594,13 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     // stream and run under the lift's Schur elimination.
     if (do_sigma) {
         if ((st = fork_side(f))) return st;
+        if (lift_chain && (f->sigma_after_lift == 1 || (f->sigma_after_lift < 0 && n >= 1024))) {
+            // ... but (for large n) not before that elimination is through: its chain kernels (one CTA, 139 KB of shared memory) cannot
+            // get an SM while 2400 long-lived GEMM CTAs keep every slot taken, and a stalled chain costs more than the
+            // GEMMs gain by starting early.  The R^T back-substitution that follows the elimination starts first.
+            CU_TRY(cudaStreamWaitEvent(f->side, f->ev_lift_elim, 0));
+            for (int d = 0; d < f->trail_delay; ++d) { launch_nop(f->side); f->launches += 1; }
+        }
         if ((st = gemm(f, 0, n, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, f->W, ld))) return st;
         if ((st = gemm(f, 0, n, n, n, -1.0, f->W, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld))) return st;
         stamp(f, f->side, ST_SIDE2_DONE);
@@ -713,9 +725,11 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
         for (cudaEvent_t* e : {&f->ev_sa, &f->ev_sb, &f->ev_st, &f->ev_la, &f->ev_lb, &f->ev_lt}) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_fork, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_done, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_elim, cudaEventDisableTiming));
     }
     f->cur = f->stream;
     if (const char* e = getenv("EQVIO_GRAPHS")) f->use_graphs = !(e[0] == '0');
+    if (const char* e = getenv("EQVIO_SIGMA_AFTER_LIFT")) f->sigma_after_lift = atoi(e);
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
     if (const char* e = getenv("EQVIO_STAMPS"))
         if (e[0] == '1') { CU_TRY(dalloc(&f->stamps, 512)); CU_TRY(cudaMemset(f->stamps, 0, 512 * 8)); }
@@ -756,7 +770,7 @@ int eqvio_destroy(eqvio_handle_t f) {
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
     cudaEventDestroy(f->stage_free);
-    cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join); cudaEventDestroy(f->ev_lift_fork); cudaEventDestroy(f->ev_lift_done);
+    cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join); cudaEventDestroy(f->ev_lift_fork); cudaEventDestroy(f->ev_lift_done); cudaEventDestroy(f->ev_lift_elim);
     cudaStreamDestroy(f->side); cudaStreamDestroy(f->lift); cudaStreamDestroy(f->main_h); cudaStreamDestroy(f->lift_h);
     for (cudaEvent_t e : {f->ev_sa, f->ev_sb, f->ev_st, f->ev_la, f->ev_lb, f->ev_lt}) cudaEventDestroy(e);
     cudaStreamDestroy(f->stream);

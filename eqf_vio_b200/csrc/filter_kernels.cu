@@ -4,7 +4,8 @@
 //   k_build_C_delta     one warp per feature: 2x3 C block + innovation delta_i
 //   k_gemv              gamma = K delta
 //   k_lift_prepare / k_lift_features / k_lift_solve / k_lift_apply   bundleLift + discrete lift + X <- Delta X
-//   k_getrf_diag_inv   diagonal-block LU + triangular inverses of the blocked Schur elimination (S^-1, Sigma_sub^-1)
+//   k_chain_block      diagonal-block link of the blocked Schur eliminations (S^-1, Sigma_sub^-1): look-ahead corner, LU, L^-1, U^-1
+//   k_lift_rsolve      Ym^T Sigma_sub^-1 by a multi-CTA wavefront back-substitution
 //   bookkeeping: outlier flags, Sigma / landmark compaction, median depth + landmark append
 #include <cstdlib>
 #include "filter_kernels.cuh"
@@ -565,259 +566,12 @@ __global__ void __launch_bounds__(128) k_lift_apply(BaseState* st, Landmarks L, 
 // the asymmetry of S is ~1e-11 relative because C annihilates the large radial variance — see
 // DESIGN.md "Numerical conditioning").
 // ------------------------------------------------------------------------------------------------
-// Reciprocal to ~1 ulp without the long IEEE division sequence (it sits on the per-pivot critical path):
-// single-precision seed + two Newton steps.  Falls back to a true division outside float range.
-__device__ __forceinline__ double fast_rcp(double x) {
-    const float xf = (float)x;
-    double y = (double)(1.0f / xf);
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return (isfinite(y) && y != 0.0) ? y : 1.0 / x;
-}
-
-// lu32: unpivoted LU of the 32 x 32 block of S at (o, o) together with both triangular inverses, run by
-// the first 128 threads of the CTA (4 warps, named barrier 1).  Thread (r, cg), r = tid & 31, cg = tid >> 5,
-// keeps its 8 entries (columns c = 8 cg + i) of row r of A, e and t in registers.
-// One sweep of 31 pivot steps gives both inverses: row-eliminating [A | I] turns I into L^-1 (e), and
-// row-eliminating [A^T | I] — whose trailing blocks are the transposes of A's, so only its identity part
-// (t) needs storage, with multipliers taken from the pivot ROW of A — turns I into D U^-T, i.e.
-// U^-1[c][r] = t[r][c] / d_r.  Per step only the pivot rows of A / e / t, the multiplier column and the
-// pivot reciprocal go through shared memory (double-buffered, one 128-thread barrier per step).
 #ifdef EQVIO_DEBUG_CLOCKS
 __device__ long long g_dbg_clk[16];
 #define DBG_CLK(i) do { if (threadIdx.x == 0) g_dbg_clk[i] = clock64(); } while (0)
 #else
 #define DBG_CLK(i) do { } while (0)
 #endif
-struct __align__(16) Lu32Scratch {
-    double row_a[2][32], row_e[2][32], row_t[2][32], colb[2][32], rp[32];
-};
-__device__ __forceinline__ void bar128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// Branch-free inner step: every thread applies all 24 fused updates each step; a row r <= k gets a zero
-// multiplier, the published pivot row of A is zeroed for c <= k (so the stored multipliers left of the
-// pivot are not touched) and e / t are lower triangular, so their entries right of the pivot are
-// multiplied by zeros.  One warp per scheduler runs this chain in order, so instruction count and
-// dependent latency per step — not FMA throughput — set the time: contiguous columns (c = 8 cg + i) let
-// the pivot rows come in with 128-bit shared loads, and the 24 chains are independent.
-__device__ void lu32(double (*S)[65], double (*LI)[65], double (*UI)[65], Lu32Scratch& w, int o, int* flags) {
-    const int tid = threadIdx.x, r = tid & 31, cg = tid >> 5, c0 = 8 * cg;
-    double a[8], e[8], t[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        a[i] = S[o + r][o + c0 + i];
-        e[i] = (r == c0 + i) ? 1.0 : 0.0;
-        t[i] = e[i];
-    }
-    if (r == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            w.row_a[0][c0 + i] = (c0 + i > 0) ? a[i] : 0.0;
-            w.row_e[0][c0 + i] = e[i];
-            w.row_t[0][c0 + i] = t[i];
-        }
-        if (cg == 0) {
-            if (!(fabs(a[0]) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
-            w.rp[0] = fast_rcp(a[0]);
-        }
-    }
-    if (cg == 0) w.colb[0][r] = a[0];
-    bar128();
-#pragma unroll 1
-    for (int k = 0; k < 31; ++k) {
-        const int b = k & 1;
-        // all shared loads of the step first (12 x 128-bit + 3 x 64-bit in flight together) ...
-        const double2* ra = reinterpret_cast<const double2*>(&w.row_a[b][c0]);
-        const double2* re = reinterpret_cast<const double2*>(&w.row_e[b][c0]);
-        const double2* rt = reinterpret_cast<const double2*>(&w.row_t[b][c0]);
-        double2 va[4], ve[4], vt[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) { va[h] = ra[h]; ve[h] = re[h]; vt[h] = rt[h]; }
-        const double rk = (r > k) ? w.rp[k] : 0.0;
-        const double l = -(w.colb[b][r] * rk);     // -a[r][k] / pivot (0 for rows at or above the pivot)
-        const double lt = -(w.row_a[b][r] * rk);   // -a[k][r] / pivot: multiplier of row r of the transposed problem
-        // ... then the A updates, the next pivot column / reciprocal, and the e / t updates behind them
-#pragma unroll
-        for (int h = 0; h < 4; ++h) { a[2 * h] = fma(l, va[h].x, a[2 * h]); a[2 * h + 1] = fma(l, va[h].y, a[2 * h + 1]); }
-        const bool own = (cg == ((k + 1) >> 3));   // warp-uniform: this warp holds column k+1
-        double nxt = 0.0;
-        if (own) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) nxt = (c0 + i == k + 1) ? a[i] : nxt;
-            w.colb[b ^ 1][r] = nxt;
-            if (r == k + 1) {
-                if (!(fabs(nxt) > 0.0)) atomicOr(flags, FLAG_NOT_SPD);
-                w.rp[k + 1] = fast_rcp(nxt);
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            e[2 * h] = fma(l, ve[h].x, e[2 * h]);     e[2 * h + 1] = fma(l, ve[h].y, e[2 * h + 1]);
-            t[2 * h] = fma(lt, vt[h].x, t[2 * h]);    t[2 * h + 1] = fma(lt, vt[h].y, t[2 * h + 1]);
-        }
-        if (r == k + 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                w.row_a[b ^ 1][c0 + i] = (c0 + i > k + 1) ? a[i] : 0.0;
-                w.row_e[b ^ 1][c0 + i] = e[i];
-                w.row_t[b ^ 1][c0 + i] = t[i];
-            }
-        }
-        bar128();
-    }
-    const double rr = w.rp[r];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        S[o + r][o + c] = (c >= r) ? a[i] : a[i] * w.rp[c];   // U on/above the diagonal, L multipliers below
-        LI[o + r][o + c] = (c <= r) ? e[i] : 0.0;
-        UI[o + c][o + r] = (c <= r) ? t[i] * rr : 0.0;        // U^-1[c][r] = t[r][c] / d_r; strictly lower part 0
-    }
-}
-
-// 32-long dot product with four independent partial sums (the dependent DFMA chain, not throughput,
-// bounds these small products).  X(q), Y(q) are expressions in q.
-#define DOT32(acc, X, Y)                                                        \
-    do {                                                                        \
-        double p0_ = 0.0, p1_ = 0.0, p2_ = 0.0, p3_ = 0.0;                      \
-        _Pragma("unroll") for (int q = 0; q < 32; q += 4) {                     \
-            p0_ = fma(X(q), Y(q), p0_);                                         \
-            p1_ = fma(X(q + 1), Y(q + 1), p1_);                                 \
-            p2_ = fma(X(q + 2), Y(q + 2), p2_);                                 \
-            p3_ = fma(X(q + 3), Y(q + 3), p3_);                                 \
-        }                                                                       \
-        acc = (p0_ + p1_) + (p2_ + p3_);                                        \
-    } while (0)
-
-// k_getrf_diag_inv: one CTA factors the nb x nb (nb <= 64) diagonal block at (j, j) of A in place
-// (unit-lower L below the diagonal, U on and above it) and produces the two triangular inverses
-// L^-1, U^-1 (64 x 64, column-major, identity-padded), so that the panel solves X U = B and L X = B of
-// the blocked Schur elimination become small GEMMs on the DMMA kernel instead of per-row substitutions.
-// The 64 x 64 block is treated as 2 x 2 blocks of 32: lu32 on the leading block, the two off-diagonal
-// solves and the Schur update as 32^3 products by all 512 threads, lu32 on the trailing block, and the
-// off-diagonal blocks of the inverses as two more triple products.  The pivot chain (the sequential
-// part) therefore runs on 4 warps with a 128-thread barrier per step instead of 16 warps.
-// `Ain` (leading dimension ldin) is where the block is read from — the matrix itself, or a 64 x 64 scratch
-// holding the already-updated block when the trailing update of the previous step is still in flight
-// (look-ahead); `Aout` (may be null) receives the factors.
-__global__ void __launch_bounds__(512) k_getrf_diag_inv(const double* Ain, int ldin, double* Aout, int ldout, int nb, double* Linv,
-                                                        double* Uinv, int* flags) {
-    extern __shared__ double sm_lu[];
-    double(*S)[65] = reinterpret_cast<double(*)[65]>(sm_lu);
-    double(*LI)[65] = reinterpret_cast<double(*)[65]>(sm_lu + 64 * 65);
-    double(*UI)[65] = reinterpret_cast<double(*)[65]>(sm_lu + 2 * 64 * 65);
-    double(*T1)[33] = reinterpret_cast<double(*)[33]>(sm_lu + 3 * 64 * 65);
-    double(*T2)[33] = reinterpret_cast<double(*)[33]>(sm_lu + 3 * 64 * 65 + 32 * 33);
-    Lu32Scratch& w = *reinterpret_cast<Lu32Scratch*>(sm_lu + 3 * 64 * 65 + 2 * 32 * 33);
-    const int tid = threadIdx.x;
-    DBG_CLK(0);
-    for (int idx = tid; idx < 64 * 64; idx += 512) {
-        const int r = idx & 63, c = idx >> 6;
-        S[r][c] = (r < nb && c < nb) ? Ain[r + (size_t)ldin * c] : (r == c ? 1.0 : 0.0);
-        LI[r][c] = 0.0;
-        UI[r][c] = 0.0;
-    }
-    __syncthreads();
-    DBG_CLK(1);
-    if (tid < 128) lu32(S, LI, UI, w, 0, flags);
-    __syncthreads();
-    DBG_CLK(2);
-    // U12 = L11^-1 A12, L21 = A21 U11^-1 (each thread 2 + 2 outputs), then A22 -= L21 U12
-    {
-        double u12[2], l21[2];
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int idx = tid + 512 * v, r = idx & 31, c = idx >> 5;
-            double s1, s2;  // zeros outside the triangles make the full-length sums exact
-#define XA(q) LI[r][q]
-#define YA(q) S[q][32 + c]
-#define XB(q) S[32 + r][q]
-#define YB(q) UI[q][c]
-            DOT32(s1, XA, YA);
-            DOT32(s2, XB, YB);
-#undef XA
-#undef YA
-#undef XB
-#undef YB
-            u12[v] = s1; l21[v] = s2;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int idx = tid + 512 * v, r = idx & 31, c = idx >> 5;
-            S[r][32 + c] = u12[v];
-            S[32 + r][c] = l21[v];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int idx = tid + 512 * v, r = idx & 31, c = idx >> 5;
-            double s;
-#define XA(q) S[32 + r][q]
-#define YA(q) S[q][32 + c]
-            DOT32(s, XA, YA);
-#undef XA
-#undef YA
-            S[32 + r][32 + c] -= s;
-        }
-    }
-    __syncthreads();
-    DBG_CLK(3);
-    if (tid < 128) lu32(S, LI, UI, w, 32, flags);
-    __syncthreads();
-    DBG_CLK(4);
-    // off-diagonal blocks of the inverses: L^-1_21 = -L22^-1 (L21 L11^-1),  U^-1_12 = -(U11^-1 U12) U22^-1
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-        const int idx = tid + 512 * v, r = idx & 31, c = idx >> 5;
-        double s1, s2;  // (L21 L11^-1), (U11^-1 U12)
-#define XA(q) S[32 + r][q]
-#define YA(q) LI[q][c]
-#define XB(q) UI[r][q]
-#define YB(q) S[q][32 + c]
-        DOT32(s1, XA, YA);
-        DOT32(s2, XB, YB);
-#undef XA
-#undef YA
-#undef XB
-#undef YB
-        T1[r][c] = s1;
-        T2[r][c] = s2;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-        const int idx = tid + 512 * v, r = idx & 31, c = idx >> 5;
-        double s1, s2;  // L22^-1 lower, U22^-1 upper
-#define XA(q) LI[32 + r][32 + q]
-#define YA(q) T1[q][c]
-#define XB(q) T2[r][q]
-#define YB(q) UI[32 + q][32 + c]
-        DOT32(s1, XA, YA);
-        DOT32(s2, XB, YB);
-#undef XA
-#undef YA
-#undef XB
-#undef YB
-        LI[32 + r][c] = -s1;
-        UI[r][32 + c] = -s2;
-    }
-    __syncthreads();
-    DBG_CLK(5);
-    for (int idx = tid; idx < 64 * 64; idx += 512) {
-        const int r = idx & 63, c = idx >> 6;
-        Linv[r + 64 * c] = LI[r][c];
-        Uinv[r + 64 * c] = UI[r][c];
-        if (Aout != nullptr && r < nb && c < nb) Aout[r + (size_t)ldout * c] = S[r][c];
-    }
-    DBG_CLK(6);
-}
-#ifdef EQVIO_DEBUG_CLOCKS
-extern "C" int eqvio_debug_clocks(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_dbg_clk, sizeof(long long) * 16); }
-#endif
-
 // ------------------------------------------------------------------------------------------------
 // k_chain_block — the sequential link of the blocked Schur eliminations, one CTA of 16 warps per 64-wide
 // diagonal block.  Everything that is a product runs on DMMA.8x8x4 from shared memory; only the 64 pivots
@@ -1039,6 +793,10 @@ __global__ void __launch_bounds__(512) k_chain_block(double* A, int lda, int j, 
     DBG_CLK(4);
 }
 
+#ifdef EQVIO_DEBUG_CLOCKS
+extern "C" int eqvio_debug_clocks(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_dbg_clk, sizeof(long long) * 16); }
+#endif
+
 // Everything of the Schur problem except the leading k x k block A and (when !identity_border) the
 // border entries written elsewhere.  Layout: A in [0,k)^2, identity padding on [k,kpad), border rows /
 // columns at offset kpad:  [[A, 0, Cc], [0, I, 0], [R, 0, 0]].  identity_border: R = Cc = I (k x k).
@@ -1210,18 +968,6 @@ void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const dou
 }
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete) {
     if (N > 0) k_lift_apply<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, gamma, discrete);
-}
-cudaError_t launch_getrf_diag_inv(cudaStream_t s, const double* Ain, int ldin, double* Aout, int ldout, int nb, double* Linv,
-                                  double* Uinv, int* flags) {
-    static bool attr_set = false;
-    const int smem = (3 * 64 * 65 + 2 * 32 * 33) * (int)sizeof(double) + (int)sizeof(Lu32Scratch) + 16;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_getrf_diag_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    k_getrf_diag_inv<<<1, 512, smem, s>>>(Ain, ldin, Aout, ldout, nb, Linv, Uinv, flags);
-    return cudaGetLastError();
 }
 cudaError_t launch_chain_block(cudaStream_t s, double* A, int lda, int j, int nb, int prev_nb, const double* Din, int ldin,
                                double* LUout, int ldout, double* Linv, double* Uinv, int* flags) {

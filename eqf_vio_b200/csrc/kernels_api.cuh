@@ -16,8 +16,6 @@ void launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, cons
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
                        const double* Rt, const double* yo, int use_lift, int discrete, double* Gamma_out, int apply);
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete);
-cudaError_t launch_getrf_diag_inv(cudaStream_t s, const double* Ain, int ldin, double* Aout, int ldout, int nb, double* Linv,
-                                  double* Uinv, int* flags);
 // Diagonal block j (nb x nb, nb <= 64) of the blocked Schur elimination of A: D = A[j,j] (or Din) minus, when
 // prev_nb > 0, the product of the panel blocks L[j, j-prev_nb] U[j-prev_nb, j] that the trailing update skipped;
 // writes L^-1, U^-1 (64 x 64, identity-padded) and optionally the factors.
