@@ -578,10 +578,11 @@ __device__ long long g_dbg_clk[16];
 // themselves are scalar.
 //   prologue (block j > 0): D_j = A[j,j] - L[j,j-1] U[j-1,j]  (the look-ahead "corner": the trailing update of
 //             step j-1 skips this block, so the diagonal block never waits for that GEMM)
-//   LU:       eight 8-wide sub-steps: LU of the 8 x 8 diagonal block (one thread, registers), its two
-//             triangular inverses by substitution (16 threads), the 8-wide row / column panels as products
-//             with those inverses, rank-8 trailing update
-//   inverses: L^-1, U^-1 (64 x 64) by recursive doubling over the 8 x 8 diagonal inverses:
+//   LU:       eight 8-wide sub-steps: LU of the 8 x 8 diagonal block (8 lanes of warp 0, rows in registers, pivot row
+//             by shuffle), the 8-wide row / column panels by substitution (one thread per row / column), rank-8
+//             trailing update on DMMA (each warp a 2 x 2 group of 8 x 8 blocks)
+//   inverses: the eight 8 x 8 diagonal inverses of L and U at once (128 threads, substitution), then L^-1, U^-1
+//             (64 x 64) by recursive doubling:
 //             X21 = -L22^-1 (L21 L11^-1),  X12 = -U11^-1 (U12 U22^-1)   for block sizes 8, 16, 32
 // Shared-memory matrices are column-major with leading dimension 68 (= 4 mod 16 doubles): every DMMA fragment
 // load (A: row g, k t;  B: k t, column g) hits 16 distinct 8-byte slots per half-warp, and the global <-> shared
@@ -625,36 +626,72 @@ __device__ __forceinline__ void blk8(double* C, const double* A, const double* B
     C[g + (2 * t + 1) * LDW] = c1;
 }
 
-// C (8 mb x 8 nb blocks, mb, nb <= 8) = (ACC ? C : 0) + sign * A B: the output blocks are dealt to the 16 warps as a
-// 4 x 4 grid (no divisions, at most four blocks per warp).  The kernel's code is executed once per launch, so
-// instruction fetch is part of the critical path: loops stay rolled wherever a register array does not force
-// unrolling.
+// C (8 mb x 8 nb blocks, mb, nb <= 8) = (ACC ? C : 0) + sign * A B.  The 16 warps form a 4 x 4 grid, warp (wi, wj)
+// owns the 2 x 2 group of 8 x 8 output blocks at block row 2 wi, block column 2 wj: four independent DMMA chains per
+// warp and each operand fragment is loaded once for two blocks.  No divisions; the kernel's code runs once per
+// launch, so instruction fetch is part of the critical path and loops stay rolled wherever a register array does
+// not force unrolling.
 template <int K, bool ACC>
 __device__ __forceinline__ void mm_smem(double* C, const double* A, const double* B, int mb, int nb, double sign, int warp, int lane) {
-#pragma unroll 1
-    for (int bj = warp >> 2; bj < nb; bj += 4)
-#pragma unroll 1
-        for (int bi = warp & 3; bi < mb; bi += 4) blk8<K, ACC>(C + 8 * bi + 8 * bj * LDW, A + 8 * bi, B + 8 * bj * LDW, sign, lane);
+    const int g = lane >> 2, t = lane & 3;
+    const int bi0 = 2 * (warp & 3), bj0 = 2 * (warp >> 2);
+    const int ni = min(2, mb - bi0), nj = min(2, nb - bj0);   // warp-uniform
+    if (ni <= 0 || nj <= 0) return;
+    const bool i1 = ni > 1, j1 = nj > 1;
+    const double* A0 = A + 8 * bi0 + g;              // + (k) * LDW; second row block at + 8
+    const double* B0 = B + (8 * bj0 + g) * LDW;      // + k;         second column block at + 8 * LDW
+    double* C0 = C + 8 * bi0 + g + (8 * bj0 + 2 * t) * LDW;
+    double c[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+    if (ACC) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if ((i == 0 || i1) && (j == 0 || j1)) {
+                    c[i][j][0] = C0[8 * i + (8 * j) * LDW];
+                    c[i][j][1] = C0[8 * i + (8 * j + 1) * LDW];
+                }
+    }
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+        const double a0 = sign * A0[(k + t) * LDW], a1 = i1 ? sign * A0[8 + (k + t) * LDW] : 0.0;
+        const double b0 = B0[k + t], b1 = j1 ? B0[k + t + 8 * LDW] : 0.0;
+        dmma_f64(c[0][0][0], c[0][0][1], a0, b0);
+        if (j1) dmma_f64(c[0][1][0], c[0][1][1], a0, b1);
+        if (i1) dmma_f64(c[1][0][0], c[1][0][1], a1, b0);
+        if (i1 && j1) dmma_f64(c[1][1][0], c[1][1][1], a1, b1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if ((i == 0 || i1) && (j == 0 || j1)) {
+                C0[8 * i + (8 * j) * LDW] = c[i][j][0];
+                C0[8 * i + (8 * j + 1) * LDW] = c[i][j][1];
+            }
 }
 
-// Sub-step pb of the 64 x 64 LU: 8 x 8 diagonal LU + its triangular inverses (warp 0), 8-wide panels, rank-8 update.
-__device__ __forceinline__ void lu_substep(int pb, double* S, double* LI, double* UI, int warp, int lane, int& bad) {
+// Sub-step pb of the 64 x 64 LU: LU of the 8 x 8 diagonal block (warp 0), the 8-wide panels by substitution (one
+// thread per row / column), rank-8 update of the rest on DMMA.  rp[0..64) collects the pivot reciprocals.
+__device__ __forceinline__ void lu_substep(int pb, double* S, double* rp, int tid, int warp, int lane, int& bad) {
     const int c0 = 8 * pb, rem = 7 - pb;   // rem: 8-blocks right of / below the diagonal block
     double* Sd = S + c0 + c0 * LDW;
     if (pb == 0) DBG_CLK(5);
     if (warp == 0) {
-        // LU of the diagonal block: lane r (< 8; the other lanes mirror) keeps row r in registers, the pivot row
-        // travels by shuffle, every lane forms the pivot reciprocal itself
+        // lane r (< 8; the other lanes mirror) keeps row r in registers, the pivot row travels by shuffle, every lane
+        // forms the pivot reciprocal itself
         const int r = lane & 7;
-        double a[8], rk[8];
+        double a[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) a[c] = Sd[r + c * LDW];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const double piv = __shfl_sync(0xffffffffu, a[k], k);
             bad |= !(fabs(piv) > 0.0);
-            rk[k] = pivot_rcp(piv);
-            const double l = (r > k) ? a[k] * rk[k] : 0.0;
+            const double rk = pivot_rcp(piv);
+            if (lane == k) rp[c0 + k] = rk;
+            const double l = (r > k) ? a[k] * rk : 0.0;
 #pragma unroll
             for (int c = k + 1; c < 8; ++c) {
                 const double u = __shfl_sync(0xffffffffu, a[c], k);
@@ -662,55 +699,80 @@ __device__ __forceinline__ void lu_substep(int pb, double* S, double* LI, double
             }
             if (r > k) a[k] = l;
         }
+        __syncwarp();   // the mirror lanes have read the block before lanes 0..7 overwrite it
         if (lane < 8) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) Sd[r + c * LDW] = a[c];
         }
-        __syncwarp();
-        if (pb == 0) DBG_CLK(6);
-        // both triangular inverses by one substitution code path: lanes 0..7 column `cc` of L8^-1 (unit lower,
-        // forward), lanes 8..15 column of U8^-1 on the index-reversed block (upper -> lower, diagonal 1 / pivot)
-        if (lane < 16) {
-            const bool up = lane >= 8;
-            const int cc = lane & 7;
-            double x[8], sacc[8];
+    }
+    if (pb == 0) DBG_CLK(6);
+    __syncthreads();
+    if (pb == 0) DBG_CLK(7);
+    if (rem > 0) {
+        // panels, in place, by substitution: threads [0, 8 rem) one row each of L[c0+8.., c0..c0+8) = A U8^-1,
+        // threads [64, 64 + 8 rem) one column each of U[c0..c0+8, c0+8..) = L8^-1 A
+        if (tid < 8 * rem) {
+            double* row = S + (c0 + 8 + tid) + c0 * LDW;
+            double x[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sacc[i] = 0.0;
+            for (int c = 0; c < 8; ++c) x[c] = row[c * LDW];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const double d = up ? rk[7 - i] : 1.0;
-                x[i] = (i < cc) ? 0.0 : (i == cc ? d : -(d * sacc[i]));
+            for (int c = 0; c < 8; ++c) {
+                x[c] *= rp[c0 + c];
 #pragma unroll
-                for (int q = i + 1; q < 8; ++q) {
-                    const double mqi = up ? Sd[(7 - q) + (7 - i) * LDW] : Sd[q + i * LDW];
-                    sacc[q] = fma(mqi, x[i], sacc[q]);
-                }
+                for (int q = c + 1; q < 8; ++q) x[q] = fma(-x[c], Sd[c + q * LDW], x[q]);
             }
-            double* XI = up ? UI : LI;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int ri = up ? 7 - i : i, ci = up ? 7 - cc : cc;
-                XI[(c0 + ri) + (c0 + ci) * LDW] = x[i];
-            }
+            for (int c = 0; c < 8; ++c) row[c * LDW] = x[c];
+        } else if (tid >= 64 && tid < 64 + 8 * rem) {
+            double* col = S + c0 + (c0 + 8 + (tid - 64)) * LDW;
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = col[i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int q = i + 1; q < 8; ++q) x[q] = fma(-Sd[q + i * LDW], x[i], x[q]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) col[i] = x[i];
+        }
+        if (pb == 0) DBG_CLK(8);
+        __syncthreads();
+        if (pb == 0) DBG_CLK(9);
+        mm_smem<8, true>(S + (c0 + 8) + (c0 + 8) * LDW, S + (c0 + 8) + c0 * LDW, S + c0 + (c0 + 8) * LDW, rem, rem, -1.0, warp, lane);
+        if (pb == 0) DBG_CLK(10);
+        __syncthreads();
+        if (pb == 0) DBG_CLK(11);
+    }
+}
+
+// The eight 8 x 8 diagonal blocks of L^-1 and U^-1, all at once after the LU: 16 lanes per block, lanes 0..7 column
+// `cc` of L8^-1 (unit lower, forward substitution), lanes 8..15 a column of U8^-1 on the index-reversed block
+// (upper -> lower, diagonal 1 / pivot) — one code path for both.
+__device__ __forceinline__ void diag_inverses(const double* S, double* LI, double* UI, const double* rp, int tid) {
+    if (tid >= 128) return;
+    const int blk = tid >> 4, c0 = 8 * blk, l16 = tid & 15;
+    const bool up = l16 >= 8;
+    const int cc = l16 & 7;
+    const double* Sd = S + c0 + c0 * LDW;
+    double x[8], sacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sacc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double d = up ? rp[c0 + 7 - i] : 1.0;
+        x[i] = (i < cc) ? 0.0 : (i == cc ? d : -(d * sacc[i]));
+#pragma unroll
+        for (int q = i + 1; q < 8; ++q) {
+            const double mqi = up ? Sd[(7 - q) + (7 - i) * LDW] : Sd[q + i * LDW];
+            sacc[q] = fma(mqi, x[i], sacc[q]);
         }
     }
-    if (pb == 0) DBG_CLK(7);
-    __syncthreads();
-    if (pb == 0) DBG_CLK(8);
-    if (rem > 0) {
-        // panels, in place: L[c0+8.., c0..c0+8) = A U8^-1 (warps 0..rem-1), U[c0..c0+8, c0+8..) = L8^-1 A (warps 8..8+rem-1)
-        if ((warp & 7) < rem) {
-            const bool isU = warp >= 8;
-            double* blk = isU ? S + c0 + (c0 + 8 + 8 * (warp - 8)) * LDW : S + (c0 + 8 + 8 * warp) + c0 * LDW;
-            blk8<8, false>(blk, isU ? LI + c0 + c0 * LDW : blk, isU ? blk : UI + c0 + c0 * LDW, 1.0, lane);
-        }
-        if (pb == 0) DBG_CLK(9);
-        __syncthreads();
-        if (pb == 0) DBG_CLK(10);
-        mm_smem<8, true>(S + (c0 + 8) + (c0 + 8) * LDW, S + (c0 + 8) + c0 * LDW, S + c0 + (c0 + 8) * LDW, rem, rem, -1.0, warp, lane);
-        if (pb == 0) DBG_CLK(11);
-        __syncthreads();
-        if (pb == 0) DBG_CLK(12);
+    double* XI = up ? UI : LI;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int ri = up ? 7 - i : i, ci = up ? 7 - cc : cc;
+        XI[(c0 + ri) + (c0 + ci) * LDW] = x[i];
     }
 }
 
@@ -749,6 +811,7 @@ __global__ void __launch_bounds__(512) k_chain_block(double* A, int lda, int j, 
     double* LI = sm_ch + 64 * LDW;      // L^-1 (prologue: the L panel block)
     double* UI = sm_ch + 2 * 64 * LDW;  // U^-1 (prologue: the U panel block)
     double* TMP = sm_ch + 3 * 64 * LDW;
+    double* rp = sm_ch + 4 * 64 * LDW;  // 64 pivot reciprocals
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     DBG_CLK(0);
     // ---- load: the diagonal block (identity-padded to 64), and for j > 0 the two panel blocks next to it ----
@@ -777,7 +840,9 @@ __global__ void __launch_bounds__(512) k_chain_block(double* A, int lda, int j, 
     DBG_CLK(1);
     int bad = 0;
 #pragma unroll 1
-    for (int pb = 0; pb < 8; ++pb) lu_substep(pb, S, LI, UI, warp, lane, bad);
+    for (int pb = 0; pb < 8; ++pb) lu_substep(pb, S, rp, tid, warp, lane, bad);
+    diag_inverses(S, LI, UI, rp, tid);
+    __syncthreads();
     if (bad && tid == 0) atomicOr(flags, FLAG_NOT_SPD);
     DBG_CLK(2);
     inv_level<8>(S, LI, UI, TMP, warp, lane);
@@ -972,8 +1037,7 @@ void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const 
 cudaError_t launch_chain_block(cudaStream_t s, double* A, int lda, int j, int nb, int prev_nb, const double* Din, int ldin,
                                double* LUout, int ldout, double* Linv, double* Uinv, int* flags) {
     static bool attr_done = false;
-    static int smem = 0;
-    if (!smem) { const char* e = getenv("EQVIO_CHAIN_SMEM_KB"); smem = e ? atoi(e) * 1024 : (4 * 64 * LDW + 16) * (int)sizeof(double); }
+    const int smem = (4 * 64 * LDW + 64) * (int)sizeof(double);
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_chain_block, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;

@@ -63,7 +63,7 @@ def main():
         abi.lib().eqvio_debug_clocks(out)
         c = list(out)
         print("clock64 phase marks 0-4 (load, LU, inverses, store):", [c[i + 1] - c[i] for i in range(4)])
-        print("sub-step 0, marks 5-12 (LU8, 8x8 inverses, bar, panels, bar, trailing, bar):", [c[i + 1] - c[i] for i in range(5, 12)])
+        print("sub-step 0, marks 5-11 (LU8, bar, panels, bar, trailing, bar):", [c[i + 1] - c[i] for i in range(5, 11)])
 
 
 if __name__ == "__main__":

@@ -20,6 +20,20 @@ for N, s in ((9, template_settings()), (70, conditioned_settings())):
     e = f.stateEstimate()
     S = f.stateCovariance()
     print("N", N, "landmarks", f.numLandmarks, "finite", np.isfinite(S).all(), "launches", f.launch_count())
+# fixed landmark count: the update and the Riccati step run as replayed CUDA graphs from the third frame on
+s = conditioned_settings(outlierThreshold=1e9)
+seq = period_sequence(40, 5, camera_offset=tuple(s.cameraOffset))
+f = VIOFilter(s)
+for kind, i in seq.events():
+    if kind == "imu":
+        f.processIMUData(seq.imu[i, 0], seq.imu[i, 1:4], seq.imu[i, 4:7])
+    else:
+        f.processVisionData(seq.vision_stamps[i], seq.ids, seq.bearings[i])
+print("N 40 fixed: graph replays", f.graph_stats(), "finite", np.isfinite(f.stateCovariance()).all())
+from eqf_vio_b200.filter import getrf_block
+Bm = rng.standard_normal((48, 48))
+LU, Li, Ui, _ = getrf_block(Bm @ Bm.T + 48 * np.eye(48))
+print("chain block", np.isfinite(LU).all())
 A = rng.standard_normal((45, 37)); B = rng.standard_normal((37, 50))
 C, _ = dgemm(A, B)
 print("gemm", np.abs(C - A @ B).max())
