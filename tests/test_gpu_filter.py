@@ -323,3 +323,30 @@ def test_graph_cache_follows_landmark_churn():
         feed(a, seq, kind, i, sel=sel)
         feed(b, seq, kind, i, sel=sel)
     assert np.array_equal(a.get_snapshot(), b.get_snapshot())
+
+
+def test_baseline_config2_full_length_N64():
+    """BASELINE.json configs[1] at full length: N = 64, IMU 200 Hz / vision 20 Hz, 10 s (2000 IMU ticks + 200 vision
+    frames), free-running on the GPU (graph replay from frame 3 on) against the numpy restatement of the reference
+    fed the same rows.  Well-conditioned start-up; tolerance = the north_star's: Sigma rel-Frobenius < 1e-9, lifted
+    state < 1e-8, at every 10th frame and at the end."""
+    from eqf_vio_b200.settings import conditioned_settings
+    from helpers import np_settings
+    from oracle import eqvio_numpy as onp
+
+    s = conditioned_settings()
+    seq = period_sequence(64, 200, camera_offset=tuple(s.cameraOffset))
+    f, o = gpu_filter(s), onp.VIOFilter(np_settings(s))
+    worst_s = worst_h = 0.0
+    n_imu = n_vis = 0
+    for kind, i in seq.events():
+        assert feed(f, seq, kind, i) == feed(o, seq, kind, i)
+        n_imu += kind == "imu"
+        n_vis += kind == "vision"
+        if kind == "vision" and (i % 10 == 0 or i == 200):
+            h1, S1 = split_snapshot(f.get_snapshot())
+            h2, S2 = split_snapshot(o.get_snapshot())
+            worst_s, worst_h = max(worst_s, rel(S1, S2)), max(worst_h, np.abs(h1 - h2).max())
+    assert n_imu >= 2000 and n_vis == 201
+    assert f.graph_stats()[0] > 2000          # the Riccati step and the update ran as replayed graphs
+    assert worst_s < 1e-9 and worst_h < 1e-8, (worst_s, worst_h)
