@@ -1,5 +1,5 @@
 // filter_kernels.cu — O(N) kernels of the EqF-VIO hot path (everything except the dense GEMMs):
-//   k_step_prepare      base rows of F/B_b, derived step quantities, X.A / X.w propagate, velocity latch
+//   k_step_prepare      base rows of F/B_b, derived step quantities, X.A / X.w propagate, velocity latch (4 warps, one piece each)
 //   k_feature_step      one warp per feature: F / B_b landmark rows + Q_i propagate
 //   k_build_C_delta     one warp per feature: 2x3 C block + innovation delta_i
 //   k_gemv              gamma = K delta
@@ -29,90 +29,115 @@ __device__ __forceinline__ void store_Q(const Landmarks& L, int i, Sot3 Q) {
 __device__ __forceinline__ V3 load_q0(const Landmarks& L, int i) { return v3(L.q0(0)[i], L.q0(1)[i], L.q0(2)[i]); }
 
 // ------------------------------------------------------------------------------------------------
-// k_step_prepare — single thread.  processIMUData / integrateUpToTime bookkeeping that is O(1):
+// k_step_prepare — one CTA, four working threads.  processIMUData / integrateUpToTime bookkeeping that is O(1):
 //   VIOFilter.cpp:120-131 (unbias, initialise, latch), :154-155 (accumulate), :162-185 base rows of
 //   A/B (EqFMatrices.cpp:289, 364-368), :196-203 with liftVelocityDiscrete (VIOGroup.cpp:209-243)
 //   / liftVelocity (VIOGroup.cpp:178-207) for the SE(3) x R^3 part, X <- X * lift (VIOGroup.cpp:92-97).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_step_prepare(BaseState* st, StepScratch* sc, ImuArgs a, RiccatiOut ro) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int sing = 0;
-    sc->stamp = a.stamp;
-    V3 uo = v3(a.omega[0] - st->bias[0], a.omega[1] - st->bias[1], a.omega[2] - st->bias[2]);
-    V3 ua = v3(a.accel[0] - st->bias[3], a.accel[1] - st->bias[4], a.accel[2] - st->bias[5]);
-    if (a.do_init) {  // initialiseFromIMUData, VIOFilter.cpp:133-144
-        st->pose0 = se3_identity();
-        st->vel0 = v3(0, 0, 0);
-        st->pose0.R = so3_from_vectors(normalized(ua), v3(0, 0, 1), &sing);
+// The work is O(1) but ~6000 dependent fp64 instructions; run by one thread it took 12.8 us, the largest item of an
+// IMU tick at small N.  Four warps (lane 0 of each) take one independent piece each — all read the pre-step state
+// first, a barrier separates those reads from the writes of the propagate:
+//   warp 0: accumulators, scalars for the kernels behind (T, dt, stamp), A0 gravity block, velocity latch
+//   warp 1: base rows of B_b / F / W (EqFMatrices.cpp:364-368)
+//   warp 2: R_IC^T R_A^T, v_C, R_IC^-1, R_IC^-1 [x_IC]x for the per-feature blocks
+//   warp 3: X.A / X.w propagate and the camera-frame increment of the feature propagate
+__global__ void __launch_bounds__(128) k_step_prepare(BaseState* st, StepScratch* sc, ImuArgs a, RiccatiOut ro) {
+    const int role = threadIdx.x >> 5;
+    const bool lead = (threadIdx.x & 31) == 0;
+    if (a.do_init) {  // initialiseFromIMUData, VIOFilter.cpp:133-144 (first sample only)
+        if (threadIdx.x == 0) {
+            int sing0 = 0;
+            const V3 ua0 = v3(a.accel[0] - st->bias[3], a.accel[1] - st->bias[4], a.accel[2] - st->bias[5]);
+            st->pose0 = se3_identity();
+            st->vel0 = v3(0, 0, 0);
+            st->pose0.R = so3_from_vectors(normalized(ua0), v3(0, 0, 1), &sing0);
+            if (sing0) atomicOr(&st->flags, FLAG_SINGULAR);
+        }
+        __syncthreads();
     }
+    int sing = 0;
+    // ---- every warp reads the pre-step state it needs ----
+    const V3 uo = v3(a.omega[0] - st->bias[0], a.omega[1] - st->bias[1], a.omega[2] - st->bias[2]);
+    const V3 ua = v3(a.accel[0] - st->bias[3], a.accel[1] - st->bias[4], a.accel[2] - st->bias[5]);
+    const V3 co = ld3(st->curOmega), ca = ld3(st->curAccel);
+    V3 ao = ld3(st->accOmega) + co * a.dt, aa = ld3(st->accAccel) + ca * a.dt;
+    const Se3 XA = st->XA, pose0 = st->pose0, cam = st->cam;
+    const V3 Xw = st->Xw, vel0 = st->vel0;
+    __syncthreads();
+    if (!lead) return;
+    if (role == 0) sc->stamp = a.stamp;
     if (a.do_integrate) {
-        const V3 co = ld3(st->curOmega), ca = ld3(st->curAccel);
-        V3 ao = ld3(st->accOmega) + co * a.dt, aa = ld3(st->accAccel) + ca * a.dt;
-        const Se3 XA = st->XA;
-        const V3 eta0 = rotate_inv(st->pose0.R, v3(0, 0, 1));       // projectToManifold, VIOState.cpp:90
-        const V3 eta_hat = rotate_inv(XA.R, eta0);                  // VIOGroup.cpp:49
-        const V3 v_hat = rotate_inv(XA.R, st->vel0 - st->Xw);       // VIOGroup.cpp:25,50
-        const Se3 camInvT = inverse(st->cam);
-        const M3 RA = to_matrix(XA.R);
+        const V3 eta0 = rotate_inv(pose0.R, v3(0, 0, 1));          // projectToManifold, VIOState.cpp:90
+        const V3 eta_hat = rotate_inv(XA.R, eta0);                 // VIOGroup.cpp:49
+        const V3 v_hat = rotate_inv(XA.R, vel0 - Xw);              // VIOGroup.cpp:25,50
         if (a.do_riccati) {
-            const V3 om = ao * (1.0 / a.T);
             const int ld = ro.ld, n16 = ro.n16;
             double* F = ro.F; double* W = ro.W; double* Bb = ro.Bb;
-            sc->T = a.T;
-            // A0[2:5,0:2] = -g * stereoSphereChartInvDiff(0, eta0)   (EqFMatrices.cpp:289)
-            M32 D = stereo_sphere_chart_inv_diff(0.0, 0.0, eta0, &sing);
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 2; ++c) F[(8 + r) + (size_t)ld * (6 + c)] = (-D.m[r][c] * GRAV) * a.T;
-            const M3 RIC = to_matrix(st->cam.R);
-            sc->RICt_RAt = transpose(RIC) * transpose(RA);
-            V3 omC, vC;
-            se3_adjoint_apply(camInvT, om, v_hat, &omC, &vC);       // EqFMatrices.cpp:302-304
-            sc->vC = vC;
-            // B rows (EqFMatrices.cpp:364-368)
-            M23 Dg = stereo_sphere_chart_diff(eta0, eta0, &sing);
-            M3 RAse = RA * skew(eta_hat);
-            double Bbase[5][6];
-            for (int r = 0; r < 2; ++r)
-                for (int c = 0; c < 3; ++c) {
-                    Bbase[r][c] = Dg.m[r][0] * RAse.m[0][c] + Dg.m[r][1] * RAse.m[1][c] + Dg.m[r][2] * RAse.m[2][c];
-                    Bbase[r][3 + c] = 0.0;
-                }
-            M3 RAsv = RA * skew(v_hat);
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) { Bbase[2 + r][c] = RAsv.m[r][c]; Bbase[2 + r][3 + c] = RA.m[r][c]; }
-            for (int r = 0; r < 5; ++r)
-                for (int c = 0; c < 6; ++c) {
-                    const double b = Bbase[r][c];
-                    F[(6 + r) + (size_t)ld * c] = -b * a.T;                           // A_b = [[0,0],[-Bt,A0t]]; F = I + A_b T
-                    Bb[(6 + r) + (size_t)ld * c] = b;
-                    F[(6 + r) + (size_t)ld * (n16 + c)] = b;                          // [F | B_b]
-                    W[(6 + r) + (size_t)ld * (n16 + c)] = a.T * (b * sc->Rd[c]);      // [F Sigma | T B_b R]
-                }
-            sc->RT_IC = to_matrix(q_inverse(st->cam.R));
-            sc->RT_IC_sx = sc->RT_IC * skew(st->cam.x);
+            if (role == 0) {
+                sc->T = a.T;
+                // A0[2:5,0:2] = -g * stereoSphereChartInvDiff(0, eta0)   (EqFMatrices.cpp:289)
+                M32 D = stereo_sphere_chart_inv_diff(0.0, 0.0, eta0, &sing);
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 2; ++c) F[(8 + r) + (size_t)ld * (6 + c)] = (-D.m[r][c] * GRAV) * a.T;
+            } else if (role == 1) {
+                // B rows (EqFMatrices.cpp:364-368)
+                const M3 RA = to_matrix(XA.R);
+                M23 Dg = stereo_sphere_chart_diff(eta0, eta0, &sing);
+                M3 RAse = RA * skew(eta_hat);
+                double Bbase[5][6];
+                for (int r = 0; r < 2; ++r)
+                    for (int c = 0; c < 3; ++c) {
+                        Bbase[r][c] = Dg.m[r][0] * RAse.m[0][c] + Dg.m[r][1] * RAse.m[1][c] + Dg.m[r][2] * RAse.m[2][c];
+                        Bbase[r][3 + c] = 0.0;
+                    }
+                M3 RAsv = RA * skew(v_hat);
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) { Bbase[2 + r][c] = RAsv.m[r][c]; Bbase[2 + r][3 + c] = RA.m[r][c]; }
+                for (int r = 0; r < 5; ++r)
+                    for (int c = 0; c < 6; ++c) {
+                        const double b = Bbase[r][c];
+                        F[(6 + r) + (size_t)ld * c] = -b * a.T;                           // A_b = [[0,0],[-Bt,A0t]]; F = I + A_b T
+                        Bb[(6 + r) + (size_t)ld * c] = b;
+                        F[(6 + r) + (size_t)ld * (n16 + c)] = b;                          // [F | B_b]
+                        W[(6 + r) + (size_t)ld * (n16 + c)] = a.T * (b * sc->Rd[c]);      // [F Sigma | T B_b R]
+                    }
+            } else if (role == 2) {
+                const V3 om = ao * (1.0 / a.T);
+                const M3 RA = to_matrix(XA.R);
+                const M3 RIC = to_matrix(cam.R);
+                sc->RICt_RAt = transpose(RIC) * transpose(RA);
+                V3 omC, vC;
+                se3_adjoint_apply(inverse(cam), om, v_hat, &omC, &vC);   // EqFMatrices.cpp:302-304
+                sc->vC = vC;
+                sc->RT_IC = to_matrix(q_inverse(cam.R));
+                sc->RT_IC_sx = sc->RT_IC * skew(cam.x);
+            }
             ao = v3(0, 0, 0); aa = v3(0, 0, 0);  // VIOFilter.cpp:192-193
         }
-        st3(st->accOmega, ao); st3(st->accAccel, aa);
-        // state propagate of the SE(3) x R^3 part
-        sc->dt = a.dt;
-        V3 omC, vC;
-        se3_adjoint_apply(camInvT, co, v_hat, &omC, &vC);
-        if (a.discrete_lift) {
-            Se3 LA = se3_exp(co * a.dt, v_hat * a.dt);
-            V3 inner = v_hat + a.dt * (-cross(co, v_hat) + ca - eta_hat * GRAV);
-            V3 Lw = v_hat - rotate(LA.R, inner);
-            sc->camInv = se3_exp(omC * (-a.dt), vC * (-a.dt));
-            st->Xw = st->Xw + rotate(XA.R, Lw);
-            st->XA = XA * LA;
-        } else {
-            sc->omC = omC; sc->vCcur = vC;
-            V3 u = -ca + eta_hat * GRAV;
-            Se3 EA = se3_exp(co * a.dt, v_hat * a.dt);
-            st->Xw = st->Xw + rotate(XA.R, u * a.dt);
-            st->XA = XA * EA;
+        if (role == 0) {
+            st3(st->accOmega, ao); st3(st->accAccel, aa);
+            sc->dt = a.dt;
+        } else if (role == 3) {
+            // state propagate of the SE(3) x R^3 part
+            V3 omC, vC;
+            se3_adjoint_apply(inverse(cam), co, v_hat, &omC, &vC);
+            if (a.discrete_lift) {
+                Se3 LA = se3_exp(co * a.dt, v_hat * a.dt);
+                V3 inner = v_hat + a.dt * (-cross(co, v_hat) + ca - eta_hat * GRAV);
+                V3 Lw = v_hat - rotate(LA.R, inner);
+                sc->camInv = se3_exp(omC * (-a.dt), vC * (-a.dt));
+                st->Xw = Xw + rotate(XA.R, Lw);
+                st->XA = XA * LA;
+            } else {
+                sc->omC = omC; sc->vCcur = vC;
+                V3 u = -ca + eta_hat * GRAV;
+                Se3 EA = se3_exp(co * a.dt, v_hat * a.dt);
+                st->Xw = Xw + rotate(XA.R, u * a.dt);
+                st->XA = XA * EA;
+            }
         }
     }
-    if (a.do_latch) { st3(st->curOmega, uo); st3(st->curAccel, ua); }
+    if (role == 0 && a.do_latch) { st3(st->curOmega, uo); st3(st->curAccel, ua); }
     if (sing) atomicOr(&st->flags, FLAG_SINGULAR);
 }
 
@@ -999,7 +1024,7 @@ __global__ void k_set_inertial_points(const BaseState* st, Landmarks L, int N, c
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 void launch_step_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const ImuArgs& a, const RiccatiOut& ro) {
-    k_step_prepare<<<1, 32, 0, s>>>(st, sc, a, ro);
+    k_step_prepare<<<1, 128, 0, s>>>(st, sc, a, ro);
 }
 void launch_feature_step(cudaStream_t s, BaseState* st, const StepScratch* sc, Landmarks L, int N, int do_riccati,
                          int discrete, const RiccatiOut& ro) {
