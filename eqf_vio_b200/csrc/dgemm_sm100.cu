@@ -115,11 +115,22 @@ __device__ __forceinline__ double process_diag(const KernelParams& p, int m) {
     return m < 3 ? p.Pd[0] : m < 6 ? p.Pd[1] : m < 8 ? p.Pd[2] : m < 11 ? p.Pd[3] : p.Pd[4];
 }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One CTA tile of D = alpha A op(B) + beta Cin.  `wait_flag` (may be null): the producer does not touch A before
+// *wait_flag >= wait_count (A's rows of this tile are being written by other CTAs of the same launch);
+// `signal_flag` (may be null): incremented once this tile's output is globally visible.
 template <class Cfg, bool TRANSB>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
-dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KernelParams p) {
+__device__ __forceinline__ void gemm_tile(const CUtensorMap* tmAp, const CUtensorMap* tmBp, const KernelParams& p, const int tile_m,
+                                          const int tile_n, const int* wait_flag, const int wait_count, int* signal_flag) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
     constexpr int MB = WM / 8, NB = WN / 8;
+    const CUtensorMap& tmA = *tmAp;
+    const CUtensorMap& tmB = *tmBp;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -129,21 +140,6 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t* empty = full + STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // 1-D grid, full tiles first and the partial edge tiles last: in an edge tile the warps whose
-    // sub-tile is entirely outside the matrix do no MMAs, so it is cheap, and cheap work dispatched last
-    // fills the tail of the last wave (n = 11 + 3N is never a multiple of the tile size).
-    int tile_m, tile_n;
-    {
-        const int Tm = (p.M + BM - 1) / BM, Tn = (p.N + BN - 1) / BN, Fm = p.M / BM, Fn = p.N / BN;
-        const int id = blockIdx.x, interior = Fm * Fn;
-        if (id < interior) { tile_m = id % Fm; tile_n = id / Fm; }
-        else {
-            const int e = id - interior;
-            if (Tn > Fn && e < Fm) { tile_m = e; tile_n = Fn; }          // partial last tile column
-            else { tile_m = Fm; tile_n = e - (Tn > Fn ? Fm : 0); }       // partial last tile row (incl. corner)
-        }
-        (void)Tm;
-    }
     const int KT = (p.K + 15) >> 4;
     if ((tile_m + 1) * BM <= p.skip_m && (tile_n + 1) * BN <= p.skip_n) return;  // whole tile inside the skipped box
 
@@ -161,6 +157,11 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
+            if (wait_flag) {
+                while (ld_acquire_gpu(wait_flag) < wait_count) __nanosleep(64);
+                // the rows were written with generic-proxy stores by other CTAs; TMA reads them through the async proxy
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
             for (int kt = 0; kt < KT; ++kt) {
                 const int s = kt % STAGES;
                 const uint32_t ph = (kt / STAGES) & 1;
@@ -271,6 +272,76 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
         }
     }
+    if (signal_flag) {
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::CONSUMER_WARPS * 32) : "memory");   // consumer warps only (the producer has left)
+        if (threadIdx.x == 0) atomicAdd(signal_flag, 1);
+    }
+}
+
+template <class Cfg, bool TRANSB>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
+dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KernelParams p) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN;
+    // 1-D grid, full tiles first and the partial edge tiles last: in an edge tile the warps whose
+    // sub-tile is entirely outside the matrix do no MMAs, so it is cheap, and cheap work dispatched last
+    // fills the tail of the last wave (n = 11 + 3N is never a multiple of the tile size).
+    int tile_m, tile_n;
+    {
+        const int Tn = (p.N + BN - 1) / BN, Fm = p.M / BM, Fn = p.N / BN;
+        const int id = blockIdx.x, interior = Fm * Fn;
+        if (id < interior) { tile_m = id % Fm; tile_n = id / Fm; }
+        else {
+            const int e = id - interior;
+            if (Tn > Fn && e < Fm) { tile_m = e; tile_n = Fn; }          // partial last tile column
+            else { tile_m = Fm; tile_n = e - (Tn > Fn ? Fm : 0); }       // partial last tile row (incl. corner)
+        }
+    }
+    gemm_tile<Cfg, TRANSB>(&tmA, &tmB, p, tile_m, tile_n, nullptr, 0, nullptr);
+}
+
+// Two dependent GEMMs in one launch — the reference's left-to-right products (A B) C (eqf_vio/src/VIOFilter.cpp:188-189
+// (F Sigma) F^T, :276 (C Sigma) C^T, :297 (K C) Sigma):
+//   phase 1:  W = A1 B1                (p1, NN)   tiles in row-major order, each one counted in rows[tile_m]
+//   phase 2:  D = W op(B2) (+ epilogue) (p2)       tile (i, j) starts once rows[i] == all tiles of row-block i of W
+// Phase-2 CTAs fill the SM slots that the tail of phase 1 leaves empty (one drain per step instead of two) and have
+// their barriers / descriptors set up by the time their rows are complete.  Logical CTA ids are tickets taken in
+// start order, so a CTA only ever waits for CTAs that are already running; the CTA that finishes last resets the
+// counters for the next launch.   sync[0] ticket, sync[1] finished CTAs, sync[8 + i] row-block counters.
+template <class Cfg, bool TRANSB2>
+__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::STAGES == 4 ? 6 : Cfg::MINB))   // 6 CTAs / SM like the single-product kernel (64 registers)
+dgemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const KernelParams p1,
+                          const KernelParams p2, int* sync) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN;
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&sync[0], 1);
+    __syncthreads();
+    const int id = s_ticket;
+    const int Tm1 = (p1.M + BM - 1) / BM, Tn1 = (p1.N + BN - 1) / BN, T1 = Tm1 * Tn1;
+    const int Tm2 = (p2.M + BM - 1) / BM, Tn2 = (p2.N + BN - 1) / BN, Fn2 = p2.N / BN;
+    if (id < T1) {
+        const int tile_m = id / Tn1, tile_n = id - tile_m * Tn1;
+        gemm_tile<Cfg, false>(&tmA1, &tmB1, p1, tile_m, tile_n, nullptr, 0, &sync[8 + tile_m]);
+    } else {
+        // row-major over the full-width tile columns (rows of W become ready in that order), the partial last tile
+        // column (cheap tiles) at the very end
+        const int e = id - T1, body = Tm2 * Fn2;
+        int tile_m, tile_n;
+        if (e < body) { tile_m = e / Fn2; tile_n = e - tile_m * Fn2; }
+        else { tile_m = e - body; tile_n = Fn2; }
+        (void)Tn2;
+        gemm_tile<Cfg, TRANSB2>(&tmA2, &tmB2, p2, tile_m, tile_n, &sync[8 + tile_m], Tn1, nullptr);
+    }
+    if (threadIdx.x == 0) {   // a consumer thread: its tile is complete (and its wait / signal on the counters behind it)
+        const int total = gridDim.x;
+        if (atomicAdd(&sync[1], 1) == total - 1) {
+            for (int i = 0; i < Tm1; ++i) sync[8 + i] = 0;
+            sync[0] = 0;
+            sync[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -320,15 +391,7 @@ static CUresult encode_k_major(CUtensorMap* map, const double* X, int K, int N, 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
-template <class Cfg>
-static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
-    if (!get_encode()) return cudaErrorNotSupported;
-    CUtensorMap tmA, tmB;
-    if (encode_mn_major(&tmA, g.A, g.M, g.K, g.lda, Cfg::BM) != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    CUresult rb = g.transB ? encode_mn_major(&tmB, g.B, g.N, g.K, g.ldb, Cfg::BN)
-                           : encode_k_major(&tmB, g.B, g.K, g.N, g.ldb, Cfg::BN);
-    if (rb != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    KernelParams p;
+static void fill_params(KernelParams& p, const GemmProblem& g) {
     p.M = g.M; p.N = g.N; p.K = g.K;
     p.D = g.D; p.ldd = g.ldd;
     p.Cin = g.epi.Cin; p.ldcin = g.epi.ldcin;
@@ -344,6 +407,18 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     p.skip_m = g.skip_m; p.skip_n = g.skip_n;
     p.T_dev = g.epi.T_dev;
     for (int i = 0; i < 5; ++i) p.Pd[i] = g.epi.Pd[i];
+}
+
+template <class Cfg>
+static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
+    if (!get_encode()) return cudaErrorNotSupported;
+    CUtensorMap tmA, tmB;
+    if (encode_mn_major(&tmA, g.A, g.M, g.K, g.lda, Cfg::BM) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    CUresult rb = g.transB ? encode_mn_major(&tmB, g.B, g.N, g.K, g.ldb, Cfg::BN)
+                           : encode_k_major(&tmB, g.B, g.K, g.N, g.ldb, Cfg::BN);
+    if (rb != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    KernelParams p;
+    fill_params(p, g);
     dim3 grid(((g.M + Cfg::BM - 1) / Cfg::BM) * ((g.N + Cfg::BN - 1) / Cfg::BN));
     cudaError_t e;
     static bool attr_done[2] = {false, false};  // per template instantiation (function-local static)
@@ -365,6 +440,52 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
         k<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
     }
     return cudaGetLastError();
+}
+
+template <class Cfg, bool TB2>
+static cudaError_t launch_pair_cfg(const GemmProblem& g1, const GemmProblem& g2, int* sync, cudaStream_t stream) {
+    if (!get_encode()) return cudaErrorNotSupported;
+    CUtensorMap tmA1, tmB1, tmA2, tmB2;
+    if (encode_mn_major(&tmA1, g1.A, g1.M, g1.K, g1.lda, Cfg::BM) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    if (encode_k_major(&tmB1, g1.B, g1.K, g1.N, g1.ldb, Cfg::BN) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    if (encode_mn_major(&tmA2, g2.A, g2.M, g2.K, g2.lda, Cfg::BM) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    const CUresult rb = TB2 ? encode_mn_major(&tmB2, g2.B, g2.N, g2.K, g2.ldb, Cfg::BN) : encode_k_major(&tmB2, g2.B, g2.K, g2.N, g2.ldb, Cfg::BN);
+    if (rb != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    KernelParams p1, p2;
+    fill_params(p1, g1);
+    fill_params(p2, g2);
+    const int T1 = ((g1.M + Cfg::BM - 1) / Cfg::BM) * ((g1.N + Cfg::BN - 1) / Cfg::BN);
+    const int T2 = ((g2.M + Cfg::BM - 1) / Cfg::BM) * ((g2.N + Cfg::BN - 1) / Cfg::BN);
+    auto k = dgemm_pair_kernel<Cfg, TB2>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    k<<<dim3(T1 + T2), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA1, tmB1, tmA2, tmB2, p1, p2, sync);
+    return cudaGetLastError();
+}
+
+// When the single launch pays (measured on B200, bench.py at N = 64 / 256 / 512): the first product must run for more
+// than one wave of the 148 x 6 CTA slots, so that second-phase CTAs are dispatched into its tail and find their rows
+// complete (N = 512: +5.4 % on the Riccati step); with a single partial wave (N = 256: 625 tiles) the second phase's CTAs
+// would occupy the free slots at once, spin, and skew the SM load (-10 %).  Tiny problems whose two phases fit the GPU
+// one CTA per SM save the second launch's set-up.
+bool dgemm_pair_pays(const GemmProblem& g1, const GemmProblem& g2) {
+    const long t1 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32), t2 = (long)((g2.M + 31) / 32) * ((g2.N + 31) / 32);
+    if ((g1.M + 31) / 32 > DGEMM_PAIR_MAX_ROW_BLOCKS) return false;
+    return t1 + t2 <= 148 || t1 >= 1110;
+}
+
+cudaError_t dgemm_pair_launch(const GemmProblem& g1, const GemmProblem& g2, int* sync, cudaStream_t stream) {
+    if (g1.M <= 0 || g1.N <= 0 || g2.N <= 0) return cudaSuccess;
+    if (g1.transB || g1.D != g2.A || g1.M != g2.M || g1.skip_m || g2.skip_m || (g1.M + 31) / 32 > DGEMM_PAIR_MAX_ROW_BLOCKS)
+        return cudaErrorInvalidValue;
+    const long tiles32 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32);
+    if (tiles32 <= 148)
+        return g2.transB ? launch_pair_cfg<Cfg32x32s6, true>(g1, g2, sync, stream) : launch_pair_cfg<Cfg32x32s6, false>(g1, g2, sync, stream);
+    return g2.transB ? launch_pair_cfg<Cfg32x32, true>(g1, g2, sync, stream) : launch_pair_cfg<Cfg32x32, false>(g1, g2, sync, stream);
 }
 
 int dgemm_num_configs() { return 8; }

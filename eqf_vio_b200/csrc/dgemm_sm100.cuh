@@ -53,6 +53,16 @@ struct GemmProblem {
 // be readable up to the next multiple of 16 rows (the library's buffers are padded accordingly).
 // Returns cudaSuccess or the launch / encode error.  `flops_out` (optional) receives 2*M*N*K.
 cudaError_t dgemm_launch(const GemmProblem& p, cudaStream_t stream, int force_config = -1);
+// Two dependent products W = A1 B1 (NN) and D = W op(B2) (+ epilogue) as ONE launch — the reference's (A B) C chains
+// (F Sigma) F^T, (C Sigma) C^T, (K C) Sigma.  The second product's tiles start as soon as their row block of W is
+// complete (per-row-block counters in `sync`: DGEMM_PAIR_SYNC_INTS ints, zero before the first use and left zero) and
+// fill the SM slots the first product's tail leaves idle.  Requires second.A == first.D, equal M, first not transposed.
+// Launches on one stream must not overlap launches on another with the same `sync` buffer.
+static const int DGEMM_PAIR_MAX_ROW_BLOCKS = 8192;
+static const int DGEMM_PAIR_SYNC_INTS = 8 + DGEMM_PAIR_MAX_ROW_BLOCKS;
+cudaError_t dgemm_pair_launch(const GemmProblem& first, const GemmProblem& second, int* sync, cudaStream_t stream);
+// Whether the single launch is the faster choice for these shapes (else: two dgemm_launch calls).
+bool dgemm_pair_pays(const GemmProblem& first, const GemmProblem& second);
 // Which tile configuration dgemm_launch would pick (for DESIGN.md / tests).
 int dgemm_pick_config(int M, int N, int K);
 const char* dgemm_config_name(int cfg);

@@ -64,6 +64,19 @@ struct eqvio_filter {
     cudaStream_t lift = nullptr;   // third stream: the Sigma_sub elimination of bundleLift, concurrent with the S / K / gamma chain
     cudaEvent_t ev_lift_fork = nullptr, ev_lift_done = nullptr, ev_lift_elim = nullptr;
     cudaStream_t cur = nullptr;    // stream the next gemm() goes to (main unless forked)
+    // State stream: k_step_prepare / k_feature_step of tick t+1 depend only on the SE(3) x R^3 / landmark state, not on
+    // Sigma, so they run here underneath the two Sigma GEMMs of tick t (main stream).  What they write for the GEMMs
+    // (F, the border columns of W, the step length T) is double-buffered by tick parity.
+    cudaStream_t state = nullptr;
+    cudaEvent_t ev_state = nullptr, ev_main = nullptr, ev_gemm[2] = {nullptr, nullptr};
+    bool main_dirty = true;        // main-stream work since the last tick may have touched what the state stream reads / writes
+    // EQVIO_PAIRS bit mask over the call sites (PAIR_*); 0 = every (A B) C chain as two launches.  Default: the Riccati step only —
+    // measured at N = 512, the (C Sigma) C^T and (K C) Sigma pairs of the update change the period by < 0.5 % either way
+    // (they overlap the latency-bound Schur chains, whose kernels compete for the same SM slots)
+    int use_pairs = 1;
+    int* pair_sync = nullptr;      // ticket / row-block counters of dgemm_pair_launch, one set per call site
+    int par = 0;                   // parity of the current Riccati tick: F == Fpp[par], W == Wpp[par]
+    double *Fpp[2] = {nullptr, nullptr}, *Wpp[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     eqvio_settings_t s;
     // host-side scalars of the reference class (VIOFilter.h:49-55)
@@ -190,12 +203,13 @@ static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, co
 
 static void free_device(Filter* f) {
     cudaFree(f->L.base); cudaFree(f->L2.base);
-    cudaFree(f->Sigma); cudaFree(f->Sigma2); cudaFree(f->F); cudaFree(f->W); cudaFree(f->Bb); cudaFree(f->Aug);
+    cudaFree(f->Sigma); cudaFree(f->Sigma2); cudaFree(f->Fpp[0]); cudaFree(f->Fpp[1]); cudaFree(f->Wpp[0]); cudaFree(f->Wpp[1]); cudaFree(f->Bb); cudaFree(f->Aug);
     cudaFree(f->C); cudaFree(f->CS); cudaFree(f->SCt); cudaFree(f->K); cudaFree(f->Saug); cudaFree(f->Sinv);
     cudaFree(f->delta); cudaFree(f->gamma); cudaFree(f->y_in); cudaFree(f->y); cudaFree(f->scratch); cudaFree(f->Gamma);
     cudaFree(f->d_flags); cudaFree(f->d_map); cudaFree(f->LinvL); cudaFree(f->yo); cudaFree(f->Rt); cudaFree(f->wave);
     f->LinvL = f->yo = f->Rt = nullptr; f->wave = nullptr;
     f->L.base = f->L2.base = nullptr;
+    f->Fpp[0] = f->Fpp[1] = f->Wpp[0] = f->Wpp[1] = nullptr;
     f->Sigma = f->Sigma2 = f->F = f->W = f->Bb = f->Aug = f->C = f->CS = f->SCt = f->K = f->Saug = f->Sinv = nullptr;
     f->delta = f->gamma = f->y_in = f->y = f->scratch = f->Gamma = nullptr;
     f->d_flags = f->d_map = nullptr;
@@ -214,7 +228,7 @@ static int ensure_capacity(Filter* f, int needN) {
     drop_graphs(f);  // captured launches hold the old buffers
     Filter o = *f;  // old pointers
     Landmarks L{nullptr, cap}, L2{nullptr, cap};
-    double *Sigma, *Sigma2, *F, *W, *Bb, *Aug, *C, *CS, *SCt, *K, *Saug, *Sinv, *delta, *gamma, *y_in, *y, *scratch, *Gamma;
+    double *Sigma, *Sigma2, *F, *W, *F1, *W1, *Bb, *Aug, *C, *CS, *SCt, *K, *Saug, *Sinv, *delta, *gamma, *y_in, *y, *scratch, *Gamma;
     int *d_flags, *d_map;
     double *LinvL, *yo, *Rt;
     int* wave;
@@ -225,6 +239,7 @@ static int ensure_capacity(Filter* f, int needN) {
     CU_TRY(dalloc(&L.base, (size_t)LM_FIELDS * cap));
     CU_TRY(dalloc(&L2.base, (size_t)LM_FIELDS * cap));
     CU_TRY(dalloc(&Sigma, nn)); CU_TRY(dalloc(&Sigma2, nn)); CU_TRY(dalloc(&F, nn)); CU_TRY(dalloc(&W, nn));
+    CU_TRY(dalloc(&F1, nn)); CU_TRY(dalloc(&W1, nn));
     CU_TRY(dalloc(&Aug, nn));
     CU_TRY(dalloc(&Bb, (size_t)ld * 8));
     CU_TRY(dalloc(&C, (size_t)ldm * (ld + 32))); CU_TRY(dalloc(&CS, (size_t)ldm * (ld + 32)));
@@ -252,12 +267,15 @@ static int ensure_capacity(Filter* f, int needN) {
     }
     f->cap = cap; f->ld = ld; f->ldm = ldm; f->ld2m = ld2m;
     f->L = L; f->L2 = L2;
-    f->Sigma = Sigma; f->Sigma2 = Sigma2; f->F = F; f->W = W; f->Bb = Bb; f->Aug = Aug;
+    f->Sigma = Sigma; f->Sigma2 = Sigma2; f->Bb = Bb; f->Aug = Aug;
+    f->Fpp[0] = F; f->Fpp[1] = F1; f->Wpp[0] = W; f->Wpp[1] = W1;
+    f->F = f->Fpp[f->par]; f->W = f->Wpp[f->par];
     f->C = C; f->CS = CS; f->SCt = SCt; f->K = K; f->Saug = Saug; f->Sinv = Sinv;
     f->delta = delta; f->gamma = gamma; f->y_in = y_in; f->y = y; f->scratch = scratch; f->Gamma = Gamma;
     f->d_flags = d_flags; f->d_map = d_map;
     f->LinvL = LinvL; f->yo = yo; f->Rt = Rt; f->wave = wave;
     f->layoutN = -1;
+    f->main_dirty = true;
     // pinned staging sized for the capacity
     size_t need_d = (size_t)LM_FIELDS * cap + 3 * (size_t)cap + 256, need_i = (size_t)ld + cap + 64;
     if (need_d > f->h_stage_doubles) {
@@ -279,12 +297,15 @@ static int prepare_layout(Filter* f) {
     if (f->layoutN == f->N) return EQVIO_OK;
     const size_t nn = (size_t)f->ld * (f->ld + 32);
     cudaStream_t s = f->stream;
-    CU_TRY(cudaMemsetAsync(f->F, 0, nn * 8, s));
-    CU_TRY(cudaMemsetAsync(f->W, 0, nn * 8, s));
+    for (int b = 0; b < 2; ++b) {
+        CU_TRY(cudaMemsetAsync(f->Fpp[b], 0, nn * 8, s));
+        CU_TRY(cudaMemsetAsync(f->Wpp[b], 0, nn * 8, s));
+        launch_set_diag_one(s, f->Fpp[b], f->ld, n_of(f->N));
+    }
     CU_TRY(cudaMemsetAsync(f->Bb, 0, (size_t)f->ld * 8 * 8, s));
     CU_TRY(cudaMemsetAsync(f->C, 0, (size_t)f->ldm * (f->ld + 32) * 8, s));
-    launch_set_diag_one(s, f->F, f->ld, n_of(f->N));
-    f->launches += 1;
+    f->launches += 2;
+    f->main_dirty = true;   // the state stream's next kernels write F / W: behind these memsets
     f->layoutN = f->N;
     return EQVIO_OK;
 }
@@ -293,7 +314,7 @@ static int prepare_layout(Filter* f) {
 // GEMM wrapper with launch counting and optional event bracketing
 // ------------------------------------------------------------------------------------------------
 static int lane_of(const Filter* f, cudaStream_t s) {
-    return s == f->stream ? 0 : s == f->side ? 1 : s == f->lift ? 2 : s == f->main_h ? 3 : s == f->lift_h ? 4 : 5;
+    return s == f->stream ? 0 : s == f->side ? 1 : s == f->lift ? 2 : s == f->main_h ? 3 : s == f->lift_h ? 4 : s == f->state ? 5 : 6;
 }
 // Event bracket around the launches that follow on stream `s` (only while profiling is enabled).
 static void prof_begin(Filter* f, ProfEvent& pe, cudaStream_t s, int cls, double flops) {
@@ -319,10 +340,8 @@ struct ProfScope {  // brackets the launches of a block: { ProfScope ps(f, strea
     ~ProfScope() { prof_end(f, pe, s); }
 };
 
-static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
-                double beta, const double* Cin, int ldcin, double* D, int ldd, int riccati_diag = 0, double T = 0.0,
-                int force_config = -1, int skip = 0) {
-    if (M <= 0 || N <= 0) return EQVIO_OK;
+static GemmProblem make_problem(Filter* f, int transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
+                                int ldb, double beta, const double* Cin, int ldcin, double* D, int ldd, int riccati_diag, double T, int skip = 0) {
     GemmProblem g;
     g.M = M; g.N = N; g.K = K;
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.transB = transB;
@@ -330,14 +349,41 @@ static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const 
     g.skip_m = g.skip_n = skip;
     g.epilogue = riccati_diag ? EPI_RICCATI : EPI_AXPBY;
     g.epi.alpha = alpha; g.epi.beta = beta; g.epi.Cin = Cin; g.epi.ldcin = ldcin;
-    g.epi.T = T; g.epi.T_dev = riccati_diag ? &f->sc->T : nullptr; g.epi.Bb = nullptr; g.epi.ldbb = 0;
+    g.epi.T = T; g.epi.T_dev = riccati_diag ? &f->sc->Tpp[f->par] : nullptr; g.epi.Bb = nullptr; g.epi.ldbb = 0;
     for (int i = 0; i < 6; ++i) g.epi.Rd[i] = 0;
     g.epi.Pd[0] = f->s.biasOmegaProcessVariance; g.epi.Pd[1] = f->s.biasAccelProcessVariance;
     g.epi.Pd[2] = f->s.gravityProcessVariance; g.epi.Pd[3] = f->s.velocityProcessVariance;
     g.epi.Pd[4] = f->s.pointProcessVariance;
+    return g;
+}
+
+static int gemm(Filter* f, const GemmProblem& g, int force_config = -1) {
+    if (g.M <= 0 || g.N <= 0) return EQVIO_OK;
     ProfEvent pe;
-    prof_begin(f, pe, f->cur, f->prof_cls, 2.0 * M * N * K);
+    prof_begin(f, pe, f->cur, f->prof_cls, 2.0 * g.M * g.N * g.K);
     CU_TRY(dgemm_launch(g, f->cur, force_config));
+    prof_end(f, pe, f->cur);
+    f->launches += 1;
+    return EQVIO_OK;
+}
+
+static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
+                double beta, const double* Cin, int ldcin, double* D, int ldd, int riccati_diag = 0, double T = 0.0,
+                int force_config = -1, int skip = 0) {
+    return gemm(f, make_problem(f, transB, M, N, K, alpha, A, lda, B, ldb, beta, Cin, ldcin, D, ldd, riccati_diag, T, skip), force_config);
+}
+
+// (A B) C as the reference associates it: W = g1, then g2 with A == W.  One launch when that pays (dgemm_pair_pays),
+// else two.  Each call site has its own counter buffer (pairs on different streams never share one).
+enum { PAIR_RICCATI = 0, PAIR_S = 1, PAIR_SIGMA = 2, PAIR_SITES = 3 };
+static int gemm_pair(Filter* f, const GemmProblem& g1, const GemmProblem& g2, int site) {
+    if (!((f->use_pairs >> site) & 1) || !dgemm_pair_pays(g1, g2)) {
+        const int st = gemm(f, g1);
+        return st ? st : gemm(f, g2);
+    }
+    ProfEvent pe;
+    prof_begin(f, pe, f->cur, f->prof_cls, 2.0 * g1.M * g1.N * g1.K + 2.0 * g2.M * g2.N * g2.K);
+    CU_TRY(dgemm_pair_launch(g1, g2, f->pair_sync + (size_t)site * DGEMM_PAIR_SYNC_INTS, f->cur));
     prof_end(f, pe, f->cur);
     f->launches += 1;
     return EQVIO_OK;
@@ -432,13 +478,13 @@ static RiccatiOut riccati_out(Filter* f) {
 }
 
 // The two Sigma GEMMs of the Riccati step (VIOFilter.cpp:188-189); F, B_b already built.
+//   W = F Sigma;   Sigma = [W | T B_b R] [F | B_b]^T + T P      (K runs over n16 + 6 columns; [n, n16) are zero)
 static int riccati_gemms(Filter* f, double T) {
     const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld;
     f->prof_cls = PROF_RICCATI;
-    int st = gemm(f, 0, n, n, n, 1.0, f->F, ld, f->Sigma, ld, 0.0, nullptr, 0, f->W, ld);  // W = F Sigma
-    if (st) return st;
-    // Sigma = [W | T B_b R] [F | B_b]^T + T P      (K runs over n16 + 6 columns; [n, n16) are zero)
-    st = gemm(f, 1, n, n, n16 + 6, 1.0, f->W, ld, f->F, ld, 0.0, nullptr, 0, f->Sigma, ld, 1, T);
+    const GemmProblem g1 = make_problem(f, 0, n, n, n, 1.0, f->F, ld, f->Sigma, ld, 0.0, nullptr, 0, f->W, ld, 0, 0.0);
+    const GemmProblem g2 = make_problem(f, 1, n, n, n16 + 6, 1.0, f->W, ld, f->F, ld, 0.0, nullptr, 0, f->Sigma, ld, 1, T);
+    const int st = gemm_pair(f, g1, g2, PAIR_RICCATI);
     f->prof_cls = PROF_UPDATE;
     return st;
 }
@@ -464,26 +510,45 @@ static int integrate(Filter* f, double newTime, bool doRiccati, const double* om
         }
     }
     if (!a.do_init && !a.do_integrate && !a.do_latch) return 0;
-    if (a.do_riccati) { int st = prepare_layout(f); if (st) return st; }
+    if (a.do_riccati) {
+        int st = prepare_layout(f);
+        if (st) return st;
+        f->par ^= 1;                       // this tick's F / W border / T go to the other buffer
+        f->F = f->Fpp[f->par]; f->W = f->Wpp[f->par];
+    }
+    a.parity = f->par;
     RiccatiOut ro = riccati_out(f);
+    // ---- state stream: behind whatever the main stream did to the state since the last tick (vision update,
+    // bookkeeping, snapshot ...) and behind the GEMMs that last read this parity's F / W (two ticks ago)
+    cudaStream_t ss = f->state;
+    if (f->main_dirty) {
+        CU_TRY(cudaEventRecord(f->ev_main, f->stream));
+        CU_TRY(cudaStreamWaitEvent(ss, f->ev_main, 0));
+        f->main_dirty = false;
+    } else if (a.do_riccati) {
+        CU_TRY(cudaStreamWaitEvent(ss, f->ev_gemm[f->par], 0));
+    }
     {
-        ProfScope ps(f, f->stream, PROF_MISC);
-        launch_step_prepare(f->stream, f->st, f->sc, a, ro);   // the sample, dt and T travel as kernel arguments
+        ProfScope ps(f, ss, PROF_MISC);
+        launch_step_prepare(ss, f->st, f->sc, a, ro);   // the sample, dt and T travel as kernel arguments
         f->launches += 1;
     }
+    if (a.do_integrate && f->N > 0) {
+        ProfScope ps(f, ss, PROF_MISC);
+        launch_feature_step(ss, f->st, f->sc, f->L, f->N, a.do_riccati, a.discrete_lift, ro);
+        f->launches += 1;
+    }
+    // ---- main stream: everything queued there from now on sees this tick's state
+    CU_TRY(cudaEventRecord(f->ev_state, ss));
+    CU_TRY(cudaStreamWaitEvent(f->stream, f->ev_state, 0));
     if (a.do_integrate) {
-        // everything behind k_step_prepare reads its scalars (T, dt, stamp) from device memory: replayable
-        auto tail = [&]() -> int {
-            if (f->N > 0) {
-                ProfScope ps(f, f->stream, PROF_MISC);
-                launch_feature_step(f->stream, f->st, f->sc, f->L, f->N, a.do_riccati, a.discrete_lift, ro);
-                f->launches += 1;
-            }
-            return a.do_riccati ? riccati_gemms(f, a.T) : EQVIO_OK;
-        };
-        const int st = a.do_riccati ? run_graphed(f, GRAPH_RICCATI, a.discrete_lift, tail) : tail();
-        if (st) return st;
-        if (a.do_riccati) f->accTime = 0.0;
+        if (a.do_riccati) {
+            // the two Sigma GEMMs read T from device memory (written by k_step_prepare): replayable
+            const int st = run_graphed(f, GRAPH_RICCATI, f->par, [&]() { return riccati_gemms(f, a.T); });
+            if (st) return st;
+            CU_TRY(cudaEventRecord(f->ev_gemm[f->par], f->stream));
+            f->accTime = 0.0;
+        }
         f->currentTime = newTime;
     }
     return integrated;
@@ -554,8 +619,8 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     f->launches += 1;
     stamp(f, s, ST_C_DELTA);
     // S = (C Sigma) C^T + Q                                        VIOFilter.cpp:276
-    if ((st = gemm(f, 0, m, n, n, 1.0, f->C, ldm, f->Sigma, ld, 0.0, nullptr, 0, f->CS, ldm))) return st;
-    if ((st = gemm(f, 1, m, m, n, 1.0, f->CS, ldm, f->C, ldm, 0.0, nullptr, 0, f->Saug, f->ld2m))) return st;
+    if ((st = gemm_pair(f, make_problem(f, 0, m, n, n, 1.0, f->C, ldm, f->Sigma, ld, 0.0, nullptr, 0, f->CS, ldm, 0, 0.0),
+                        make_problem(f, 1, m, m, n, 1.0, f->CS, ldm, f->C, ldm, 0.0, nullptr, 0, f->Saug, f->ld2m, 0, 0.0), PAIR_S))) return st;
     {
         ProfScope ps(f, s, PROF_MISC);
         launch_add_diag_const(s, f->Saug, f->ld2m, m, f->s.measurementVariance);
@@ -601,11 +666,12 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
             CU_TRY(cudaStreamWaitEvent(f->side, f->ev_lift_elim, 0));
             for (int d = 0; d < f->trail_delay; ++d) { launch_nop(f->side); f->launches += 1; }
         }
-        if ((st = gemm(f, 0, n, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, f->W, ld))) return st;
-        if ((st = gemm(f, 0, n, n, n, -1.0, f->W, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld))) return st;
+        double* KC = f->Wpp[0];   // columns [0, n) of a Riccati work buffer; fixed (not parity-dependent) so that the update graph's key is not
+        if ((st = gemm_pair(f, make_problem(f, 0, n, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, KC, ld, 0, 0.0),
+                            make_problem(f, 0, n, n, n, -1.0, KC, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld, 0, 0.0), PAIR_SIGMA))) return st;
         stamp(f, f->side, ST_SIDE2_DONE);
         if ((st = end_side(f))) return st;
-        // W's columns [0, n) now hold K C; the Riccati step rewrites them (W = F Sigma) before use.
+        // Wpp[0]'s columns [0, n) now hold K C; the Riccati step rewrites them (W = F Sigma) before use.
     }
     if (do_lift) {
         const int use_lift = f->s.useInnovationLift, discrete = f->s.useDiscreteInnovationLift;
@@ -634,6 +700,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
 }
 
 static int update(Filter* f, bool do_lift, bool do_sigma) {
+    f->main_dirty = true;
     int st = prepare_layout(f);
     if (st) return st;
     const int flags = (do_lift ? 1 : 0) | (do_sigma ? 2 : 0);
@@ -656,6 +723,7 @@ static int flags_to_status(int flags) {
 }
 
 static int init_state(Filter* f) {
+    f->main_dirty = true;
     // VIOFilter::VIOFilter(const Settings&), VIOFilter.cpp:60-73 + member defaults VIOFilter.h:46-55
     BaseState b;
     memset(&b, 0, sizeof b);
@@ -722,6 +790,8 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
         CU_TRY(cudaStreamCreateWithPriority(&f->lift, cudaStreamNonBlocking, hi));
         CU_TRY(cudaStreamCreateWithPriority(&f->main_h, cudaStreamNonBlocking, hi));
         CU_TRY(cudaStreamCreateWithPriority(&f->lift_h, cudaStreamNonBlocking, hi));
+        CU_TRY(cudaStreamCreateWithPriority(&f->state, cudaStreamNonBlocking, hi));
+        for (cudaEvent_t* e : {&f->ev_state, &f->ev_main, &f->ev_gemm[0], &f->ev_gemm[1]}) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         for (cudaEvent_t* e : {&f->ev_sa, &f->ev_sb, &f->ev_st, &f->ev_la, &f->ev_lb, &f->ev_lt}) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_fork, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_done, cudaEventDisableTiming));
@@ -729,6 +799,9 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     }
     f->cur = f->stream;
     if (const char* e = getenv("EQVIO_GRAPHS")) f->use_graphs = !(e[0] == '0');
+    if (const char* e = getenv("EQVIO_PAIRS")) f->use_pairs = atoi(e);
+    CU_TRY(dalloc(&f->pair_sync, (size_t)PAIR_SITES * DGEMM_PAIR_SYNC_INTS));
+    CU_TRY(cudaMemset(f->pair_sync, 0, (size_t)PAIR_SITES * DGEMM_PAIR_SYNC_INTS * sizeof(int)));
     if (const char* e = getenv("EQVIO_SIGMA_AFTER_LIFT")) f->sigma_after_lift = atoi(e);
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
     if (const char* e = getenv("EQVIO_STAMPS"))
@@ -761,11 +834,13 @@ int eqvio_destroy(eqvio_handle_t f) {
     cudaStreamSynchronize(f->lift);
     cudaStreamSynchronize(f->main_h);
     cudaStreamSynchronize(f->lift_h);
+    cudaStreamSynchronize(f->state);
     for (auto& e : f->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (f->prof_base) cudaEventDestroy(f->prof_base);
     drop_graphs(f);
     free_device(f);
     cudaFree(f->stamps);
+    cudaFree(f->pair_sync);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
@@ -773,6 +848,8 @@ int eqvio_destroy(eqvio_handle_t f) {
     cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join); cudaEventDestroy(f->ev_lift_fork); cudaEventDestroy(f->ev_lift_done); cudaEventDestroy(f->ev_lift_elim);
     cudaStreamDestroy(f->side); cudaStreamDestroy(f->lift); cudaStreamDestroy(f->main_h); cudaStreamDestroy(f->lift_h);
     for (cudaEvent_t e : {f->ev_sa, f->ev_sb, f->ev_st, f->ev_la, f->ev_lb, f->ev_lt}) cudaEventDestroy(e);
+    for (cudaEvent_t e : {f->ev_state, f->ev_main, f->ev_gemm[0], f->ev_gemm[1]}) cudaEventDestroy(e);
+    cudaStreamDestroy(f->state);
     cudaStreamDestroy(f->stream);
     delete f;
     return EQVIO_OK;
@@ -808,6 +885,7 @@ static int process_vision_impl(Filter* f, double stamp, int nmeas, const int* mi
     if (r < 0) return r;
     if (r == 0) return EQVIO_SKIPPED_DT;
     if (!f->initialised) return EQVIO_NOT_INITIALISED;
+    f->main_dirty = true;   // bookkeeping and the update below change the state on the main stream
     for (int i = 1; i < nmeas; ++i)
         if (mids[i] < mids[i - 1]) return EQVIO_ERR_UNSORTED;
     cudaStream_t s = f->stream;
@@ -907,6 +985,7 @@ int eqvio_set_inertial_points(eqvio_handle_t f, int n, const int* ids, const dou
     CU_TRY(cudaSetDevice(f->device));
     int st = ensure_capacity(f, n);
     if (st) return st;
+    f->main_dirty = true;
     cudaEventSynchronize(f->stage_free);
     memcpy(f->h_stage, points, (size_t)3 * n * 8);
     CU_TRY(cudaMemcpyAsync(f->y_in, f->h_stage, (size_t)3 * n * 8, cudaMemcpyHostToDevice, f->stream));
@@ -1052,6 +1131,7 @@ int eqvio_set_snapshot(eqvio_handle_t f, const double* d, size_t len) {
     if (N < 0 || len < eqvio_snapshot_size(N)) return EQVIO_ERR_ARG;
     CU_TRY(cudaSetDevice(f->device));
     CU_TRY(cudaStreamSynchronize(f->stream));
+    f->main_dirty = true;
     int st = ensure_capacity(f, std::max(N, 1));
     if (st) return st;
     BaseState b;
@@ -1096,6 +1176,7 @@ static int upload_bearings(Filter* f, const double* bearings) {
 // Builds F and B_b for (T, omega) without touching the filter state: the state kernels are run with
 // do_integrate on a scratch copy is avoided by saving / restoring the small state and landmark arrays.
 static int build_FB_only(Filter* f, double T, const double omega[3]) {
+    f->main_dirty = true;   // everything here runs on the main stream
     // Save the mutable state that k_step_prepare / k_feature_step would change.
     BaseState saved;
     int st = fetch_base(f, &saved);
@@ -1109,7 +1190,7 @@ static int build_FB_only(Filter* f, double T, const double omega[3]) {
     if ((st = prepare_layout(f))) return st;
     ImuArgs a;
     memset(&a, 0, sizeof a);
-    a.do_integrate = 1; a.do_riccati = 1; a.dt = 0.0; a.T = T; a.discrete_lift = 1;
+    a.do_integrate = 1; a.do_riccati = 1; a.dt = 0.0; a.T = T; a.discrete_lift = 1; a.parity = f->par;
     RiccatiOut ro = riccati_out(f);
     launch_step_prepare(f->stream, f->st, f->sc, a, ro);
     if (f->N > 0) launch_feature_step(f->stream, f->st, f->sc, f->L, f->N, 1, 1, ro);
@@ -1178,6 +1259,7 @@ int eqvio_bundle_lift(eqvio_handle_t f, const double* gamma_eqf, double* Gamma) 
     if (!f || !gamma_eqf || !Gamma) return EQVIO_ERR_ARG;
     CU_TRY(cudaSetDevice(f->device));
     const int N = f->N, p = 5 + 3 * N, ld = f->ld;
+    f->main_dirty = true;
     std::vector<double> g(n_of(N), 0.0);
     memcpy(g.data() + 6, gamma_eqf, (size_t)p * 8);
     CU_TRY(cudaMemcpy(f->gamma, g.data(), g.size() * 8, cudaMemcpyHostToDevice));

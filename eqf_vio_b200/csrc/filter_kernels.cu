@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(128) k_step_prepare(BaseState* st, StepScratch
             double* F = ro.F; double* W = ro.W; double* Bb = ro.Bb;
             if (role == 0) {
                 sc->T = a.T;
+                sc->Tpp[a.parity & 1] = a.T;
                 // A0[2:5,0:2] = -g * stereoSphereChartInvDiff(0, eta0)   (EqFMatrices.cpp:289)
                 M32 D = stereo_sphere_chart_inv_diff(0.0, 0.0, eta0, &sing);
                 for (int r = 0; r < 3; ++r)

@@ -40,7 +40,8 @@ struct StepScratch {
     M3 RT_IC;      // R_IC^-1 as a matrix                  (EqFMatrices.cpp:371)
     M3 RT_IC_sx;   // R_IC^-1 [x_IC]x                      (EqFMatrices.cpp:376)
     V3 vC;         // camera-frame linear velocity, mean omega (EqFMatrices.cpp:302-304)
-    double T;      // accumulated time of this Riccati step (also read by the Riccati GEMM epilogue)
+    double T;      // accumulated time of this Riccati step
+    double Tpp[2]; // the same, by tick parity: read by the Riccati GEMM epilogue while the next tick's k_step_prepare runs
     double stamp;  // stamp of the step being processed (pose record of the vision update)
     double Rd[6];
     // state propagate
@@ -66,6 +67,7 @@ struct ImuArgs {
     double T;           // accumulatedTime including dt (valid when do_riccati)
     int do_init, do_integrate, do_riccati, do_latch;
     int discrete_lift;
+    int parity;         // which of the two F / W / T buffers this tick writes
 };
 
 struct RiccatiOut {

@@ -42,6 +42,12 @@ class VIOFilter:
         self._h = C.c_void_p()
         abi.check(self._L.eqvio_create(C.byref(self.settings), int(device), C.byref(self._h)), "eqvio_create")
         self.device = device
+        # the IMU call runs 200 times per second of data: its six doubles go through one preallocated ctypes buffer
+        # (numpy -> ctypes pointer conversion costs ~4 us per array, more than the C call itself)
+        self._imu6 = (C.c_double * 6)()
+        self._imu_om = C.cast(self._imu6, C.POINTER(C.c_double))
+        self._imu_ac = C.cast(C.byref(self._imu6, 24), C.POINTER(C.c_double))
+        self._process_imu = self._L.eqvio_process_imu
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -59,8 +65,13 @@ class VIOFilter:
         abi.check(self._L.eqvio_reset(self._h), "eqvio_reset")
 
     def processIMUData(self, stamp, omega, accel) -> int:
-        o, a = _vec(omega, 3), _vec(accel, 3)
-        return abi.check(self._L.eqvio_process_imu(self._h, float(stamp), _p(o), _p(a)), "eqvio_process_imu")
+        o = omega.tolist() if hasattr(omega, "tolist") else list(omega)
+        a = accel.tolist() if hasattr(accel, "tolist") else list(accel)
+        if len(o) != 3 or len(a) != 3:
+            raise ValueError("omega and accel must have 3 values each")
+        self._imu6[:] = o + a
+        st = self._process_imu(self._h, float(stamp), self._imu_om, self._imu_ac)
+        return st if st >= 0 else abi.check(st, "eqvio_process_imu")
 
     def processVisionData(self, stamp, ids, bearings) -> int:
         ids = np.ascontiguousarray(ids, dtype=np.int32)
