@@ -364,14 +364,21 @@ def main():
         peak_tf = 2 * 8192**3 / (best * 1e-3) / 1e12
         del a, b
         fm = flop_model(N)
-        # dominant kernel: the 32x32-tile instantiation of the DMMA GEMM that runs the reference's four dense Sigma
-        # contractions (Riccati pair + the six update products); the 64-deep panel / trailing GEMMs of the Schur
-        # eliminations and their chain kernels are latency-bound and reported per class below
-        dom = [classes["riccati_gemm"], classes["update_gemm"]]
+        # dominant kernel: the Riccati step's two Sigma contractions (F Sigma) F^T — one launch of the pair kernel when the
+        # first product runs for more than a wave of CTA slots (or both fit one CTA per SM), else two launches of the
+        # single-product kernel; same 32x32 DMMA tile code either way.  The update's GEMMs, the 64-deep panel / trailing
+        # GEMMs of the Schur eliminations and their chain kernels are reported per class below.
+        n_sigma = 11 + 3 * N
+        t1 = ((n_sigma + 31) // 32) ** 2
+        paired = (2 * t1 <= 148) or (t1 >= 1110)
+        dom = [classes["riccati_gemm"]]
         d_ms, d_flops, d_launches = sum(c["ms"] for c in dom), sum(c["flops"] for c in dom), sum(c["launches"] for c in dom)
         achieved_tf = d_flops / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
+        kernel_name = ("eqvio::dgemm_pair_kernel<TileCfg<32,32,16,16,...>> (fp64 DMMA.8x8x4, TMA-staged; W = F Sigma and Sigma' = [W|T B R][F|B]^T + T P in one launch, "
+                       "second product gated per row block of W)" if paired else
+                       "eqvio::dgemm_dmma_tma_kernel<TileCfg<32,32,16,16,4,4>> (fp64 DMMA.8x8x4, TMA-staged), two launches per Riccati step: W = F Sigma, Sigma' = [W|T B R][F|B]^T + T P")
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r01c_gemm_traffic.json")
         if os.path.exists(tpath):
             try:
                 traffic = json.load(open(tpath)).get(f"N{N}")
@@ -395,12 +402,13 @@ def main():
             "cuda_graphs": {"replays_so_far": graph_replays, "instantiated": graphs_held,
                             "note": "gpu_launches counts this library's kernels, those inside replayed graphs included"},
             "roofline": {
-                "bound": "tensor", "kernel": "eqvio::dgemm_dmma_tma_kernel<TileCfg<32,32,16,16,4,4>> (fp64 DMMA.8x8x4, TMA-staged): Riccati (F Sigma, W F^T) and update (C Sigma, S, Sigma C^T, K, K C, Sigma - K C Sigma) GEMMs",
+                "bound": "tensor", "kernel": kernel_name,
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                 "traffic": traffic,
                 "launches": d_launches, "avg_launch_ms": d_ms / d_launches if d_launches else None,
                 "flops_per_launch_avg": d_flops / d_launches if d_launches else None,
-                "how": "every launch bracketed by CUDA events on its own stream inside the library (eqvio_profile_enable, direct launches instead of graph replay) over K periods; achieved = executed 2MNK flops / summed launch time",
+                "how": "every launch of the Riccati contractions bracketed by CUDA events on its stream inside the library (eqvio_profile_enable, direct launches instead of graph replay) over K periods; achieved = executed 2MNK flops (4n^3 + 2n^2(n16-n+6) per step) / summed launch time",
+                "algorithmic_bytes_per_launch": (4 if paired else 3) * 8 * n_sigma * n_sigma,
                 "peak_source": "measured live: torch.matmul fp64 8192^3 (cuBLAS DGEMM), best of 5, same GPU; MEASURED_PEAKS.json holds no fp64 figure. DMMA pipe ceiling measured at 37.1 TFLOP/s (profiles/r01_dmma_microbench.md)",
                 "kernel_share_of_step": d_ms / (dev_ms / world) if dev_ms else None,
                 "all_gemm_launches": {"launches": g_launches, "ms": g_ms, "tflops": g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,

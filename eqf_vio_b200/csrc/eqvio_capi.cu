@@ -1326,6 +1326,54 @@ int eqvio_dgemm(int device, int transB, int M, int N, int K, double alpha, const
     return EQVIO_OK;
 }
 
+int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int lda1, const double* B1, int ldb1, int transB2, int N2,
+                     double alpha2, const double* B2, int ldb2, double* W, int ldw, double* D, int ldd, int reps, float* ms) {
+    if (M <= 0 || N1 <= 0 || K1 <= 0 || N2 <= 0 || !A1 || !B1 || !B2) return EQVIO_ERR_ARG;
+    if ((M + 31) / 32 > DGEMM_PAIR_MAX_ROW_BLOCKS) return EQVIO_ERR_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return EQVIO_ERR_NO_DEVICE;
+    CU_TRY(cudaSetDevice(device));
+    const int b2row = transB2 ? N2 : N1, b2col = transB2 ? N1 : N2;
+    const int dlda = round_up(M, 16) + 16, dldb1 = round_up(K1, 16) + 16, dldb2 = round_up(b2row, 16) + 16;
+    double *dA, *dB1, *dB2, *dW, *dD;
+    int* sync;
+    CU_TRY(dalloc(&dA, (size_t)dlda * (K1 + 32))); CU_TRY(dalloc(&dB1, (size_t)dldb1 * (N1 + 32)));
+    CU_TRY(dalloc(&dB2, (size_t)dldb2 * (b2col + 32))); CU_TRY(dalloc(&dW, (size_t)dlda * (N1 + 32))); CU_TRY(dalloc(&dD, (size_t)dlda * (N2 + 32)));
+    CU_TRY(dalloc(&sync, DGEMM_PAIR_SYNC_INTS));
+    CU_TRY(cudaMemset(sync, 0, DGEMM_PAIR_SYNC_INTS * sizeof(int)));
+    CU_TRY(cudaMemset(dA, 0, (size_t)dlda * (K1 + 32) * 8)); CU_TRY(cudaMemset(dB1, 0, (size_t)dldb1 * (N1 + 32) * 8));
+    CU_TRY(cudaMemset(dB2, 0, (size_t)dldb2 * (b2col + 32) * 8)); CU_TRY(cudaMemset(dW, 0, (size_t)dlda * (N1 + 32) * 8));
+    CU_TRY(cudaMemcpy2D(dA, (size_t)dlda * 8, A1, (size_t)lda1 * 8, (size_t)M * 8, K1, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy2D(dB1, (size_t)dldb1 * 8, B1, (size_t)ldb1 * 8, (size_t)K1 * 8, N1, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy2D(dB2, (size_t)dldb2 * 8, B2, (size_t)ldb2 * 8, (size_t)b2row * 8, b2col, cudaMemcpyHostToDevice));
+    GemmProblem g1, g2;
+    g1.M = M; g1.N = N1; g1.K = K1; g1.A = dA; g1.lda = dlda; g1.B = dB1; g1.ldb = dldb1; g1.transB = 0; g1.D = dW; g1.ldd = dlda;
+    g1.epilogue = EPI_AXPBY; memset(&g1.epi, 0, sizeof g1.epi); g1.epi.alpha = 1.0;
+    g2.M = M; g2.N = N2; g2.K = N1; g2.A = dW; g2.lda = dlda; g2.B = dB2; g2.ldb = dldb2; g2.transB = transB2; g2.D = dD; g2.ldd = dlda;
+    g2.epilogue = EPI_AXPBY; memset(&g2.epi, 0, sizeof g2.epi); g2.epi.alpha = alpha2;
+    CU_TRY(dgemm_pair_launch(g1, g2, sync, 0));
+    CU_TRY(cudaDeviceSynchronize());
+    if (reps > 1 && ms) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < reps; ++i) CU_TRY(dgemm_pair_launch(g1, g2, sync, 0));
+        cudaEventRecord(e1, 0);
+        CU_TRY(cudaEventSynchronize(e1));
+        float t;
+        cudaEventElapsedTime(&t, e0, e1);
+        *ms = t / reps;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    } else if (ms) *ms = 0;
+    int hs[2] = {-1, -1};
+    CU_TRY(cudaMemcpy(hs, sync, 8, cudaMemcpyDeviceToHost));   // the kernel must leave its counters zero
+    if (W) CU_TRY(cudaMemcpy2D(W, (size_t)ldw * 8, dW, (size_t)dlda * 8, (size_t)M * 8, N1, cudaMemcpyDeviceToHost));
+    if (D) CU_TRY(cudaMemcpy2D(D, (size_t)ldd * 8, dD, (size_t)dlda * 8, (size_t)M * 8, N2, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB1); cudaFree(dB2); cudaFree(dW); cudaFree(dD); cudaFree(sync);
+    if (hs[0] != 0 || hs[1] != 0) { snprintf(g_last_error, sizeof g_last_error, "pair kernel left its counters at %d / %d", hs[0], hs[1]); return EQVIO_ERR_CUDA; }
+    return EQVIO_OK;
+}
+
 // One diagonal block of the Schur eliminations on its own (unit parity + timing): unpivoted LU of the nb x nb
 // block A (nb <= 64) and the two 64 x 64 identity-padded triangular inverses.
 int eqvio_getrf_block(int device, int nb, const double* A, int lda, double* LU, double* Linv, double* Uinv, int reps, float* us) {

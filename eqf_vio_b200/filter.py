@@ -248,6 +248,27 @@ def getrf_block(A, device=0, reps=1):
     return LU, Li, Ui, us.value
 
 
+def dgemm_pair(A1, B1, B2, transB2=True, alpha2=1.0, device=0, reps=1):
+    """W = A1 @ B1, D = alpha2 * W @ op(B2) as ONE launch of the library's pair kernel (host arrays).  Returns (W, D, ms)."""
+    L = abi.lib()
+    A1 = np.asfortranarray(A1, dtype=np.float64)
+    B1 = np.asfortranarray(B1, dtype=np.float64)
+    B2 = np.asfortranarray(B2, dtype=np.float64)
+    M, K1 = A1.shape
+    N1 = B1.shape[1]
+    assert B1.shape[0] == K1
+    N2 = B2.shape[0] if transB2 else B2.shape[1]
+    assert (B2.shape[1] if transB2 else B2.shape[0]) == N1
+    W = np.zeros((M, N1), order="F")
+    D = np.zeros((M, N2), order="F")
+    ms = C.c_float()
+    abi.check(
+        L.eqvio_dgemm_pair(int(device), M, N1, K1, _p(A1), M, _p(B1), K1, int(transB2), N2, float(alpha2), _p(B2), B2.shape[0], _p(W), M, _p(D), M, int(reps), C.byref(ms)),
+        "eqvio_dgemm_pair",
+    )
+    return W, D, ms.value
+
+
 def dgemm(A, B, transB=False, alpha=1.0, beta=0.0, Cin=None, device=0, reps=1):
     """C = alpha * A @ op(B) + beta * Cin on the library's DMMA kernel (host arrays).  Returns (C, ms)."""
     L = abi.lib()

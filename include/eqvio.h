@@ -169,6 +169,15 @@ int eqvio_bundle_lift(eqvio_handle_t h, const double* gamma_eqf, double* Gamma);
 int eqvio_dgemm(int device, int transB, int M, int N, int K, double alpha, const double* A, int lda,
                 const double* B, int ldb, double beta, double* C, int ldc, int reps, float* ms);
 
+/* The reference's left-to-right product chains (A B) C — (F Sigma) F^T VIOFilter.cpp:189, (C Sigma) C^T :276,
+ * (K C) Sigma :297 — as ONE launch of the library's pair kernel: W = A1 * B1 (M x N1, K1 deep), then
+ * D = alpha2 * W * op(B2) (M x N2, N1 deep; transB2: B2 stored N2 x N1), the second product's tiles starting as
+ * their row block of W completes.  Host buffers, column-major; W and D are outputs (either may be NULL).
+ * `reps` > 1 repeats the launch and *ms receives the mean CUDA-event time per launch (may be NULL). */
+int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int lda1, const double* B1, int ldb1,
+                     int transB2, int N2, double alpha2, const double* B2, int ldb2, double* W, int ldw, double* D,
+                     int ldd, int reps, float* ms);
+
 /* One diagonal block of the blocked Schur eliminations that stand in for `S.inverse()` (VIOFilter.cpp:277)
  * and `Sigma.inverse()` (EqFMatrices.cpp:239): unpivoted LU of the nb x nb block A (nb <= 64, col-major,
  * host) and the triangular inverses L^-1, U^-1 as 64 x 64 identity-padded col-major matrices.  LU (nb x nb,

@@ -304,6 +304,28 @@ def test_graph_replay_is_bit_identical(fast):
     assert a.launch_count() == b.launch_count()
 
 
+def test_pair_launch_and_state_stream_are_bit_identical(monkeypatch):
+    """The Riccati step as one pair launch (EQVIO_PAIRS bit 0, default) against the same two GEMMs as separate launches,
+    every call site paired (EQVIO_PAIRS=7) included: same tiles, same instruction order, so Sigma and the state agree
+    bit for bit over a sequence — which also exercises the double-buffered F / W / T of the state stream (tick t+1's
+    state kernels run under tick t's GEMMs)."""
+    import os
+
+    from eqf_vio_b200.settings import conditioned_settings
+
+    s = conditioned_settings(outlierThreshold=1e9)
+    seq = period_sequence(40, 6, camera_offset=tuple(s.cameraOffset))
+    snaps = []
+    for mask in ("0", "1", "7"):
+        monkeypatch.setenv("EQVIO_PAIRS", mask)
+        f = gpu_filter(s)
+        for kind, i in seq.events():
+            feed(f, seq, kind, i)
+        snaps.append(f.get_snapshot())
+    assert np.array_equal(snaps[0], snaps[1])
+    assert np.array_equal(snaps[0], snaps[2])
+
+
 def test_graph_cache_follows_landmark_churn():
     """Landmark count changes every frame (features dropped and re-added): keys change, graphs are only built for
     keys seen twice, results stay those of the direct path."""
@@ -350,3 +372,65 @@ def test_baseline_config2_full_length_N64():
     assert n_imu >= 2000 and n_vis == 201
     assert f.graph_stats()[0] > 2000          # the Riccati step and the update ran as replayed graphs
     assert worst_s < 1e-9 and worst_h < 1e-8, (worst_s, worst_h)
+
+
+def _long_run_with_checkpoints(N, periods, checkpoints, oracle_periods=1):
+    """Free-run the GPU filter over `periods` vision periods; at each checkpoint frame hand the GPU's own state to the
+    numpy restatement of the reference and compare one further vision period (11 filter steps) from that identical
+    state; return the properties that need no oracle."""
+    from eqf_vio_b200.settings import conditioned_settings
+    from helpers import np_settings
+    from oracle import eqvio_numpy as onp
+
+    s = conditioned_settings()
+    seq = period_sequence(N, periods, camera_offset=tuple(s.cameraOffset))
+    f = gpu_filter(s)
+    ev = list(seq.events())
+    worst_s = worst_h = 0.0
+    o, o_left, steps = None, 0, 0
+    for kind, i in ev:
+        r = feed(f, seq, kind, i)
+        steps += 1
+        if o is not None:
+            assert feed(o, seq, kind, i) == r
+            if kind == "vision":
+                o_left -= 1
+                if o_left == 0:
+                    h1, S1 = split_snapshot(f.get_snapshot())
+                    h2, S2 = split_snapshot(o.get_snapshot())
+                    worst_s, worst_h = max(worst_s, rel(S1, S2)), max(worst_h, np.abs(h1 - h2).max())
+                    o = None
+        if kind == "vision" and i in checkpoints:
+            o = onp.VIOFilter(np_settings(s))
+            o.set_snapshot(f.get_snapshot())
+            o_left = oracle_periods
+    S = f.stateCovariance()
+    e = f.stateEstimate()
+    return dict(steps=steps, worst_s=worst_s, worst_h=worst_h, S=S, est=e, seq=seq, replays=f.graph_stats()[0], N=f.numLandmarks)
+
+
+def test_baseline_config3_full_length_N256():
+    """BASELINE.json configs[2] at full length: N = 256 (Sigma 779 x 779), 60 s = 12000 IMU ticks + 1200 vision frames,
+    free-running on the GPU.  The CPU restatement needs ~15 minutes for that, so parity is checked where it is cheap
+    and exact in meaning: at frames 5, 400 and 1190 the oracle is started from the GPU's own state and both run one
+    further vision period (north_star tolerance: Sigma 1e-9, state 1e-8).  Size-independent properties over the whole
+    run: Sigma finite, symmetric to round-off, positive diagonal, landmark count unchanged, a finite pose."""
+    r = _long_run_with_checkpoints(256, 1200, checkpoints={5, 400, 1190})
+    assert r["steps"] >= 13200 and r["N"] == 256
+    assert r["replays"] > 12000
+    assert r["worst_s"] < 1e-9 and r["worst_h"] < 1e-8, (r["worst_s"], r["worst_h"])
+    S = r["S"]
+    assert np.isfinite(S).all() and rel(S, S.T) < 1e-9 and np.min(np.diag(S)) > 0
+    assert np.isfinite(r["est"].pose).all() and np.isfinite(r["est"].bodyLandmarks).all()
+    assert abs(np.linalg.norm(r["est"].pose[3:7]) - 1.0) < 1e-9
+
+
+def test_baseline_config4_truncated_N1024():
+    """BASELINE.json configs[3], N = 1024 (Sigma 3083 x 3083; the Riccati pair launch runs 10.6 waves of CTAs), 3 s of
+    the 60 s sequence (60 vision periods, 660 filter steps): one checkpointed vision period against the numpy
+    restatement from the GPU's own state at frame 50, and the size-independent properties."""
+    r = _long_run_with_checkpoints(1024, 60, checkpoints={50})
+    assert r["steps"] >= 660 and r["N"] == 1024
+    assert r["worst_s"] < 1e-9 and r["worst_h"] < 1e-8, (r["worst_s"], r["worst_h"])
+    S = r["S"]
+    assert np.isfinite(S).all() and rel(S, S.T) < 1e-9 and np.min(np.diag(S)) > 0

@@ -67,3 +67,40 @@ def test_gemm_full_size_property():
     C12, _ = dgemm(A1 + A2, B)
     assert rel(C12, C1 + C2) < 1e-13
     assert rel(C1, A1 @ B) < 1e-13
+
+
+PAIR_SHAPES = [(26, 26, 26, 26), (203, 203, 203, 203), (128, 203, 77, 128), (33, 65, 17, 40), (1, 1, 1, 1), (300, 31, 200, 64)]
+
+
+@pytest.mark.parametrize("transB2", [True, False])
+def test_gemm_pair_matches_two_launches(transB2):
+    """(A1 B1) op(B2) in ONE launch (row-block counters between the two products, dgemm_pair_launch) against the same
+    two products as separate launches: every tile runs the same instruction sequence on the same data, so W and D must
+    agree bit for bit; and against numpy at 1e-13."""
+    from eqf_vio_b200.filter import dgemm, dgemm_pair
+
+    rng = np.random.default_rng(5)
+    for (M, K1, N1, N2) in PAIR_SHAPES:
+        A1 = rng.standard_normal((M, K1)); B1 = rng.standard_normal((K1, N1))
+        B2 = rng.standard_normal((N2, N1) if transB2 else (N1, N2))
+        W, D, _ = dgemm_pair(A1, B1, B2, transB2=transB2, alpha2=-0.75)
+        W2, _ = dgemm(A1, B1)
+        D2, _ = dgemm(W2, B2, transB=transB2, alpha=-0.75)
+        assert np.array_equal(W, W2), (M, K1, N1, N2)
+        assert np.array_equal(D, D2), (M, K1, N1, N2)
+        assert rel(D, -0.75 * (A1 @ B1) @ (B2.T if transB2 else B2)) < TOL
+
+
+def test_gemm_pair_full_size_repeated():
+    """n = 1547 (N = 512): 2401 + 2401 tiles, 5.4 waves of the 888 CTA slots, so second-phase tiles really wait on row
+    counters; repeated launches reuse the self-resetting counters (the entry point checks they are left zero)."""
+    from eqf_vio_b200.filter import dgemm_pair
+
+    rng = np.random.default_rng(6)
+    n = 1547
+    F = np.eye(n) + 1e-3 * rng.standard_normal((n, n))
+    S = rng.standard_normal((n, n))
+    W, D, ms = dgemm_pair(F, S, F, transB2=True, reps=5)
+    assert rel(W, F @ S) < TOL
+    assert rel(D, (F @ S) @ F.T) < TOL
+    assert ms > 0
