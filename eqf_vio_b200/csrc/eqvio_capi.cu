@@ -1030,21 +1030,44 @@ static void pose7(double* o, const Se3& P) {
     o[0] = P.x.x; o[1] = P.x.y; o[2] = P.x.z; o[3] = P.R.w; o[4] = P.R.x; o[5] = P.R.y; o[6] = P.R.z;
 }
 
+// Base state and landmark arrays in one round trip: the copies are queued back to back into the pinned staging
+// area and the stream is synchronised once (stateEstimate() runs after every vision frame in the reference's
+// drivers, main.cpp:134).  lm receives LM_FIELDS x N doubles, field-major.
+static int fetch_state(Filter* f, BaseState* b, std::vector<double>& lm) {
+    const int N = f->N;
+    const size_t base_doubles = (sizeof(BaseState) + 7) / 8;
+    cudaEventSynchronize(f->stage_free);
+    CU_TRY(cudaMemcpyAsync(f->h_stage, f->st, sizeof(BaseState), cudaMemcpyDeviceToHost, f->stream));
+    double* hl = f->h_stage + base_doubles;
+    const bool whole = N > 0 && (size_t)LM_FIELDS * f->cap * 8 <= (size_t)256 * 1024 && base_doubles + (size_t)LM_FIELDS * f->cap <= f->h_stage_doubles;
+    if (whole) {
+        CU_TRY(cudaMemcpyAsync(hl, f->L.base, (size_t)LM_FIELDS * f->cap * 8, cudaMemcpyDeviceToHost, f->stream));   // one copy beats eight small ones
+    } else {
+        for (int k = 0; k < LM_FIELDS && N > 0; ++k)
+            CU_TRY(cudaMemcpyAsync(hl + (size_t)k * N, f->L.base + (size_t)k * f->cap, (size_t)N * 8, cudaMemcpyDeviceToHost, f->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    memcpy(b, f->h_stage, sizeof(BaseState));
+    lm.resize((size_t)LM_FIELDS * std::max(N, 1));
+    for (int k = 0; k < LM_FIELDS && N > 0; ++k) memcpy(lm.data() + (size_t)k * N, hl + (size_t)k * (whole ? f->cap : N), (size_t)N * 8);
+    return EQVIO_OK;
+}
+
 int eqvio_get_state(eqvio_handle_t f, double pose[7], double velocity[3], double cam_offset[7], int* n, int cap, int* ids,
                     double* landmarks) {
     if (!f) return EQVIO_ERR_ARG;
     CU_TRY(cudaSetDevice(f->device));
     BaseState b;
-    int st = fetch_base(f, &b);
+    std::vector<double> lm;
+    const bool want_lm = (ids || landmarks) && f->N > 0;
+    int st = want_lm ? fetch_state(f, &b, lm) : fetch_base(f, &b);
     if (st) return st;
     // stateGroupAction(X, xi0), VIOGroup.cpp:23-45
     if (pose) pose7(pose, b.pose0 * b.XA);
     if (velocity) { V3 v = rotate_inv(b.XA.R, b.vel0 - b.Xw); velocity[0] = v.x; velocity[1] = v.y; velocity[2] = v.z; }
     if (cam_offset) pose7(cam_offset, b.cam);
     if (n) *n = f->N;
-    if ((ids || landmarks) && f->N > 0) {
-        std::vector<double> lm;
-        if ((st = fetch_landmarks(f, lm))) return st;
+    if (want_lm) {
         const int N = f->N;
         for (int i = 0; i < N && i < cap; ++i) {
             if (ids) ids[i] = f->ids[i];
