@@ -170,7 +170,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gflops_dense_equiv": flop_model(N)["period"] * len(per) / total / 1e9,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(N, periods):
@@ -197,8 +197,23 @@ def cpu_baseline(N, periods):
             "ms_per_period": 1e3 * total / len(per)}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The contract is ONE JSON line on stdout: native libraries (NCCL prints its version banner to fd 1 when the
+    box sets NCCL_DEBUG) are kept off it by pointing fd 1 at stderr for the run and writing the line to the saved fd."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -423,7 +438,7 @@ def main():
             cb = cpu_baseline(N, args.cpu_periods)
             line["cpu_baseline"] = cb
             line["speedup_vs_cpu_baseline_e2e"] = e2e_value / cb["value"]
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
