@@ -99,6 +99,8 @@ struct eqvio_filter {
     double *C = nullptr, *CS = nullptr, *SCt = nullptr, *K = nullptr, *Saug = nullptr, *Sinv = nullptr;
     double *delta = nullptr, *gamma = nullptr, *y_in = nullptr, *y = nullptr, *scratch = nullptr, *Gamma = nullptr;
     int *d_flags = nullptr, *d_map = nullptr;
+    double* gemv_part = nullptr;   // partial sums of gamma = K delta (8 x ld)
+    int* gemv_cnt = nullptr;       // its per-row-block arrival counters
     // pinned staging
     double* h_stage = nullptr;  // bearings in / state out
     int* h_istage = nullptr;
@@ -206,6 +208,7 @@ static void free_device(Filter* f) {
     cudaFree(f->Sigma); cudaFree(f->Sigma2); cudaFree(f->Fpp[0]); cudaFree(f->Fpp[1]); cudaFree(f->Wpp[0]); cudaFree(f->Wpp[1]); cudaFree(f->Bb); cudaFree(f->Aug);
     cudaFree(f->C); cudaFree(f->CS); cudaFree(f->SCt); cudaFree(f->K); cudaFree(f->Saug); cudaFree(f->Sinv);
     cudaFree(f->delta); cudaFree(f->gamma); cudaFree(f->y_in); cudaFree(f->y); cudaFree(f->scratch); cudaFree(f->Gamma);
+    cudaFree(f->gemv_part); cudaFree(f->gemv_cnt); f->gemv_part = nullptr; f->gemv_cnt = nullptr;
     cudaFree(f->d_flags); cudaFree(f->d_map); cudaFree(f->LinvL); cudaFree(f->yo); cudaFree(f->Rt); cudaFree(f->wave);
     f->LinvL = f->yo = f->Rt = nullptr; f->wave = nullptr;
     f->L.base = f->L2.base = nullptr;
@@ -248,6 +251,9 @@ static int ensure_capacity(Filter* f, int needN) {
     CU_TRY(dalloc(&delta, (size_t)ldm)); CU_TRY(dalloc(&gamma, (size_t)ld)); CU_TRY(dalloc(&Gamma, (size_t)ld));
     CU_TRY(dalloc(&y_in, (size_t)3 * cap + 8)); CU_TRY(dalloc(&y, (size_t)3 * cap + 8)); CU_TRY(dalloc(&scratch, (size_t)cap + 8));
     CU_TRY(dalloc(&d_flags, (size_t)cap + 8)); CU_TRY(dalloc(&d_map, (size_t)ld + 8));
+    double* gemv_part; int* gemv_cnt;
+    CU_TRY(dalloc(&gemv_part, (size_t)8 * ld)); CU_TRY(dalloc(&gemv_cnt, (size_t)ld / 32 + 8));
+    CU_TRY(cudaMemsetAsync(gemv_cnt, 0, ((size_t)ld / 32 + 8) * sizeof(int), f->stream));
     cudaStream_t s = f->stream;
     CU_TRY(cudaMemsetAsync(Sigma, 0, nn * 8, s)); CU_TRY(cudaMemsetAsync(Sigma2, 0, nn * 8, s));
     CU_TRY(cudaMemsetAsync(Aug, 0, nn * 8, s));
@@ -273,6 +279,7 @@ static int ensure_capacity(Filter* f, int needN) {
     f->C = C; f->CS = CS; f->SCt = SCt; f->K = K; f->Saug = Saug; f->Sinv = Sinv;
     f->delta = delta; f->gamma = gamma; f->y_in = y_in; f->y = y; f->scratch = scratch; f->Gamma = Gamma;
     f->d_flags = d_flags; f->d_map = d_map;
+    f->gemv_part = gemv_part; f->gemv_cnt = gemv_cnt;
     f->LinvL = LinvL; f->yo = yo; f->Rt = Rt; f->wave = wave;
     f->layoutN = -1;
     f->main_dirty = true;
@@ -633,7 +640,8 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     }
     f->launches += 2;
     stamp(f, s, ST_S_FORMED);
-    // Sigma C^T does not depend on S^-1: it runs on the side stream under the (latency-bound) elimination
+    // Sigma C^T does not depend on S^-1: it runs on the side stream under the (latency-bound) elimination.  (Queued
+    // earlier, next to the two products that form S, it was measured 0.2 - 1 % slower at N = 256 / 512 / 1024.)
     if ((st = fork_side(f))) return st;
     // (a few empty kernels first: the S chain's first kernel becomes ready at the same moment and must get its SM
     // before this GEMM's 2400 CTAs occupy every slot for the next 170 us)
@@ -650,7 +658,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     stamp(f, s, ST_K);
     {
         ProfScope ps(f, s, PROF_MISC);
-        launch_gemv(s, f->K, ld, n, m, f->delta, f->gamma);  // :279
+        launch_gemv(s, f->K, ld, n, m, f->delta, f->gamma, f->gemv_part, f->gemv_cnt);  // :279
     }
     f->launches += 1;
     stamp(f, s, ST_GAMMA);

@@ -255,21 +255,49 @@ __global__ void __launch_bounds__(256) k_build_C_delta(BaseState* st, Landmarks 
     if (delta && bearings && lane < 2) delta[2 * i + lane] = sm[6 + lane];
 }
 
-// gamma = K delta  (VIOFilter.cpp:279).  K is n x m column-major.  Block = 32 rows x 8 column groups.
-__global__ void __launch_bounds__(256) k_gemv(const double* K, int ldk, int n, int m, const double* x, double* y) {
+// gamma = K delta  (VIOFilter.cpp:279).  K is n x m column-major.  It sits on the update's critical path between K and
+// the Sigma update, so the column range is split over GEMV_SPLIT CTAs per 32-row block (one CTA per row block took 48 us
+// at n = 1547: 128 dependent loads + adds per thread); each CTA leaves its partial sums in `part`, the CTA that arrives
+// last at the row block's counter adds them in a fixed order (deterministic, unlike fp64 atomics) and re-arms the counter.
+constexpr int GEMV_SPLIT = 8;
+__global__ void __launch_bounds__(256) k_gemv(const double* K, int ldk, int n, int m, const double* x, double* y, double* part, int* cnt) {
     __shared__ double red[8][33];
+    __shared__ int s_last;
     const int rx = threadIdx.x & 31, cy = threadIdx.x >> 5;
     const int r = blockIdx.x * 32 + rx;
-    double s = 0.0;
-    if (r < n)
-        for (int c = cy; c < m; c += 8) s += K[r + (size_t)ldk * c] * x[c];
-    red[cy][rx] = s;
+    const int per = (m + GEMV_SPLIT - 1) / GEMV_SPLIT, c_lo = blockIdx.y * per, c_hi = min(m, c_lo + per);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (r < n) {
+        int c = c_lo + cy;
+        for (; c + 24 < c_hi; c += 32) {
+            s0 += K[r + (size_t)ldk * c] * x[c];
+            s1 += K[r + (size_t)ldk * (c + 8)] * x[c + 8];
+            s2 += K[r + (size_t)ldk * (c + 16)] * x[c + 16];
+            s3 += K[r + (size_t)ldk * (c + 24)] * x[c + 24];
+        }
+        for (; c < c_hi; c += 8) s0 += K[r + (size_t)ldk * c] * x[c];
+    }
+    red[cy][rx] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (cy == 0 && r < n) {
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][rx];
-        y[r] = t;
+        part[(size_t)blockIdx.y * n + r] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&cnt[blockIdx.x], 1) == GEMV_SPLIT - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (cy == 0 && r < n) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < GEMV_SPLIT; ++k) t += __ldcg(&part[(size_t)k * n + r]);
+            y[r] = t;
+        }
+        if (threadIdx.x == 0) cnt[blockIdx.x] = 0;
     }
 }
 
@@ -1035,8 +1063,8 @@ void launch_build_C_delta(cudaStream_t s, BaseState* st, Landmarks L, int N, con
                           double* delta) {
     if (N > 0) k_build_C_delta<<<cdiv(N, 8), 256, 0, s>>>(st, L, N, bearings, C, ldc, delta);
 }
-void launch_gemv(cudaStream_t s, const double* K, int ldk, int n, int m, const double* x, double* y) {
-    k_gemv<<<cdiv(n, 32), 256, 0, s>>>(K, ldk, n, m, x, y);
+void launch_gemv(cudaStream_t s, const double* K, int ldk, int n, int m, const double* x, double* y, double* part, int* cnt) {
+    k_gemv<<<dim3(cdiv(n, 32), GEMV_SPLIT), 256, 0, s>>>(K, ldk, n, m, x, y, part, cnt);
 }
 void launch_lift_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma) {
     k_lift_prepare<<<1, 32, 0, s>>>(st, sc, gamma);

@@ -8,7 +8,8 @@ void launch_feature_step(cudaStream_t s, BaseState* st, const StepScratch* sc, L
                          int discrete, const RiccatiOut& ro);
 void launch_build_C_delta(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* bearings, double* C, int ldc,
                           double* delta);
-void launch_gemv(cudaStream_t s, const double* K, int ldk, int n, int m, const double* x, double* y);
+// y = K x (K n x m column-major).  part: 8 n doubles of scratch; cnt: ceil(n/32) ints, zero before the first use (left zero).
+void launch_gemv(cudaStream_t s, const double* K, int ldk, int n, int m, const double* x, double* y, double* part, int* cnt);
 void launch_lift_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma);
 void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, int N, const double* gamma, double* Aug,
                           int lda, int pb, double* yo);
