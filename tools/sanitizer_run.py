@@ -30,6 +30,12 @@ for kind, i in seq.events():
     else:
         f.processVisionData(seq.vision_stamps[i], seq.ids, seq.bearings[i])
 print("N 40 fixed: graph replays", f.graph_stats(), "finite", np.isfinite(f.stateCovariance()).all())
+# the pair kernel (ticket + row-block counters between CTAs) at a ragged multi-row-block size, both second-product layouts
+from eqf_vio_b200.filter import dgemm_pair
+for tB2 in (True, False):
+    A1 = rng.standard_normal((75, 41)); B1 = rng.standard_normal((41, 70)); B2 = rng.standard_normal((50, 70) if tB2 else (70, 50))
+    W, D, _ = dgemm_pair(A1, B1, B2, transB2=tB2)
+    print("gemm pair", tB2, np.abs(D - (A1 @ B1) @ (B2.T if tB2 else B2)).max())
 from eqf_vio_b200.filter import getrf_block
 Bm = rng.standard_normal((48, 48))
 LU, Li, Ui, _ = getrf_block(Bm @ Bm.T + 48 * np.eye(48))
