@@ -99,6 +99,7 @@ struct eqvio_filter {
     double *C = nullptr, *CS = nullptr, *SCt = nullptr, *K = nullptr, *Saug = nullptr, *Sinv = nullptr;
     double *delta = nullptr, *gamma = nullptr, *y_in = nullptr, *y = nullptr, *scratch = nullptr, *Gamma = nullptr;
     int *d_flags = nullptr, *d_map = nullptr;
+    bool lift_wide = false;        // Sigma_sub bordered by the identity as well (capacity <= 256): the elimination leaves Ym^T Sigma_sub^-1 itself
     double* gemv_part = nullptr;   // partial sums of gamma = K delta (8 x ld)
     int* gemv_cnt = nullptr;       // its per-row-block arrival counters
     // pinned staging
@@ -243,7 +244,10 @@ static int ensure_capacity(Filter* f, int needN) {
     CU_TRY(dalloc(&L2.base, (size_t)LM_FIELDS * cap));
     CU_TRY(dalloc(&Sigma, nn)); CU_TRY(dalloc(&Sigma2, nn)); CU_TRY(dalloc(&F, nn)); CU_TRY(dalloc(&W, nn));
     CU_TRY(dalloc(&F1, nn)); CU_TRY(dalloc(&W1, nn));
-    CU_TRY(dalloc(&Aug, nn));
+    // bundleLift's work matrix; for small capacities it also holds an identity border of p columns (see lift_eliminate)
+    const bool lift_wide = cap <= 256 && !getenv("EQVIO_LIFT_NARROW");
+    const size_t aug_doubles = lift_wide ? (size_t)ld * (2 * (size_t)ld + 64) : nn;
+    CU_TRY(dalloc(&Aug, aug_doubles));
     CU_TRY(dalloc(&Bb, (size_t)ld * 8));
     CU_TRY(dalloc(&C, (size_t)ldm * (ld + 32))); CU_TRY(dalloc(&CS, (size_t)ldm * (ld + 32)));
     CU_TRY(dalloc(&SCt, (size_t)ld * (ldm + 32))); CU_TRY(dalloc(&K, (size_t)ld * (ldm + 32)));
@@ -256,7 +260,7 @@ static int ensure_capacity(Filter* f, int needN) {
     CU_TRY(cudaMemsetAsync(gemv_cnt, 0, ((size_t)ld / 32 + 8) * sizeof(int), f->stream));
     cudaStream_t s = f->stream;
     CU_TRY(cudaMemsetAsync(Sigma, 0, nn * 8, s)); CU_TRY(cudaMemsetAsync(Sigma2, 0, nn * 8, s));
-    CU_TRY(cudaMemsetAsync(Aug, 0, nn * 8, s));
+    CU_TRY(cudaMemsetAsync(Aug, 0, aug_doubles * 8, s));
     CU_TRY(cudaMemsetAsync(CS, 0, (size_t)ldm * (ld + 32) * 8, s));
     CU_TRY(cudaMemsetAsync(SCt, 0, (size_t)ld * (ldm + 32) * 8, s)); CU_TRY(cudaMemsetAsync(K, 0, (size_t)ld * (ldm + 32) * 8, s));
     CU_TRY(cudaMemsetAsync(Saug, 0, (size_t)ld2m * (ld2m + 32) * 8, s)); CU_TRY(cudaMemsetAsync(Sinv, 0, (size_t)ldm * (ldm + 32) * 8, s));
@@ -280,6 +284,7 @@ static int ensure_capacity(Filter* f, int needN) {
     f->delta = delta; f->gamma = gamma; f->y_in = y_in; f->y = y; f->scratch = scratch; f->Gamma = Gamma;
     f->d_flags = d_flags; f->d_map = d_map;
     f->gemv_part = gemv_part; f->gemv_cnt = gemv_cnt;
+    f->lift_wide = lift_wide;
     f->LinvL = LinvL; f->yo = yo; f->Rt = Rt; f->wave = wave;
     f->layoutN = -1;
     f->main_dirty = true;
@@ -585,6 +590,47 @@ static int compact(Filter* f, const std::vector<int>& keep) {
     return EQVIO_OK;
 }
 
+// bundleLift's elimination (EqFMatrices.cpp:239-242 needs Ym^T Sigma_sub^-1 [Ym | yo] only): set up
+// [[Sigma_sub, Ym], [Ym^T, 0]] from the PRIOR Sigma block and eliminate Sigma_sub; the 4 x 4 corner becomes
+// -Ym^T Sigma_sub^-1 Ym.  The gamma-independent factor R^T = Ym^T Sigma_sub^-1 (4 x p) comes out in one of two ways:
+//   * capacity > 256: k_lift_rsolve, a wavefront back-substitution with L behind the elimination (6 us per 64-block);
+//   * capacity <= 256: Sigma_sub is bordered by p identity columns as well, [[Sigma_sub, Ym, I], [Ym^T, 0, 0]], and the
+//     elimination itself leaves -R^T in the border rows.  Twice the (off-critical-path) trailing-update flops, but nothing
+//     follows the chain: at these sizes the lift chain is the update's critical path and the back-substitution was
+//     22 us (N = 64) / 53 us (N = 256) of it.
+static int lift_eliminate(Filter* f, const SchurChain& ch) {
+    const int N = f->N, p = 5 + 3 * N, pb = round_up(p, 16), ld = f->ld;
+    int st;
+    {
+        ProfScope ps(f, ch.s, PROF_MISC);
+        launch_lift_prepare(ch.s, f->st, f->sc, nullptr);
+        launch_copy_block(ch.s, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
+        launch_schur_setup(ch.s, f->Aug, ld, p, pb, 4, 4, 0);
+        if (f->lift_wide) { launch_schur_identity_cols(ch.s, f->Aug, ld, pb + 4, p, pb + 4, pb); f->launches += 1; }
+        launch_lift_features(ch.s, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
+    }
+    f->launches += 4;
+    stamp(f, ch.s, ST_LIFT_SETUP);
+    if ((st = schur_lu(f, ch, f->Aug, ld, pb, 4, f->lift_wide ? 4 + pb : 4))) return st;
+    stamp(f, ch.s, ST_LIFT_CHAIN);
+    CU_TRY(cudaEventRecord(f->ev_lift_elim, ch.s));
+    if (!f->lift_wide) {
+        ProfScope ps(f, ch.s, PROF_MISC);
+        launch_lift_rsolve(ch.s, f->Aug, ld, pb, f->LinvL, f->Rt, f->wave);
+        f->launches += 1;
+    }
+    stamp(f, ch.s, ST_LIFT_RSOLVE);
+    return EQVIO_OK;
+}
+// k_lift_solve behind it (on stream s)
+static void lift_solve(Filter* f, cudaStream_t s, int use_lift, int discrete, double* Gamma_out, int apply) {
+    const int pb = round_up(5 + 3 * f->N, 16), ld = f->ld;
+    if (f->lift_wide)
+        launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, 1, ld, -1.0, f->Aug + pb + (size_t)ld * (pb + 4), f->yo, use_lift, discrete, Gamma_out, apply);
+    else
+        launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, pb, 1, 1.0, f->Rt, f->yo, use_lift, discrete, Gamma_out, apply);
+}
+
 // The measurement update, VIOFilter.cpp:264-297, on matched bearings f->y (3N, device).
 // want_lift = 0 stops after gamma / Sigma update (kernel-level entry point).
 static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
@@ -599,24 +645,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
         // goes through S, S^-1, K and gamma; the gamma-independent factor Ym^T Sigma_sub^-1 follows it there (k_lift_rsolve).
         CU_TRY(cudaEventRecord(f->ev_lift_fork, s));
         CU_TRY(cudaStreamWaitEvent(f->lift, f->ev_lift_fork, 0));
-        {
-            ProfScope ps(f, f->lift, PROF_MISC);
-            launch_lift_prepare(f->lift, f->st, f->sc, nullptr);
-            launch_copy_block(f->lift, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
-            launch_schur_setup(f->lift, f->Aug, ld, p, pb, 4, 4, 0);
-            launch_lift_features(f->lift, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
-        }
-        f->launches += 4;
-        stamp(f, f->lift, ST_LIFT_SETUP);
-        if ((st = schur_lu(f, SchurChain{f->lift, f->lift_h, f->ev_la, f->ev_lb, f->ev_lt, f->LinvL, f->UinvL, true}, f->Aug, ld, pb, 4, 4))) return st;
-        stamp(f, f->lift, ST_LIFT_CHAIN);
-        CU_TRY(cudaEventRecord(f->ev_lift_elim, f->lift));
-        {
-            ProfScope ps(f, f->lift, PROF_MISC);
-            launch_lift_rsolve(f->lift, f->Aug, ld, pb, f->LinvL, f->Rt, f->wave);
-        }
-        f->launches += 1;
-        stamp(f, f->lift, ST_LIFT_RSOLVE);
+        if ((st = lift_eliminate(f, SchurChain{f->lift, f->lift_h, f->ev_la, f->ev_lb, f->ev_lt, f->LinvL, f->UinvL, true}))) return st;
         CU_TRY(cudaEventRecord(f->ev_lift_done, f->lift));
     }
     {
@@ -684,8 +713,9 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     if (do_lift) {
         const int use_lift = f->s.useInnovationLift, discrete = f->s.useDiscreteInnovationLift;
         if (use_lift) {
-            CU_TRY(cudaStreamWaitEvent(s, f->ev_lift_done, 0));
-            stamp(f, s, ST_LIFT_JOIN);
+            // the gamma-dependent right-hand side (DUF, yo = D obs) touches nothing the lift chain works on: it is formed
+            // before the join, so that only the 4 x 4 solve and the apply follow the chain (which is the critical path of
+            // the update for N <= 256)
             {
                 ProfScope ps(f, s, PROF_MISC);
                 launch_lift_prepare(s, f->st, f->sc, f->gamma);
@@ -693,10 +723,12 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
             }
             f->launches += 2;
             stamp(f, s, ST_LIFT_FEATURES);
+            CU_TRY(cudaStreamWaitEvent(s, f->ev_lift_done, 0));
+            stamp(f, s, ST_LIFT_JOIN);
         }
         {
             ProfScope ps(f, s, PROF_MISC);
-            launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->Rt, f->yo, use_lift, discrete, nullptr, 1);
+            lift_solve(f, s, use_lift, discrete, nullptr, 1);
             launch_lift_apply(s, f->st, f->L, N, f->gamma, use_lift ? discrete : 0);
         }
         f->launches += 2;
@@ -1296,18 +1328,12 @@ int eqvio_bundle_lift(eqvio_handle_t f, const double* gamma_eqf, double* Gamma) 
     CU_TRY(cudaMemcpy(f->gamma, g.data(), g.size() * 8, cudaMemcpyHostToDevice));
     cudaStream_t s = f->stream;
     const int pb = round_up(p, 16);
-    launch_lift_prepare(s, f->st, f->sc, nullptr);
-    launch_copy_block(s, f->Sigma + 6 + (size_t)ld * 6, ld, f->Aug, ld, p, p);
-    launch_schur_setup(s, f->Aug, ld, p, pb, 4, 4, 0);
-    launch_lift_features(s, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
-    f->launches += 4;
-    int st = schur_lu(f, SchurChain{s, f->main_h, f->ev_sa, f->ev_sb, f->ev_st, f->LinvL, f->UinvL, true}, f->Aug, ld, pb, 4, 4);
+    int st = lift_eliminate(f, SchurChain{s, f->main_h, f->ev_sa, f->ev_sb, f->ev_st, f->LinvL, f->UinvL, true});
     if (st) return st;
-    launch_lift_rsolve(s, f->Aug, ld, pb, f->LinvL, f->Rt, f->wave);
     launch_lift_prepare(s, f->st, f->sc, f->gamma);
     launch_lift_features(s, f->sc, f->L, N, f->gamma, f->Aug, ld, pb, f->yo);
-    launch_lift_solve(s, f->st, f->sc, f->gamma, f->Aug, ld, pb, f->Rt, f->yo, 1, 1, f->Gamma, 0);
-    f->launches += 4;
+    lift_solve(f, s, 1, 1, f->Gamma, 0);
+    f->launches += 3;
     CU_TRY(cudaStreamSynchronize(s));
     CU_TRY(cudaMemcpy(Gamma, f->Gamma, 48, cudaMemcpyDeviceToHost));
     memcpy(Gamma + 6, gamma_eqf + 2, (size_t)(3 + 3 * N) * 8);  // EqFMatrices.cpp:246-249

@@ -524,14 +524,16 @@ __device__ void qr_solve4(double A[4][4], double b[4], double x[4]) {
 // use_lift = 0 (useInnovationLift = false): VIOExp(liftInnovation(gamma, xi0)) EqFMatrices.cpp:35-48.
 // Then VIOFilter.cpp:295-296 and the pose record.
 __global__ void __launch_bounds__(128) k_lift_solve(BaseState* st, StepScratch* sc, const double* gamma, const double* Aug,
-                                                    int lda, int p, const double* Rt, const double* yo, int use_lift,
-                                                    int discrete, double* Gamma_out, int apply) {
+                                                    int lda, int p, const double* Rt, long rt_rs, long rt_cs, double rt_sign,
+                                                    const double* yo, int use_lift, int discrete, double* Gamma_out, int apply) {
     __shared__ double b4[4];
     const int tid = threadIdx.x;
     if (use_lift) {   // M^T W obs = R^T yo: warp a forms entry a
         const int a = tid >> 5;
         double sacc = 0.0;
-        for (int col = tid & 31; col < p; col += 32) sacc = fma(Rt[(size_t)a * p + col], yo[col], sacc);
+        // R^T entry (a, col) = rt_sign * Rt[a * rt_rs + col * rt_cs]: row-major from k_lift_rsolve, or (negated) the border block
+        // the elimination leaves when Sigma_sub was bordered by the identity (small N)
+        for (int col = tid & 31; col < p; col += 32) sacc = fma(rt_sign * Rt[a * rt_rs + col * rt_cs], yo[col], sacc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
         if ((tid & 31) == 0) b4[a] = sacc;
@@ -938,6 +940,13 @@ __global__ void k_schur_setup(double* A, int lda, int k, int kpad, int r, int c,
     A[row + (size_t)lda * col] = v;
 }
 
+// Identity border columns [col0, col0 + ncols) over `rows` rows: entry (r, col0 + c) = (r == c && r < k).
+__global__ void k_schur_identity_cols(double* A, int lda, int rows, int k, int col0, int ncols) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (row >= rows || c >= ncols) return;
+    A[row + (size_t)lda * (col0 + c)] = (row == c && row < k) ? 1.0 : 0.0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------------
@@ -1081,9 +1090,9 @@ void launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, cons
     cudaMemsetAsync(ready, 0, (size_t)nblk * sizeof(int), s);
     k_lift_rsolve<<<nblk, 256, smem, s>>>(Aug, lda, pb, LinvBlocks, Rt, ready);
 }
-void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
+void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p, long rt_rs, long rt_cs, double rt_sign,
                        const double* Rt, const double* yo, int use_lift, int discrete, double* Gamma_out, int apply) {
-    k_lift_solve<<<1, 128, 0, s>>>(st, sc, gamma, Aug, lda, p, Rt, yo, use_lift, discrete, Gamma_out, apply);
+    k_lift_solve<<<1, 128, 0, s>>>(st, sc, gamma, Aug, lda, p, Rt, rt_rs, rt_cs, rt_sign, yo, use_lift, discrete, Gamma_out, apply);
 }
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete) {
     if (N > 0) k_lift_apply<<<cdiv(N, 128), 128, 0, s>>>(st, L, N, gamma, discrete);
@@ -1102,6 +1111,9 @@ cudaError_t launch_chain_block(cudaStream_t s, double* A, int lda, int j, int nb
 }
 void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border) {
     k_schur_setup<<<dim3(cdiv(kpad + r, 256), kpad + c), 256, 0, s>>>(A, lda, k, kpad, r, c, identity_border);
+}
+void launch_schur_identity_cols(cudaStream_t s, double* A, int lda, int rows, int k, int col0, int ncols) {
+    if (rows > 0 && ncols > 0) k_schur_identity_cols<<<dim3(cdiv(rows, 256), ncols), 256, 0, s>>>(A, lda, rows, k, col0, ncols);
 }
 void launch_copy_block(cudaStream_t s, const double* src, int lds, double* dst, int ldd, int rows, int cols) {
     if (rows > 0 && cols > 0) k_copy_block<<<dim3(cdiv(rows, 256), cols), 256, 0, s>>>(src, lds, dst, ldd, rows, cols);

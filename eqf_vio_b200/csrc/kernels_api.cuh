@@ -14,8 +14,10 @@ void launch_lift_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const d
 void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, int N, const double* gamma, double* Aug,
                           int lda, int pb, double* yo);
 void launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt, int* ready);
-void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p,
+// R^T = Ym^T Sigma_sub^-1, entry (a, col) = rt_sign * Rt[a * rt_rs + col * rt_cs]
+void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p, long rt_rs, long rt_cs, double rt_sign,
                        const double* Rt, const double* yo, int use_lift, int discrete, double* Gamma_out, int apply);
+void launch_schur_identity_cols(cudaStream_t s, double* A, int lda, int rows, int k, int col0, int ncols);
 void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const double* gamma, int discrete);
 // Diagonal block j (nb x nb, nb <= 64) of the blocked Schur elimination of A: D = A[j,j] (or Din) minus, when
 // prev_nb > 0, the product of the panel blocks L[j, j-prev_nb] U[j-prev_nb, j] that the trailing update skipped;
