@@ -374,6 +374,10 @@ using Cfg32x64 = TileCfg<32, 64, 16, 32, 4, 4>;
 using Cfg64x32 = TileCfg<64, 32, 32, 16, 4, 4>;
 using Cfg32x32s6 = TileCfg<32, 32, 16, 16, 6, 5>;
 using Cfg48x48 = TileCfg<48, 48, 16, 48, 4, 4>;
+// 64-deep in-place panel solves of the Schur chains: the tile spans the whole 64-wide side it shares with its neighbours (so
+// a CTA reads exactly the rows / columns it later overwrites) and two stages keep it within one freed 32x32-GEMM slot (25 KB)
+using Cfg32x64s2 = TileCfg<32, 64, 16, 32, 2, 6>;
+using Cfg64x32s2 = TileCfg<64, 32, 32, 16, 2, 6>;
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -510,7 +514,7 @@ cudaError_t dgemm_pair_launch(const GemmProblem& g1, const GemmProblem& g2, int*
     return g2.transB ? launch_pair_cfg<Cfg32x32, true>(g1, g2, sync, stream) : launch_pair_cfg<Cfg32x32, false>(g1, g2, sync, stream);
 }
 
-int dgemm_num_configs() { return 8; }
+int dgemm_num_configs() { return 10; }
 const char* dgemm_config_name(int cfg) {
     switch (cfg) {
         case 0: return "128x128x16 (8 DMMA warps 64x32, 4 stages)";
@@ -521,6 +525,8 @@ const char* dgemm_config_name(int cfg) {
         case 5: return "64x32x16 (4 DMMA warps 32x16, 4 stages)";
         case 6: return "32x32x16 (4 DMMA warps 16x16, 6 stages, 5 CTA/SM)";
         case 7: return "48x48x16 (3 DMMA warps 16x48, 4 stages)";
+        case 8: return "32x64x16 (4 DMMA warps 16x32, 2 stages, 6 CTA/SM: in-place column-panel solves)";
+        case 9: return "64x32x16 (4 DMMA warps 32x16, 2 stages, 6 CTA/SM: in-place row-panel solves)";
     }
     return "?";
 }
@@ -547,6 +553,8 @@ cudaError_t dgemm_launch(const GemmProblem& g, cudaStream_t stream, int force_co
         case 5: return launch_cfg<Cfg64x32>(g, stream);
         case 6: return launch_cfg<Cfg32x32s6>(g, stream);
         case 7: return launch_cfg<Cfg48x48>(g, stream);
+        case 8: return launch_cfg<Cfg32x64s2>(g, stream);
+        case 9: return launch_cfg<Cfg64x32s2>(g, stream);
         default: return launch_cfg<Cfg32x32>(g, stream);
     }
 }

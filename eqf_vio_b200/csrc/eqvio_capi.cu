@@ -53,11 +53,12 @@ struct eqvio_filter {
     int device = 0;
     bool use_graphs = true;            // EQVIO_GRAPHS=0 disables
     int sigma_after_lift = -1;         // EQVIO_SIGMA_AFTER_LIFT: 0 / 1 / -1 = only for n >= 1024
-    // EQVIO_PANEL_CFG: tile config of the 64-deep panel solves; -1 = the library's own pick (32x32 tiles).  The 64x64 config
-    // used before is faster alone (7.4 vs 8.2 us) but needs 66 KB of shared memory per CTA — two freed 32x32-GEMM slots on
-    // one SM — and waited 20-60 us for them next to the Sigma C^T / trailing-update GEMMs (in-graph stamps); a 32x32 CTA fits
-    // any freed slot.  N = 256: 7765 -> 8008 steps/s, N = 512: 1602 -> 1618.
-    int panel_cfg = -1;
+    // EQVIO_PANEL_SLIM=0: the 64-deep in-place panel solves on 64x64 tiles (config 2) as before.  Default: tiles that span
+    // only the shared 64-wide side (32x64 for X U = B, 64x32 for L X = B: a CTA still reads exactly what it overwrites, which
+    // 32x32 tiles would not) with two stages, 25 KB of shared memory: the 64x64 config is faster alone (7.4 vs ~8 us) but
+    // needs 66 KB per CTA — two freed 32x32-GEMM slots on one SM — and waited 20-60 us for them next to the Sigma C^T /
+    // trailing-update GEMMs (in-graph stamps, profiles/r01c_update_stamps_n512_chain_server.txt).
+    bool panel_slim = true;
     int trail_delay = 2;               // EQVIO_TRAIL_DELAY: empty kernels in front of each trailing update (see schur_lu)
     unsigned long long* stamps = nullptr;   // EQVIO_STAMPS=1: %globaltimer marks inside the update (64 slots)
     std::vector<CachedGraph> graphs;
@@ -67,7 +68,7 @@ struct eqvio_filter {
     cudaStream_t main_h = nullptr, lift_h = nullptr;  // helper streams of the two Schur chains (look-ahead)
     cudaEvent_t ev_sa = nullptr, ev_sb = nullptr, ev_st = nullptr, ev_la = nullptr, ev_lb = nullptr, ev_lt = nullptr;
     cudaStream_t lift = nullptr;   // third stream: the Sigma_sub elimination of bundleLift, concurrent with the S / K / gamma chain
-    cudaEvent_t ev_lift_fork = nullptr, ev_lift_done = nullptr, ev_lift_elim = nullptr;
+    cudaEvent_t ev_lift_fork = nullptr, ev_lift_done = nullptr, ev_lift_elim = nullptr, ev_lift_setup = nullptr;
     cudaStream_t cur = nullptr;    // stream the next gemm() goes to (main unless forked)
     // State stream: k_step_prepare / k_feature_step of tick t+1 depend only on the SE(3) x R^3 / landmark state, not on
     // Sigma, so they run here underneath the two Sigma GEMMs of tick t (main stream).  What they write for the GEMMs
@@ -460,10 +461,10 @@ static int schur_lu(Filter* f, const SchurChain& ch, double* Aug, int lda, int k
         CU_TRY(cudaStreamWaitEvent(ch.h, ch.ev_a, 0));
         if (j > 0) CU_TRY(cudaStreamWaitEvent(ch.s, ch.ev_t, 0));
         f->cur = ch.h;
-        if ((st = gemm(f, 0, nb, cols, nb, 1.0, Linv, 64, Up, lda, 0.0, nullptr, 0, Up, lda, 0, 0.0, f->panel_cfg))) return st;   // L X = B
+        if ((st = gemm(f, 0, nb, cols, nb, 1.0, Linv, 64, Up, lda, 0.0, nullptr, 0, Up, lda, 0, 0.0, f->panel_slim ? 9 : 2))) return st;   // L X = B
         CU_TRY(cudaEventRecord(ch.ev_b, ch.h));
         f->cur = ch.s;
-        if ((st = gemm(f, 0, rows, nb, nb, 1.0, Lp, lda, Uinv, 64, 0.0, nullptr, 0, Lp, lda, 0, 0.0, f->panel_cfg))) return st;   // X U = B
+        if ((st = gemm(f, 0, rows, nb, nb, 1.0, Lp, lda, Uinv, 64, 0.0, nullptr, 0, Lp, lda, 0, 0.0, f->panel_slim ? 8 : 2))) return st;   // X U = B
         if (sbase + 2 < 512) stamp(f, ch.s, sbase + 1);
         // trailing update on the helper stream; the next diagonal block is the next chain kernel's
         CU_TRY(cudaEventRecord(ch.ev_a, ch.s));
@@ -615,6 +616,7 @@ static int lift_eliminate(Filter* f, const SchurChain& ch) {
         launch_lift_features(ch.s, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
     }
     f->launches += 4;
+    CU_TRY(cudaEventRecord(f->ev_lift_setup, ch.s));   // the gamma-dependent right-hand side reads what k_lift_prepare(nullptr) left in the scratch
     stamp(f, ch.s, ST_LIFT_SETUP);
     if ((st = schur_lu(f, ch, f->Aug, ld, pb, 4, f->lift_wide ? 4 + pb : 4))) return st;
     stamp(f, ch.s, ST_LIFT_CHAIN);
@@ -721,6 +723,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
             // the gamma-dependent right-hand side (DUF, yo = D obs) touches nothing the lift chain works on: it is formed
             // before the join, so that only the 4 x 4 solve and the apply follow the chain (which is the critical path of
             // the update for N <= 256)
+            CU_TRY(cudaStreamWaitEvent(s, f->ev_lift_setup, 0));
             {
                 ProfScope ps(f, s, PROF_MISC);
                 launch_lift_prepare(s, f->st, f->sc, f->gamma);
@@ -841,11 +844,12 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_fork, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_done, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_elim, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_setup, cudaEventDisableTiming));
     }
     f->cur = f->stream;
     if (const char* e = getenv("EQVIO_GRAPHS")) f->use_graphs = !(e[0] == '0');
     if (const char* e = getenv("EQVIO_PAIRS")) f->use_pairs = atoi(e);
-    if (const char* e = getenv("EQVIO_PANEL_CFG")) f->panel_cfg = atoi(e);
+    if (const char* e = getenv("EQVIO_PANEL_SLIM")) f->panel_slim = !(e[0] == '0');
     CU_TRY(dalloc(&f->pair_sync, (size_t)PAIR_SITES * DGEMM_PAIR_SYNC_INTS));
     CU_TRY(cudaMemset(f->pair_sync, 0, (size_t)PAIR_SITES * DGEMM_PAIR_SYNC_INTS * sizeof(int)));
     if (const char* e = getenv("EQVIO_SIGMA_AFTER_LIFT")) f->sigma_after_lift = atoi(e);
@@ -891,7 +895,7 @@ int eqvio_destroy(eqvio_handle_t f) {
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
     cudaEventDestroy(f->stage_free);
-    cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join); cudaEventDestroy(f->ev_lift_fork); cudaEventDestroy(f->ev_lift_done); cudaEventDestroy(f->ev_lift_elim);
+    cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join); cudaEventDestroy(f->ev_lift_fork); cudaEventDestroy(f->ev_lift_done); cudaEventDestroy(f->ev_lift_elim); cudaEventDestroy(f->ev_lift_setup);
     cudaStreamDestroy(f->side); cudaStreamDestroy(f->lift); cudaStreamDestroy(f->main_h); cudaStreamDestroy(f->lift_h);
     for (cudaEvent_t e : {f->ev_sa, f->ev_sb, f->ev_st, f->ev_la, f->ev_lb, f->ev_lt}) cudaEventDestroy(e);
     for (cudaEvent_t e : {f->ev_state, f->ev_main, f->ev_gemm[0], f->ev_gemm[1]}) cudaEventDestroy(e);

@@ -15,7 +15,7 @@ SHAPES = [(26, 26, 26), (10, 26, 26), (26, 10, 26), (203, 203, 203), (128, 203, 
           (64, 64, 64), (129, 127, 131), (779, 779, 779), (512, 779, 779), (779, 512, 512)]
 
 
-@pytest.fixture(params=[None, 0, 1, 2, 3, 4, 5, 6, 7], ids=lambda c: f"cfg{c}")
+@pytest.fixture(params=[None, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9], ids=lambda c: f"cfg{c}")
 def tile_config(request):
     old = os.environ.pop("EQVIO_GEMM_CONFIG", None)
     if request.param is not None:
