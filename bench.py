@@ -430,6 +430,7 @@ def main():
                                       "note": "includes the 64-deep Schur panel / trailing GEMMs, which overlap each other on five streams"},
                 "by_class": {k: {"launches": v["launches"], "ms_per_period": v["ms"] / K, "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0)}
                              for k, v in classes.items()},
+                "by_class_note": "in-stream time between two events around each launch, summed per class: classes overlap each other (five update streams + the state stream), and a launch's time includes its wait for SM slots — the small state kernels of tick t+1 sit under the Riccati launch of tick t, which costs no wall time",
             },
             "gflops_dense_equiv": fm["period"] * K * world / (dev_ms * 1e-3) / 1e9,
             "flop_model_period_gflop": fm["period"] / 1e9,
