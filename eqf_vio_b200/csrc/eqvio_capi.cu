@@ -1352,6 +1352,29 @@ int eqvio_bundle_lift(eqvio_handle_t f, const double* gamma_eqf, double* Gamma) 
     return flags_to_status(flags);
 }
 
+int eqvio_schur_inverse(eqvio_handle_t f, int m, const double* S, int lds, double* Sinv, int ldsi) {
+    if (!f || m < 1 || !S || !Sinv || lds < m || ldsi < m) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    int st = ensure_capacity(f, std::max(f->N, (m + 1) / 2));
+    if (st) return st;
+    f->main_dirty = true;
+    cudaStream_t s = f->stream;
+    const int mp = round_up(m, 16), ld2m = f->ld2m;
+    CU_TRY(cudaMemcpy2DAsync(f->Saug, (size_t)ld2m * 8, S, (size_t)lds * 8, (size_t)m * 8, m, cudaMemcpyHostToDevice, s));
+    launch_schur_setup(s, f->Saug, ld2m, m, mp, m, m, 1);
+    f->launches += 1;
+    // exactly the S chain of the update: chain kernels, in-place panel solves, look-ahead trailing updates
+    if ((st = schur_lu(f, SchurChain{s, f->main_h, f->ev_sa, f->ev_sb, f->ev_st, f->Linv, f->Uinv, false}, f->Saug, ld2m, mp, m, m))) return st;
+    CU_TRY(cudaStreamSynchronize(s));
+    CU_TRY(cudaMemcpy2D(Sinv, (size_t)ldsi * 8, f->Saug + mp + (size_t)ld2m * mp, (size_t)ld2m * 8, (size_t)m * 8, m, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < m; ++c)
+        for (int r = 0; r < m; ++r) Sinv[r + (size_t)ldsi * c] = -Sinv[r + (size_t)ldsi * c];   // the elimination leaves -S^-1
+    int flags = 0;
+    if ((st = read_flags(f, &flags))) return st;
+    return flags_to_status(flags);
+}
+
 int eqvio_dgemm(int device, int transB, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb,
                 double beta, double* C, int ldc, int reps, float* ms) {
     if (M < 0 || N < 0 || K < 0 || !A || !B || !C) return EQVIO_ERR_ARG;

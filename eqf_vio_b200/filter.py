@@ -139,6 +139,14 @@ class VIOFilter:
         abi.check(self._L.eqvio_get_bias(self._h, _p(b)), "eqvio_get_bias")
         return b
 
+    def schur_inverse(self, S) -> np.ndarray:
+        """S^-1 by the update's own blocked Schur elimination (kernel-level entry point, eqvio_schur_inverse)."""
+        S = np.asfortranarray(S, dtype=np.float64)
+        m = S.shape[0]
+        out = np.zeros((m, m), order="F")
+        abi.check(self._L.eqvio_schur_inverse(self._h, m, _p(S), m, _p(out), m), "eqvio_schur_inverse")
+        return out
+
     # ---- snapshot / restore ----
     def get_snapshot(self) -> np.ndarray:
         d = np.zeros(self._L.eqvio_snapshot_size(self.numLandmarks))

@@ -178,6 +178,12 @@ int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int ld
                      int transB2, int N2, double alpha2, const double* B2, int ldb2, double* W, int ldw, double* D,
                      int ldd, int reps, float* ms);
 
+/* `S.inverse()` (VIOFilter.cpp:277) on its own: the blocked Schur elimination of [[S, I], [I, 0]] by unpivoted LU that the
+ * update runs (chain kernels, in-place panel solves, look-ahead trailing updates), for an m x m matrix S (col-major, host;
+ * symmetric positive definite up to round-off — no pivoting).  Uses the handle's work buffers (its capacity grows to m/2
+ * landmarks if needed); the filter state is not touched. */
+int eqvio_schur_inverse(eqvio_handle_t h, int m, const double* S, int lds, double* Sinv, int ldsi);
+
 /* One diagonal block of the blocked Schur eliminations that stand in for `S.inverse()` (VIOFilter.cpp:277)
  * and `Sigma.inverse()` (EqFMatrices.cpp:239): unpivoted LU of the nb x nb block A (nb <= 64, col-major,
  * host) and the triangular inverses L^-1, U^-1 as 64 x 64 identity-padded col-major matrices.  LU (nb x nb,

@@ -119,3 +119,26 @@ def test_timeline_and_graph_instrumentation():
     assert set(np.unique(lane).astype(int)) >= {0, 1, 2}            # main, side, lift streams all carried work
     # m = 140 -> 3 chain blocks for S, p = 215 -> pb = 224 -> 4 for the lift
     assert int(np.sum(cls == 3)) == 3 + 4
+
+
+@pytest.mark.parametrize("m", [10, 64, 130, 517, 1024])
+def test_schur_inverse_against_numpy(m):
+    """`S.inverse()` through the update's blocked Schur elimination on its own (eqvio_schur_inverse): chain kernels,
+    IN-PLACE panel solves (tiles must span the 64-wide side they share — a tile shape that does not reads what a
+    neighbour already overwrote), look-ahead corners and skipped trailing tiles, at sizes that are / are not multiples of
+    the 64-wide block.  S is SPD with a condition number ~1e4: tolerance 1e-10 on S^-1 and on S S^-1 = I."""
+    from eqf_vio_b200.filter import VIOFilter
+    from eqf_vio_b200.settings import template_settings
+    from helpers import rel
+
+    rng = np.random.default_rng(100 + m)
+    Q, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    S = (Q * (10.0 ** rng.uniform(-2, 2, m))) @ Q.T
+    S = 0.5 * (S + S.T)
+    f = VIOFilter(template_settings())
+    Si = f.schur_inverse(S)
+    ref = np.linalg.inv(S)
+    assert rel(Si, ref) < 1e-10, rel(Si, ref)
+    assert np.abs(S @ Si - np.eye(m)).max() < 1e-9
+    Si2 = f.schur_inverse(S)          # the handle's buffers are reusable and the result is deterministic
+    assert np.array_equal(Si, Si2)
