@@ -49,3 +49,49 @@ def test_period_sequence_event_order():
     # 10 IMU ticks between consecutive vision frames (IMU 200 Hz / vision 20 Hz)
     idx = [i for i, k in enumerate(ev) if k == "vision"]
     assert all(b - a == 11 for a, b in zip(idx, idx[1:]))
+
+
+def _run_bench(*args, env_extra=None):
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, os.path.join(root, "bench.py"), *args], capture_output=True, text=True, env=env, timeout=600)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """The reference arm (the CPU restatement of the reference timed on the host cores) honours the bench contract:
+    exactly ONE line on stdout, JSON, with the keys the driver reads — also when a library writes to fd 1."""
+    import json
+
+    r = _run_bench("--impl", "reference", "--features", "8", "--steps", "1", "--warmup", "1")
+    assert r.returncode == 0, r.stderr[-400:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:400]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "steps/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("N=8")
+
+
+def test_bench_reference_arm_other_ranks_do_no_work():
+    """Under torchrun only rank 0 runs the reference arm; the other ranks exit 0 without output."""
+    r = _run_bench("--impl", "reference", "--features", "8", "--steps", "1", "--warmup", "1", "--gpus", "2",
+                   env_extra={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_product_arm_fails_loudly_without_a_gpu():
+    """No CUDA device: the product arm must not fall back to anything."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = _run_bench("--features", "8", "--steps", "1", "--warmup", "1")
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stderr + r.stdout)
