@@ -133,6 +133,20 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(rs), "how": "nvidia-smi -lms 100"}
 
 
+def use_all_host_threads() -> int:
+    """The CPU arm runs its dense products on every host core whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1 for its workers, which would make the baseline ~10x slower than the box can do)."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=cores)
+        got = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(got) if got else cores
+    except Exception:
+        return cores
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference-equivalent CPU path on the host cores (rank 0 only)."""
     if rank != 0:
@@ -142,7 +156,7 @@ def run_reference(args, rank, world):
     from oracle import eqvio_numpy as onp
 
     N, K, W = args.features, args.steps, args.warmup
-    cores = os.cpu_count() or 1
+    cores = use_all_host_threads()
     s = conditioned_settings()
     seq = period_sequence(N, W + K, camera_offset=tuple(s.cameraOffset))
     f = onp.VIOFilter(onp.Settings(**s.as_dict()))
@@ -178,7 +192,7 @@ def cpu_baseline(N, periods):
     from eqf_vio_b200.synthetic import period_sequence
     from oracle import eqvio_numpy as onp
 
-    cores = os.cpu_count() or 1
+    cores = use_all_host_threads()
     s = conditioned_settings()
     seq = period_sequence(N, periods + 1, camera_offset=tuple(s.cameraOffset))
     f = onp.VIOFilter(onp.Settings(**s.as_dict()))
