@@ -25,6 +25,9 @@ SIGNATURES = {
     "eqvio_create": (C.c_int, [C.POINTER(Settings), C.c_int, C.POINTER(_h)]),
     "eqvio_destroy": (C.c_int, [_h]),
     "eqvio_reset": (C.c_int, [_h]),
+    "eqvio_set_settings": (C.c_int, [_h, C.POINTER(Settings)]),
+    "eqvio_set_auxiliary_data": (C.c_int, [_h, _dp, _dp, _dp]),
+    "eqvio_initialise_from_imu": (C.c_int, [_h, _dp, _dp]),
     "eqvio_process_imu": (C.c_int, [_h, C.c_double, _dp, _dp]),
     "eqvio_process_vision": (C.c_int, [_h, C.c_double, C.c_int, _ip, _dp]),
     "eqvio_process_vision_dev": (C.c_int, [_h, C.c_double, C.c_int, _ip, C.c_void_p]),
@@ -34,6 +37,8 @@ SIGNATURES = {
     "eqvio_get_state": (C.c_int, [_h, _dp, _dp, _dp, _ip, C.c_int, _ip, _dp]),
     "eqvio_get_pose_record": (C.c_int, [_h, _dp]),
     "eqvio_pose_record_dev": (C.c_int, [_h, C.POINTER(C.c_void_p)]),
+    "eqvio_pose_publish": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "eqvio_get_flags": (C.c_int, [_h, _ip, C.c_int]),
     "eqvio_get_covariance": (C.c_int, [_h, _dp, C.c_int]),
     "eqvio_get_bias": (C.c_int, [_h, _dp]),
     "eqvio_snapshot_size": (C.c_size_t, [C.c_int]),

@@ -443,25 +443,11 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     KernelParams p;
     fill_params(p, g);
     dim3 grid(((g.M + Cfg::BM - 1) / Cfg::BM) * ((g.N + Cfg::BN - 1) / Cfg::BN));
-    cudaError_t e;
-    static bool attr_done[2] = {false, false};  // per template instantiation (function-local static)
-    if (g.transB) {
-        auto k = dgemm_dmma_tma_kernel<Cfg, true>;
-        if (!attr_done[1]) {
-            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            attr_done[1] = true;
-        }
-        k<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-    } else {
-        auto k = dgemm_dmma_tma_kernel<Cfg, false>;
-        if (!attr_done[0]) {
-            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            attr_done[0] = true;
-        }
-        k<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
-    }
+    // the dynamic shared-memory opt-in is per device: dgemm_init_device() has set it for the current one
+    if (g.transB)
+        dgemm_dmma_tma_kernel<Cfg, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    else
+        dgemm_dmma_tma_kernel<Cfg, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
 
@@ -479,14 +465,7 @@ static cudaError_t launch_pair_cfg(const GemmProblem& g1, const GemmProblem& g2,
     fill_params(p2, g2);
     const int T1 = ((g1.M + Cfg::BM - 1) / Cfg::BM) * ((g1.N + Cfg::BN - 1) / Cfg::BN);
     const int T2 = ((g2.M + Cfg::BM - 1) / Cfg::BM) * ((g2.N + Cfg::BN - 1) / Cfg::BN);
-    auto k = dgemm_pair_kernel<Cfg, TB2>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    k<<<dim3(T1 + T2), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA1, tmB1, tmA2, tmB2, p1, p2, sync);
+    dgemm_pair_kernel<Cfg, TB2><<<dim3(T1 + T2), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA1, tmB1, tmA2, tmB2, p1, p2, sync);
     return cudaGetLastError();
 }
 
@@ -504,10 +483,38 @@ bool dgemm_pair_pays(const GemmProblem& g1, const GemmProblem& g2) {
     return t1 + t2 <= 148 || t1 >= 1110;
 }
 
+// Per-device opt-in to more than 48 KB of dynamic shared memory for every instantiation this file can launch.
+template <class Cfg>
+static cudaError_t opt_in_cfg() {
+    cudaError_t e = cudaFuncSetAttribute(dgemm_dmma_tma_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(dgemm_dmma_tma_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+}
+template <class Cfg>
+static cudaError_t opt_in_pair_cfg() {
+    cudaError_t e = cudaFuncSetAttribute(dgemm_pair_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(dgemm_pair_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+}
+cudaError_t dgemm_init_device() {
+    cudaError_t e;
+#define EQVIO_OPT_IN(call) if ((e = (call)) != cudaSuccess) return e
+    EQVIO_OPT_IN(opt_in_cfg<Cfg128x128>()); EQVIO_OPT_IN(opt_in_cfg<Cfg128x64>()); EQVIO_OPT_IN(opt_in_cfg<Cfg64x64>());
+    EQVIO_OPT_IN(opt_in_cfg<Cfg32x32>()); EQVIO_OPT_IN(opt_in_cfg<Cfg32x64>()); EQVIO_OPT_IN(opt_in_cfg<Cfg64x32>());
+    EQVIO_OPT_IN(opt_in_cfg<Cfg32x32s6>()); EQVIO_OPT_IN(opt_in_cfg<Cfg48x48>()); EQVIO_OPT_IN(opt_in_cfg<Cfg32x64s2>());
+    EQVIO_OPT_IN(opt_in_cfg<Cfg64x32s2>());
+    EQVIO_OPT_IN(opt_in_pair_cfg<Cfg32x32>()); EQVIO_OPT_IN(opt_in_pair_cfg<Cfg32x32s6>());
+#undef EQVIO_OPT_IN
+    return cudaSuccess;
+}
+
 cudaError_t dgemm_pair_launch(const GemmProblem& g1, const GemmProblem& g2, int* sync, cudaStream_t stream) {
     if (g1.M <= 0 || g1.N <= 0 || g2.N <= 0) return cudaSuccess;
     if (g1.transB || g1.D != g2.A || g1.M != g2.M || g1.skip_m || g2.skip_m || (g1.M + 31) / 32 > DGEMM_PAIR_MAX_ROW_BLOCKS)
         return cudaErrorInvalidValue;
+    // the second product's tiles are stored while first-product tiles of later row blocks may still be reading their
+    // operands: its output must not alias anything the first product reads
+    if (g2.D == g1.B || g2.D == g1.A) return cudaErrorInvalidValue;
     const long tiles32 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32);
     if (tiles32 <= 148)
         return g2.transB ? launch_pair_cfg<Cfg32x32s6, true>(g1, g2, sync, stream) : launch_pair_cfg<Cfg32x32s6, false>(g1, g2, sync, stream);

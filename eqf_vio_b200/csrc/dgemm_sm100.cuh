@@ -49,6 +49,10 @@ struct GemmProblem {
     int skip_m = 0, skip_n = 0;
 };
 
+// Once per device before the first launch on it (the > 48 KB dynamic shared-memory opt-in is a per-device function
+// attribute): call with that device current.  eqvio_create and the handle-less entry points do.
+cudaError_t dgemm_init_device();
+
 // Host API.  All pointers are device pointers; A, B must be 16-byte aligned with even lda/ldb and
 // be readable up to the next multiple of 16 rows (the library's buffers are padded accordingly).
 // Returns cudaSuccess or the launch / encode error.  `flops_out` (optional) receives 2*M*N*K.
@@ -57,6 +61,8 @@ cudaError_t dgemm_launch(const GemmProblem& p, cudaStream_t stream, int force_co
 // (F Sigma) F^T, (C Sigma) C^T, (K C) Sigma.  The second product's tiles start as soon as their row block of W is
 // complete (per-row-block counters in `sync`: DGEMM_PAIR_SYNC_INTS ints, zero before the first use and left zero) and
 // fill the SM slots the first product's tail leaves idle.  Requires second.A == first.D, equal M, first not transposed.
+// second.D must not alias first.A / first.B (rejected): second-product tiles are stored while first-product tiles of
+// later row blocks still read their operands.
 // Launches on one stream must not overlap launches on another with the same `sync` buffer.
 static const int DGEMM_PAIR_MAX_ROW_BLOCKS = 8192;
 static const int DGEMM_PAIR_SYNC_INTS = 8 + DGEMM_PAIR_MAX_ROW_BLOCKS;

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -41,6 +42,20 @@ static void set_error(cudaError_t e, const char* what, int line) {
 }
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Function attributes (the > 48 KB dynamic shared-memory opt-in of the GEMM, chain and back-substitution kernels) are
+// per device: set once for every device a handle or a handle-less entry point touches.  Called with `device` current.
+static int init_device(int device) {
+    static std::mutex mu;
+    static std::vector<char> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < (int)done.size() && done[device]) return EQVIO_OK;
+    CU_TRY(dgemm_init_device());
+    CU_TRY(kernels_init_device());
+    if (device >= (int)done.size()) done.resize(device + 1, 0);
+    done[device] = 1;
+    return EQVIO_OK;
+}
 
 struct ProfEvent { cudaEvent_t a, b; double flops; int cls; int lane; };
 enum { PROF_RICCATI = 0, PROF_UPDATE = 1, PROF_SCHUR_GEMM = 2, PROF_SCHUR_DIAG = 3, PROF_MISC = 4, PROF_CLASSES = 5 };
@@ -74,6 +89,12 @@ struct eqvio_filter {
     // Sigma, so they run here underneath the two Sigma GEMMs of tick t (main stream).  What they write for the GEMMs
     // (F, the border columns of W, the step length T) is double-buffered by tick parity.
     cudaStream_t state = nullptr;
+    // Gather stream: a caller's collective over the pose record (eqvio_pose_gather_stream) waits here for the update that
+    // wrote the record and never sits in front of the next tick on the main stream.
+    cudaStream_t gather = nullptr;
+    cudaEvent_t ev_pose = nullptr, ev_pub = nullptr;
+    double* pose_pub = nullptr;   // the record as published on the gather stream (8 doubles)
+    bool pose_publish = false;
     cudaEvent_t ev_state = nullptr, ev_main = nullptr, ev_gemm[2] = {nullptr, nullptr};
     bool main_dirty = true;        // main-stream work since the last tick may have touched what the state stream reads / writes
     // EQVIO_PAIRS bit mask over the call sites (PAIR_*); 0 = every (A B) C chain as two launches.  Default: the Riccati step only —
@@ -260,7 +281,7 @@ static int ensure_capacity(Filter* f, int needN) {
     CU_TRY(dalloc(&Saug, (size_t)ld2m * (ld2m + 32))); CU_TRY(dalloc(&Sinv, (size_t)ldm * (ldm + 32)));
     CU_TRY(dalloc(&delta, (size_t)ldm)); CU_TRY(dalloc(&gamma, (size_t)ld)); CU_TRY(dalloc(&Gamma, (size_t)ld));
     CU_TRY(dalloc(&y_in, (size_t)3 * cap + 8)); CU_TRY(dalloc(&y, (size_t)3 * cap + 8)); CU_TRY(dalloc(&scratch, (size_t)cap + 8));
-    CU_TRY(dalloc(&d_flags, (size_t)cap + 8)); CU_TRY(dalloc(&d_map, (size_t)ld + 8));
+    CU_TRY(dalloc(&d_flags, (size_t)cap + 8)); CU_TRY(dalloc(&d_map, (size_t)ld + cap + 64));   // Sigma row map (n) + landmark keep list (N)
     double* gemv_part; int* gemv_cnt;
     CU_TRY(dalloc(&gemv_part, (size_t)8 * ld)); CU_TRY(dalloc(&gemv_cnt, (size_t)ld / 32 + 8));
     CU_TRY(cudaMemsetAsync(gemv_cnt, 0, ((size_t)ld / 32 + 8) * sizeof(int), f->stream));
@@ -395,7 +416,7 @@ static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const 
 // else two.  Each call site has its own counter buffer (pairs on different streams never share one).
 enum { PAIR_RICCATI = 0, PAIR_S = 1, PAIR_SIGMA = 2, PAIR_SITES = 3 };
 static int gemm_pair(Filter* f, const GemmProblem& g1, const GemmProblem& g2, int site) {
-    if (!((f->use_pairs >> site) & 1) || !dgemm_pair_pays(g1, g2)) {
+    if (!((f->use_pairs >> site) & 1) || !dgemm_pair_pays(g1, g2) || g2.D == g1.A || g2.D == g1.B) {
         const int st = gemm(f, g1);
         return st ? st : gemm(f, g2);
     }
@@ -501,7 +522,9 @@ static int riccati_gemms(Filter* f, double T) {
     const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld;
     f->prof_cls = PROF_RICCATI;
     const GemmProblem g1 = make_problem(f, 0, n, n, n, 1.0, f->F, ld, f->Sigma, ld, 0.0, nullptr, 0, f->W, ld, 0, 0.0);
-    const GemmProblem g2 = make_problem(f, 1, n, n, n16 + 6, 1.0, f->W, ld, f->F, ld, 0.0, nullptr, 0, f->Sigma, ld, 1, T);
+    // Sigma' goes to the twin buffer (the caller swaps): inside the pair launch second-product tiles are stored while
+    // first-product tiles of later row blocks may still be reading Sigma, so the step must not be in place
+    const GemmProblem g2 = make_problem(f, 1, n, n, n16 + 6, 1.0, f->W, ld, f->F, ld, 0.0, nullptr, 0, f->Sigma2, ld, 1, T);
     const int st = gemm_pair(f, g1, g2, PAIR_RICCATI);
     f->prof_cls = PROF_UPDATE;
     return st;
@@ -564,6 +587,7 @@ static int integrate(Filter* f, double newTime, bool doRiccati, const double* om
             // the two Sigma GEMMs read T from device memory (written by k_step_prepare): replayable
             const int st = run_graphed(f, GRAPH_RICCATI, f->par, [&]() { return riccati_gemms(f, a.T); });
             if (st) return st;
+            std::swap(f->Sigma, f->Sigma2);   // the step wrote the twin buffer
             CU_TRY(cudaEventRecord(f->ev_gemm[f->par], f->stream));
             f->accTime = 0.0;
         }
@@ -623,7 +647,7 @@ static int lift_eliminate(Filter* f, const SchurChain& ch) {
     CU_TRY(cudaEventRecord(f->ev_lift_elim, ch.s));
     if (!f->lift_wide) {
         ProfScope ps(f, ch.s, PROF_MISC);
-        launch_lift_rsolve(ch.s, f->Aug, ld, pb, f->LinvL, f->Rt, f->wave);
+        CU_TRY(launch_lift_rsolve(ch.s, f->Aug, ld, pb, f->LinvL, f->Rt, f->wave));
         f->launches += 1;
     }
     stamp(f, ch.s, ST_LIFT_RSOLVE);
@@ -770,29 +794,46 @@ static int flags_to_status(int flags) {
     return EQVIO_OK;
 }
 
-static int init_state(Filter* f) {
+// ctor = true : VIOFilter::VIOFilter(const Settings&), VIOFilter.cpp:60-73 + member defaults VIOFilter.h:46-55
+// ctor = false: VIOFilter::reset(), VIOFilter.cpp:84-91 (see eqvio_reset)
+static int init_state(Filter* f, bool ctor) {
     f->main_dirty = true;
-    // VIOFilter::VIOFilter(const Settings&), VIOFilter.cpp:60-73 + member defaults VIOFilter.h:46-55
     BaseState b;
     memset(&b, 0, sizeof b);
+    if (!ctor) {   // reset keeps inputBias and the accumulated velocity
+        CU_TRY(cudaStreamSynchronize(f->stream));
+        CU_TRY(cudaMemcpy(&b, f->st, sizeof b, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 3; ++i) b.curOmega[i] = b.curAccel[i] = 0.0;
+        memset(b.pose_record, 0, sizeof b.pose_record);
+        b.flags = 0;
+    }
     b.pose0 = se3_identity(); b.vel0 = v3(0, 0, 0);
-    b.cam.x = v3(f->s.cameraOffset[0], f->s.cameraOffset[1], f->s.cameraOffset[2]);
-    b.cam.R.w = f->s.cameraOffset[3]; b.cam.R.x = f->s.cameraOffset[4]; b.cam.R.y = f->s.cameraOffset[5]; b.cam.R.z = f->s.cameraOffset[6];
+    b.cam = se3_identity();
     b.XA = se3_identity(); b.Xw = v3(0, 0, 0);
-    for (int i = 0; i < 3; ++i) { b.bias[i] = f->s.initialOmegaBias[i]; b.bias[3 + i] = f->s.initialAccelBias[i]; }
-    StepScratch sc;
-    memset(&sc, 0, sizeof sc);
-    for (int i = 0; i < 3; ++i) { sc.Rd[i] = f->s.velOmegaVariance; sc.Rd[3 + i] = f->s.velAccelVariance; }
+    if (ctor) {
+        b.cam.x = v3(f->s.cameraOffset[0], f->s.cameraOffset[1], f->s.cameraOffset[2]);
+        b.cam.R.w = f->s.cameraOffset[3]; b.cam.R.x = f->s.cameraOffset[4]; b.cam.R.y = f->s.cameraOffset[5]; b.cam.R.z = f->s.cameraOffset[6];
+        for (int i = 0; i < 3; ++i) { b.bias[i] = f->s.initialOmegaBias[i]; b.bias[3 + i] = f->s.initialAccelBias[i]; }
+    }
     CU_TRY(cudaMemcpyAsync(f->st, &b, sizeof b, cudaMemcpyHostToDevice, f->stream));
-    CU_TRY(cudaMemcpyAsync(f->sc, &sc, sizeof sc, cudaMemcpyHostToDevice, f->stream));
+    if (ctor) {
+        StepScratch sc;
+        memset(&sc, 0, sizeof sc);
+        for (int i = 0; i < 3; ++i) { sc.Rd[i] = f->s.velOmegaVariance; sc.Rd[3 + i] = f->s.velAccelVariance; }
+        CU_TRY(cudaMemcpyAsync(f->sc, &sc, sizeof sc, cudaMemcpyHostToDevice, f->stream));
+    }
     const size_t nn = (size_t)f->ld * (f->ld + 32);
     CU_TRY(cudaMemsetAsync(f->Sigma, 0, nn * 8, f->stream));
     double d[11];
-    for (int i = 0; i < 3; ++i) { d[i] = f->s.initialBiasOmegaVariance; d[3 + i] = f->s.initialBiasAccelVariance; d[8 + i] = f->s.initialVelocityVariance; }
-    d[6] = d[7] = f->s.initialGravityVariance;
+    for (int i = 0; i < 11; ++i) d[i] = 1.0;
+    if (ctor) {
+        for (int i = 0; i < 3; ++i) { d[i] = f->s.initialBiasOmegaVariance; d[3 + i] = f->s.initialBiasAccelVariance; d[8 + i] = f->s.initialVelocityVariance; }
+        d[6] = d[7] = f->s.initialGravityVariance;
+    }
     CU_TRY(cudaMemcpy2DAsync(f->Sigma, (size_t)(f->ld + 1) * 8, d, 8, 8, 11, cudaMemcpyHostToDevice, f->stream));
     CU_TRY(cudaStreamSynchronize(f->stream));
-    f->initialised = false; f->currentTime = -1; f->accTime = 0; f->N = 0; f->ids.clear(); f->layoutN = -1;
+    f->currentTime = -1; f->N = 0; f->ids.clear(); f->layoutN = -1;
+    if (ctor) { f->initialised = false; f->accTime = 0; }
     return EQVIO_OK;
 }
 
@@ -817,17 +858,30 @@ int eqvio_settings_default(eqvio_settings_t* s) {
     return EQVIO_OK;
 }
 
-int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* out) {
-    if (!settings || !out) return EQVIO_ERR_ARG;
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
-        snprintf(g_last_error, sizeof g_last_error, "no CUDA device %d (found %d): the B200 path has no CPU fallback", device, count);
-        return EQVIO_ERR_NO_DEVICE;
-    }
-    CU_TRY(cudaSetDevice(device));
-    Filter* f = new Filter();
-    f->device = device;
-    f->s = *settings;
+// Everything eqvio_create acquires, released member by member (null-safe): also the clean-up path of a failed create.
+static void destroy_filter(Filter* f) {
+    cudaSetDevice(f->device);
+    for (cudaStream_t st : {f->stream, f->side, f->lift, f->main_h, f->lift_h, f->state, f->gather})
+        if (st) cudaStreamSynchronize(st);
+    for (auto& e : f->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (f->prof_base) cudaEventDestroy(f->prof_base);
+    drop_graphs(f);
+    free_device(f);
+    cudaFree(f->stamps);
+    cudaFree(f->pair_sync);
+    cudaFree(f->st); cudaFree(f->sc); cudaFree(f->pose_pub); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
+    if (f->h_stage) cudaFreeHost(f->h_stage);
+    if (f->h_istage) cudaFreeHost(f->h_istage);
+    for (cudaEvent_t e : {f->stage_free, f->ev_fork, f->ev_join, f->ev_lift_fork, f->ev_lift_done, f->ev_lift_elim, f->ev_lift_setup,
+                          f->ev_sa, f->ev_sb, f->ev_st, f->ev_la, f->ev_lb, f->ev_lt, f->ev_state, f->ev_main, f->ev_gemm[0], f->ev_gemm[1],
+                          f->ev_pose, f->ev_pub})
+        if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : {f->side, f->lift, f->main_h, f->lift_h, f->state, f->gather, f->stream})
+        if (st) cudaStreamDestroy(st);
+    delete f;
+}
+
+static int create_impl(Filter* f) {
     {
         // the main stream carries the latency-bound chains (Schur pivots): highest priority, so its small kernels
         // get SM slots as soon as CTAs of the big side-stream GEMMs retire
@@ -839,7 +893,8 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
         CU_TRY(cudaStreamCreateWithPriority(&f->main_h, cudaStreamNonBlocking, hi));
         CU_TRY(cudaStreamCreateWithPriority(&f->lift_h, cudaStreamNonBlocking, hi));
         CU_TRY(cudaStreamCreateWithPriority(&f->state, cudaStreamNonBlocking, hi));
-        for (cudaEvent_t* e : {&f->ev_state, &f->ev_main, &f->ev_gemm[0], &f->ev_gemm[1]}) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        CU_TRY(cudaStreamCreateWithPriority(&f->gather, cudaStreamNonBlocking, lo));
+        for (cudaEvent_t* e : {&f->ev_state, &f->ev_main, &f->ev_gemm[0], &f->ev_gemm[1], &f->ev_pose, &f->ev_pub}) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         for (cudaEvent_t* e : {&f->ev_sa, &f->ev_sb, &f->ev_st, &f->ev_la, &f->ev_lb, &f->ev_lt}) CU_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_fork, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&f->ev_lift_done, cudaEventDisableTiming));
@@ -862,6 +917,8 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     CU_TRY(cudaEventRecord(f->stage_free, f->stream));
     CU_TRY(dalloc(&f->st, 1));
     CU_TRY(dalloc(&f->sc, 1));
+    CU_TRY(dalloc(&f->pose_pub, 8));
+    CU_TRY(cudaMemset(f->pose_pub, 0, 64));
     CU_TRY(dalloc(&f->Linv, 64 * 80));
     CU_TRY(dalloc(&f->Uinv, 64 * 80));
     CU_TRY(dalloc(&f->UinvL, 64 * 80));
@@ -870,52 +927,59 @@ int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* o
     CU_TRY(cudaMemset(f->Uinv, 0, 64 * 80 * 8));
     int st = ensure_capacity(f, 64);
     if (st) return st;
-    st = init_state(f);
+    return init_state(f, true);
+}
+
+int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* out) {
+    if (!settings || !out) return EQVIO_ERR_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        snprintf(g_last_error, sizeof g_last_error, "no CUDA device %d (found %d): the B200 path has no CPU fallback", device, count);
+        return EQVIO_ERR_NO_DEVICE;
+    }
+    CU_TRY(cudaSetDevice(device));
+    int st = init_device(device);
     if (st) return st;
+    Filter* f = new Filter();
+    f->device = device;
+    f->s = *settings;
+    if ((st = create_impl(f))) {
+        destroy_filter(f);   // nothing acquired so far outlives a failed create
+        return st;
+    }
     *out = f;
     return EQVIO_OK;
 }
 
 int eqvio_destroy(eqvio_handle_t f) {
     if (!f) return EQVIO_ERR_ARG;
-    cudaSetDevice(f->device);
-    cudaStreamSynchronize(f->stream);
-    cudaStreamSynchronize(f->side);
-    cudaStreamSynchronize(f->lift);
-    cudaStreamSynchronize(f->main_h);
-    cudaStreamSynchronize(f->lift_h);
-    cudaStreamSynchronize(f->state);
-    for (auto& e : f->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    if (f->prof_base) cudaEventDestroy(f->prof_base);
+    destroy_filter(f);
+    return EQVIO_OK;
+}
+
+int eqvio_set_settings(eqvio_handle_t f, const eqvio_settings_t* settings) {
+    if (!f || !settings) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    // rare call: quiesce, then swap.  Captured graphs hold the old process variances as kernel arguments.
+    CU_TRY(cudaStreamSynchronize(f->state));
+    CU_TRY(cudaStreamSynchronize(f->stream));
+    f->s = *settings;
+    double Rd[6];
+    for (int i = 0; i < 3; ++i) { Rd[i] = f->s.velOmegaVariance; Rd[3 + i] = f->s.velAccelVariance; }
+    CU_TRY(cudaMemcpy(f->sc->Rd, Rd, sizeof Rd, cudaMemcpyHostToDevice));
     drop_graphs(f);
-    free_device(f);
-    cudaFree(f->stamps);
-    cudaFree(f->pair_sync);
-    cudaFree(f->st); cudaFree(f->sc); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
-    if (f->h_stage) cudaFreeHost(f->h_stage);
-    if (f->h_istage) cudaFreeHost(f->h_istage);
-    cudaEventDestroy(f->stage_free);
-    cudaEventDestroy(f->ev_fork); cudaEventDestroy(f->ev_join); cudaEventDestroy(f->ev_lift_fork); cudaEventDestroy(f->ev_lift_done); cudaEventDestroy(f->ev_lift_elim); cudaEventDestroy(f->ev_lift_setup);
-    cudaStreamDestroy(f->side); cudaStreamDestroy(f->lift); cudaStreamDestroy(f->main_h); cudaStreamDestroy(f->lift_h);
-    for (cudaEvent_t e : {f->ev_sa, f->ev_sb, f->ev_st, f->ev_la, f->ev_lb, f->ev_lt}) cudaEventDestroy(e);
-    for (cudaEvent_t e : {f->ev_state, f->ev_main, f->ev_gemm[0], f->ev_gemm[1]}) cudaEventDestroy(e);
-    cudaStreamDestroy(f->state);
-    cudaStreamDestroy(f->stream);
-    delete f;
+    f->main_dirty = true;
     return EQVIO_OK;
 }
 
 int eqvio_reset(eqvio_handle_t f) {
-    // VIOFilter::reset(), VIOFilter.cpp:84-91: xi0 = VIOState(), X = Identity, Sigma = I(11), time = -1.
+    // VIOFilter::reset(), VIOFilter.cpp:84-91 — exactly its member list: xi0 = VIOState(), X = Identity, Sigma = I(11),
+    // currentTime = -1, currentVelocity = Zero.  inputBias, initialisedFlag, accumulatedVelocity / accumulatedTime and
+    // the settings are NOT touched (the reference does not touch them either).  `VIOState()` leaves its Eigen members
+    // uninitialised in the reference; here it reads as identity pose, zero velocity, identity camera offset.
     if (!f) return EQVIO_ERR_ARG;
     CU_TRY(cudaSetDevice(f->device));
-    int st = init_state(f);
-    if (st) return st;
-    double ones[11];
-    for (int i = 0; i < 11; ++i) ones[i] = 1.0;
-    CU_TRY(cudaMemcpy2DAsync(f->Sigma, (size_t)(f->ld + 1) * 8, ones, 8, 8, 11, cudaMemcpyHostToDevice, f->stream));
-    CU_TRY(cudaStreamSynchronize(f->stream));
-    return EQVIO_OK;
+    return init_state(f, false);
 }
 
 int eqvio_process_imu(eqvio_handle_t f, double stamp, const double omega[3], const double accel[3]) {
@@ -931,14 +995,17 @@ int eqvio_process_imu(eqvio_handle_t f, double stamp, const double omega[3], con
 
 static int process_vision_impl(Filter* f, double stamp, int nmeas, const int* mids, const double* y_host, const double* y_dev) {
     CU_TRY(cudaSetDevice(f->device));
+    // the id-order precondition (an assert in the reference, VIOFilter.cpp:239-240) is checked before anything is
+    // integrated: a rejected frame leaves the filter exactly as it was
+    for (int i = 1; i < nmeas; ++i)
+        if (mids[i] < mids[i - 1]) return EQVIO_ERR_UNSORTED;
     int r = integrate(f, stamp, true, nullptr, nullptr, false, false);  // VIOFilter.cpp:234
     if (r < 0) return r;
     if (r == 0) return EQVIO_SKIPPED_DT;
     if (!f->initialised) return EQVIO_NOT_INITIALISED;
     f->main_dirty = true;   // bookkeeping and the update below change the state on the main stream
-    for (int i = 1; i < nmeas; ++i)
-        if (mids[i] < mids[i - 1]) return EQVIO_ERR_UNSORTED;
     cudaStream_t s = f->stream;
+    if (f->pose_publish) CU_TRY(cudaStreamWaitEvent(s, f->ev_pub, 0));   // the previous record has been copied out
     // removeOldLandmarks, VIOFilter.cpp:393-419
     {
         std::vector<int> keep;
@@ -1018,7 +1085,16 @@ static int process_vision_impl(Filter* f, double stamp, int nmeas, const int* mi
         f->N = nmeas;
     }
     if (nmeas == 0) return EQVIO_EMPTY_MEASUREMENT;
-    return update(f, true, true);
+    if ((st = update(f, true, true))) return st;
+    if (f->pose_publish) {
+        // the caller's collective over the pose record lives on the gather stream: it waits for this update there, and the
+        // next tick (main / state streams) never queues behind it
+        CU_TRY(cudaEventRecord(f->ev_pose, s));
+        CU_TRY(cudaStreamWaitEvent(f->gather, f->ev_pose, 0));
+        CU_TRY(cudaMemcpyAsync(f->pose_pub, f->st->pose_record, 64, cudaMemcpyDeviceToDevice, f->gather));
+        CU_TRY(cudaEventRecord(f->ev_pub, f->gather));
+    }
+    return EQVIO_OK;
 }
 
 int eqvio_process_vision(eqvio_handle_t f, double stamp, int n, const int* ids, const double* bearings) {
@@ -1143,6 +1219,69 @@ int eqvio_get_pose_record(eqvio_handle_t f, double rec[8]) {
 int eqvio_pose_record_dev(eqvio_handle_t f, double** dev_ptr) {
     if (!f || !dev_ptr) return EQVIO_ERR_ARG;
     *dev_ptr = f->st->pose_record;
+    return EQVIO_OK;
+}
+
+int eqvio_pose_publish(eqvio_handle_t f, void** gather_stream, double** published_dev) {
+    if (!f || !gather_stream || !published_dev) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    if (!f->pose_publish) {
+        f->pose_publish = true;
+        CU_TRY(cudaEventRecord(f->ev_pub, f->gather));
+    }
+    *gather_stream = (void*)f->gather;
+    *published_dev = f->pose_pub;
+    return EQVIO_OK;
+}
+
+// VIOFilter::setAuxiliaryData, VIOFilter.cpp:75-82: xi0.pose = (attitude, position), xi0.velocity = 0, initialisedFlag = true,
+// xi0.cameraOffset = the given one.  (The variances in AuxiliaryFilterData are not used by the reference's filter.)
+int eqvio_set_auxiliary_data(eqvio_handle_t f, const double attitude_wxyz[4], const double position[3], const double cam_offset[7]) {
+    if (!f || !attitude_wxyz || !position || !cam_offset) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    BaseState b;
+    int st = fetch_base(f, &b);
+    if (st) return st;
+    // SO3(Quaterniond) stores the quaternion as given (SO3.cpp:100)
+    b.pose0.R.w = attitude_wxyz[0]; b.pose0.R.x = attitude_wxyz[1]; b.pose0.R.y = attitude_wxyz[2]; b.pose0.R.z = attitude_wxyz[3];
+    b.pose0.x = v3(position[0], position[1], position[2]);
+    b.vel0 = v3(0, 0, 0);
+    b.cam.x = v3(cam_offset[0], cam_offset[1], cam_offset[2]);
+    b.cam.R.w = cam_offset[3]; b.cam.R.x = cam_offset[4]; b.cam.R.y = cam_offset[5]; b.cam.R.z = cam_offset[6];
+    f->main_dirty = true;
+    CU_TRY(cudaMemcpy(f->st, &b, sizeof b, cudaMemcpyHostToDevice));
+    f->initialised = true;
+    return EQVIO_OK;
+}
+
+// VIOFilter::initialiseFromIMUData, VIOFilter.cpp:133-144 as a public call: the velocity is used as given (processIMUData
+// passes the un-biased sample, :121-124).  SO3FromVectors throws on opposing vectors (SO3.cpp:160): here a status.
+int eqvio_initialise_from_imu(eqvio_handle_t f, const double omega[3], const double accel[3]) {
+    if (!f || !omega || !accel) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    int sing = 0;
+    const Quat R = so3_from_vectors(normalized(v3(accel[0], accel[1], accel[2])), v3(0, 0, 1), &sing);
+    if (sing) return EQVIO_ERR_SINGULAR_CHART;
+    BaseState b;
+    int st = fetch_base(f, &b);
+    if (st) return st;
+    b.pose0 = se3_identity();
+    b.pose0.R = R;
+    b.vel0 = v3(0, 0, 0);
+    f->main_dirty = true;
+    CU_TRY(cudaMemcpy(f->st, &b, sizeof b, cudaMemcpyHostToDevice));
+    f->initialised = true;
+    return EQVIO_OK;
+}
+
+int eqvio_get_flags(eqvio_handle_t f, int* status, int clear) {
+    if (!f || !status) return EQVIO_ERR_ARG;
+    CU_TRY(cudaSetDevice(f->device));
+    int flags = 0;
+    int st = read_flags(f, &flags);
+    if (st) return st;
+    *status = flags_to_status(flags);
+    if (clear && flags) CU_TRY(cudaMemsetAsync(&f->st->flags, 0, sizeof(int), f->stream));
     return EQVIO_OK;
 }
 
@@ -1294,6 +1433,7 @@ int eqvio_riccati_propagate(eqvio_handle_t f, double T, const double omega[3]) {
     int st = build_FB_only(f, T, omega);
     if (st) return st;
     if ((st = riccati_gemms(f, T))) return st;
+    std::swap(f->Sigma, f->Sigma2);
     CU_TRY(cudaStreamSynchronize(f->stream));
     return EQVIO_OK;
 }
@@ -1381,6 +1521,7 @@ int eqvio_dgemm(int device, int transB, int M, int N, int K, double alpha, const
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return EQVIO_ERR_NO_DEVICE;
     CU_TRY(cudaSetDevice(device));
+    if (int ist = init_device(device)) return ist;
     const int brow = transB ? N : K, bcol = transB ? K : N;
     const int dlda = round_up(std::max(M, 1), 16) + 16, dldb = round_up(std::max(brow, 1), 16) + 16, dldc = round_up(std::max(M, 1), 16);
     double *dA, *dB, *dC, *dD;
@@ -1423,6 +1564,7 @@ int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int ld
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return EQVIO_ERR_NO_DEVICE;
     CU_TRY(cudaSetDevice(device));
+    if (int ist = init_device(device)) return ist;
     const int b2row = transB2 ? N2 : N1, b2col = transB2 ? N1 : N2;
     const int dlda = round_up(M, 16) + 16, dldb1 = round_up(K1, 16) + 16, dldb2 = round_up(b2row, 16) + 16;
     double *dA, *dB1, *dB2, *dW, *dD;
@@ -1471,6 +1613,7 @@ int eqvio_getrf_block(int device, int nb, const double* A, int lda, double* LU, 
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return EQVIO_ERR_NO_DEVICE;
     CU_TRY(cudaSetDevice(device));
+    if (int ist = init_device(device)) return ist;
     double *dA, *dLU, *dL, *dU;
     int* dflags;
     CU_TRY(dalloc(&dA, 64 * 64)); CU_TRY(dalloc(&dLU, 64 * 64)); CU_TRY(dalloc(&dL, 64 * 64)); CU_TRY(dalloc(&dU, 64 * 64));
@@ -1607,7 +1750,7 @@ const char* eqvio_status_string(int status) {
         case EQVIO_ERR_CUDA: return g_last_error[0] ? g_last_error : "CUDA error";
         case EQVIO_ERR_NAN: return "NaN in Sigma or X";
         case EQVIO_ERR_SINGULAR_CHART: return "SO3FromVectors: the vectors cannot be exactly opposing";
-        case EQVIO_ERR_NOT_SPD: return "Cholesky failed: matrix not positive definite";
+        case EQVIO_ERR_NOT_SPD: return "unpivoted LU of S or Sigma_sub met a zero / non-finite pivot (matrix not positive definite)";
         case EQVIO_ERR_NO_DEVICE: return g_last_error[0] ? g_last_error : "no CUDA device";
         case EQVIO_ERR_UNSORTED: return "bearings are not sorted by ascending id";
     }

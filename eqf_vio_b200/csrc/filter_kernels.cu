@@ -1061,6 +1061,15 @@ __global__ void k_set_inertial_points(const BaseState* st, Landmarks L, int N, c
 // ------------------------------------------------------------------------------------------------
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+static const int LIFT_RSOLVE_SMEM = (3 * 64 * 65 + 4 * 64) * (int)sizeof(double);
+static const int CHAIN_BLOCK_SMEM = (4 * 64 * LDW + 64) * (int)sizeof(double);
+// The > 48 KB dynamic shared-memory opt-in is a per-device function attribute: once per device, with it current.
+cudaError_t kernels_init_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_lift_rsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, LIFT_RSOLVE_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_chain_block, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_BLOCK_SMEM);
+}
+
 void launch_step_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const ImuArgs& a, const RiccatiOut& ro) {
     k_step_prepare<<<1, 128, 0, s>>>(st, sc, a, ro);
 }
@@ -1082,13 +1091,12 @@ void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, in
                           int lda, int pb, double* yo) {
     k_lift_features<<<cdiv(N > 16 ? N : 16, 128), 128, 0, s>>>(sc, L, N, gamma, Aug, lda, pb, yo);
 }
-void launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt, int* ready) {
+cudaError_t launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt, int* ready) {
     const int nblk = (pb + 63) / 64;
-    const int smem = (3 * 64 * 65 + 4 * 64) * (int)sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(k_lift_rsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_done = true; }
-    cudaMemsetAsync(ready, 0, (size_t)nblk * sizeof(int), s);
-    k_lift_rsolve<<<nblk, 256, smem, s>>>(Aug, lda, pb, LinvBlocks, Rt, ready);
+    cudaError_t e = cudaMemsetAsync(ready, 0, (size_t)nblk * sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    k_lift_rsolve<<<nblk, 256, LIFT_RSOLVE_SMEM, s>>>(Aug, lda, pb, LinvBlocks, Rt, ready);
+    return cudaGetLastError();
 }
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p, long rt_rs, long rt_cs, double rt_sign,
                        const double* Rt, const double* yo, int use_lift, int discrete, double* Gamma_out, int apply) {
@@ -1099,14 +1107,7 @@ void launch_lift_apply(cudaStream_t s, BaseState* st, Landmarks L, int N, const 
 }
 cudaError_t launch_chain_block(cudaStream_t s, double* A, int lda, int j, int nb, int prev_nb, const double* Din, int ldin,
                                double* LUout, int ldout, double* Linv, double* Uinv, int* flags) {
-    static bool attr_done = false;
-    const int smem = (4 * 64 * LDW + 64) * (int)sizeof(double);
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain_block, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    k_chain_block<<<1, 512, smem, s>>>(A, lda, j, nb, prev_nb, Din, ldin, LUout, ldout, Linv, Uinv, flags);
+    k_chain_block<<<1, 512, CHAIN_BLOCK_SMEM, s>>>(A, lda, j, nb, prev_nb, Din, ldin, LUout, ldout, Linv, Uinv, flags);
     return cudaGetLastError();
 }
 void launch_schur_setup(cudaStream_t s, double* A, int lda, int k, int kpad, int r, int c, int identity_border) {

@@ -64,6 +64,14 @@ class VIOFilter:
     def reset(self):
         abi.check(self._L.eqvio_reset(self._h), "eqvio_reset")
 
+    def setAuxiliaryData(self, attitude_wxyz, position, cameraOffset):
+        """VIOFilter::setAuxiliaryData (VIOFilter.cpp:75-82); cameraOffset is x y z qw qx qy qz."""
+        abi.check(self._L.eqvio_set_auxiliary_data(self._h, _p(_vec(attitude_wxyz, 4)), _p(_vec(position, 3)), _p(_vec(cameraOffset, 7))), "eqvio_set_auxiliary_data")
+
+    def initialiseFromIMUData(self, omega, accel):
+        """VIOFilter::initialiseFromIMUData (VIOFilter.cpp:133-144): the sample is used as given."""
+        abi.check(self._L.eqvio_initialise_from_imu(self._h, _p(_vec(omega, 3)), _p(_vec(accel, 3))), "eqvio_initialise_from_imu")
+
     def processIMUData(self, stamp, omega, accel) -> int:
         o = omega.tolist() if hasattr(omega, "tolist") else list(omega)
         a = accel.tolist() if hasattr(accel, "tolist") else list(accel)
@@ -127,6 +135,18 @@ class VIOFilter:
         p = C.c_void_p()
         abi.check(self._L.eqvio_pose_record_dev(self._h, C.byref(p)), "eqvio_pose_record_dev")
         return p.value
+
+    def posePublish(self):
+        """(gather stream handle, device pointer of the published 8-double pose record): see eqvio_pose_publish."""
+        st, p = C.c_void_p(), C.c_void_p()
+        abi.check(self._L.eqvio_pose_publish(self._h, C.byref(st), C.byref(p)), "eqvio_pose_publish")
+        return st.value or 0, p.value
+
+    def deviceFlags(self, clear=False) -> int:
+        """Sticky device-side error bits as a status code (abi.OK / ERR_SINGULAR_CHART / ERR_NOT_SPD / ERR_NAN)."""
+        v = C.c_int()
+        abi.check(self._L.eqvio_get_flags(self._h, C.byref(v), int(clear)), "eqvio_get_flags")
+        return v.value
 
     def stateCovariance(self) -> np.ndarray:
         n = 11 + 3 * self.numLandmarks

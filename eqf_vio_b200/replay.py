@@ -59,10 +59,16 @@ def write_meas_csv(path, stamps, ids, bearings):
             f.write(", ".join(parts) + "\n")
 
 
+def _stream_double(v, precision):
+    """What `os << std::setprecision(p) << v` prints for a double with the default float field: C's %.{p}g
+    (exponent notation for small / large magnitudes, trailing zeros dropped)."""
+    return "%.*g" % (precision, float(v))
+
+
 def format_state_row(t, est, precision=5):
     """`setprecision(20) time, setprecision(5) state` (main.cpp:135-137; operator<< VIOState.cpp:72-84)."""
-    g = lambda v: np.format_float_positional(v, precision=precision, unique=True, fractional=False, trim="-") if v != 0 else "0"
-    parts = [np.format_float_positional(t, precision=20, unique=True, fractional=False, trim="-")]
+    g = lambda v: _stream_double(v, precision)
+    parts = [_stream_double(t, 20)]
     p = est.pose
     parts += [g(p[0]), g(p[1]), g(p[2]), g(p[3]), g(p[4]), g(p[5]), g(p[6])]
     parts += [g(v) for v in est.velocity]
@@ -74,10 +80,10 @@ def format_state_row(t, est, precision=5):
 
 def format_filter_row(t, snap, precision=5):
     """operator<<(ostream&, VIOFilter) (VIOFilter.cpp:311-341) from a snapshot (include/eqvio.h layout)."""
-    g = lambda v: np.format_float_positional(v, precision=precision, unique=True, fractional=False, trim="-") if v != 0 else "0"
+    g = lambda v: _stream_double(v, precision)
     N = int(snap[0])
     n = 11 + 3 * N
-    parts = [np.format_float_positional(t, precision=20, unique=True, fractional=False, trim="-")]
+    parts = [_stream_double(t, 20)]
     parts += [g(v) for v in (*snap[26:29], *snap[22:26], *snap[29:32], *snap[43:46], *snap[39:43], *snap[46:49])]
     parts.append(str(N))
     L = snap[49 : 49 + 9 * N].reshape(N, 9)

@@ -70,7 +70,7 @@ enum {
     EQVIO_ERR_CUDA = -2,
     EQVIO_ERR_NAN = -3,            /* NaN in Sigma or X (the reference's asserts) */
     EQVIO_ERR_SINGULAR_CHART = -4, /* SO3FromVectors on opposing vectors (SO3.cpp:160) */
-    EQVIO_ERR_NOT_SPD = -5,        /* Cholesky of S or Sigma failed */
+    EQVIO_ERR_NOT_SPD = -5,        /* the unpivoted LU of S or Sigma_sub met a zero / non-finite pivot */
     EQVIO_ERR_NO_DEVICE = -6,
     EQVIO_ERR_UNSORTED = -7        /* bearings not sorted by ascending id (VIOFilter.cpp:239-240) */
 };
@@ -83,10 +83,33 @@ int eqvio_settings_default(eqvio_settings_t* s);
 /* VIOFilter::VIOFilter(const Settings&) (VIOFilter.cpp:60-73).  `device` is the CUDA ordinal. */
 int eqvio_create(const eqvio_settings_t* settings, int device, eqvio_handle_t* out);
 int eqvio_destroy(eqvio_handle_t h);
-/* VIOFilter::reset() (VIOFilter.cpp:84-91) */
+/* The reference's `settings` member is public and read at use time (VIOFilter.cpp:126,163-175,269,293): this
+ * replaces the settings the handle works with from the next call on.  Like assigning through the reference's
+ * pointer it does not re-apply constructor-time effects (initial variances, initial biases, camera offset). */
+int eqvio_set_settings(eqvio_handle_t h, const eqvio_settings_t* settings);
+/* VIOFilter::reset() (VIOFilter.cpp:84-91), exactly its member list: xi0 = VIOState(), X = Identity (no landmarks),
+ * Sigma = I(11), currentTime = -1, currentVelocity = 0.  Like the reference it does NOT touch inputBias,
+ * initialisedFlag, the accumulated velocity / time or the settings.  One stated deviation: `VIOState()` leaves its
+ * Eigen members uninitialised in the reference; here xi0 becomes identity pose, zero velocity, identity camera
+ * offset. */
 int eqvio_reset(eqvio_handle_t h);
+/* VIOFilter::setAuxiliaryData (VIOFilter.cpp:75-82): xi0.pose = (attitude (w,x,y,z), position), xi0.velocity = 0,
+ * xi0.cameraOffset = cam_offset (x y z qw qx qy qz), initialisedFlag = true. */
+int eqvio_set_auxiliary_data(eqvio_handle_t h, const double attitude_wxyz[4], const double position[3],
+                             const double cam_offset[7]);
+/* VIOFilter::initialiseFromIMUData (VIOFilter.cpp:133-144) as a public call: attitude from the accelerometer direction
+ * of the sample AS GIVEN (no un-biasing), xi0.velocity = 0, initialisedFlag = true.  Opposing vectors (the reference
+ * throws, SO3.cpp:160) return EQVIO_ERR_SINGULAR_CHART. */
+int eqvio_initialise_from_imu(eqvio_handle_t h, const double omega[3], const double accel[3]);
 
-/* ---- inputs -------------------------------------------------------------------------------- */
+/* ---- inputs --------------------------------------------------------------------------------
+ * Error model.  process_imu / process_vision are ASYNCHRONOUS: they validate their arguments, enqueue the step
+ * and return.  Argument errors (EQVIO_ERR_ARG, EQVIO_ERR_UNSORTED — checked before anything is integrated, so a
+ * rejected frame leaves the filter untouched) and CUDA launch errors are returned by the call itself.  Conditions
+ * only the device can see — a singular chart (SO3FromVectors on opposing vectors), a zero / non-finite pivot,
+ * a NaN — set sticky bits in device memory; they surface as the return value of the next synchronising call
+ * (eqvio_get_state, eqvio_synchronize, the kernel-level entry points) or through eqvio_get_flags, which can also
+ * clear them.  set_snapshot and reset clear them too. */
 
 /* VIOFilter::processIMUData (VIOFilter.cpp:120-131).  Asynchronous: enqueues on the handle's stream
  * and returns; the 7 doubles travel as kernel arguments.  Returns EQVIO_SKIPPED_DT when nothing was
@@ -121,6 +144,15 @@ int eqvio_get_pose_record(eqvio_handle_t h, double rec[8]);
 /* Device pointer to the 8-double pose record refreshed by every vision update (t x y z qw qx qy qz);
  * valid for the lifetime of the handle; stream-ordered after the update. */
 int eqvio_pose_record_dev(eqvio_handle_t h, double** dev_ptr);
+/* Multi-session pose gather without the main stream: the first call switches publishing on and returns a side
+ * stream (cudaStream_t as void*) and a device buffer of 8 doubles; from then on every vision update is followed, ON
+ * THAT STREAM, by a copy of the pose record into the buffer.  A caller's collective (NCCL all-gather of the buffer)
+ * enqueued on the returned stream therefore waits for the update that produced the record but never sits in front
+ * of the next IMU tick; the next frame's copy is stream-ordered behind the collective. */
+int eqvio_pose_publish(eqvio_handle_t h, void** gather_stream, double** published_dev);
+/* Sticky device-side error bits as a status code (EQVIO_OK / ERR_SINGULAR_CHART / ERR_NOT_SPD / ERR_NAN); synchronises
+ * the handle's stream; `clear` != 0 resets them. */
+int eqvio_get_flags(eqvio_handle_t h, int* status, int clear);
 /* VIOFilter::stateCovariance (VIOFilter.cpp:306-309): n x n column-major into dst with leading
  * dimension ld >= n. */
 int eqvio_get_covariance(eqvio_handle_t h, double* dst, int ld);
