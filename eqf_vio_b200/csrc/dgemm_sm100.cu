@@ -135,6 +135,70 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     return v;
 }
 
+// The four k4 MMA groups of one 16-deep k tile for this warp's WM x WN sub-tile: fragments from the swizzled stage
+// buffers (layout comment at the top of the file), accumulators in registers.
+template <class Cfg, bool TRANSB>
+__device__ __forceinline__ void mma_ktile(double (&acc)[Cfg::WM / 8][Cfg::WN / 8][2], const uint32_t sa, const uint32_t sb,
+                                          const uint32_t mn_off0, const uint32_t km_off0, const int b_half) {
+    constexpr int MB = Cfg::WM / 8, NB = Cfg::WN / 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int j1 = j >> 1, j0 = j & 1;
+        // XOR constants move k by (j1<<3 | j0): k*128 bits [7,10], chunk bit j0 for MN-major;
+        // chunk bit (j1<<2) and half bit j0 for K-major
+        const uint32_t mn_x = (uint32_t)((((j1 << 3) | j0) << 7) | (j0 << 4));
+        const uint32_t km_x = (uint32_t)((j1 << 6) | (j0 << 3));
+        double af[MB], bf[NB];
+#pragma unroll
+        for (int i = 0; i < MB; ++i) {
+            const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((i & 1) << 6)) + (uint32_t)((i >> 1) * 2048);
+            af[i] = lds_f64(sa + off);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (TRANSB) {
+                const int blk = i + b_half;
+                const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((blk & 1) << 6)) + (uint32_t)((blk >> 1) * 2048);
+                bf[i] = lds_f64(sb + off);
+            } else {
+                const uint32_t off = (km_off0 ^ km_x) + (uint32_t)(i * 1024);
+                bf[i] = lds_f64(sb + off);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MB; ++i)
+#pragma unroll
+            for (int jn = 0; jn < NB; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i], bf[jn]);
+    }
+}
+
+// Fused epilogue of one warp sub-tile: D = alpha acc + beta Cin (+ T P on the diagonal), bounds- and skip-box-checked.
+// m_base / n_base: global row of this thread's first accumulator row, global column of its first accumulator column.
+template <class Cfg>
+__device__ __forceinline__ void store_tile(const double (&acc)[Cfg::WM / 8][Cfg::WN / 8][2], const KernelParams& p, const int m_base,
+                                           const int n_base) {
+    constexpr int MB = Cfg::WM / 8, NB = Cfg::WN / 8;
+    const double Tstep = (p.add_diag && p.T_dev != nullptr) ? *p.T_dev : p.T;
+#pragma unroll
+    for (int jn = 0; jn < NB; ++jn) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int n = n_base + jn * 8 + c;
+            if (n >= p.N) continue;
+#pragma unroll
+            for (int i = 0; i < MB; ++i) {
+                const int m = m_base + i * 8;
+                if (m >= p.M) continue;
+                if (m < p.skip_m && n < p.skip_n) continue;
+                double v = p.alpha * acc[i][jn][c];
+                if (p.beta != 0.0) v += p.beta * p.Cin[(size_t)m + (size_t)p.ldcin * n];
+                if (p.add_diag && m == n) v += Tstep * process_diag(p, m);
+                p.D[(size_t)m + (size_t)p.ldd * n] = v;
+            }
+        }
+    }
+}
+
 // One CTA tile of D = alpha A op(B) + beta Cin.  `wait_flag` (may be null): the producer does not touch A before
 // *wait_flag >= wait_count (A's rows of this tile are being written by other CTAs of the same launch);
 // `signal_flag` (may be null): incremented once this tile's output is globally visible.
@@ -234,63 +298,13 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmAp, const CUtenso
         mbar_wait(&full[s], ph);
         const uint32_t sa = base + s * Cfg::STAGE_BYTES + a_warp;
         const uint32_t sb = base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + b_warp;
-        if (!idle) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int j1 = j >> 1, j0 = j & 1;
-                // XOR constants move k by (j1<<3 | j0): k*128 bits [7,10], chunk bit j0 for MN-major;
-                // chunk bit (j1<<2) and half bit j0 for K-major
-                const uint32_t mn_x = (uint32_t)((((j1 << 3) | j0) << 7) | (j0 << 4));
-                const uint32_t km_x = (uint32_t)((j1 << 6) | (j0 << 3));
-                double af[MB], bf[NB];
-#pragma unroll
-                for (int i = 0; i < MB; ++i) {
-                    const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((i & 1) << 6)) + (uint32_t)((i >> 1) * 2048);
-                    af[i] = lds_f64(sa + off);
-                }
-#pragma unroll
-                for (int i = 0; i < NB; ++i) {
-                    if (TRANSB) {
-                        const int blk = i + b_half;
-                        const uint32_t off = (mn_off0 ^ mn_x ^ (uint32_t)((blk & 1) << 6)) + (uint32_t)((blk >> 1) * 2048);
-                        bf[i] = lds_f64(sb + off);
-                    } else {
-                        const uint32_t off = (km_off0 ^ km_x) + (uint32_t)(i * 1024);
-                        bf[i] = lds_f64(sb + off);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < MB; ++i)
-#pragma unroll
-                    for (int jn = 0; jn < NB; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i], bf[jn]);
-            }
-        }
+        if (!idle) mma_ktile<Cfg, TRANSB>(acc, sa, sb, mn_off0, km_off0, b_half);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
     }
 
     // ===== epilogue: registers -> global =====
-    const double Tstep = (p.add_diag && p.T_dev != nullptr) ? *p.T_dev : p.T;
-    const int m_base = tile_m * BM + wm * WM + g;
-    const int n_base = tile_n * BN + wn * WN + 2 * t;
-#pragma unroll
-    for (int jn = 0; jn < NB; ++jn) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int n = n_base + jn * 8 + c;
-            if (n >= p.N) continue;
-#pragma unroll
-            for (int i = 0; i < MB; ++i) {
-                const int m = m_base + i * 8;
-                if (m >= p.M) continue;
-                if (m < p.skip_m && n < p.skip_n) continue;
-                double v = p.alpha * acc[i][jn][c];
-                if (p.beta != 0.0) v += p.beta * p.Cin[(size_t)m + (size_t)p.ldcin * n];
-                if (p.add_diag && m == n) v += Tstep * process_diag(p, m);
-                p.D[(size_t)m + (size_t)p.ldd * n] = v;
-            }
-        }
-    }
+    store_tile<Cfg>(acc, p, tile_m * BM + wm * WM + g, tile_n * BN + wn * WN + 2 * t);
     if (signal_flag) {
         __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(Cfg::CONSUMER_WARPS * 32) : "memory");   // consumer warps only (the producer has left)
@@ -356,6 +370,231 @@ dgemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         const int total = gridDim.x;
         if (atomicAdd(&sync[1], 1) == total - 1) {
             for (int i = 0; i < Tm1; ++i) sync[8 + i] = 0;
+            sync[0] = 0;
+            sync[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stream-K form of the same two-product step, for the sizes where one product is a single partial wave of tiles
+// (N = 256: 625 tiles of 32 x 32 on 148 SMs = 4.2 per SM, so some SMs carry 5 tiles and some 4, and launch, pipeline
+// fill and drain are paid per product with nothing behind them to hide in).  G = 148 k persistent CTAs, all
+// co-resident; the work of a product is its T tiles x KT k-tiles laid end to end ("units"), and CTA c takes the
+// contiguous range [c U / G, (c + 1) U / G): every SM issues the same number of DMMAs.  A range is cut at tile
+// boundaries; the piece that does not reach its tile's end is computed FIRST and posted (workspace slot + flag) for
+// the CTA that finishes that tile, then come the whole tiles, last the piece that finishes the tile the range starts
+// in, which adds the partials of the lower-numbered CTAs (already posted, or being computed without waiting on
+// anyone: no cycle) in ascending-k order and then its own: a fixed order, so results are bit-stable run to run.  One grid-wide barrier separates the products (W must be complete), after which the
+// producer warps fence the async proxy (W was written with generic stores, TMA reads it).  The producer warp runs
+// ahead across tile and segment boundaries, so the pipeline never drains inside a product.
+//   sync[0] barrier arrivals, sync[1] finished CTAs (the last one re-arms both), sync[8 + c] partial-ready flag of CTA c
+//   ws: G slots of Cfg::BM * Cfg::BN doubles (fragment order: [register][consumer thread])
+// ------------------------------------------------------------------------------------------------
+struct StreamKSeg { int tile, k0, k1; };   // k-tiles [k0, k1) of one tile; k1 < KT: post a partial; k0 > 0 && k1 == KT: gather the partials
+
+// The range [u0, u1) of CTA `c` cut at tile boundaries, in processing order: the piece that does not reach its tile's end
+// (at most one: the last) FIRST — it is posted for the CTA that finishes that tile and never waits on anyone — then the
+// whole tiles, then the piece that finishes the tile the range starts in (it gathers what lower-numbered CTAs posted).
+struct StreamKPlan {
+    long long u0, u1;
+    int KT, t_first, t_last, count;
+    bool open_end;          // the range ends inside tile t_last
+    __device__ StreamKPlan(int c, int G, int T, int KT_) : KT(KT_) {
+        const long long U = (long long)T * KT;
+        u0 = U * c / G; u1 = U * (c + 1) / G;
+        t_first = (int)(u0 / KT);
+        t_last = (int)((u1 - 1) / KT);
+        open_end = (u1 % KT) != 0;
+        count = u1 > u0 ? t_last - t_first + 1 : 0;
+    }
+    __device__ StreamKSeg seg(int i) const {
+        // natural order: tile t_first + j, j = 0 .. count - 1; processing order: [last if open_end], 1 .. , 0
+        int j;
+        if (open_end) j = (i == 0) ? count - 1 : (i < count - 1 ? i : 0);
+        else j = (i < count - 1) ? i + 1 : 0;
+        if (count == 1) j = 0;
+        StreamKSeg s;
+        s.tile = t_first + j;
+        s.k0 = (j == 0) ? (int)(u0 % KT) : 0;
+        s.k1 = (j == count - 1 && open_end) ? (int)(u1 % KT) : KT;
+        return s;
+    }
+};
+
+template <class Cfg>
+__device__ __forceinline__ void streamk_tile_coords(const KernelParams& p, int tile, int& tile_m, int& tile_n) {
+    const int Tn = (p.N + Cfg::BN - 1) / Cfg::BN;
+    tile_m = tile / Tn;            // row-major: a row block of the first product's output completes early and in order
+    tile_n = tile - tile_m * Tn;
+}
+
+template <class Cfg, bool TRANSB>
+__device__ __forceinline__ void streamk_produce(const CUtensorMap* tmA, const CUtensorMap* tmB, const KernelParams& p, const int c, const int G,
+                                                uint8_t* smem, uint64_t* full, uint64_t* empty, uint32_t& it) {
+    constexpr int STAGES = Cfg::STAGES;
+    const int KT = (p.K + 15) >> 4, T = ((p.M + Cfg::BM - 1) / Cfg::BM) * ((p.N + Cfg::BN - 1) / Cfg::BN);
+    const StreamKPlan plan(c, G, T, KT);
+    for (int i = 0; i < plan.count; ++i) {
+        const StreamKSeg sg = plan.seg(i);
+        int tile_m, tile_n;
+        streamk_tile_coords<Cfg>(p, sg.tile, tile_m, tile_n);
+        for (int kt = sg.k0; kt < sg.k1; ++kt, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+            uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            tma_load_3d(sa, tmA, 0, kt * 16, tile_m * (Cfg::BM / 16), &full[s]);
+            if (TRANSB)
+                tma_load_3d(sb, tmB, 0, kt * 16, tile_n * (Cfg::BN / 16), &full[s]);
+            else
+                tma_load_2d(sb, tmB, kt * 16, tile_n * Cfg::BN, &full[s]);
+        }
+    }
+}
+
+template <class Cfg, bool TRANSB>
+__device__ __forceinline__ void streamk_consume(const KernelParams& p, const int c, const int G, const uint32_t base, uint64_t* full,
+                                                uint64_t* empty, uint32_t& it, double* ws, int* flags) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
+    constexpr int MB = WM / 8, NB = WN / 8, NREG = MB * NB * 2, CT = Cfg::CONSUMER_WARPS * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = warp % Cfg::NWM, wn = warp / Cfg::NWM;
+    const int g = lane >> 2, t = lane & 3, t1 = t >> 1, t0 = t & 1;
+    const int k0f = (t1 << 3) | (t1 << 2) | (t0 << 1) | t0;
+    const uint32_t mn_off0 = (uint32_t)(k0f * 128 + (((g >> 1) ^ (k0f & 7)) << 4) + (g & 1) * 8);
+    const uint32_t km_off0 = (uint32_t)(g * 128 + ((((k0f >> 1) ^ g) & 7) << 4) + (k0f & 1) * 8);
+    const uint32_t a_warp = (uint32_t)((wm * WM / 16) * 2048);
+    const uint32_t b_warp = TRANSB ? (uint32_t)((wn * WN / 16) * 2048) : (uint32_t)(wn * WN * 128);
+    const int b_half = TRANSB ? ((wn * WN) & 8) >> 3 : 0;
+    const int KT = (p.K + 15) >> 4, T = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+    const StreamKPlan plan(c, G, T, KT);
+    const long long U = (long long)T * KT;
+    for (int i = 0; i < plan.count; ++i) {
+        const StreamKSeg sg = plan.seg(i);
+        int tile_m, tile_n;
+        streamk_tile_coords<Cfg>(p, sg.tile, tile_m, tile_n);
+        const int m_rem = p.M - (tile_m * BM + wm * WM), n_rem = p.N - (tile_n * BN + wn * WN);
+        const bool idle = (m_rem <= 0 || n_rem <= 0) && !p.no_edge_skip;
+        double acc[MB][NB][2];
+#pragma unroll
+        for (int a = 0; a < MB; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int kt = sg.k0; kt < sg.k1; ++kt, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            const uint32_t sa = base + s * Cfg::STAGE_BYTES + a_warp;
+            const uint32_t sb = base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES + b_warp;
+            if (!idle) mma_ktile<Cfg, TRANSB>(acc, sa, sb, mn_off0, km_off0, b_half);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        if (sg.k1 < KT) {
+            // this piece does not finish its tile: post the partial accumulators (fragment order, coalesced) for the CTA that does
+            double* slot = ws + (size_t)c * (BM * BN) + threadIdx.x;
+#pragma unroll
+            for (int a = 0; a < MB; ++a)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    __stcg(slot + (size_t)((a * NB + b) * 2) * CT, acc[a][b][0]);
+                    __stcg(slot + (size_t)((a * NB + b) * 2 + 1) * CT, acc[a][b][1]);
+                }
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");   // consumer warps only
+            if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + c), "r"(1) : "memory");
+            continue;
+        }
+        if (sg.k0 > 0) {
+            // this piece finishes a tile other CTAs started: add their partials in ascending-k order (the lowest-numbered CTA holds
+            // the tile's first k-tiles), then this CTA's own — a fixed order, so the result is bit-stable
+            const long long tile_u0 = (long long)sg.tile * KT;
+            int cf = c - 1;
+            while (cf > 0 && U * cf / G > tile_u0) --cf;
+            double sum[MB][NB][2];
+#pragma unroll
+            for (int a = 0; a < MB; ++a)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) sum[a][b][0] = sum[a][b][1] = 0.0;
+            for (int cc = cf; cc < c; ++cc) {
+                if (threadIdx.x == 0) {
+                    while (ld_acquire_gpu(flags + cc) == 0) __nanosleep(32);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
+                const double* slot = ws + (size_t)cc * (BM * BN) + threadIdx.x;
+#pragma unroll
+                for (int a = 0; a < MB; ++a)
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        sum[a][b][0] += __ldcg(slot + (size_t)((a * NB + b) * 2) * CT);
+                        sum[a][b][1] += __ldcg(slot + (size_t)((a * NB + b) * 2 + 1) * CT);
+                    }
+                asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");   // every thread has read the slot
+                if (threadIdx.x == 0) flags[cc] = 0;                      // re-armed for the next product / launch
+            }
+#pragma unroll
+            for (int a = 0; a < MB; ++a)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) { acc[a][b][0] = sum[a][b][0] + acc[a][b][0]; acc[a][b][1] = sum[a][b][1] + acc[a][b][1]; }
+        }
+        store_tile<Cfg>(acc, p, tile_m * BM + wm * WM + g, tile_n * BN + wn * WN + 2 * t);
+    }
+    (void)NREG;
+}
+
+template <class Cfg, bool TRANSB2>
+__global__ void __launch_bounds__(Cfg::THREADS, 6)
+dgemm_streamk_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                          const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const KernelParams p1,
+                          const KernelParams p2, const int two_products, int* sync, double* ws) {
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x, G = gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], Cfg::CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t it = 0;   // k-tiles through the ring so far: producer and consumers walk the same sequence
+    int* flags = sync + 8;
+    if (warp == Cfg::CONSUMER_WARPS) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA1);
+            tma_prefetch_desc(&tmB1);
+            streamk_produce<Cfg, false>(&tmA1, &tmB1, p1, c, G, smem, full, empty, it);
+            if (two_products) {
+                tma_prefetch_desc(&tmA2);
+                tma_prefetch_desc(&tmB2);
+                // grid-wide barrier: thread 0 of every CTA arrives once its first-product stores are visible
+                while (ld_acquire_gpu(sync) < G) __nanosleep(64);
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                streamk_produce<Cfg, TRANSB2>(&tmA2, &tmB2, p2, c, G, smem, full, empty, it);
+            }
+        }
+        return;
+    }
+    streamk_consume<Cfg, false>(p1, c, G, base, full, empty, it, ws, flags);
+    if (two_products) {
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::CONSUMER_WARPS * 32) : "memory");
+        if (threadIdx.x == 0) atomicAdd(sync, 1);
+        streamk_consume<Cfg, TRANSB2>(p2, c, G, base, full, empty, it, ws, flags);
+    }
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&sync[1], 1) == G - 1) {   // everyone is past the barrier: re-arm for the next launch
             sync[0] = 0;
             sync[1] = 0;
             __threadfence();
@@ -504,6 +743,8 @@ cudaError_t dgemm_init_device() {
     EQVIO_OPT_IN(opt_in_cfg<Cfg32x32s6>()); EQVIO_OPT_IN(opt_in_cfg<Cfg48x48>()); EQVIO_OPT_IN(opt_in_cfg<Cfg32x64s2>());
     EQVIO_OPT_IN(opt_in_cfg<Cfg64x32s2>());
     EQVIO_OPT_IN(opt_in_pair_cfg<Cfg32x32>()); EQVIO_OPT_IN(opt_in_pair_cfg<Cfg32x32s6>());
+    EQVIO_OPT_IN(cudaFuncSetAttribute(dgemm_streamk_pair_kernel<Cfg32x32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg32x32::SMEM_BYTES));
+    EQVIO_OPT_IN(cudaFuncSetAttribute(dgemm_streamk_pair_kernel<Cfg32x32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg32x32::SMEM_BYTES));
 #undef EQVIO_OPT_IN
     return cudaSuccess;
 }
@@ -519,6 +760,60 @@ cudaError_t dgemm_pair_launch(const GemmProblem& g1, const GemmProblem& g2, int*
     if (tiles32 <= 148)
         return g2.transB ? launch_pair_cfg<Cfg32x32s6, true>(g1, g2, sync, stream) : launch_pair_cfg<Cfg32x32s6, false>(g1, g2, sync, stream);
     return g2.transB ? launch_pair_cfg<Cfg32x32, true>(g1, g2, sync, stream) : launch_pair_cfg<Cfg32x32, false>(g1, g2, sync, stream);
+}
+
+// ---- stream-K launch -------------------------------------------------------------------------------------------
+static const int STREAMK_MAX_PER_SM = 6;
+int dgemm_streamk_ctas(int tiles) {
+    // k persistent CTAs on every SM, all co-resident (6 fit: 64 registers x 160 threads, 34 KB of shared memory each)
+    static int per_sm = -1;   // EQVIO_STREAMK_PER_SM: experiments
+    if (per_sm < 0) { const char* e = getenv("EQVIO_STREAMK_PER_SM"); per_sm = e ? atoi(e) : 6; if (per_sm < 1 || per_sm > STREAMK_MAX_PER_SM) per_sm = 6; }
+    return tiles >= 148 ? 148 * per_sm : 0;
+}
+size_t dgemm_streamk_ws_doubles() { return (size_t)148 * STREAMK_MAX_PER_SM * 32 * 32; }
+
+template <bool TB2>
+static cudaError_t launch_streamk(const GemmProblem& g1, const GemmProblem* g2, int* sync, double* ws, cudaStream_t stream) {
+    using Cfg = Cfg32x32;
+    if (!get_encode()) return cudaErrorNotSupported;
+    CUtensorMap tmA1, tmB1, tmA2, tmB2;
+    if (encode_mn_major(&tmA1, g1.A, g1.M, g1.K, g1.lda, Cfg::BM) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    if (encode_k_major(&tmB1, g1.B, g1.K, g1.N, g1.ldb, Cfg::BN) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    KernelParams p1, p2;
+    fill_params(p1, g1);
+    p2 = p1;
+    tmA2 = tmA1; tmB2 = tmB1;
+    if (g2) {
+        if (encode_mn_major(&tmA2, g2->A, g2->M, g2->K, g2->lda, Cfg::BM) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+        const CUresult rb = TB2 ? encode_mn_major(&tmB2, g2->B, g2->N, g2->K, g2->ldb, Cfg::BN) : encode_k_major(&tmB2, g2->B, g2->K, g2->N, g2->ldb, Cfg::BN);
+        if (rb != CUDA_SUCCESS) return cudaErrorInvalidValue;
+        fill_params(p2, *g2);
+    }
+    const int T1 = ((g1.M + Cfg::BM - 1) / Cfg::BM) * ((g1.N + Cfg::BN - 1) / Cfg::BN);
+    const int T2 = g2 ? ((g2->M + Cfg::BM - 1) / Cfg::BM) * ((g2->N + Cfg::BN - 1) / Cfg::BN) : T1;
+    const int G = dgemm_streamk_ctas(T1 < T2 ? T1 : T2);
+    if (G == 0) return cudaErrorInvalidValue;
+    dgemm_streamk_pair_kernel<Cfg, TB2><<<dim3(G), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA1, tmB1, tmA2, tmB2, p1, p2, g2 ? 1 : 0, sync, ws);
+    return cudaGetLastError();
+}
+
+// Whether the stream-K form is the better choice for a two-product step of these shapes: a single partial wave of
+// 32 x 32 tiles (more than one tile per SM, fewer than the 1110 from which the ticketed pair launch pays).
+bool dgemm_streamk_pays(const GemmProblem& g1, const GemmProblem& g2) {
+    static int mode = -1;   // EQVIO_STREAMK=0 never, 1 whenever legal; default: by shape
+    if (mode < 0) { const char* e = getenv("EQVIO_STREAMK"); mode = e ? atoi(e) : 2; }
+    const long t1 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32), t2 = (long)((g2.M + 31) / 32) * ((g2.N + 31) / 32);
+    const long tmin = t1 < t2 ? t1 : t2;
+    if (mode == 0 || tmin < 148) return false;
+    if (g1.skip_m || g2.skip_m || g1.skip_n || g2.skip_n) return false;
+    if (mode == 1) return true;
+    return t1 < 1110;
+}
+
+cudaError_t dgemm_streamk_pair_launch(const GemmProblem& g1, const GemmProblem& g2, int* sync, double* ws, cudaStream_t stream) {
+    if (g1.M <= 0 || g1.N <= 0 || g2.N <= 0) return cudaSuccess;
+    if (g1.transB || g1.D != g2.A || g1.M != g2.M || g2.D == g1.A || g2.D == g1.B) return cudaErrorInvalidValue;
+    return g2.transB ? launch_streamk<true>(g1, &g2, sync, ws, stream) : launch_streamk<false>(g1, &g2, sync, ws, stream);
 }
 
 int dgemm_num_configs() { return 10; }

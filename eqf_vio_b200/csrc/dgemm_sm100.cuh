@@ -67,6 +67,14 @@ cudaError_t dgemm_launch(const GemmProblem& p, cudaStream_t stream, int force_co
 static const int DGEMM_PAIR_MAX_ROW_BLOCKS = 8192;
 static const int DGEMM_PAIR_SYNC_INTS = 8 + DGEMM_PAIR_MAX_ROW_BLOCKS;
 cudaError_t dgemm_pair_launch(const GemmProblem& first, const GemmProblem& second, int* sync, cudaStream_t stream);
+// Stream-K form of the same two-product step (persistent CTAs, equal DMMA work per SM, one grid barrier between the
+// products) for shapes whose products are a single partial wave of tiles.  `sync`: DGEMM_STREAMK_SYNC_INTS ints, zero
+// before the first use and left zero; `ws`: dgemm_streamk_ws_doubles() doubles of scratch.  Same operand rules as
+// dgemm_pair_launch.  Requires all its CTAs co-resident (6 per SM): not for use concurrently with other big launches.
+static const int DGEMM_STREAMK_SYNC_INTS = 8 + 148 * 6;
+size_t dgemm_streamk_ws_doubles();
+bool dgemm_streamk_pays(const GemmProblem& first, const GemmProblem& second);
+cudaError_t dgemm_streamk_pair_launch(const GemmProblem& first, const GemmProblem& second, int* sync, double* ws, cudaStream_t stream);
 // Whether the single launch is the faster choice for these shapes (else: two dgemm_launch calls).
 bool dgemm_pair_pays(const GemmProblem& first, const GemmProblem& second);
 // Which tile configuration dgemm_launch would pick (for DESIGN.md / tests).

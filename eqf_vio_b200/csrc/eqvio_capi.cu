@@ -102,6 +102,8 @@ struct eqvio_filter {
     // (they overlap the latency-bound Schur chains, whose kernels compete for the same SM slots)
     int use_pairs = 1;
     int* pair_sync = nullptr;      // ticket / row-block counters of dgemm_pair_launch, one set per call site
+    int* sk_sync = nullptr;        // barrier / flag words and partial-tile workspace of the stream-K Riccati launch
+    double* sk_ws = nullptr;
     int par = 0;                   // parity of the current Riccati tick: F == Fpp[par], W == Wpp[par]
     double *Fpp[2] = {nullptr, nullptr}, *Wpp[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -416,6 +418,16 @@ static int gemm(Filter* f, int transB, int M, int N, int K, double alpha, const 
 // else two.  Each call site has its own counter buffer (pairs on different streams never share one).
 enum { PAIR_RICCATI = 0, PAIR_S = 1, PAIR_SIGMA = 2, PAIR_SITES = 3 };
 static int gemm_pair(Filter* f, const GemmProblem& g1, const GemmProblem& g2, int site) {
+    // Single-partial-wave shapes (N = 256): the stream-K form, but only where the step has the GPU to itself — the Riccati
+    // step (its persistent CTAs must all be resident; the update's pairs share the SMs with the Schur chains).
+    if (site == PAIR_RICCATI && ((f->use_pairs >> site) & 1) && dgemm_streamk_pays(g1, g2) && g2.D != g1.A && g2.D != g1.B) {
+        ProfEvent pe;
+        prof_begin(f, pe, f->cur, f->prof_cls, 2.0 * g1.M * g1.N * g1.K + 2.0 * g2.M * g2.N * g2.K);
+        CU_TRY(dgemm_streamk_pair_launch(g1, g2, f->sk_sync, f->sk_ws, f->cur));
+        prof_end(f, pe, f->cur);
+        f->launches += 1;
+        return EQVIO_OK;
+    }
     if (!((f->use_pairs >> site) & 1) || !dgemm_pair_pays(g1, g2) || g2.D == g1.A || g2.D == g1.B) {
         const int st = gemm(f, g1);
         return st ? st : gemm(f, g2);
@@ -869,6 +881,7 @@ static void destroy_filter(Filter* f) {
     free_device(f);
     cudaFree(f->stamps);
     cudaFree(f->pair_sync);
+    cudaFree(f->sk_sync); cudaFree(f->sk_ws);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->pose_pub); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
@@ -907,6 +920,9 @@ static int create_impl(Filter* f) {
     if (const char* e = getenv("EQVIO_PANEL_SLIM")) f->panel_slim = !(e[0] == '0');
     CU_TRY(dalloc(&f->pair_sync, (size_t)PAIR_SITES * DGEMM_PAIR_SYNC_INTS));
     CU_TRY(cudaMemset(f->pair_sync, 0, (size_t)PAIR_SITES * DGEMM_PAIR_SYNC_INTS * sizeof(int)));
+    CU_TRY(dalloc(&f->sk_sync, (size_t)DGEMM_STREAMK_SYNC_INTS));
+    CU_TRY(cudaMemset(f->sk_sync, 0, (size_t)DGEMM_STREAMK_SYNC_INTS * sizeof(int)));
+    CU_TRY(dalloc(&f->sk_ws, dgemm_streamk_ws_doubles()));
     if (const char* e = getenv("EQVIO_SIGMA_AFTER_LIFT")) f->sigma_after_lift = atoi(e);
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
     if (const char* e = getenv("EQVIO_STAMPS"))
@@ -1583,13 +1599,23 @@ int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int ld
     g1.epilogue = EPI_AXPBY; memset(&g1.epi, 0, sizeof g1.epi); g1.epi.alpha = 1.0;
     g2.M = M; g2.N = N2; g2.K = N1; g2.A = dW; g2.lda = dlda; g2.B = dB2; g2.ldb = dldb2; g2.transB = transB2; g2.D = dD; g2.ldd = dlda;
     g2.epilogue = EPI_AXPBY; memset(&g2.epi, 0, sizeof g2.epi); g2.epi.alpha = alpha2;
-    CU_TRY(dgemm_pair_launch(g1, g2, sync, 0));
+    // the form the filter would pick for these shapes: stream-K for a single partial wave of tiles, else the ticketed pair
+    const bool sk = dgemm_streamk_pays(g1, g2);
+    double* ws = nullptr;
+    int* sk_sync = nullptr;
+    if (sk) {
+        CU_TRY(dalloc(&ws, dgemm_streamk_ws_doubles()));
+        CU_TRY(dalloc(&sk_sync, (size_t)DGEMM_STREAMK_SYNC_INTS));
+        CU_TRY(cudaMemset(sk_sync, 0, (size_t)DGEMM_STREAMK_SYNC_INTS * sizeof(int)));
+    }
+    auto launch = [&]() { return sk ? dgemm_streamk_pair_launch(g1, g2, sk_sync, ws, 0) : dgemm_pair_launch(g1, g2, sync, 0); };
+    CU_TRY(launch());
     CU_TRY(cudaDeviceSynchronize());
     if (reps > 1 && ms) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, 0);
-        for (int i = 0; i < reps; ++i) CU_TRY(dgemm_pair_launch(g1, g2, sync, 0));
+        for (int i = 0; i < reps; ++i) CU_TRY(launch());
         cudaEventRecord(e1, 0);
         CU_TRY(cudaEventSynchronize(e1));
         float t;
@@ -1598,7 +1624,13 @@ int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int ld
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     } else if (ms) *ms = 0;
     int hs[2] = {-1, -1};
-    CU_TRY(cudaMemcpy(hs, sync, 8, cudaMemcpyDeviceToHost));   // the kernel must leave its counters zero
+    CU_TRY(cudaMemcpy(hs, sk ? sk_sync : sync, 8, cudaMemcpyDeviceToHost));   // the kernel must leave its counters zero
+    if (sk) {
+        std::vector<int> fl(DGEMM_STREAMK_SYNC_INTS);
+        CU_TRY(cudaMemcpy(fl.data(), sk_sync, fl.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int v : fl) if (v != 0) hs[1] = v;
+        cudaFree(ws); cudaFree(sk_sync);
+    }
     if (W) CU_TRY(cudaMemcpy2D(W, (size_t)ldw * 8, dW, (size_t)dlda * 8, (size_t)M * 8, N1, cudaMemcpyDeviceToHost));
     if (D) CU_TRY(cudaMemcpy2D(D, (size_t)ldd * 8, dD, (size_t)dlda * 8, (size_t)M * 8, N2, cudaMemcpyDeviceToHost));
     cudaFree(dA); cudaFree(dB1); cudaFree(dB2); cudaFree(dW); cudaFree(dD); cudaFree(sync);

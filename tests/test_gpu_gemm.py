@@ -104,3 +104,54 @@ def test_gemm_pair_full_size_repeated():
     assert rel(W, F @ S) < TOL
     assert rel(D, (F @ S) @ F.T) < TOL
     assert ms > 0
+
+
+STREAMK_SHAPES = [(779, 779, 779, 779), (500, 300, 450, 620), (779, 779, 779, 790), (417, 1000, 390, 401)]
+
+
+@pytest.mark.parametrize("transB2", [True, False])
+def test_gemm_streamk_pair(transB2):
+    """Shapes whose products are a single partial wave of 32 x 32 tiles (148 <= tiles < 1110) take the stream-K form of
+    the pair launch (persistent CTAs, equal k-tile counts per CTA, a tile shared by two CTAs summed head + tail, one
+    grid barrier between the products): against numpy at 1e-13, bit-stable from run to run (fixed split, fixed summation
+    order), flags / counters left zero (checked by the entry point), repeated launches."""
+    from eqf_vio_b200.filter import dgemm, dgemm_pair
+
+    rng = np.random.default_rng(9)
+    for (M, K1, N1, N2) in STREAMK_SHAPES:
+        A1 = rng.standard_normal((M, K1)); B1 = rng.standard_normal((K1, N1))
+        B2 = rng.standard_normal((N2, N1) if transB2 else (N1, N2))
+        W, D, _ = dgemm_pair(A1, B1, B2, transB2=transB2, alpha2=1.25)
+        Wb, Db, ms = dgemm_pair(A1, B1, B2, transB2=transB2, alpha2=1.25, reps=4)
+        assert np.array_equal(W, Wb) and np.array_equal(D, Db), (M, K1, N1, N2)
+        assert ms > 0
+        Wr = A1 @ B1
+        assert rel(W, Wr) < TOL and rel(D, 1.25 * Wr @ (B2.T if transB2 else B2)) < TOL, (M, K1, N1, N2)
+        # same products as two plain launches: not bit-identical (a shared tile adds head + tail), but to round-off
+        W2, _ = dgemm(A1, B1)
+        assert rel(W, W2) < 1e-15 * np.sqrt(K1) * 4
+
+
+def test_streamk_riccati_in_the_filter_matches_two_launches(monkeypatch):
+    """N = 256 (n = 779: 625 tiles, the stream-K Riccati step) against the same filter with every pair as two launches
+    (EQVIO_PAIRS=0): Sigma agrees to round-off after two vision periods and is bit-stable between two stream-K runs."""
+    from eqf_vio_b200.filter import VIOFilter
+    from eqf_vio_b200.settings import conditioned_settings
+    from eqf_vio_b200.synthetic import period_sequence
+
+    s = conditioned_settings()
+    seq = period_sequence(256, 2, camera_offset=tuple(s.cameraOffset))
+    snaps = []
+    for mask in ("1", "1", "0"):
+        monkeypatch.setenv("EQVIO_PAIRS", mask)
+        f = VIOFilter(s)
+        for kind, i in seq.events():
+            if kind == "imu":
+                f.processIMUData(seq.imu[i, 0], seq.imu[i, 1:4], seq.imu[i, 4:7])
+            else:
+                f.processVisionData(seq.vision_stamps[i], seq.ids, seq.bearings[i])
+        snaps.append(f.get_snapshot())
+        f.close()
+    assert np.array_equal(snaps[0], snaps[1])
+    hn = 49 + 9 * 256
+    assert rel(snaps[0][hn:], snaps[2][hn:]) < 1e-12 and np.abs(snaps[0][:hn] - snaps[2][:hn]).max() < 1e-11
