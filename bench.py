@@ -256,7 +256,10 @@ def emit(line: dict):
 def riccati_kernel_name(N):
     n_sigma = 11 + 3 * N
     t1 = ((n_sigma + 31) // 32) ** 2
-    if (2 * t1 <= 148) or (t1 >= 1110):
+    if 324 <= t1 < 888:
+        return True, ("eqvio::dgemm_pair_kernel<TileCfg<32,32,16,16,...>> with every tile split over 3-4 k-ranges (fp64 DMMA.8x8x4, TMA-staged; W = F Sigma and Sigma' = [W|T B R][F|B]^T + T P in one launch, "
+                      "partials summed in a fixed order by the chunk that arrives last, second product gated per row block of W)")
+    if (2 * t1 <= 148) or (t1 >= 888):
         return True, ("eqvio::dgemm_pair_kernel<TileCfg<32,32,16,16,...>> (fp64 DMMA.8x8x4, TMA-staged; W = F Sigma and Sigma' = [W|T B R][F|B]^T + T P in one launch, "
                       "second product gated per row block of W)")
     return False, "eqvio::dgemm_dmma_tma_kernel<TileCfg<32,32,16,16,4,4>> (fp64 DMMA.8x8x4, TMA-staged), two launches per Riccati step: W = F Sigma, Sigma' = [W|T B R][F|B]^T + T P"

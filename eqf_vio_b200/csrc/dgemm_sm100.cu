@@ -202,9 +202,19 @@ __device__ __forceinline__ void store_tile(const double (&acc)[Cfg::WM / 8][Cfg:
 // One CTA tile of D = alpha A op(B) + beta Cin.  `wait_flag` (may be null): the producer does not touch A before
 // *wait_flag >= wait_count (A's rows of this tile are being written by other CTAs of the same launch);
 // `signal_flag` (may be null): incremented once this tile's output is globally visible.
+// Split-K (sk.ks > 1): the CTA computes k-tiles [chunk KT / ks, (chunk + 1) KT / ks) of the tile, leaves its partial accumulators in
+// the tile's workspace slots and counts itself in; the chunk that arrives last adds the ks partials in ascending chunk order (its own
+// from registers, at its position: the same sum whoever is last, so results are bit-stable), runs the epilogue and signals.
+struct SplitK {
+    double* ws;      // [tile][chunk][BM * BN] partial accumulators, fragment order
+    int* cnt;        // [tile] arrival counters, zero before the first use and left zero
+    int ks, chunk, tile;
+};
+
 template <class Cfg, bool TRANSB>
 __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmAp, const CUtensorMap* tmBp, const KernelParams& p, const int tile_m,
-                                          const int tile_n, const int* wait_flag, const int wait_count, int* signal_flag) {
+                                          const int tile_n, const int* wait_flag, const int wait_count, int* signal_flag,
+                                          const SplitK sk = SplitK{nullptr, nullptr, 1, 0, 0}) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN, WM = Cfg::WM, WN = Cfg::WN, STAGES = Cfg::STAGES;
     constexpr int MB = WM / 8, NB = WN / 8;
     const CUtensorMap& tmA = *tmAp;
@@ -218,7 +228,9 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmAp, const CUtenso
     uint64_t* empty = full + STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KT = (p.K + 15) >> 4;
+    const int KTall = (p.K + 15) >> 4;
+    const int kt_begin = sk.ks > 1 ? (int)((long long)KTall * sk.chunk / sk.ks) : 0;
+    const int KT = (sk.ks > 1 ? (int)((long long)KTall * (sk.chunk + 1) / sk.ks) : KTall) - kt_begin;   // k-tiles of this CTA
     if ((tile_m + 1) * BM <= p.skip_m && (tile_n + 1) * BN <= p.skip_n) return;  // whole tile inside the skipped box
 
     if (threadIdx.x == 0) {
@@ -247,11 +259,11 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmAp, const CUtenso
                 mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
                 uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
                 uint8_t* sb = sa + Cfg::A_BYTES;
-                tma_load_3d(sa, &tmA, 0, kt * 16, tile_m * (BM / 16), &full[s]);
+                tma_load_3d(sa, &tmA, 0, (kt_begin + kt) * 16, tile_m * (BM / 16), &full[s]);
                 if (TRANSB)
-                    tma_load_3d(sb, &tmB, 0, kt * 16, tile_n * (BN / 16), &full[s]);
+                    tma_load_3d(sb, &tmB, 0, (kt_begin + kt) * 16, tile_n * (BN / 16), &full[s]);
                 else
-                    tma_load_2d(sb, &tmB, kt * 16, tile_n * BN, &full[s]);
+                    tma_load_2d(sb, &tmB, (kt_begin + kt) * 16, tile_n * BN, &full[s]);
             }
         }
         return;
@@ -304,6 +316,48 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmAp, const CUtenso
     }
 
     // ===== epilogue: registers -> global =====
+    if (sk.ks > 1) {
+        constexpr int CT = Cfg::CONSUMER_WARPS * 32;
+        __shared__ int s_last;
+        double* slot = sk.ws + ((size_t)sk.tile * sk.ks + sk.chunk) * (BM * BN) + threadIdx.x;
+#pragma unroll
+        for (int a = 0; a < MB; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                __stcg(slot + (size_t)((a * NB + b) * 2) * CT, acc[a][b][0]);
+                __stcg(slot + (size_t)((a * NB + b) * 2 + 1) * CT, acc[a][b][1]);
+            }
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");   // consumer warps only (the producer has left)
+        if (threadIdx.x == 0) {
+            const int last = atomicAdd(sk.cnt + sk.tile, 1) == sk.ks - 1;
+            if (last) sk.cnt[sk.tile] = 0;      // re-armed for the next launch
+            s_last = last;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
+        if (!s_last) return;
+        __threadfence();
+        double sum[MB][NB][2];
+#pragma unroll
+        for (int a = 0; a < MB; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) sum[a][b][0] = sum[a][b][1] = 0.0;
+        for (int ch = 0; ch < sk.ks; ++ch) {
+            const double* src = sk.ws + ((size_t)sk.tile * sk.ks + ch) * (BM * BN) + threadIdx.x;
+            const bool own = ch == sk.chunk;
+#pragma unroll
+            for (int a = 0; a < MB; ++a)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    sum[a][b][0] += own ? acc[a][b][0] : __ldcg(src + (size_t)((a * NB + b) * 2) * CT);
+                    sum[a][b][1] += own ? acc[a][b][1] : __ldcg(src + (size_t)((a * NB + b) * 2 + 1) * CT);
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < MB; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) { acc[a][b][0] = sum[a][b][0]; acc[a][b][1] = sum[a][b][1]; }
+    }
     store_tile<Cfg>(acc, p, tile_m * BM + wm * WM + g, tile_n * BN + wn * WN + 2 * t);
     if (signal_flag) {
         __threadfence();
@@ -311,6 +365,8 @@ __device__ __forceinline__ void gemm_tile(const CUtensorMap* tmAp, const CUtenso
         if (threadIdx.x == 0) atomicAdd(signal_flag, 1);
     }
 }
+
+struct SplitKArgs { double* ws; int* cnt; int ks; };
 
 template <class Cfg, bool TRANSB>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
@@ -345,17 +401,18 @@ template <class Cfg, bool TRANSB2>
 __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::STAGES == 4 ? 6 : Cfg::MINB))   // 6 CTAs / SM like the single-product kernel (64 registers)
 dgemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                           const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const KernelParams p1,
-                          const KernelParams p2, int* sync) {
+                          const KernelParams p2, int* sync, const SplitKArgs ska) {
     constexpr int BM = Cfg::BM, BN = Cfg::BN;
     __shared__ int s_ticket;
     if (threadIdx.x == 0) s_ticket = atomicAdd(&sync[0], 1);
     __syncthreads();
-    const int id = s_ticket;
+    const int ks = ska.ks;
+    const int id = s_ticket / ks, chunk = s_ticket - id * ks;    // the ks chunks of a tile hold consecutive tickets
     const int Tm1 = (p1.M + BM - 1) / BM, Tn1 = (p1.N + BN - 1) / BN, T1 = Tm1 * Tn1;
     const int Tm2 = (p2.M + BM - 1) / BM, Tn2 = (p2.N + BN - 1) / BN, Fn2 = p2.N / BN;
     if (id < T1) {
         const int tile_m = id / Tn1, tile_n = id - tile_m * Tn1;
-        gemm_tile<Cfg, false>(&tmA1, &tmB1, p1, tile_m, tile_n, nullptr, 0, &sync[8 + tile_m]);
+        gemm_tile<Cfg, false>(&tmA1, &tmB1, p1, tile_m, tile_n, nullptr, 0, &sync[8 + tile_m], SplitK{ska.ws, ska.cnt, ks, chunk, id});
     } else {
         // row-major over the full-width tile columns (rows of W become ready in that order), the partial last tile
         // column (cheap tiles) at the very end
@@ -364,7 +421,7 @@ dgemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         if (e < body) { tile_m = e / Fn2; tile_n = e - tile_m * Fn2; }
         else { tile_m = e - body; tile_n = Fn2; }
         (void)Tn2;
-        gemm_tile<Cfg, TRANSB2>(&tmA2, &tmB2, p2, tile_m, tile_n, &sync[8 + tile_m], Tn1, nullptr);
+        gemm_tile<Cfg, TRANSB2>(&tmA2, &tmB2, p2, tile_m, tile_n, &sync[8 + tile_m], Tn1, nullptr, SplitK{ska.ws, ska.cnt, ks, chunk, id});
     }
     if (threadIdx.x == 0) {   // a consumer thread: its tile is complete (and its wait / signal on the counters behind it)
         const int total = gridDim.x;
@@ -691,7 +748,7 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
 }
 
 template <class Cfg, bool TB2>
-static cudaError_t launch_pair_cfg(const GemmProblem& g1, const GemmProblem& g2, int* sync, cudaStream_t stream) {
+static cudaError_t launch_pair_cfg(const GemmProblem& g1, const GemmProblem& g2, int* sync, cudaStream_t stream, int ks = 1, double* ws = nullptr) {
     if (!get_encode()) return cudaErrorNotSupported;
     CUtensorMap tmA1, tmB1, tmA2, tmB2;
     if (encode_mn_major(&tmA1, g1.A, g1.M, g1.K, g1.lda, Cfg::BM) != CUDA_SUCCESS) return cudaErrorInvalidValue;
@@ -704,7 +761,9 @@ static cudaError_t launch_pair_cfg(const GemmProblem& g1, const GemmProblem& g2,
     fill_params(p2, g2);
     const int T1 = ((g1.M + Cfg::BM - 1) / Cfg::BM) * ((g1.N + Cfg::BN - 1) / Cfg::BN);
     const int T2 = ((g2.M + Cfg::BM - 1) / Cfg::BM) * ((g2.N + Cfg::BN - 1) / Cfg::BN);
-    dgemm_pair_kernel<Cfg, TB2><<<dim3(T1 + T2), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA1, tmB1, tmA2, tmB2, p1, p2, sync);
+    // split-K: the arrival counters of the (T1 + T2) tiles live behind the row-block counters of `sync`
+    const SplitKArgs ska{ws, sync + 8 + DGEMM_PAIR_MAX_ROW_BLOCKS, ks};
+    dgemm_pair_kernel<Cfg, TB2><<<dim3((T1 + T2) * ks), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA1, tmB1, tmA2, tmB2, p1, p2, sync, ska);
     return cudaGetLastError();
 }
 
@@ -713,13 +772,31 @@ static cudaError_t launch_pair_cfg(const GemmProblem& g1, const GemmProblem& g2,
 // complete (N = 512: +5.4 % on the Riccati step); with a single partial wave (N = 256: 625 tiles) the second phase's CTAs
 // would occupy the free slots at once, spin, and skew the SM load (-10 %).  Tiny problems whose two phases fit the GPU
 // one CTA per SM save the second launch's set-up.
+// Split-K factor of the pair launch: shapes whose products are a single partial wave of 32 x 32 tiles (N = 256 has 625 on 888 CTA slots)
+// leave SMs with 4 or 5 whole tiles and too few warps to keep the DMMA pipe busy (77 % while resident against 90 % at n = 1547); cut
+// into ks k-ranges the same work is more than a wave of finer-grained CTAs, 6 resident on every SM, and the ticketed pair launch pays
+// again.  1 elsewhere.
+int dgemm_pair_splitk(const GemmProblem& g1, const GemmProblem& g2) {
+    static int force = -1;   // EQVIO_SPLITK: 0 = never, k >= 2 = that factor for every single-wave shape; default: by shape
+    if (force < 0) { const char* e = getenv("EQVIO_SPLITK"); force = e ? atoi(e) : 1; }
+    const long t1 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32), t2 = (long)((g2.M + 31) / 32) * ((g2.N + 31) / 32);
+    const long tmin = t1 < t2 ? t1 : t2, tmax = t1 < t2 ? t2 : t1;
+    // measured (profiles/r02_streamk_splitk.md, us per pair, two launches / ks = 2 / 3 / 4): n = 395 (169 tiles) 27.0 / 31.8 / 28.9 / 28.9,
+    // n = 587 (361) 45.4 / 47.5 / 43.8 / 42.9, n = 779 (625) 84.6 / 77.4 / 75.8 / 76.9; from 888 tiles (a full wave) the plain pair wins
+    if (force == 0 || tmin < 324 || t1 >= 888 || g1.skip_m || g2.skip_m || g1.skip_n || g2.skip_n) return 1;
+    int ks = force >= 2 ? force : (tmin < 500 ? 4 : 3);
+    const int kt = ((g1.K < g2.K ? g1.K : g2.K) + 15) / 16;
+    while (ks > 1 && (kt / ks < 8 || tmax * ks > DGEMM_SPLITK_MAX_SLOTS / 2)) --ks;
+    return ks < 1 ? 1 : ks > 4 ? 4 : ks;
+}
+
 bool dgemm_pair_pays(const GemmProblem& g1, const GemmProblem& g2) {
     const long t1 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32), t2 = (long)((g2.M + 31) / 32) * ((g2.N + 31) / 32);
     if ((g1.M + 31) / 32 > DGEMM_PAIR_MAX_ROW_BLOCKS) return false;
     static int force = -1;   // EQVIO_PAIR_FORCE=1: pair whatever the shape (A/B measurements)
     if (force < 0) { const char* e = getenv("EQVIO_PAIR_FORCE"); force = (e && e[0] == '1') ? 1 : 0; }
     if (force) return true;
-    return t1 + t2 <= 148 || t1 >= 1110;
+    return t1 + t2 <= 148 || t1 >= 888;   // n = 971 (961 tiles): 132 us as a pair against 147 us as two launches
 }
 
 // Per-device opt-in to more than 48 KB of dynamic shared memory for every instantiation this file can launch.
@@ -762,6 +839,15 @@ cudaError_t dgemm_pair_launch(const GemmProblem& g1, const GemmProblem& g2, int*
     return g2.transB ? launch_pair_cfg<Cfg32x32, true>(g1, g2, sync, stream) : launch_pair_cfg<Cfg32x32, false>(g1, g2, sync, stream);
 }
 
+cudaError_t dgemm_pair_splitk_launch(const GemmProblem& g1, const GemmProblem& g2, int ks, int* sync, double* ws, cudaStream_t stream) {
+    if (g1.M <= 0 || g1.N <= 0 || g2.N <= 0) return cudaSuccess;
+    if (g1.transB || g1.D != g2.A || g1.M != g2.M || g1.skip_m || g2.skip_m || (g1.M + 31) / 32 > DGEMM_PAIR_MAX_ROW_BLOCKS || g2.D == g1.B || g2.D == g1.A)
+        return cudaErrorInvalidValue;
+    const long t1 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32), t2 = (long)((g2.M + 31) / 32) * ((g2.N + 31) / 32);
+    if (ks < 2 || (t1 + t2) * ks > DGEMM_SPLITK_MAX_SLOTS || !ws) return cudaErrorInvalidValue;
+    return g2.transB ? launch_pair_cfg<Cfg32x32, true>(g1, g2, sync, stream, ks, ws) : launch_pair_cfg<Cfg32x32, false>(g1, g2, sync, stream, ks, ws);
+}
+
 // ---- stream-K launch -------------------------------------------------------------------------------------------
 static const int STREAMK_MAX_PER_SM = 6;
 int dgemm_streamk_ctas(int tiles) {
@@ -800,8 +886,10 @@ static cudaError_t launch_streamk(const GemmProblem& g1, const GemmProblem* g2, 
 // Whether the stream-K form is the better choice for a two-product step of these shapes: a single partial wave of
 // 32 x 32 tiles (more than one tile per SM, fewer than the 1110 from which the ticketed pair launch pays).
 bool dgemm_streamk_pays(const GemmProblem& g1, const GemmProblem& g2) {
-    static int mode = -1;   // EQVIO_STREAMK=0 never, 1 whenever legal; default: by shape
-    if (mode < 0) { const char* e = getenv("EQVIO_STREAMK"); mode = e ? atoi(e) : 2; }
+    // EQVIO_STREAMK=1: whenever legal.  Default: never — measured on B200 (profiles/r02_streamk_splitk.md) the persistent form
+    // issues DMMAs ~10 % slower than hardware-dispatched CTAs at every size, which eats what the even split gains.
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("EQVIO_STREAMK"); mode = e ? atoi(e) : 0; }
     const long t1 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32), t2 = (long)((g2.M + 31) / 32) * ((g2.N + 31) / 32);
     const long tmin = t1 < t2 ? t1 : t2;
     if (mode == 0 || tmin < 148) return false;

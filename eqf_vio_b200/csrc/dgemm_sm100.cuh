@@ -65,7 +65,15 @@ cudaError_t dgemm_launch(const GemmProblem& p, cudaStream_t stream, int force_co
 // later row blocks still read their operands.
 // Launches on one stream must not overlap launches on another with the same `sync` buffer.
 static const int DGEMM_PAIR_MAX_ROW_BLOCKS = 8192;
-static const int DGEMM_PAIR_SYNC_INTS = 8 + DGEMM_PAIR_MAX_ROW_BLOCKS;
+// split-K form (dgemm_pair_splitk_launch): one arrival counter per tile of both products behind the row-block counters, and a
+// workspace of DGEMM_SPLITK_MAX_SLOTS partial tiles (32 x 32 doubles each)
+static const int DGEMM_SPLITK_MAX_SLOTS = 5120;
+static const int DGEMM_PAIR_SYNC_INTS = 8 + DGEMM_PAIR_MAX_ROW_BLOCKS + DGEMM_SPLITK_MAX_SLOTS;
+inline size_t dgemm_splitk_ws_doubles() { return (size_t)DGEMM_SPLITK_MAX_SLOTS * 32 * 32; }
+// Split-K factor the pair launch should use for these shapes (1 = none), and the launch itself: each tile of both products is
+// computed by `ks` CTAs over k-ranges, partials summed in a fixed order by the last arriver.
+int dgemm_pair_splitk(const GemmProblem& first, const GemmProblem& second);
+cudaError_t dgemm_pair_splitk_launch(const GemmProblem& first, const GemmProblem& second, int ks, int* sync, double* ws, cudaStream_t stream);
 cudaError_t dgemm_pair_launch(const GemmProblem& first, const GemmProblem& second, int* sync, cudaStream_t stream);
 // Stream-K form of the same two-product step (persistent CTAs, equal DMMA work per SM, one grid barrier between the
 // products) for shapes whose products are a single partial wave of tiles.  `sync`: DGEMM_STREAMK_SYNC_INTS ints, zero

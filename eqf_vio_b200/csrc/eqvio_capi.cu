@@ -104,6 +104,7 @@ struct eqvio_filter {
     int* pair_sync = nullptr;      // ticket / row-block counters of dgemm_pair_launch, one set per call site
     int* sk_sync = nullptr;        // barrier / flag words and partial-tile workspace of the stream-K Riccati launch
     double* sk_ws = nullptr;
+    double* splitk_ws = nullptr;   // partial tiles of the split-K pair launch
     int par = 0;                   // parity of the current Riccati tick: F == Fpp[par], W == Wpp[par]
     double *Fpp[2] = {nullptr, nullptr}, *Wpp[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -424,6 +425,16 @@ static int gemm_pair(Filter* f, const GemmProblem& g1, const GemmProblem& g2, in
         ProfEvent pe;
         prof_begin(f, pe, f->cur, f->prof_cls, 2.0 * g1.M * g1.N * g1.K + 2.0 * g2.M * g2.N * g2.K);
         CU_TRY(dgemm_streamk_pair_launch(g1, g2, f->sk_sync, f->sk_ws, f->cur));
+        prof_end(f, pe, f->cur);
+        f->launches += 1;
+        return EQVIO_OK;
+    }
+    // single-wave shapes (N = 256): the pair launch with every tile split over k (Riccati step only: the workspace is per handle)
+    const int ks = (site == PAIR_RICCATI && ((f->use_pairs >> site) & 1) && g2.D != g1.A && g2.D != g1.B) ? dgemm_pair_splitk(g1, g2) : 1;
+    if (ks > 1) {
+        ProfEvent pe;
+        prof_begin(f, pe, f->cur, f->prof_cls, 2.0 * g1.M * g1.N * g1.K + 2.0 * g2.M * g2.N * g2.K);
+        CU_TRY(dgemm_pair_splitk_launch(g1, g2, ks, f->pair_sync + (size_t)site * DGEMM_PAIR_SYNC_INTS, f->splitk_ws, f->cur));
         prof_end(f, pe, f->cur);
         f->launches += 1;
         return EQVIO_OK;
@@ -881,7 +892,7 @@ static void destroy_filter(Filter* f) {
     free_device(f);
     cudaFree(f->stamps);
     cudaFree(f->pair_sync);
-    cudaFree(f->sk_sync); cudaFree(f->sk_ws);
+    cudaFree(f->sk_sync); cudaFree(f->sk_ws); cudaFree(f->splitk_ws);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->pose_pub); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
@@ -923,6 +934,7 @@ static int create_impl(Filter* f) {
     CU_TRY(dalloc(&f->sk_sync, (size_t)DGEMM_STREAMK_SYNC_INTS));
     CU_TRY(cudaMemset(f->sk_sync, 0, (size_t)DGEMM_STREAMK_SYNC_INTS * sizeof(int)));
     CU_TRY(dalloc(&f->sk_ws, dgemm_streamk_ws_doubles()));
+    CU_TRY(dalloc(&f->splitk_ws, dgemm_splitk_ws_doubles()));
     if (const char* e = getenv("EQVIO_SIGMA_AFTER_LIFT")) f->sigma_after_lift = atoi(e);
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
     if (const char* e = getenv("EQVIO_STAMPS"))
@@ -1599,16 +1611,22 @@ int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int ld
     g1.epilogue = EPI_AXPBY; memset(&g1.epi, 0, sizeof g1.epi); g1.epi.alpha = 1.0;
     g2.M = M; g2.N = N2; g2.K = N1; g2.A = dW; g2.lda = dlda; g2.B = dB2; g2.ldb = dldb2; g2.transB = transB2; g2.D = dD; g2.ldd = dlda;
     g2.epilogue = EPI_AXPBY; memset(&g2.epi, 0, sizeof g2.epi); g2.epi.alpha = alpha2;
-    // the form the filter would pick for these shapes: stream-K for a single partial wave of tiles, else the ticketed pair
+    // the form the filter would pick for these shapes: split-K pair for a single partial wave of tiles, else the ticketed pair
+    // (EQVIO_STREAMK=1: the persistent stream-K form, kept for measurements)
     const bool sk = dgemm_streamk_pays(g1, g2);
+    const int ksplit = sk ? 1 : dgemm_pair_splitk(g1, g2);
     double* ws = nullptr;
     int* sk_sync = nullptr;
     if (sk) {
         CU_TRY(dalloc(&ws, dgemm_streamk_ws_doubles()));
         CU_TRY(dalloc(&sk_sync, (size_t)DGEMM_STREAMK_SYNC_INTS));
         CU_TRY(cudaMemset(sk_sync, 0, (size_t)DGEMM_STREAMK_SYNC_INTS * sizeof(int)));
+    } else if (ksplit > 1) {
+        CU_TRY(dalloc(&ws, dgemm_splitk_ws_doubles()));
     }
-    auto launch = [&]() { return sk ? dgemm_streamk_pair_launch(g1, g2, sk_sync, ws, 0) : dgemm_pair_launch(g1, g2, sync, 0); };
+    auto launch = [&]() {
+        return sk ? dgemm_streamk_pair_launch(g1, g2, sk_sync, ws, 0) : ksplit > 1 ? dgemm_pair_splitk_launch(g1, g2, ksplit, sync, ws, 0) : dgemm_pair_launch(g1, g2, sync, 0);
+    };
     CU_TRY(launch());
     CU_TRY(cudaDeviceSynchronize());
     if (reps > 1 && ms) {
@@ -1630,6 +1648,11 @@ int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int ld
         CU_TRY(cudaMemcpy(fl.data(), sk_sync, fl.size() * sizeof(int), cudaMemcpyDeviceToHost));
         for (int v : fl) if (v != 0) hs[1] = v;
         cudaFree(ws); cudaFree(sk_sync);
+    } else if (ksplit > 1) {
+        std::vector<int> fl(DGEMM_PAIR_SYNC_INTS);
+        CU_TRY(cudaMemcpy(fl.data(), sync, fl.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int v : fl) if (v != 0) hs[1] = v;       // row-block and arrival counters are left zero too
+        cudaFree(ws);
     }
     if (W) CU_TRY(cudaMemcpy2D(W, (size_t)ldw * 8, dW, (size_t)dlda * 8, (size_t)M * 8, N1, cudaMemcpyDeviceToHost));
     if (D) CU_TRY(cudaMemcpy2D(D, (size_t)ldd * 8, dD, (size_t)dlda * 8, (size_t)M * 8, N2, cudaMemcpyDeviceToHost));

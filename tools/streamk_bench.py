@@ -16,9 +16,9 @@ if len(sys.argv) > 1:
         _, m1 = dgemm(F, S, reps=50)
         _, m2 = dgemm(S, F, transB=True, reps=50)
         extra = f" | two launches {1e3*(m1+m2):.1f} us = {fl/(m1+m2)/1e9:.2f} TF"
-    print(f"n={n} STREAMK={os.environ.get('EQVIO_STREAMK','-')} per_sm={os.environ.get('EQVIO_STREAMK_PER_SM','-')} pair {ms*1e3:.1f} us = {fl/ms/1e9:.2f} TF{extra}")
+    print(f"n={n} STREAMK={os.environ.get('EQVIO_STREAMK','-')} SPLITK={os.environ.get('EQVIO_SPLITK','-')} pair {ms*1e3:.1f} us = {fl/ms/1e9:.2f} TF{extra}")
 else:
-    for n in (587, 779, 971, 1163, 1547):
-        for mode, per in (("0", "6"), ("1", "3"), ("1", "4"), ("1", "5"), ("1", "6")):
-            env = dict(os.environ, EQVIO_STREAMK=mode, EQVIO_PAIR_FORCE="1", EQVIO_STREAMK_PER_SM=per)
+    for n in (395, 587, 779, 971, 1163):
+        for mode, split in (("0", "0"), ("0", "2"), ("0", "3"), ("0", "4"), ("1", "0")):
+            env = dict(os.environ, EQVIO_STREAMK=mode, EQVIO_PAIR_FORCE="1", EQVIO_SPLITK=split)
             subprocess.run([sys.executable, __file__, str(n)], env=env)
