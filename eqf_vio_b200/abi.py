@@ -51,6 +51,7 @@ SIGNATURES = {
     "eqvio_bundle_lift": (C.c_int, [_h, _dp, _dp]),
     "eqvio_dgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp, C.c_int, _dp, C.c_int, C.c_double, _dp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "eqvio_dgemm_pair": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "eqvio_dgemm_ozaki": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "eqvio_schur_inverse": (C.c_int, [_h, C.c_int, _dp, C.c_int, _dp, C.c_int]),
     "eqvio_getrf_block": (C.c_int, [C.c_int, C.c_int, _dp, C.c_int, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_float)]),
     "eqvio_synchronize": (C.c_int, [_h]),

@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libeqvio_b200.so")
-SOURCES = ["dgemm_sm100.cu", "filter_kernels.cu", "eqvio_capi.cu"]
-HEADERS = ["dgemm_sm100.cuh", "filter_kernels.cuh", "kernels_api.cuh", "eqvio_math.cuh", os.path.join("..", "..", "include", "eqvio.h")]
+SOURCES = ["dgemm_sm100.cu", "ozaki_sm100.cu", "filter_kernels.cu", "eqvio_capi.cu"]
+HEADERS = ["dgemm_sm100.cuh", "ozaki_sm100.cuh", "filter_kernels.cuh", "kernels_api.cuh", "eqvio_math.cuh", os.path.join("..", "..", "include", "eqvio.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -777,8 +777,8 @@ static cudaError_t launch_pair_cfg(const GemmProblem& g1, const GemmProblem& g2,
 // into ks k-ranges the same work is more than a wave of finer-grained CTAs, 6 resident on every SM, and the ticketed pair launch pays
 // again.  1 elsewhere.
 int dgemm_pair_splitk(const GemmProblem& g1, const GemmProblem& g2) {
-    static int force = -1;   // EQVIO_SPLITK: 0 = never, k >= 2 = that factor for every single-wave shape; default: by shape
-    if (force < 0) { const char* e = getenv("EQVIO_SPLITK"); force = e ? atoi(e) : 1; }
+    const char* env = getenv("EQVIO_SPLITK");   // 0 = never, k >= 2 = that factor for every single-wave shape; default: by shape
+    const int force = env ? atoi(env) : 1;
     const long t1 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32), t2 = (long)((g2.M + 31) / 32) * ((g2.N + 31) / 32);
     const long tmin = t1 < t2 ? t1 : t2, tmax = t1 < t2 ? t2 : t1;
     // measured (profiles/r02_streamk_splitk.md, us per pair, two launches / ks = 2 / 3 / 4): n = 395 (169 tiles) 27.0 / 31.8 / 28.9 / 28.9,
@@ -888,8 +888,8 @@ static cudaError_t launch_streamk(const GemmProblem& g1, const GemmProblem* g2, 
 bool dgemm_streamk_pays(const GemmProblem& g1, const GemmProblem& g2) {
     // EQVIO_STREAMK=1: whenever legal.  Default: never — measured on B200 (profiles/r02_streamk_splitk.md) the persistent form
     // issues DMMAs ~10 % slower than hardware-dispatched CTAs at every size, which eats what the even split gains.
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("EQVIO_STREAMK"); mode = e ? atoi(e) : 0; }
+    const char* e = getenv("EQVIO_STREAMK");   // read per call (tests switch it inside one process)
+    const int mode = e ? atoi(e) : 0;
     const long t1 = (long)((g1.M + 31) / 32) * ((g1.N + 31) / 32), t2 = (long)((g2.M + 31) / 32) * ((g2.N + 31) / 32);
     const long tmin = t1 < t2 ? t1 : t2;
     if (mode == 0 || tmin < 148) return false;

@@ -23,6 +23,7 @@
 
 #include "../../include/eqvio.h"
 #include "dgemm_sm100.cuh"
+#include "ozaki_sm100.cuh"
 #include "kernels_api.cuh"
 
 using namespace eqvio;
@@ -51,6 +52,7 @@ static int init_device(int device) {
     std::lock_guard<std::mutex> lock(mu);
     if (device < (int)done.size() && done[device]) return EQVIO_OK;
     CU_TRY(dgemm_init_device());
+    CU_TRY(oz_init_device());
     CU_TRY(kernels_init_device());
     if (device >= (int)done.size()) done.resize(device + 1, 0);
     done[device] = 1;
@@ -1658,6 +1660,75 @@ int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int ld
     if (D) CU_TRY(cudaMemcpy2D(D, (size_t)ldd * 8, dD, (size_t)dlda * 8, (size_t)M * 8, N2, cudaMemcpyDeviceToHost));
     cudaFree(dA); cudaFree(dB1); cudaFree(dB2); cudaFree(dW); cudaFree(dD); cudaFree(sync);
     if (hs[0] != 0 || hs[1] != 0) { snprintf(g_last_error, sizeof g_last_error, "pair kernel left its counters at %d / %d", hs[0], hs[1]); return EQVIO_ERR_CUDA; }
+    return EQVIO_OK;
+}
+
+// fp64 GEMM assembled from int8 tensor-core products (ozaki_sm100.cuh).  The 128-aligned core block at the END of C (rows
+// [M - Mc, M), columns [N - Nc, N): in Sigma's layout the 3N landmark rows / columns, with the 11 base states in front) runs
+// on tcgen05; the thin strips in front of it run on the DMMA kernel.
+int eqvio_dgemm_ozaki(int device, int transB, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+                      int slices, int reps, float* ms_total, float* ms_gemm) {
+    if (M < OZ_TILE || N < OZ_TILE || K < 1 || !A || !B || !C || slices < 2 || slices > OZ_MAX_SLICES) return EQVIO_ERR_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return EQVIO_ERR_NO_DEVICE;
+    CU_TRY(cudaSetDevice(device));
+    if (int ist = init_device(device)) return ist;
+    const int brow = transB ? N : K, bcol = transB ? K : N;
+    const int dlda = round_up(M, 16) + 16, dldb = round_up(brow, 16) + 16, dldc = round_up(M, 16);
+    const int Mc = M / OZ_TILE * OZ_TILE, Nc = N / OZ_TILE * OZ_TILE, m0 = M - Mc, n0 = N - Nc;
+    double *dA, *dB, *dC;
+    int8_t *sA, *sB;
+    int *eA, *eB;
+    CU_TRY(dalloc(&dA, (size_t)dlda * (K + 32))); CU_TRY(dalloc(&dB, (size_t)dldb * (bcol + 32))); CU_TRY(dalloc(&dC, (size_t)dldc * (N + 1)));
+    CU_TRY(cudaMemset(dA, 0, (size_t)dlda * (K + 32) * 8)); CU_TRY(cudaMemset(dB, 0, (size_t)dldb * (bcol + 32) * 8));
+    CU_TRY(cudaMemset(dC, 0, (size_t)dldc * (N + 1) * 8));
+    CU_TRY(cudaMemcpy2D(dA, (size_t)dlda * 8, A, (size_t)lda * 8, (size_t)M * 8, K, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy2D(dB, (size_t)dldb * 8, B, (size_t)ldb * 8, (size_t)brow * 8, bcol, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMalloc((void**)&sA, oz_slices_bytes(Mc, K, slices))); CU_TRY(cudaMalloc((void**)&sB, oz_slices_bytes(Nc, K, slices)));
+    CU_TRY(cudaMemset(sA, 0, oz_slices_bytes(Mc, K, slices))); CU_TRY(cudaMemset(sB, 0, oz_slices_bytes(Nc, K, slices)));
+    CU_TRY(dalloc(&eA, (size_t)Mc + OZ_TILE)); CU_TRY(dalloc(&eB, (size_t)Nc + OZ_TILE));
+    OzOperand oa, ob;
+    auto split_both = [&]() -> cudaError_t {
+        cudaError_t e = oz_split(dA + m0, 1, dlda, Mc, K, slices, &oa, sA, eA, 0);
+        if (e != cudaSuccess) return e;
+        return transB ? oz_split(dB + n0, 1, dldb, Nc, K, slices, &ob, sB, eB, 0) : oz_split(dB + (size_t)n0 * dldb, dldb, 1, Nc, K, slices, &ob, sB, eB, 0);
+    };
+    auto core = [&]() { return oz_gemm(oa, ob, Mc, Nc, 1.0, 0.0, nullptr, 0, dC + m0 + (size_t)n0 * dldc, dldc, 0); };
+    auto strips = [&]() -> cudaError_t {
+        GemmProblem g;
+        g.K = K; g.A = dA; g.lda = dlda; g.B = dB; g.ldb = dldb; g.transB = transB; g.D = dC; g.ldd = dldc;
+        g.epilogue = EPI_AXPBY;
+        memset(&g.epi, 0, sizeof g.epi);
+        g.epi.alpha = 1.0;
+        cudaError_t e = cudaSuccess;
+        if (m0 > 0) { g.M = m0; g.N = N; e = dgemm_launch(g, 0); }                 // rows in front of the core, every column
+        if (e == cudaSuccess && n0 > 0) { g.M = M; g.N = n0; e = dgemm_launch(g, 0); }   // columns in front of the core, every row
+        return e;
+    };
+    CU_TRY(split_both()); CU_TRY(core()); CU_TRY(strips());
+    CU_TRY(cudaDeviceSynchronize());
+    if (ms_total) *ms_total = 0;
+    if (ms_gemm) *ms_gemm = 0;
+    if (reps > 1) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float t = 0;
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < reps; ++i) { CU_TRY(split_both()); CU_TRY(core()); CU_TRY(strips()); }
+        cudaEventRecord(e1, 0);
+        CU_TRY(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&t, e0, e1);
+        if (ms_total) *ms_total = t / reps;
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < reps; ++i) CU_TRY(core());
+        cudaEventRecord(e1, 0);
+        CU_TRY(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&t, e0, e1);
+        if (ms_gemm) *ms_gemm = t / reps;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    CU_TRY(cudaMemcpy2D(C, (size_t)ldc * 8, dC, (size_t)dldc * 8, (size_t)M * 8, N, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(sA); cudaFree(sB); cudaFree(eA); cudaFree(eB);
     return EQVIO_OK;
 }
 

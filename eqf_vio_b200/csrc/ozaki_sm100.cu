@@ -1,0 +1,388 @@
+// ozaki_sm100.cu — see ozaki_sm100.cuh.  Hand-written sm_100a: tcgen05.mma kind::i8 (SASS UTCIMMA / UTCQMMA family) with int32
+// accumulators in TMEM, tcgen05.ld epilogue (LDTM), TMA SWIZZLE_32B operand staging (UTMALDG), mbarrier pipelines.
+#include "ozaki_sm100.cuh"
+
+#include <cudaTypedefs.h>
+#include <limits.h>
+#include <stdio.h>
+
+namespace eqvio {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+namespace oz {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// ---- tcgen05 ----
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// all MMAs issued so far by this thread arrive on the mbarrier when they have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, M = 128, N = 128, K = 32
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// 32 lanes x 32 columns of 32-bit: thread `lane` of the warp receives its lane's 32 consecutive columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major operand tile staged by TMA with SWIZZLE_32B: rows of 32 bytes (= the 32-deep int8
+// k-block), 8-row groups 256 bytes apart (stride byte offset), leading byte offset unused for swizzled K-major layouts (1),
+// descriptor version 1 (sm_100), layout type 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
+    return d;
+}
+}  // namespace oz
+
+// Instruction descriptor: dense, no saturate, D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major (bits 15, 16 = 0),
+// N = 128 (N >> 3 at bit 17), M = 128 (M >> 4 at bit 24).
+static constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_TILE >> 3) << 17) | ((uint32_t)(OZ_TILE >> 4) << 24);
+
+static constexpr int OZ_SLICE_TILE_BYTES = OZ_TILE * OZ_KBLOCK;                     // 4096
+static constexpr int OZ_STAGE_BYTES = 2 * OZ_MAX_SLICES * OZ_SLICE_TILE_BYTES;      // A slices then B slices: 73728
+static constexpr int OZ_STAGES = 3;
+static constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 + 256;
+static constexpr int OZ_EPI_WARPS = 8, OZ_PRODUCER_WARP = 8, OZ_MMA_WARP = 9, OZ_THREADS = 320;
+static constexpr int OZ_DIAGS_PER_BATCH = 4;   // 4 x 128 TMEM columns
+
+struct OzParams {
+    int M, N, KB, S;
+    const int* exA;
+    const int* exB;
+    double alpha, beta;
+    const double* Cin;
+    int ldcin;
+    double* D;
+    int ldd;
+};
+
+__device__ __forceinline__ double oz_pow2(int e) {   // 2^e for e in the normal range
+    return __hiloint2double((e + 1023) << 20, 0);
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+k_oz_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzParams p) {
+    using namespace oz;
+    extern __shared__ uint8_t oz_smem_raw[];
+    const uint32_t raw = smem_u32(oz_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = oz_smem_raw + (base - raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
+    uint64_t* empty = full + OZ_STAGES;
+    uint64_t* acc_full = empty + OZ_STAGES;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Mt = (p.M + OZ_TILE - 1) / OZ_TILE;
+    const int tile_m = blockIdx.x % Mt, tile_n = blockIdx.x / Mt;
+    const int S = p.S, KB = p.KB;
+    const int nbatch = (S + OZ_DIAGS_PER_BATCH - 1) / OZ_DIAGS_PER_BATCH;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, OZ_EPI_WARPS);
+        mbar_fence_init();
+    }
+    if (warp == OZ_MMA_WARP) {   // one warp allocates all 512 TMEM columns (one CTA per SM: 216 KB of shared memory) and frees them at the end
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == OZ_PRODUCER_WARP) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            uint32_t it = 0;
+            for (int b = 0; b < nbatch; ++b) {
+                const int nS = min(OZ_DIAGS_PER_BATCH * (b + 1), S);   // slices 0 .. nS-1 of both operands take part in this batch's diagonals
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % OZ_STAGES;
+                    mbar_wait(&empty[s], ((it / OZ_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], (uint32_t)(2 * nS * OZ_SLICE_TILE_BYTES));
+                    const uint32_t sa = base + s * OZ_STAGE_BYTES, sb = sa + OZ_MAX_SLICES * OZ_SLICE_TILE_BYTES;
+                    for (int sl = 0; sl < nS; ++sl) {
+                        tma_load_3d(sa + sl * OZ_SLICE_TILE_BYTES, &tmA, kb * OZ_KBLOCK, tile_m * OZ_TILE, sl, &full[s]);
+                        tma_load_3d(sb + sl * OZ_SLICE_TILE_BYTES, &tmB, kb * OZ_KBLOCK, tile_n * OZ_TILE, sl, &full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == OZ_MMA_WARP) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int b = 0; b < nbatch; ++b) {
+                const int dmin = OZ_DIAGS_PER_BATCH * b, dmax = min(dmin + OZ_DIAGS_PER_BATCH - 1, S - 1);
+                if (b > 0) {   // the epilogue has read the previous batch's accumulators out of TMEM
+                    mbar_wait(acc_empty, (uint32_t)((b - 1) & 1));
+                    tc_fence_after();
+                }
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % OZ_STAGES;
+                    mbar_wait(&full[s], (it / OZ_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * OZ_STAGE_BYTES, sb = sa + OZ_MAX_SLICES * OZ_SLICE_TILE_BYTES;
+                    for (int d = dmin; d <= dmax; ++d) {
+                        const uint32_t acc = tmem_base + (uint32_t)((d - dmin) * OZ_TILE);
+                        for (int a = 0; a <= d; ++a)   // all pairs (a, d - a) of this diagonal into one int32 accumulator
+                            mma_i8(acc, smem_desc_sw32(sa + a * OZ_SLICE_TILE_BYTES), smem_desc_sw32(sb + (d - a) * OZ_SLICE_TILE_BYTES), OZ_IDESC,
+                                   (kb > 0 || a > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty[s]);       // the stage is free once these MMAs have read it
+                }
+                tc_commit(acc_full);            // the batch's accumulators are complete
+            }
+        }
+    } else {
+        // ===== epilogue warps: lane quarter q (TMEM lanes 32q .. 32q+31 = tile rows), column half h =====
+        const int q = warp & 3, h = warp >> 2;
+        double acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+        for (int b = 0; b < nbatch; ++b) {
+            const int dmin = OZ_DIAGS_PER_BATCH * b, dmax = min(dmin + OZ_DIAGS_PER_BATCH - 1, S - 1);
+            mbar_wait(acc_full, (uint32_t)(b & 1));
+            tc_fence_after();
+            for (int d = dmin; d <= dmax; ++d) {
+                const double scale = oz_pow2(-7 * d);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((d - dmin) * OZ_TILE + h * 64);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + half * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[half * 32 + j] = fma((double)(int)v[j], scale, acc[half * 32 + j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+        const int row = tile_m * OZ_TILE + q * 32 + lane;
+        if (row < p.M) {
+            const double ra = oz_pow2(max(p.exA[row], -900) - 12);
+            const int col0 = tile_n * OZ_TILE + h * 64;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int col = col0 + j;
+                if (col < p.N) {
+                    double v = p.alpha * ((acc[j] * ra) * oz_pow2(max(p.exB[col], -900)));
+                    if (p.beta != 0.0) v += p.beta * p.Cin[(size_t)row + (size_t)p.ldcin * col];
+                    p.D[(size_t)row + (size_t)p.ldd * col] = v;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == OZ_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// splitting
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void oz_load_tile(const double* X, long sr, long sk, int r0, int k0, int rows, int k, double (*t)[33]) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (sk == 1) {   // k contiguous: a warp reads 32 consecutive k of one row
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = ty + 8 * i;
+            t[r][tx] = (r0 + r < rows && k0 + tx < k) ? X[(size_t)(r0 + r) * sr + (k0 + tx)] : 0.0;
+        }
+    } else {         // rows contiguous (or general): a warp reads 32 consecutive rows at one k
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int kk = ty + 8 * i;
+            t[tx][kk] = (r0 + tx < rows && k0 + kk < k) ? X[(size_t)(r0 + tx) * sr + (size_t)(k0 + kk) * sk] : 0.0;
+        }
+    }
+}
+__device__ __forceinline__ int oz_exponent(double x) {   // e with |x| = f 2^e, f in [0.5, 1); zero / denormal: very small
+    const int hi = __double2hiint(x);
+    const int be = (hi >> 20) & 0x7ff;
+    return be == 0 ? -2000 : be - 1022;
+}
+
+__global__ void __launch_bounds__(256) k_oz_rowmax(const double* X, long sr, long sk, int rows, int k, int* ex) {
+    __shared__ double t[32][33];
+    const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    oz_load_tile(X, sr, sk, r0, k0, rows, k, t);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = threadIdx.y + 8 * i;
+        int e = oz_exponent(t[r][threadIdx.x]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+        if (threadIdx.x == 0 && r0 + r < rows) atomicMax(ex + r0 + r, e);
+    }
+}
+
+// digits: x 2^-e 2^6 = d0 + r0, |r| <= 1/2; then r 2^7 = d + r' ... every step exact in fp64, every digit in [-64, 64]
+__global__ void __launch_bounds__(256) k_oz_split(const double* X, long sr, long sk, int rows, int k, const int* ex, int8_t* slices, int rows_pad,
+                                                  int k_pad, int S) {
+    __shared__ double t[32][33];
+    const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    oz_load_tile(X, sr, sk, r0, k0, rows, k, t);
+    __syncthreads();
+    const int id = threadIdx.y * 32 + threadIdx.x, r = id >> 3, kg = id & 7;
+    if (r0 + r >= rows) return;
+    const int e = max(ex[r0 + r], -900);
+    const double up = oz_pow2(6 - e);
+    double v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = t[r][4 * kg + c] * up;
+    const size_t plane = (size_t)rows_pad * k_pad;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(slices + (size_t)(r0 + r) * k_pad + k0 + 4 * kg);
+    for (int s = 0; s < S; ++s) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const double d = rint(v[c]);
+            v[c] = (v[c] - d) * 128.0;
+            w |= ((uint32_t)(__double2int_rn(d)) & 0xffu) << (8 * c);
+        }
+        dst[(size_t)s * plane / 4] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static inline int oz_round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static PFN_cuTensorMapEncodeTiled_v12000 oz_get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+size_t oz_slices_bytes(int rows, int k, int S) { return (size_t)S * oz_round_up(rows, OZ_TILE) * oz_round_up(k, OZ_KBLOCK); }
+
+cudaError_t oz_init_device() {
+    return cudaFuncSetAttribute(k_oz_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+}
+
+cudaError_t oz_split(const double* X, long stride_r, long stride_k, int rows, int k, int S, OzOperand* op, int8_t* slices, int* ex,
+                     cudaStream_t stream) {
+    if (S < 1 || S > OZ_MAX_SLICES || rows < 1 || k < 1) return cudaErrorInvalidValue;
+    op->slices = slices; op->ex = ex; op->rows = rows; op->k = k; op->S = S;
+    op->rows_pad = oz_round_up(rows, OZ_TILE); op->k_pad = oz_round_up(k, OZ_KBLOCK);
+    cudaError_t e = cudaMemsetAsync(ex, 0xC0, (size_t)op->rows_pad * sizeof(int), stream);   // a very negative exponent everywhere
+    if (e != cudaSuccess) return e;
+    const dim3 grid((k + 31) / 32, (rows + 31) / 32), block(32, 8);
+    k_oz_rowmax<<<grid, block, 0, stream>>>(X, stride_r, stride_k, rows, k, ex);
+    k_oz_split<<<grid, block, 0, stream>>>(X, stride_r, stride_k, rows, k, ex, slices, op->rows_pad, op->k_pad, S);
+    return cudaGetLastError();
+}
+
+static CUresult oz_encode(CUtensorMap* map, const OzOperand& op) {
+    cuuint64_t dims[3] = {(cuuint64_t)op.k_pad, (cuuint64_t)op.rows_pad, (cuuint64_t)op.S};
+    cuuint64_t strides[2] = {(cuuint64_t)op.k_pad, (cuuint64_t)op.k_pad * op.rows_pad};
+    cuuint32_t box[3] = {OZ_KBLOCK, OZ_TILE, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return oz_get_encode()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, op.slices, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double alpha, double beta, const double* Cin, int ldcin, double* D,
+                    int ldd, cudaStream_t stream) {
+    if (!oz_get_encode()) return cudaErrorNotSupported;
+    if (A.k_pad != B.k_pad || A.S != B.S || M > A.rows_pad || N > B.rows_pad || M < 1 || N < 1) return cudaErrorInvalidValue;
+    if ((long long)A.k_pad * 64 * 64 * A.S >= (1LL << 31)) return cudaErrorInvalidValue;   // int32 accumulation of one diagonal must be exact
+    CUtensorMap tmA, tmB;
+    if (oz_encode(&tmA, A) != CUDA_SUCCESS || oz_encode(&tmB, B) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    OzParams p;
+    p.M = M; p.N = N; p.KB = A.k_pad / OZ_KBLOCK; p.S = A.S;
+    p.exA = A.ex; p.exB = B.ex;
+    p.alpha = alpha; p.beta = Cin ? beta : 0.0; p.Cin = Cin; p.ldcin = ldcin; p.D = D; p.ldd = ldd;
+    const int Mt = (M + OZ_TILE - 1) / OZ_TILE, Nt = (N + OZ_TILE - 1) / OZ_TILE;
+    k_oz_gemm<<<dim3(Mt * Nt), OZ_THREADS, OZ_SMEM_BYTES, stream>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
+}  // namespace eqvio

@@ -1,0 +1,51 @@
+// ozaki_sm100.cuh — fp64 GEMM on the INT8 tensor cores of sm_100a (tcgen05.mma kind::i8, accumulators in TMEM).
+//
+// The reference's dense Sigma contractions (eqf_vio/src/VIOFilter.cpp:188-189, 276-277, 297) are fp64 GEMMs and fp64 has no
+// tcgen05 kind: the native path (dgemm_sm100.cu) runs on DMMA.8x8x4, whose pipe tops out at 37.1 TFLOP/s on B200 — the Riccati
+// kernel already sits at 90 % of it.  B200's 5th-generation tensor cores do 8-bit integer MMA at ~100x that rate, and an fp64
+// product can be assembled EXACTLY from integer products (Ozaki splitting):
+//
+//   a_ik = 2^ea_i * sum_s A_s[i,k] 2^(-6-7s),   b_kj = 2^eb_j * sum_t B_t[k,j] 2^(-6-7t),   A_s, B_t in [-64, 64] (int8),
+//   ea_i / eb_j the binary exponent of the largest entry of row i of A / column j of B,
+//   c_ij = 2^(ea_i + eb_j - 12) * sum_d 2^(-7d) * ( sum_{s+t=d} A_s B_t )_ij          d = 0 .. S-1
+//
+// every inner product A_s B_t is an int8 GEMM accumulated exactly in int32 (K * 64 * 64 * S < 2^31), all pairs of one diagonal d
+// share one TMEM accumulator, and only the S per-diagonal sums are converted to fp64.  With S = 8 slices (55 mantissa bits) and the
+// 36 pairs s + t <= 7 the result is as accurate as an fp64 GEMM relative to (row max of A) x (column max of B); S = 9 (45 pairs)
+// matches fp64 entry by entry on operands with Sigma's dynamic range.
+//
+// Kernel shape: one CTA per 128 x 128 output tile; warps 0-7 epilogue (TMEM -> registers -> fp64), warp 8 TMA producer, warp 9 MMA
+// issuer.  The diagonals are processed in batches of four (4 x 128 TMEM columns = all 512); within a batch every 32-deep k-block of
+// ALL slices needed is staged once by TMA (SWIZZLE_32B, 4 KB per slice tile) and every (s, t) pair of the batch is issued against it,
+// so a slice tile is fetched from L2 once per batch instead of once per pair (36 pairs -> 2 fetches: the int8 MMA rate would need
+// 125 B/clk/SM otherwise, three times what L2 delivers).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace eqvio {
+
+static const int OZ_MAX_SLICES = 9;
+static const int OZ_TILE = 128;      // output tile (M and N), also the row padding of the slice arrays
+static const int OZ_KBLOCK = 32;     // int8 MMA depth = one SWIZZLE_32B row
+
+// One operand split into int8 slices: slices[s][row][k] (k contiguous, rows padded to 128, k to 32, zero-filled), ex[row] the row's
+// binary exponent.  "row" is a row of A or a COLUMN of B (both operands are staged K-major).
+struct OzOperand {
+    int8_t* slices;   // S * rows_pad * k_pad bytes
+    int* ex;          // rows_pad ints
+    int rows, k, rows_pad, k_pad, S;
+};
+
+size_t oz_slices_bytes(int rows, int k, int S);
+// Splits X (element (r, k) at X[r * stride_r + k * stride_k]) into S slices; `op` must have been sized with oz_slices_bytes.
+cudaError_t oz_split(const double* X, long stride_r, long stride_k, int rows, int k, int S, OzOperand* op, int8_t* slices, int* ex,
+                     cudaStream_t stream);
+// D[0:M, 0:N] (column-major, ldd) = alpha * A * B + beta * Cin for the split operands (A: M rows, B: N "rows" = columns of B), M and N
+// multiples of 128 up to the padding (rows beyond M / N are computed on zero slices and not stored).
+cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double alpha, double beta, const double* Cin, int ldcin, double* D,
+                    int ldd, cudaStream_t stream);
+cudaError_t oz_init_device();
+
+}  // namespace eqvio

@@ -312,3 +312,21 @@ def dgemm(A, B, transB=False, alpha=1.0, beta=0.0, Cin=None, device=0, reps=1):
         "eqvio_dgemm",
     )
     return Cm, ms.value
+
+
+def dgemm_ozaki(A, B, transB=False, slices=8, device=0, reps=1):
+    """C = A @ op(B) assembled from int8 tensor-core products (tcgen05, Ozaki splitting; eqvio_dgemm_ozaki).
+    Returns (C, ms per whole call, ms of the tcgen05 kernel alone)."""
+    L = abi.lib()
+    A = np.asfortranarray(A, dtype=np.float64)
+    B = np.asfortranarray(B, dtype=np.float64)
+    M, K = A.shape
+    N = B.shape[0] if transB else B.shape[1]
+    assert (B.shape[1] if transB else B.shape[0]) == K
+    Cm = np.zeros((M, N), order="F")
+    t_all, t_gemm = C.c_float(), C.c_float()
+    abi.check(
+        L.eqvio_dgemm_ozaki(int(device), int(transB), M, N, K, _p(A), M, _p(B), B.shape[0], _p(Cm), M, int(slices), int(reps), C.byref(t_all), C.byref(t_gemm)),
+        "eqvio_dgemm_ozaki",
+    )
+    return Cm, t_all.value, t_gemm.value

@@ -210,6 +210,18 @@ int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int ld
                      int transB2, int N2, double alpha2, const double* B2, int ldb2, double* W, int ldw, double* D,
                      int ldd, int reps, float* ms);
 
+/* OPT-IN, kernel level: the same product C = A * op(B) (the reference's dense Sigma contractions, VIOFilter.cpp:188-189,
+ * 276-277, 297) assembled EXACTLY from 8-bit integer products on the 5th-generation tensor cores (tcgen05.mma kind::i8,
+ * accumulators in TMEM) by Ozaki splitting: `slices` 7-bit signed digits per operand entry (8: as accurate as an fp64 GEMM
+ * relative to row-max x column-max; 9: entry by entry on operands with Sigma's dynamic range), all digit pairs of one
+ * weight summed in one int32 accumulator, only the per-weight sums converted to fp64.  The DMMA pipe the native path runs
+ * on tops out at 37 TFLOP/s; this path is not bound by it.  The 128-aligned block at the END of C runs on tcgen05, the
+ * strips in front of it on the DMMA kernel.  M, N >= 128.  Host buffers, column-major; `reps` > 1 times the whole call
+ * (split + products + strips, *ms_total) and the tcgen05 kernel alone (*ms_gemm), mean per repetition.  Not used by the
+ * filter path (eqvio_process_*) in this version. */
+int eqvio_dgemm_ozaki(int device, int transB, int M, int N, int K, const double* A, int lda, const double* B, int ldb,
+                      double* C, int ldc, int slices, int reps, float* ms_total, float* ms_gemm);
+
 /* `S.inverse()` (VIOFilter.cpp:277) on its own: the blocked Schur elimination of [[S, I], [I, 0]] by unpivoted LU that the
  * update runs (chain kernels, in-place panel solves, look-ahead trailing updates), for an m x m matrix S (col-major, host;
  * symmetric positive definite up to round-off — no pivoting).  Uses the handle's work buffers (its capacity grows to m/2

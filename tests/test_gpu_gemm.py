@@ -110,15 +110,17 @@ STREAMK_SHAPES = [(779, 779, 779, 779), (500, 300, 450, 620), (779, 779, 779, 79
 
 
 @pytest.mark.parametrize("transB2", [True, False])
-def test_gemm_streamk_pair(transB2):
-    """Shapes whose products are a single partial wave of 32 x 32 tiles (148 <= tiles < 1110) take the stream-K form of
-    the pair launch (persistent CTAs, equal k-tile counts per CTA, a tile shared by two CTAs summed head + tail, one
-    grid barrier between the products): against numpy at 1e-13, bit-stable from run to run (fixed split, fixed summation
-    order), flags / counters left zero (checked by the entry point), repeated launches."""
+def test_gemm_splitk_pair(transB2, monkeypatch):
+    """Shapes whose products are a single partial wave of 32 x 32 tiles (324 <= tiles < 888) take the split-K form of the
+    pair launch (every tile cut into 3-4 k-ranges, partials added in ascending order by the chunk that arrives last); with
+    EQVIO_STREAMK=1 the same entry point runs the persistent stream-K form instead.  Both: against numpy at 1e-13,
+    bit-stable from run to run (fixed split, fixed summation order), flags / counters left zero (checked by the entry
+    point), repeated launches."""
     from eqf_vio_b200.filter import dgemm, dgemm_pair
 
     rng = np.random.default_rng(9)
-    for (M, K1, N1, N2) in STREAMK_SHAPES:
+    for (M, K1, N1, N2), streamk in [(sh, m) for sh in STREAMK_SHAPES for m in ("0", "1")]:
+        monkeypatch.setenv("EQVIO_STREAMK", streamk)
         A1 = rng.standard_normal((M, K1)); B1 = rng.standard_normal((K1, N1))
         B2 = rng.standard_normal((N2, N1) if transB2 else (N1, N2))
         W, D, _ = dgemm_pair(A1, B1, B2, transB2=transB2, alpha2=1.25)
@@ -132,9 +134,9 @@ def test_gemm_streamk_pair(transB2):
         assert rel(W, W2) < 1e-15 * np.sqrt(K1) * 4
 
 
-def test_streamk_riccati_in_the_filter_matches_two_launches(monkeypatch):
-    """N = 256 (n = 779: 625 tiles, the stream-K Riccati step) against the same filter with every pair as two launches
-    (EQVIO_PAIRS=0): Sigma agrees to round-off after two vision periods and is bit-stable between two stream-K runs."""
+def test_splitk_riccati_in_the_filter_matches_two_launches(monkeypatch):
+    """N = 256 (n = 779: 625 tiles, the split-K Riccati pair) against the same filter with every pair as two launches
+    (EQVIO_PAIRS=0): Sigma agrees to round-off after two vision periods and is bit-stable between two split-K runs."""
     from eqf_vio_b200.filter import VIOFilter
     from eqf_vio_b200.settings import conditioned_settings
     from eqf_vio_b200.synthetic import period_sequence
