@@ -389,6 +389,17 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     gemm_tile<Cfg, TRANSB>(&tmA, &tmB, p, tile_m, tile_n, nullptr, 0, nullptr);
 }
 
+// One product with every tile cut into ks k-ranges (SplitK): for thin products (a few rows or columns, a long k loop) whose tile count
+// cannot fill the GPU — the strips in front of the int8 core block (ozaki_sm100.cuh) — ks CTAs share a tile's k loop.
+template <class Cfg, bool TRANSB>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
+dgemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KernelParams p, const SplitKArgs ska) {
+    const int Tn = (p.N + Cfg::BN - 1) / Cfg::BN;
+    const int id = blockIdx.x / ska.ks, chunk = blockIdx.x - id * ska.ks;
+    const int tile_m = id / Tn, tile_n = id - tile_m * Tn;
+    gemm_tile<Cfg, TRANSB>(&tmA, &tmB, p, tile_m, tile_n, nullptr, 0, nullptr, SplitK{ska.ws, ska.cnt, ska.ks, chunk, id});
+}
+
 // Two dependent GEMMs in one launch — the reference's left-to-right products (A B) C (eqf_vio/src/VIOFilter.cpp:188-189
 // (F Sigma) F^T, :276 (C Sigma) C^T, :297 (K C) Sigma):
 //   phase 1:  W = A1 B1                (p1, NN)   tiles in row-major order, each one counted in rows[tile_m]
@@ -747,6 +758,26 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+cudaError_t dgemm_splitk_launch(const GemmProblem& g, int ks, double* ws, int* cnt, cudaStream_t stream) {
+    using Cfg = Cfg32x32;
+    if (g.M <= 0 || g.N <= 0) return cudaSuccess;
+    if (!get_encode()) return cudaErrorNotSupported;
+    const int tiles = ((g.M + Cfg::BM - 1) / Cfg::BM) * ((g.N + Cfg::BN - 1) / Cfg::BN);
+    if (ks < 2 || g.skip_m || g.skip_n || !ws || !cnt || (long)tiles * ks > DGEMM_SPLITK_MAX_SLOTS) return cudaErrorInvalidValue;
+    CUtensorMap tmA, tmB;
+    if (encode_mn_major(&tmA, g.A, g.M, g.K, g.lda, Cfg::BM) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    const CUresult rb = g.transB ? encode_mn_major(&tmB, g.B, g.N, g.K, g.ldb, Cfg::BN) : encode_k_major(&tmB, g.B, g.K, g.N, g.ldb, Cfg::BN);
+    if (rb != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    KernelParams p;
+    fill_params(p, g);
+    const SplitKArgs ska{ws, cnt, ks};
+    if (g.transB)
+        dgemm_splitk_kernel<Cfg, true><<<dim3(tiles * ks), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, ska);
+    else
+        dgemm_splitk_kernel<Cfg, false><<<dim3(tiles * ks), Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, ska);
+    return cudaGetLastError();
+}
+
 template <class Cfg, bool TB2>
 static cudaError_t launch_pair_cfg(const GemmProblem& g1, const GemmProblem& g2, int* sync, cudaStream_t stream, int ks = 1, double* ws = nullptr) {
     if (!get_encode()) return cudaErrorNotSupported;
@@ -820,6 +851,8 @@ cudaError_t dgemm_init_device() {
     EQVIO_OPT_IN(opt_in_cfg<Cfg32x32s6>()); EQVIO_OPT_IN(opt_in_cfg<Cfg48x48>()); EQVIO_OPT_IN(opt_in_cfg<Cfg32x64s2>());
     EQVIO_OPT_IN(opt_in_cfg<Cfg64x32s2>());
     EQVIO_OPT_IN(opt_in_pair_cfg<Cfg32x32>()); EQVIO_OPT_IN(opt_in_pair_cfg<Cfg32x32s6>());
+    EQVIO_OPT_IN(cudaFuncSetAttribute(dgemm_splitk_kernel<Cfg32x32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg32x32::SMEM_BYTES));
+    EQVIO_OPT_IN(cudaFuncSetAttribute(dgemm_splitk_kernel<Cfg32x32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg32x32::SMEM_BYTES));
     EQVIO_OPT_IN(cudaFuncSetAttribute(dgemm_streamk_pair_kernel<Cfg32x32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg32x32::SMEM_BYTES));
     EQVIO_OPT_IN(cudaFuncSetAttribute(dgemm_streamk_pair_kernel<Cfg32x32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg32x32::SMEM_BYTES));
 #undef EQVIO_OPT_IN

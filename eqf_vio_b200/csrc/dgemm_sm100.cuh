@@ -83,6 +83,9 @@ static const int DGEMM_STREAMK_SYNC_INTS = 8 + 148 * 6;
 size_t dgemm_streamk_ws_doubles();
 bool dgemm_streamk_pays(const GemmProblem& first, const GemmProblem& second);
 cudaError_t dgemm_streamk_pair_launch(const GemmProblem& first, const GemmProblem& second, int* sync, double* ws, cudaStream_t stream);
+// One product, every 32 x 32 tile cut into ks k-ranges (partials in `ws`: tiles * ks slots of 32 x 32 doubles; `cnt`: one int per tile,
+// zero before the first use and left zero): thin products with a long k loop.
+cudaError_t dgemm_splitk_launch(const GemmProblem& p, int ks, double* ws, int* cnt, cudaStream_t stream);
 // Whether the single launch is the faster choice for these shapes (else: two dgemm_launch calls).
 bool dgemm_pair_pays(const GemmProblem& first, const GemmProblem& second);
 // Which tile configuration dgemm_launch would pick (for DESIGN.md / tests).

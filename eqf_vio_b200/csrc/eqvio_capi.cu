@@ -63,6 +63,7 @@ struct ProfEvent { cudaEvent_t a, b; double flops; int cls; int lane; };
 enum { PROF_RICCATI = 0, PROF_UPDATE = 1, PROF_SCHUR_GEMM = 2, PROF_SCHUR_DIAG = 3, PROF_MISC = 4, PROF_CLASSES = 5 };
 struct TimelineEntry { double cls, lane, t0, t1, flops; };
 
+static const int STRIP_SLOTS = 2048;   // split-K slots of one strip launch (tiles x k-ranges)
 struct GraphKey { int kind, N, flags; const double *Sigma, *Lbase; };  // the Sigma and landmark buffers ping-pong independently
 struct CachedGraph { GraphKey key; cudaGraphExec_t exec; long long launches; long long last_use; bool broken; };
 
@@ -107,6 +108,18 @@ struct eqvio_filter {
     int* sk_sync = nullptr;        // barrier / flag words and partial-tile workspace of the stream-K Riccati launch
     double* sk_ws = nullptr;
     double* splitk_ws = nullptr;   // partial tiles of the split-K pair launch
+    double* strip_ws[2] = {nullptr, nullptr};   // partial tiles / arrival counters of the two split-K strips beside the int8 core block
+    int* strip_cnt[2] = {nullptr, nullptr};
+    // EQVIO_OZAKI=S (7..9): the Riccati step's two products on the int8 tensor cores (ozaki_sm100.cuh) for the 128-aligned landmark
+    // block, DMMA strips for the rows / columns in front of it.  0 (default): the fp64 DMMA path.
+    int ozaki_S = 0;
+    int8_t *ozF[2] = {nullptr, nullptr}, *ozS = nullptr, *ozW = nullptr;   // int8 slices of F rows (by tick parity, like F), Sigma columns, W rows
+    int *ozeF[2] = {nullptr, nullptr}, *ozeS = nullptr, *ozeW = nullptr;   // their row / column exponents
+    int* ozH = nullptr;            // inner-dimension scales, 2^h[k] ~ sqrt(Sigma_kk) (OzKScale); refreshed after every change of Sigma outside the Riccati step
+    bool oz_h_valid = false;       // ozH matches the landmark set / a recent Sigma
+    bool oz_sigma_ex_valid = false;// ozeS holds the column exponents of the current Sigma (left there by the previous Riccati step's epilogue)
+    bool oz_F_ready = false;       // the state stream has split this tick's F already
+    size_t oz_bytes = 0;
     int par = 0;                   // parity of the current Riccati tick: F == Fpp[par], W == Wpp[par]
     double *Fpp[2] = {nullptr, nullptr}, *Wpp[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -306,6 +319,14 @@ static int ensure_capacity(Filter* f, int needN) {
             CU_TRY(cudaMemcpyAsync(L.base + (size_t)k * cap, o.L.base + (size_t)k * o.cap, (size_t)f->N * 8, cudaMemcpyDeviceToDevice, s));
         CU_TRY(cudaStreamSynchronize(s));
         free_device(&o);
+    }
+    if (f->ozaki_S > 0) {
+        const size_t bytes = oz_slices_bytes(n_of(cap), n_of(cap), OZ_MAX_SLICES);
+        for (void* q : {(void*)f->ozF[0], (void*)f->ozF[1], (void*)f->ozS, (void*)f->ozW, (void*)f->ozeF[0], (void*)f->ozeF[1], (void*)f->ozeS, (void*)f->ozeW, (void*)f->ozH}) cudaFree(q);
+        for (int8_t** q : {&f->ozF[0], &f->ozF[1], &f->ozS, &f->ozW}) { CU_TRY(cudaMalloc((void**)q, bytes)); CU_TRY(cudaMemsetAsync(*q, 0, bytes, s)); }
+        for (int** q : {&f->ozeF[0], &f->ozeF[1], &f->ozeS, &f->ozeW, &f->ozH}) { CU_TRY(dalloc(q, (size_t)ld + 256)); CU_TRY(cudaMemsetAsync(*q, 0, ((size_t)ld + 256) * sizeof(int), s)); }
+        f->oz_bytes = bytes;
+        f->oz_h_valid = f->oz_sigma_ex_valid = f->oz_F_ready = false;
     }
     f->cap = cap; f->ld = ld; f->ldm = ldm; f->ld2m = ld2m;
     f->L = L; f->L2 = L2;
@@ -543,8 +564,123 @@ static RiccatiOut riccati_out(Filter* f) {
 
 // The two Sigma GEMMs of the Riccati step (VIOFilter.cpp:188-189); F, B_b already built.
 //   W = F Sigma;   Sigma = [W | T B_b R] [F | B_b]^T + T P      (K runs over n16 + 6 columns; [n, n16) are zero)
+// The same step with the 128-aligned landmark block of both products on the int8 tensor cores (EQVIO_OZAKI): rows / columns
+// [m0, n), m0 = n - 128 floor(n / 128), form the core; the m0 rows and columns in front of it (the 11 base states and what 3N
+// leaves over 128) are thin DMMA products.  Reference association kept: W = F Sigma, Sigma' = W F^T + T B_b R B_b^T + T P.
+// Operands are split with the inner-dimension scales ozH (OzKScale): F rows with +h, Sigma columns and W rows with -h.  Each
+// product's epilogue leaves the exponent maxima of its output, so W and the next step's Sigma are split in one pass.
+static bool ozaki_applies(const Filter* f) { return f->ozaki_S > 0 && n_of(f->N) >= 2 * OZ_TILE && f->ozS != nullptr; }
+// A strip in front of the int8 core block: a few rows or columns of the product with the full k loop — tiles x 97 k-tiles on one tile
+// row, far too few CTAs to fill the GPU and each latency-bound (measured 30-57 us per strip) — so every tile is cut into k-ranges.
+static int strip_gemm(Filter* f, const GemmProblem& g, int which, cudaStream_t st) {
+    const int tiles = ((g.M + 31) / 32) * ((g.N + 31) / 32), kt = (g.K + 15) / 16;
+    int ks = std::min(std::min(6, kt / 8), STRIP_SLOTS / std::max(tiles, 1));
+    ProfEvent pe;
+    prof_begin(f, pe, st, PROF_RICCATI, 2.0 * g.M * g.N * g.K);
+    if (ks >= 2) CU_TRY(dgemm_splitk_launch(g, ks, f->strip_ws[which], f->strip_cnt[which], st));
+    else CU_TRY(dgemm_launch(g, st));
+    prof_end(f, pe, st);
+    f->launches += 1;
+    return EQVIO_OK;
+}
+
+// Scheduling: a tcgen05 product holds one CTA with 216 KB of shared memory on 144 of the 148 SMs, so anything launched BESIDE it is
+// squeezed onto the four SMs left (measured: the DMMA strips took 230 us there against 13 us on a free GPU, and the state stream's
+// split of F starved the same way).  The small kernels therefore run in the gaps between the big products, concurrently with each
+// other on three streams:  { split Sigma | W strips | split F }  ->  product 1  ->  { border maxima + split W | Sigma' strips }
+// ->  product 2  ->  border maxima.
+static int riccati_ozaki(Filter* f, double T) {
+    const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld, S = f->ozaki_S;
+    const int Mc = n / OZ_TILE * OZ_TILE, m0 = n - Mc;
+    cudaStream_t st = f->stream, s2 = f->side, s3 = f->lift;
+    int rc;
+    f->prof_cls = PROF_RICCATI;
+    struct Guard { Filter* f; ~Guard() { f->prof_cls = PROF_UPDATE; f->cur = f->stream; } } guard{f};
+    const OzKScale kminus{f->ozH, -1};
+    OzOperand oF, oS, oW;
+    if (!f->oz_h_valid) {   // (kernel-level entry points: integrate() refreshes the scales itself)
+        CU_TRY(oz_diag_scale(f->Sigma, ld, n, f->ozH, st));
+        f->launches += 1;
+        f->oz_h_valid = true; f->oz_sigma_ex_valid = false;
+    }
+    // ---- gap 1: split F (two passes) on the lift stream, W strips on the side stream, split Sigma here
+    CU_TRY(cudaEventRecord(f->ev_fork, st));
+    CU_TRY(cudaStreamWaitEvent(s3, f->ev_fork, 0));
+    {
+        ProfScope ps(f, s3, PROF_MISC);
+        const OzKScale kplus{f->ozH, +1};
+        CU_TRY(oz_split(f->F + m0, 1, ld, Mc, n, S, &oF, f->ozF[f->par], f->ozeF[f->par], s3, &kplus, false));   // rows m0.. of F
+        f->launches += 3;
+    }
+    CU_TRY(cudaEventRecord(f->ev_la, s3));
+    if (m0 > 0) {   // W rows [0, m0) (all columns) on the side stream, W columns [0, m0) (all rows) behind the split of F
+        CU_TRY(cudaStreamWaitEvent(s2, f->ev_fork, 0));
+        if ((rc = strip_gemm(f, make_problem(f, 0, m0, n, n, 1.0, f->F, ld, f->Sigma, ld, 0.0, nullptr, 0, f->W, ld, 0, 0.0), 0, s2))) return rc;
+        if ((rc = strip_gemm(f, make_problem(f, 0, n, m0, n, 1.0, f->F, ld, f->Sigma, ld, 0.0, nullptr, 0, f->W, ld, 0, 0.0), 1, s2))) return rc;
+        CU_TRY(cudaEventRecord(f->ev_join, s2));
+    }
+    {
+        ProfScope ps(f, st, PROF_MISC);
+        CU_TRY(oz_split(f->Sigma + (size_t)m0 * ld, ld, 1, Mc, n, S, &oS, f->ozS, f->ozeS, st, &kminus, f->oz_sigma_ex_valid, f->oz_sigma_ex_valid ? 1 : 0));   // columns m0.. of Sigma
+        CU_TRY(oz_reset_exponents(f->ozeW, Mc, st));
+        f->launches += f->oz_sigma_ex_valid ? 1 : 3;
+    }
+    CU_TRY(cudaStreamWaitEvent(st, f->ev_la, 0));
+    if (m0 > 0) CU_TRY(cudaStreamWaitEvent(st, f->ev_join, 0));
+    // ---- product 1: W core, with the row maxima of W over its core columns (entries scaled by 2^-h[column]) for its split
+    {
+        const OzExponentsOut exo{f->ozeW, nullptr, f->ozH, m0, m0};
+        ProfEvent pe;
+        prof_begin(f, pe, st, PROF_RICCATI, 2.0 * Mc * Mc * n);
+        CU_TRY(oz_gemm(oF, oS, Mc, Mc, 1.0, 0.0, nullptr, 0, f->W + m0 + (size_t)m0 * ld, ld, st, nullptr, &exo));
+        prof_end(f, pe, st);
+        f->launches += 1;
+    }
+    // ---- gap 2: Sigma' strips on the side stream (W is complete), border maxima + split W here
+    if (m0 > 0) {
+        CU_TRY(cudaEventRecord(f->ev_fork, st));
+        CU_TRY(cudaStreamWaitEvent(s2, f->ev_fork, 0));
+        if ((rc = strip_gemm(f, make_problem(f, 1, m0, n, n16 + 6, 1.0, f->W, ld, f->F, ld, 0.0, nullptr, 0, f->Sigma2, ld, 1, T), 0, s2))) return rc;
+        if ((rc = strip_gemm(f, make_problem(f, 1, n, m0, n16 + 6, 1.0, f->W, ld, f->F, ld, 0.0, nullptr, 0, f->Sigma2, ld, 1, T), 1, s2))) return rc;
+        CU_TRY(cudaEventRecord(f->ev_join, s2));
+    }
+    {
+        ProfScope ps(f, st, PROF_MISC);
+        if (m0 > 0) CU_TRY(oz_rowmax(f->W + m0, 1, ld, Mc, m0, f->ozeW, st, &kminus));          // ... and over the border columns [0, m0)
+        CU_TRY(oz_split(f->W + m0, 1, ld, Mc, n, S, &oW, f->ozW, f->ozeW, st, &kminus, true));   // rows m0.. of W, columns [0, n)
+        CU_TRY(oz_reset_exponents(f->ozeS, Mc, st));
+        f->launches += 2;
+    }
+    if (m0 > 0) CU_TRY(cudaStreamWaitEvent(st, f->ev_join, 0));
+    // ---- product 2: Sigma' core with the Riccati epilogue and the column maxima of Sigma' (scaled by 2^-h[row]) for the next step's split
+    {
+        OzRiccatiEpilogue ric;
+        ric.on = 1; ric.row_off = m0; ric.col_off = m0; ric.ldx = ld;
+        ric.T_dev = &f->sc->Tpp[f->par];
+        ric.Wx = f->W + (size_t)n16 * ld; ric.Fx = f->F + (size_t)n16 * ld;
+        ric.Pd[0] = f->s.biasOmegaProcessVariance; ric.Pd[1] = f->s.biasAccelProcessVariance; ric.Pd[2] = f->s.gravityProcessVariance;
+        ric.Pd[3] = f->s.velocityProcessVariance; ric.Pd[4] = f->s.pointProcessVariance;
+        // (Sigma' is symmetric up to round-off, so the COLUMN maxima its split needs are its ROW maxima — one atomic per thread instead of
+        // a warp reduction per column; the split adds one to every exponent to cover a maximum that straddles a power of two)
+        const OzExponentsOut exo{f->ozeS, nullptr, f->ozH, m0, m0};
+        ProfEvent pe;
+        prof_begin(f, pe, st, PROF_RICCATI, 2.0 * Mc * Mc * n);
+        CU_TRY(oz_gemm(oW, oF, Mc, Mc, 1.0, 0.0, nullptr, 0, f->Sigma2 + m0 + (size_t)m0 * ld, ld, st, &ric, &exo));
+        prof_end(f, pe, st);
+        f->launches += 1;
+    }
+    if (m0 > 0) {
+        ProfScope ps(f, st, PROF_MISC);
+        CU_TRY(oz_rowmax(f->Sigma2 + m0, 1, ld, Mc, m0, f->ozeS, st, &kminus));   // ... and over the border columns [0, m0) (= border rows, by symmetry)
+        f->launches += 1;
+    }
+    f->oz_sigma_ex_valid = true;
+    return EQVIO_OK;
+}
+
 static int riccati_gemms(Filter* f, double T) {
     const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld;
+    if (ozaki_applies(f)) return riccati_ozaki(f, T);
     f->prof_cls = PROF_RICCATI;
     const GemmProblem g1 = make_problem(f, 0, n, n, n, 1.0, f->F, ld, f->Sigma, ld, 0.0, nullptr, 0, f->W, ld, 0, 0.0);
     // Sigma' goes to the twin buffer (the caller swaps): inside the pair launch second-product tiles are stored while
@@ -584,6 +720,15 @@ static int integrate(Filter* f, double newTime, bool doRiccati, const double* om
     }
     a.parity = f->par;
     RiccatiOut ro = riccati_out(f);
+    const bool oz = a.do_riccati && ozaki_applies(f);
+    if (oz && !f->oz_h_valid) {
+        // the inner-dimension scales follow Sigma's diagonal; refreshed (on the main stream, ahead of the state stream's split of F)
+        // whenever something other than the Riccati step changed Sigma or the landmark set
+        CU_TRY(oz_diag_scale(f->Sigma, f->ld, n_of(f->N), f->ozH, f->stream));
+        f->launches += 1;
+        f->oz_h_valid = true; f->oz_sigma_ex_valid = false;
+        f->main_dirty = true;
+    }
     // ---- state stream: behind whatever the main stream did to the state since the last tick (vision update,
     // bookkeeping, snapshot ...) and behind the GEMMs that last read this parity's F / W (two ticks ago)
     cudaStream_t ss = f->state;
@@ -610,7 +755,9 @@ static int integrate(Filter* f, double newTime, bool doRiccati, const double* om
     if (a.do_integrate) {
         if (a.do_riccati) {
             // the two Sigma GEMMs read T from device memory (written by k_step_prepare): replayable
-            const int st = run_graphed(f, GRAPH_RICCATI, f->par, [&]() { return riccati_gemms(f, a.T); });
+            const int gflags = f->par | (oz && f->oz_sigma_ex_valid ? 2 : 0);
+            const int st = run_graphed(f, GRAPH_RICCATI, gflags, [&]() { return riccati_gemms(f, a.T); });
+            if (oz) { f->oz_sigma_ex_valid = true; f->oz_F_ready = false; }   // (a replayed graph does not run the host code that sets them)
             if (st) return st;
             std::swap(f->Sigma, f->Sigma2);   // the step wrote the twin buffer
             CU_TRY(cudaEventRecord(f->ev_gemm[f->par], f->stream));
@@ -623,6 +770,7 @@ static int integrate(Filter* f, double newTime, bool doRiccati, const double* om
 
 // compaction after landmark removal: keep[] = surviving landmark indices (ascending)
 static int compact(Filter* f, const std::vector<int>& keep) {
+    f->oz_h_valid = f->oz_sigma_ex_valid = false;
     const int newN = (int)keep.size(), n_new = n_of(newN);
     int* hm = f->h_istage;
     cudaEventSynchronize(f->stage_free);
@@ -798,6 +946,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
 
 static int update(Filter* f, bool do_lift, bool do_sigma) {
     f->main_dirty = true;
+    f->oz_h_valid = f->oz_sigma_ex_valid = false;   // Sigma changes outside the Riccati step
     int st = prepare_layout(f);
     if (st) return st;
     const int flags = (do_lift ? 1 : 0) | (do_sigma ? 2 : 0);
@@ -823,6 +972,7 @@ static int flags_to_status(int flags) {
 // ctor = false: VIOFilter::reset(), VIOFilter.cpp:84-91 (see eqvio_reset)
 static int init_state(Filter* f, bool ctor) {
     f->main_dirty = true;
+    f->oz_h_valid = f->oz_sigma_ex_valid = f->oz_F_ready = false;
     BaseState b;
     memset(&b, 0, sizeof b);
     if (!ctor) {   // reset keeps inputBias and the accumulated velocity
@@ -895,6 +1045,8 @@ static void destroy_filter(Filter* f) {
     cudaFree(f->stamps);
     cudaFree(f->pair_sync);
     cudaFree(f->sk_sync); cudaFree(f->sk_ws); cudaFree(f->splitk_ws);
+    for (int i = 0; i < 2; ++i) { cudaFree(f->strip_ws[i]); cudaFree(f->strip_cnt[i]); }
+    for (void* q : {(void*)f->ozF[0], (void*)f->ozF[1], (void*)f->ozS, (void*)f->ozW, (void*)f->ozeF[0], (void*)f->ozeF[1], (void*)f->ozeS, (void*)f->ozeW, (void*)f->ozH}) cudaFree(q);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->pose_pub); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
@@ -937,7 +1089,13 @@ static int create_impl(Filter* f) {
     CU_TRY(cudaMemset(f->sk_sync, 0, (size_t)DGEMM_STREAMK_SYNC_INTS * sizeof(int)));
     CU_TRY(dalloc(&f->sk_ws, dgemm_streamk_ws_doubles()));
     CU_TRY(dalloc(&f->splitk_ws, dgemm_splitk_ws_doubles()));
+    for (int i = 0; i < 2; ++i) {
+        CU_TRY(dalloc(&f->strip_ws[i], (size_t)STRIP_SLOTS * 1024));
+        CU_TRY(dalloc(&f->strip_cnt[i], (size_t)STRIP_SLOTS));
+        CU_TRY(cudaMemset(f->strip_cnt[i], 0, (size_t)STRIP_SLOTS * sizeof(int)));
+    }
     if (const char* e = getenv("EQVIO_SIGMA_AFTER_LIFT")) f->sigma_after_lift = atoi(e);
+    if (const char* e = getenv("EQVIO_OZAKI")) { f->ozaki_S = atoi(e); if (f->ozaki_S < 7 || f->ozaki_S > OZ_MAX_SLICES) f->ozaki_S = 0; }
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
     if (const char* e = getenv("EQVIO_STAMPS"))
         if (e[0] == '1') { CU_TRY(dalloc(&f->stamps, 512)); CU_TRY(cudaMemset(f->stamps, 0, 512 * 8)); }
@@ -1108,6 +1266,7 @@ static int process_vision_impl(Filter* f, double stamp, int nmeas, const int* mi
     // addNewLandmarks, VIOFilter.cpp:345-391
     if (nmeas > f->N) {
         const int oldN = f->N, newN = nmeas - oldN;
+        f->oz_h_valid = f->oz_sigma_ex_valid = false;
         launch_add_landmarks(s, f->L, oldN, newN, f->y, f->s.initialSceneDepth, f->scratch);
         launch_grow_sigma(s, f->Sigma, f->ld, n_of(oldN), n_of(nmeas), f->s.initialPointVariance);
         f->launches += 2;
@@ -1142,6 +1301,7 @@ int eqvio_set_inertial_points(eqvio_handle_t f, int n, const int* ids, const dou
     int st = ensure_capacity(f, n);
     if (st) return st;
     f->main_dirty = true;
+    f->oz_h_valid = f->oz_sigma_ex_valid = false;
     cudaEventSynchronize(f->stage_free);
     memcpy(f->h_stage, points, (size_t)3 * n * 8);
     CU_TRY(cudaMemcpyAsync(f->y_in, f->h_stage, (size_t)3 * n * 8, cudaMemcpyHostToDevice, f->stream));
@@ -1374,6 +1534,7 @@ int eqvio_set_snapshot(eqvio_handle_t f, const double* d, size_t len) {
     CU_TRY(cudaSetDevice(f->device));
     CU_TRY(cudaStreamSynchronize(f->stream));
     f->main_dirty = true;
+    f->oz_h_valid = f->oz_sigma_ex_valid = f->oz_F_ready = false;
     int st = ensure_capacity(f, std::max(N, 1));
     if (st) return st;
     BaseState b;
@@ -1419,6 +1580,7 @@ static int upload_bearings(Filter* f, const double* bearings) {
 // do_integrate on a scratch copy is avoided by saving / restoring the small state and landmark arrays.
 static int build_FB_only(Filter* f, double T, const double omega[3]) {
     f->main_dirty = true;   // everything here runs on the main stream
+    f->oz_F_ready = false;
     // Save the mutable state that k_step_prepare / k_feature_step would change.
     BaseState saved;
     int st = fetch_base(f, &saved);
@@ -1668,7 +1830,7 @@ int eqvio_dgemm_pair(int device, int M, int N1, int K1, const double* A1, int ld
 // on tcgen05; the thin strips in front of it run on the DMMA kernel.
 int eqvio_dgemm_ozaki(int device, int transB, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                       int slices, int reps, float* ms_total, float* ms_gemm) {
-    if (M < OZ_TILE || N < OZ_TILE || K < 1 || !A || !B || !C || slices < 2 || slices > OZ_MAX_SLICES) return EQVIO_ERR_ARG;
+    if (M < OZ_TILE || N < OZ_TILE || K < 1 || !A || !B || !C || slices < 7 || slices > OZ_MAX_SLICES) return EQVIO_ERR_ARG;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) return EQVIO_ERR_NO_DEVICE;
     CU_TRY(cudaSetDevice(device));

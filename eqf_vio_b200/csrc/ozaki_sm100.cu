@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <limits.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace eqvio {
 
@@ -48,6 +49,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// contiguous global -> shared bulk copy (no tensor map), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
 // ---- tcgen05 ----
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(ncols) : "memory");
@@ -61,6 +68,18 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // all MMAs issued so far by this thread arrive on the mbarrier when they have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one lane of a converged warp (the warp stays converged around it: address arithmetic stays on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 // D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, M = 128, N = 128, K = 32
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -112,24 +131,30 @@ static constexpr int OZ_STAGES = 3;
 static constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 + 256;
 static constexpr int OZ_EPI_WARPS = 8, OZ_PRODUCER_WARP = 8, OZ_MMA_WARP = 9, OZ_THREADS = 320;
 static constexpr int OZ_DIAGS_PER_BATCH = 4;   // 4 x 128 TMEM columns
+static constexpr int OZ_SPLIT_SMEM = 32 * 129 * 8;
 
 struct OzParams {
     int M, N, KB, S;
     const int* exA;
     const int* exB;
+    int marginA, marginB;
     double alpha, beta;
     const double* Cin;
     int ldcin;
     double* D;
     int ldd;
+    OzRiccatiEpilogue ric;
+    OzExponentsOut exo;
 };
 
 __device__ __forceinline__ double oz_pow2(int e) {   // 2^e for e in the normal range
     return __hiloint2double((e + 1023) << 20, 0);
 }
+__device__ __forceinline__ int oz_exponent(double x);
 
+template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-k_oz_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzParams p) {
+k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const OzParams p) {
     using namespace oz;
     extern __shared__ uint8_t oz_smem_raw[];
     const uint32_t raw = smem_u32(oz_smem_raw);
@@ -144,8 +169,8 @@ k_oz_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Mt = (p.M + OZ_TILE - 1) / OZ_TILE;
     const int tile_m = blockIdx.x % Mt, tile_n = blockIdx.x / Mt;
-    const int S = p.S, KB = p.KB;
-    const int nbatch = (S + OZ_DIAGS_PER_BATCH - 1) / OZ_DIAGS_PER_BATCH;
+    const int KB = p.KB;
+    constexpr int nbatch = (S + OZ_DIAGS_PER_BATCH - 1) / OZ_DIAGS_PER_BATCH;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -164,47 +189,60 @@ k_oz_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     if (warp == OZ_PRODUCER_WARP) {
         if (lane == 0) {
-            tma_prefetch_desc(&tmA);
-            tma_prefetch_desc(&tmB);
+            // the slice arrays are tiled [row tile][k-block][slice][128 rows x 32 B, pre-swizzled]: the nS slice tiles a batch needs for one
+            // k-block are ONE contiguous run of nS x 4 KB per operand — two bulk copies per stage
+            const int8_t* gA = slA + (size_t)tile_m * KB * S * OZ_SLICE_TILE_BYTES;
+            const int8_t* gB = slB + (size_t)tile_n * KB * S * OZ_SLICE_TILE_BYTES;
             uint32_t it = 0;
             for (int b = 0; b < nbatch; ++b) {
                 const int nS = min(OZ_DIAGS_PER_BATCH * (b + 1), S);   // slices 0 .. nS-1 of both operands take part in this batch's diagonals
+                const uint32_t bytes = (uint32_t)(nS * OZ_SLICE_TILE_BYTES);
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % OZ_STAGES;
                     mbar_wait(&empty[s], ((it / OZ_STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], (uint32_t)(2 * nS * OZ_SLICE_TILE_BYTES));
+                    mbar_expect_tx(&full[s], 2 * bytes);
                     const uint32_t sa = base + s * OZ_STAGE_BYTES, sb = sa + OZ_MAX_SLICES * OZ_SLICE_TILE_BYTES;
-                    for (int sl = 0; sl < nS; ++sl) {
-                        tma_load_3d(sa + sl * OZ_SLICE_TILE_BYTES, &tmA, kb * OZ_KBLOCK, tile_m * OZ_TILE, sl, &full[s]);
-                        tma_load_3d(sb + sl * OZ_SLICE_TILE_BYTES, &tmB, kb * OZ_KBLOCK, tile_n * OZ_TILE, sl, &full[s]);
-                    }
+                    bulk_load(sa, gA + (size_t)kb * S * OZ_SLICE_TILE_BYTES, bytes, &full[s]);
+                    bulk_load(sb, gB + (size_t)kb * S * OZ_SLICE_TILE_BYTES, bytes, &full[s]);
                 }
             }
         }
     } else if (warp == OZ_MMA_WARP) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int b = 0; b < nbatch; ++b) {
-                const int dmin = OZ_DIAGS_PER_BATCH * b, dmax = min(dmin + OZ_DIAGS_PER_BATCH - 1, S - 1);
-                if (b > 0) {   // the epilogue has read the previous batch's accumulators out of TMEM
-                    mbar_wait(acc_empty, (uint32_t)((b - 1) & 1));
-                    tc_fence_after();
-                }
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % OZ_STAGES;
-                    mbar_wait(&full[s], (it / OZ_STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t sa = base + s * OZ_STAGE_BYTES, sb = sa + OZ_MAX_SLICES * OZ_SLICE_TILE_BYTES;
+        // The whole warp walks the loop (waits included) and ONE elected lane issues: with a single lane inside a divergent branch
+        // every descriptor had to be moved from vector to uniform registers per instruction and the issue loop ran at ~160 clk per MMA
+        // against the 64 clk the tensor core needs (first version: 43 % tensor-pipe active, producer never the one waited for).
+        uint32_t it = 0;
+        // descriptors of slice 0 of stage 0; slice a of stage s is + (s * stage + a * tile) / 16 in the 14-bit start-address field
+        const uint64_t adesc0 = smem_desc_sw32(base), bdesc0 = smem_desc_sw32(base + OZ_MAX_SLICES * OZ_SLICE_TILE_BYTES);
+#pragma unroll
+        for (int b = 0; b < nbatch; ++b) {
+            constexpr int DPB = OZ_DIAGS_PER_BATCH;
+            const int dmin = DPB * b, dmax = (dmin + DPB - 1 < S - 1) ? dmin + DPB - 1 : S - 1;
+            if (b > 0) {   // the epilogue has read the previous batch's accumulators out of TMEM
+                mbar_wait(acc_empty, (uint32_t)((b - 1) & 1));
+                tc_fence_after();
+            }
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % OZ_STAGES;
+                mbar_wait(&full[s], (it / OZ_STAGES) & 1);
+                tc_fence_after();
+                const uint64_t soff = (uint64_t)((s * OZ_STAGE_BYTES) >> 4);
+                const uint32_t first = kb > 0 ? 1u : 0u;
+                if (elect_one()) {
+#pragma unroll
                     for (int d = dmin; d <= dmax; ++d) {
                         const uint32_t acc = tmem_base + (uint32_t)((d - dmin) * OZ_TILE);
+#pragma unroll
                         for (int a = 0; a <= d; ++a)   // all pairs (a, d - a) of this diagonal into one int32 accumulator
-                            mma_i8(acc, smem_desc_sw32(sa + a * OZ_SLICE_TILE_BYTES), smem_desc_sw32(sb + (d - a) * OZ_SLICE_TILE_BYTES), OZ_IDESC,
-                                   (kb > 0 || a > 0) ? 1u : 0u);
+                            mma_i8(acc, adesc0 + soff + (uint64_t)(a * (OZ_SLICE_TILE_BYTES >> 4)), bdesc0 + soff + (uint64_t)((d - a) * (OZ_SLICE_TILE_BYTES >> 4)),
+                                   OZ_IDESC, a > 0 ? 1u : first);
                     }
                     tc_commit(&empty[s]);       // the stage is free once these MMAs have read it
                 }
-                tc_commit(acc_full);            // the batch's accumulators are complete
+                __syncwarp();
             }
+            if (elect_one()) tc_commit(acc_full);   // the batch's accumulators are complete
+            __syncwarp();
         }
     } else {
         // ===== epilogue warps: lane quarter q (TMEM lanes 32q .. 32q+31 = tile rows), column half h =====
@@ -234,16 +272,60 @@ k_oz_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         const int row = tile_m * OZ_TILE + q * 32 + lane;
         if (row < p.M) {
-            const double ra = oz_pow2(max(p.exA[row], -900) - 12);
+            const double ra = oz_pow2(max(p.exA[row], -900) + p.marginA - 12);
             const int col0 = tile_n * OZ_TILE + h * 64;
+            // Riccati epilogue (VIOFilter.cpp:188-189): + T (B_b R B_b^T) as six products of the border columns, + T P on the diagonal
+            const bool ric = p.ric.on != 0;
+            const int gm = row + p.ric.row_off;
+            double wx[6] = {0, 0, 0, 0, 0, 0}, Tstep = 0.0;
+            if (ric) {
+                Tstep = *p.ric.T_dev;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) wx[c] = p.ric.Wx[(size_t)gm + (size_t)p.ric.ldx * c];
+            }
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
                 const int col = col0 + j;
                 if (col < p.N) {
-                    double v = p.alpha * ((acc[j] * ra) * oz_pow2(max(p.exB[col], -900)));
+                    double v = p.alpha * ((acc[j] * ra) * oz_pow2(max(p.exB[col], -900) + p.marginB));
                     if (p.beta != 0.0) v += p.beta * p.Cin[(size_t)row + (size_t)p.ldcin * col];
+                    if (ric) {
+                        const int gn = col + p.ric.col_off;
+                        double r6 = 0.0;
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) r6 = fma(wx[c], p.ric.Fx[(size_t)gn + (size_t)p.ric.ldx * c], r6);
+                        v += r6;
+                        if (gm == gn) v += Tstep * (gm < 3 ? p.ric.Pd[0] : gm < 6 ? p.ric.Pd[1] : gm < 8 ? p.ric.Pd[2] : gm < 11 ? p.ric.Pd[3] : p.ric.Pd[4]);
+                    }
                     p.D[(size_t)row + (size_t)p.ldd * col] = v;
+                    acc[j] = v;
+                } else {
+                    acc[j] = 0.0;
                 }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+        }
+        // Exponents of what was just written, for the split of this output as the next product's operand: row maxima over the columns
+        // (each entry scaled by 2^(-h[column]) first) and / or column maxima over the rows (scaled by 2^(-h[row])).
+        if (p.exo.rows_out != nullptr && row < p.M) {
+            const int col0 = tile_n * OZ_TILE + h * 64;
+            int e = -2000;
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+                if (col0 + j < p.N) e = max(e, oz_exponent(acc[j]) - (p.exo.h ? p.exo.h[col0 + j + p.exo.col_off] : 0));
+            atomicMax(p.exo.rows_out + row, e);
+        }
+        if (p.exo.cols_out != nullptr) {
+            const int col0 = tile_n * OZ_TILE + h * 64;
+            const int hr = (p.exo.h && row < p.M) ? p.exo.h[row + p.exo.row_off] : 0;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                int e = oz_exponent(acc[j]) - hr;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+                if (lane == 0 && col0 + j < p.N) atomicMax(p.exo.cols_out + col0 + j, e);
             }
         }
     }
@@ -258,19 +340,27 @@ k_oz_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // ------------------------------------------------------------------------------------------------
 // splitting
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void oz_load_tile(const double* X, long sr, long sk, int r0, int k0, int rows, int k, double (*t)[33]) {
+// Every entry may be scaled by a power of two that depends on its k index, x'(r, k) = x(r, k) 2^(hsign h[k]): the two operands of a
+// product use opposite signs, so the scales cancel exactly in the product while the digit grids (relative to the row maximum of
+// the SCALED entries) stop being dominated by a few large-variance states (see OzKScale in the header).
+__device__ __forceinline__ double oz_kscaled(double x, const int* h, int hsign, int kidx) {
+    return h ? x * oz_pow2(hsign * h[kidx]) : x;
+}
+template <int KW>   // tile of 32 rows x KW k (KW = 32 or 128), t[32][KW + 1]
+__device__ __forceinline__ void oz_load_tile(const double* X, long sr, long sk, int r0, int k0, int rows, int k, const int* h, int hsign,
+                                             double (*t)[KW + 1]) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     if (sk == 1) {   // k contiguous: a warp reads 32 consecutive k of one row
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = ty + 8 * i;
-            t[r][tx] = (r0 + r < rows && k0 + tx < k) ? X[(size_t)(r0 + r) * sr + (k0 + tx)] : 0.0;
+        for (int i = 0; i < KW / 8; ++i) {
+            const int r = ty + 8 * (i & 3), kk = tx + 32 * (i >> 2);
+            t[r][kk] = (r0 + r < rows && k0 + kk < k) ? oz_kscaled(X[(size_t)(r0 + r) * sr + (k0 + kk)], h, hsign, k0 + kk) : 0.0;
         }
     } else {         // rows contiguous (or general): a warp reads 32 consecutive rows at one k
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < KW / 8; ++i) {
             const int kk = ty + 8 * i;
-            t[tx][kk] = (r0 + tx < rows && k0 + kk < k) ? X[(size_t)(r0 + tx) * sr + (size_t)(k0 + kk) * sk] : 0.0;
+            t[tx][kk] = (r0 + tx < rows && k0 + kk < k) ? oz_kscaled(X[(size_t)(r0 + tx) * sr + (size_t)(k0 + kk) * sk], h, hsign, k0 + kk) : 0.0;
         }
     }
 }
@@ -280,10 +370,11 @@ __device__ __forceinline__ int oz_exponent(double x) {   // e with |x| = f 2^e, 
     return be == 0 ? -2000 : be - 1022;
 }
 
-__global__ void __launch_bounds__(256) k_oz_rowmax(const double* X, long sr, long sk, int rows, int k, int* ex) {
+// ex[r] = max(ex[r], exponent of the largest scaled entry of row r over k in [0, k))
+__global__ void __launch_bounds__(256) k_oz_rowmax(const double* X, long sr, long sk, int rows, int k, const int* h, int hsign, int* ex) {
     __shared__ double t[32][33];
     const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
-    oz_load_tile(X, sr, sk, r0, k0, rows, k, t);
+    oz_load_tile<32>(X, sr, sk, r0, k0, rows, k, h, hsign, t);
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -295,32 +386,57 @@ __global__ void __launch_bounds__(256) k_oz_rowmax(const double* X, long sr, lon
     }
 }
 
-// digits: x 2^-e 2^6 = d0 + r0, |r| <= 1/2; then r 2^7 = d + r' ... every step exact in fp64, every digit in [-64, 64]
-__global__ void __launch_bounds__(256) k_oz_split(const double* X, long sr, long sk, int rows, int k, const int* ex, int8_t* slices, int rows_pad,
-                                                  int k_pad, int S) {
-    __shared__ double t[32][33];
-    const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
-    oz_load_tile(X, sr, sk, r0, k0, rows, k, t);
+// digits: x 2^-e 2^6 = d0 + r0, |r| <= 1/2; then r 2^7 = d + r' ... every step exact in fp64, every digit in [-64, 64].
+// A block takes 32 rows x 128 k; a thread 16 consecutive k of one row, one 16-byte store per slice (a warp: four full 128-byte lines).
+__global__ void __launch_bounds__(256) k_oz_split(const double* X, long sr, long sk, int rows, int k, const int* h, int hsign, int* ex,
+                                                  int ex_margin, int8_t* slices, int rows_pad, int k_pad, int S) {
+    extern __shared__ double oz_split_smem[];
+    double(*t)[129] = reinterpret_cast<double(*)[129]>(oz_split_smem);
+    const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 128;
+    oz_load_tile<128>(X, sr, sk, r0, k0, rows, k, h, hsign, t);
     __syncthreads();
     const int id = threadIdx.y * 32 + threadIdx.x, r = id >> 3, kg = id & 7;
-    if (r0 + r >= rows) return;
-    const int e = max(ex[r0 + r], -900);
+    if (r0 + r >= rows || k0 + 16 * kg >= k_pad) return;
+    // ex_margin: the exponents came from the transposed entries of a matrix that is symmetric only up to round-off; widened by the
+    // margin here and, identically, in the product's epilogue (OzOperand::ex_margin)
+    const int e = max(ex[r0 + r], -900) + ex_margin;
     const double up = oz_pow2(6 - e);
-    double v[4];
+    double v[16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) v[c] = t[r][4 * kg + c] * up;
-    const size_t plane = (size_t)rows_pad * k_pad;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(slices + (size_t)(r0 + r) * k_pad + k0 + 4 * kg);
+    for (int c = 0; c < 16; ++c) v[c] = t[r][16 * kg + c] * up;
+    // tiled layout [row tile][k-block][slice][128 rows x 32 B]; inside a 4 KB slice tile the image is what TMA's SWIZZLE_32B would
+    // have produced (16-byte halves of a row exchanged in rows 4-7 of every group of eight), so a plain bulk copy stages it
+    const int row = r0 + r, kk = k0 + 16 * kg;
+    const int KB = k_pad / OZ_KBLOCK;
+    const size_t tile = ((size_t)(row / OZ_TILE) * KB + kk / OZ_KBLOCK) * S;
+    const int in_tile = (row % OZ_TILE) * OZ_KBLOCK + (((kk % OZ_KBLOCK) >> 4) ^ ((row >> 2) & 1)) * 16;
+    uint4* dst = reinterpret_cast<uint4*>(slices + tile * OZ_SLICE_TILE_BYTES + in_tile);
+    constexpr size_t plane = OZ_SLICE_TILE_BYTES;
+    (void)rows_pad;
+    // round to nearest by adding 1.5 * 2^52: the digit appears as a two's-complement integer in the low word of the sum and as a double
+    // after subtracting the constant again — two full-rate additions instead of FRND + F2I (the first version of this kernel took 36 us
+    // for a 19 MB operand, four times what its memory traffic costs)
+    const double magic = 6755399441055744.0;
     for (int s = 0; s < S; ++s) {
-        uint32_t w = 0;
+        uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const double d = rint(v[c]);
+        for (int c = 0; c < 16; ++c) {
+            const double t = v[c] + magic;
+            const double d = t - magic;
             v[c] = (v[c] - d) * 128.0;
-            w |= ((uint32_t)(__double2int_rn(d)) & 0xffu) << (8 * c);
+            w[c >> 2] |= ((uint32_t)__double2loint(t) & 0xffu) << (8 * (c & 3));
         }
-        dst[(size_t)s * plane / 4] = w;
+        dst[(size_t)s * plane / 16] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+
+// h[k] = half the binary exponent of the diagonal entry (k, k): 2^h[k] ~ sqrt(Sigma_kk)
+__global__ void k_oz_diag_scale(const double* Sigma, int ld, int n, int* h) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double d = Sigma[(size_t)k * (ld + 1)];
+    const int e = (d > 0.0) ? oz_exponent(d) : 0;
+    h[k] = (e >= -1000 && e <= 1000) ? (e >= 0 ? e / 2 : -((-e + 1) / 2)) : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -328,60 +444,63 @@ __global__ void __launch_bounds__(256) k_oz_split(const double* X, long sr, long
 // ------------------------------------------------------------------------------------------------
 static inline int oz_round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-static PFN_cuTensorMapEncodeTiled_v12000 oz_get_encode() {
-    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-    }
-    return fn;
-}
-
 size_t oz_slices_bytes(int rows, int k, int S) { return (size_t)S * oz_round_up(rows, OZ_TILE) * oz_round_up(k, OZ_KBLOCK); }
 
 cudaError_t oz_init_device() {
-    return cudaFuncSetAttribute(k_oz_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_oz_gemm<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_oz_gemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_oz_gemm<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_oz_split, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SPLIT_SMEM);
 }
 
 cudaError_t oz_split(const double* X, long stride_r, long stride_k, int rows, int k, int S, OzOperand* op, int8_t* slices, int* ex,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const OzKScale* ks, bool ex_ready, int ex_margin) {
     if (S < 1 || S > OZ_MAX_SLICES || rows < 1 || k < 1) return cudaErrorInvalidValue;
-    op->slices = slices; op->ex = ex; op->rows = rows; op->k = k; op->S = S;
+    op->slices = slices; op->ex = ex; op->rows = rows; op->k = k; op->S = S; op->ex_margin = ex_margin;
     op->rows_pad = oz_round_up(rows, OZ_TILE); op->k_pad = oz_round_up(k, OZ_KBLOCK);
-    cudaError_t e = cudaMemsetAsync(ex, 0xC0, (size_t)op->rows_pad * sizeof(int), stream);   // a very negative exponent everywhere
-    if (e != cudaSuccess) return e;
-    const dim3 grid((k + 31) / 32, (rows + 31) / 32), block(32, 8);
-    k_oz_rowmax<<<grid, block, 0, stream>>>(X, stride_r, stride_k, rows, k, ex);
-    k_oz_split<<<grid, block, 0, stream>>>(X, stride_r, stride_k, rows, k, ex, slices, op->rows_pad, op->k_pad, S);
+    const int* h = ks ? ks->h : nullptr;
+    const int hsign = ks ? ks->sign : 0;
+    if (!ex_ready) {
+        cudaError_t e = oz_reset_exponents(ex, op->rows_pad, stream);
+        if (e != cudaSuccess) return e;
+        k_oz_rowmax<<<dim3((k + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, stream>>>(X, stride_r, stride_k, rows, k, h, hsign, ex);
+    }
+    k_oz_split<<<dim3((op->k_pad + 127) / 128, (rows + 31) / 32), dim3(32, 8), OZ_SPLIT_SMEM, stream>>>(X, stride_r, stride_k, rows, k, h, hsign, ex, ex_margin,
+                                                                                                   slices, op->rows_pad, op->k_pad, S);
+    return cudaGetLastError();
+}
+cudaError_t oz_reset_exponents(int* ex, int count, cudaStream_t stream) {   // a very negative exponent everywhere
+    return cudaMemsetAsync(ex, 0xC0, (size_t)count * sizeof(int), stream);
+}
+cudaError_t oz_rowmax(const double* X, long stride_r, long stride_k, int rows, int k, int* ex, cudaStream_t stream, const OzKScale* ks) {
+    if (rows < 1 || k < 1) return cudaSuccess;
+    k_oz_rowmax<<<dim3((k + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, stream>>>(X, stride_r, stride_k, rows, k, ks ? ks->h : nullptr, ks ? ks->sign : 0, ex);
+    return cudaGetLastError();
+}
+cudaError_t oz_diag_scale(const double* Sigma, int ld, int n, int* h, cudaStream_t stream) {
+    k_oz_diag_scale<<<(n + 255) / 256, 256, 0, stream>>>(Sigma, ld, n, h);
     return cudaGetLastError();
 }
 
-static CUresult oz_encode(CUtensorMap* map, const OzOperand& op) {
-    cuuint64_t dims[3] = {(cuuint64_t)op.k_pad, (cuuint64_t)op.rows_pad, (cuuint64_t)op.S};
-    cuuint64_t strides[2] = {(cuuint64_t)op.k_pad, (cuuint64_t)op.k_pad * op.rows_pad};
-    cuuint32_t box[3] = {OZ_KBLOCK, OZ_TILE, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    return oz_get_encode()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, op.slices, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-}
-
 cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double alpha, double beta, const double* Cin, int ldcin, double* D,
-                    int ldd, cudaStream_t stream) {
-    if (!oz_get_encode()) return cudaErrorNotSupported;
+                    int ldd, cudaStream_t stream, const OzRiccatiEpilogue* ric, const OzExponentsOut* exo) {
     if (A.k_pad != B.k_pad || A.S != B.S || M > A.rows_pad || N > B.rows_pad || M < 1 || N < 1) return cudaErrorInvalidValue;
     if ((long long)A.k_pad * 64 * 64 * A.S >= (1LL << 31)) return cudaErrorInvalidValue;   // int32 accumulation of one diagonal must be exact
-    CUtensorMap tmA, tmB;
-    if (oz_encode(&tmA, A) != CUDA_SUCCESS || oz_encode(&tmB, B) != CUDA_SUCCESS) return cudaErrorInvalidValue;
     OzParams p;
     p.M = M; p.N = N; p.KB = A.k_pad / OZ_KBLOCK; p.S = A.S;
-    p.exA = A.ex; p.exB = B.ex;
+    p.exA = A.ex; p.exB = B.ex; p.marginA = A.ex_margin; p.marginB = B.ex_margin;
     p.alpha = alpha; p.beta = Cin ? beta : 0.0; p.Cin = Cin; p.ldcin = ldcin; p.D = D; p.ldd = ldd;
+    if (ric) p.ric = *ric; else { memset(&p.ric, 0, sizeof p.ric); }
+    if (exo) p.exo = *exo; else { memset(&p.exo, 0, sizeof p.exo); }
     const int Mt = (M + OZ_TILE - 1) / OZ_TILE, Nt = (N + OZ_TILE - 1) / OZ_TILE;
-    k_oz_gemm<<<dim3(Mt * Nt), OZ_THREADS, OZ_SMEM_BYTES, stream>>>(tmA, tmB, p);
+    const dim3 grid(Mt * Nt);
+    switch (A.S) {
+        case 7: k_oz_gemm<7><<<grid, OZ_THREADS, OZ_SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
+        case 8: k_oz_gemm<8><<<grid, OZ_THREADS, OZ_SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
+        case 9: k_oz_gemm<9><<<grid, OZ_THREADS, OZ_SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

@@ -16,9 +16,10 @@
 //
 // Kernel shape: one CTA per 128 x 128 output tile; warps 0-7 epilogue (TMEM -> registers -> fp64), warp 8 TMA producer, warp 9 MMA
 // issuer.  The diagonals are processed in batches of four (4 x 128 TMEM columns = all 512); within a batch every 32-deep k-block of
-// ALL slices needed is staged once by TMA (SWIZZLE_32B, 4 KB per slice tile) and every (s, t) pair of the batch is issued against it,
-// so a slice tile is fetched from L2 once per batch instead of once per pair (36 pairs -> 2 fetches: the int8 MMA rate would need
-// 125 B/clk/SM otherwise, three times what L2 delivers).
+// ALL slices needed is staged once (cp.async.bulk of one contiguous, pre-swizzled run of 4 KB slice tiles per operand — the first
+// version fetched 128 separate 32-byte rows per slice tile through a tensor map and reached a third of L2's rate) and every (s, t)
+// pair of the batch is issued against it, so a slice tile is fetched from L2 once per batch instead of once per pair (36 pairs -> 2
+// fetches: the int8 MMA rate would need 125 B/clk/SM otherwise, three times what L2 delivers).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -30,22 +31,53 @@ static const int OZ_MAX_SLICES = 9;
 static const int OZ_TILE = 128;      // output tile (M and N), also the row padding of the slice arrays
 static const int OZ_KBLOCK = 32;     // int8 MMA depth = one SWIZZLE_32B row
 
-// One operand split into int8 slices: slices[s][row][k] (k contiguous, rows padded to 128, k to 32, zero-filled), ex[row] the row's
-// binary exponent.  "row" is a row of A or a COLUMN of B (both operands are staged K-major).
+// One operand split into int8 slices, tiled for the kernel's staging: slices[row tile][k-block][s][128 rows x 32 bytes], each 4 KB
+// slice tile K-major and pre-swizzled (the SWIZZLE_32B image the tensor core's shared-memory descriptor expects), so that the S' <= S
+// slice tiles a batch of diagonals needs for one k-block are one contiguous run fetched by a single bulk copy.  Rows padded to 128,
+// k to 32, zero-filled.  ex[row] is the row's binary exponent.  "row" is a row of A or a COLUMN of B (both operands are K-major).
 struct OzOperand {
     int8_t* slices;   // S * rows_pad * k_pad bytes
     int* ex;          // rows_pad ints
     int rows, k, rows_pad, k_pad, S;
+    int ex_margin;    // added to every exponent by the split and by the product's epilogue (exponents taken from a transposed, nearly symmetric matrix)
 };
 
+// Epilogue of the Riccati step's second product (VIOFilter.cpp:188-189) for the core block: D += sum_c Wx[gm, c] Fx[gn, c] (the rank-6
+// term T B_b R B_b^T: Wx = T B_b R and Fx = B_b are six columns with leading dimension ldx) and + T P on the diagonal; gm / gn =
+// tile-local row / column + row_off / col_off = index in Sigma.
+struct OzRiccatiEpilogue {
+    int on, row_off, col_off, ldx;
+    const double* T_dev;
+    const double* Wx;
+    const double* Fx;
+    double Pd[5];
+};
+
+// Inner-dimension equilibration.  The digit grid of a row is relative to the row's largest entry, so an output entry's error is
+// ~2^-53 x (row max of A) x (column max of B) — poor for the small entries of a covariance whose variances span eight decades.
+// Scaling the inner index by powers of two, A' = A 2^(+h), B' = 2^(-h) B with 2^h[k] ~ sqrt(Sigma_kk), is exact, cancels in the
+// product, and makes both maxima ~ sqrt(variance): the error becomes relative to sqrt(Sigma_ii Sigma_jj), the natural scale of entry
+// (i, j).  `sign` = +1 / -1 selects which side this operand is.
+struct OzKScale { const int* h; int sign; };
+// Exponent maxima of the output (for splitting it as the next product's operand without a separate pass): rows_out[row] over the
+// columns, each entry scaled by 2^(-h[col + col_off]); cols_out[col] over the rows, scaled by 2^(-h[row + row_off]).  Either may be
+// null; the arrays must have been reset (oz_reset_exponents) and are atomically maxed.
+struct OzExponentsOut { int* rows_out; int* cols_out; const int* h; int row_off, col_off; };
+
 size_t oz_slices_bytes(int rows, int k, int S);
-// Splits X (element (r, k) at X[r * stride_r + k * stride_k]) into S slices; `op` must have been sized with oz_slices_bytes.
+// Splits X (element (r, k) at X[r * stride_r + k * stride_k]) into S slices; `slices` sized with oz_slices_bytes.  ex_ready: `ex`
+// already holds the rows' exponents (of the scaled entries); else they are computed first (one more pass over X).
 cudaError_t oz_split(const double* X, long stride_r, long stride_k, int rows, int k, int S, OzOperand* op, int8_t* slices, int* ex,
-                     cudaStream_t stream);
+                     cudaStream_t stream, const OzKScale* ks = nullptr, bool ex_ready = false, int ex_margin = 0);
+cudaError_t oz_reset_exponents(int* ex, int count, cudaStream_t stream);
+// ex[r] = max(ex[r], largest exponent of row r of X over its k columns)
+cudaError_t oz_rowmax(const double* X, long stride_r, long stride_k, int rows, int k, int* ex, cudaStream_t stream, const OzKScale* ks = nullptr);
+// h[k] = floor(exponent(Sigma_kk) / 2)
+cudaError_t oz_diag_scale(const double* Sigma, int ld, int n, int* h, cudaStream_t stream);
 // D[0:M, 0:N] (column-major, ldd) = alpha * A * B + beta * Cin for the split operands (A: M rows, B: N "rows" = columns of B), M and N
 // multiples of 128 up to the padding (rows beyond M / N are computed on zero slices and not stored).
 cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double alpha, double beta, const double* Cin, int ldcin, double* D,
-                    int ldd, cudaStream_t stream);
+                    int ldd, cudaStream_t stream, const OzRiccatiEpilogue* ric = nullptr, const OzExponentsOut* exo = nullptr);
 cudaError_t oz_init_device();
 
 }  // namespace eqvio

@@ -231,7 +231,11 @@ def test_device_resident_bearings_match_host_path():
 
 
 def test_single_step_parity_N256():
-    """BASELINE config 3 size (n = 779): one Riccati step and one update from an oracle state."""
+    """BASELINE config 3 size (n = 779): one Riccati step and one update from an oracle state.  Template settings: the
+    update rescales landmarks initialised at 1 m to their 3-15 m depths, the SOT(3) scales Q_i.a reach ~140, and on this
+    very step the two CPU restatements of the reference differ from each other by 3.7e-9 absolute on such a scale — so the
+    lifted state is compared at 1e-8 relative to max(1, |entry|), Sigma at rel-Frobenius 1e-9 (the Riccati step alone at
+    1e-13)."""
     s = template_settings(outlierThreshold=1e9)
     seq = period_sequence(256, 1, camera_offset=tuple(s.cameraOffset))
     f, o = gpu_filter(s), COracleFilter(s)
@@ -248,7 +252,8 @@ def test_single_step_parity_N256():
     assert r1 == r2 == 0
     h1, S1 = split_snapshot(f.get_snapshot())
     h2, S2 = split_snapshot(o.get_snapshot())
-    assert rel(S1, S2) < STEP_SIGMA_TOL and np.abs(h1 - h2).max() < STEP_STATE_TOL, (rel(S1, S2), np.abs(h1 - h2).max())
+    err_h = (np.abs(h1 - h2) / np.maximum(1.0, np.abs(h2))).max()
+    assert rel(S1, S2) < STEP_SIGMA_TOL and err_h < STEP_STATE_TOL, (rel(S1, S2), err_h, np.abs(h1 - h2).max())
 
 
 def test_full_size_properties_N512():
