@@ -426,7 +426,56 @@ class Session:
         self.f.close()
 
 
-def roofline_record(N, K, classes, g, dev_ms_local, peak_tf):
+def int8_roofline_record(N, K, classes, g, dev_ms_local, peak_tf, peak_i8, slices):
+    """Roofline of the dominant kernel when the Riccati products run on the int8 tensor cores: executed int8 operations
+    (2 M N K per slice pair, S (S + 1) / 2 pairs per fp64 product) against the int8 dense peak."""
+    g_launches, g_ms, g_flops = g
+    dom = classes["riccati_i8_gemm"]
+    d_ms, d_flops, d_launches = dom["ms"], dom["flops"], dom["launches"]
+    pairs = slices * (slices + 1) // 2
+    tops = d_flops * pairs / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
+    eq_tf = d_flops / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
+    n_sigma = 11 + 3 * N
+    mc = n_sigma // 128 * 128
+    kpad = (n_sigma + 31) // 32 * 32
+    whole = {k: classes[k] for k in ("riccati_gemm", "riccati_i8_gemm")}
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_oz_gemm_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"N{N}")
+            traffic_src = "NOT measured by this run: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this kernel (profiles/r02_oz_gemm_traffic.json; cold L2)"
+        except Exception:
+            traffic = None
+    return {
+        "bound": "tensor",
+        "kernel": f"eqvio::k_oz_gemm<{slices}> (tcgen05.mma.cta_group::1.kind::i8 128x128x32, int32 accumulators in TMEM, bulk-copy staged pre-swizzled int8 slice tiles): "
+                  f"the {mc} x {mc} landmark block of W = F Sigma and of Sigma' = W F^T + T B R B^T + T P, each fp64 product an exact sum of {pairs} int8 products ({slices} slices of 7 bits per operand); "
+                  "the rows / columns in front of the block run on fp64 DMMA strips (class riccati_gemm)",
+        "achieved": tops, "peak": peak_i8["value"], "unit": "TOP/s (int8 dense)", "frac": tops / peak_i8["value"] if peak_i8["value"] else None,
+        "peak_source": peak_i8["source"],
+        "traffic": traffic, "traffic_source": traffic_src,
+        "launches": d_launches, "avg_launch_ms": d_ms / d_launches if d_launches else None,
+        "int8_ops_per_launch": 2.0 * mc * mc * n_sigma * pairs,
+        "algorithmic_bytes_per_launch": 2 * slices * mc * kpad + 8 * mc * mc,
+        "algorithmic_bytes_note": "both operands' int8 slice arrays read once + the fp64 result block written once",
+        "fp64_equivalent": {"achieved_tflops": eq_tf, "dgemm_peak_tflops": peak_tf, "ratio": eq_tf / peak_tf if peak_tf else None,
+                            "note": "2 M N K of the fp64 product the int8 launches stand for, over their time; the DMMA pipe tops out at 37.1 TFLOP/s (profiles/r01_dmma_microbench.md)"},
+        "riccati_step_fp64_equivalent_tflops": (sum(v["flops"] for v in whole.values()) / (K * STEPS_PER_PERIOD)) / 1e12,
+        "how": "every launch of the int8 products bracketed by CUDA events on its stream inside the library (eqvio_profile_enable, direct launches instead of graph replay) over K periods; "
+               "achieved = executed int8 operations / summed launch time",
+        "kernel_share_of_step": d_ms / dev_ms_local if dev_ms_local else None,
+        "all_gemm_launches": {"launches": g_launches, "ms": g_ms, "tflops": g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,
+                              "note": "fp64-equivalent; includes the 64-deep Schur panel / trailing GEMMs, which overlap each other on five streams"},
+        "by_class": {k: {"launches": v["launches"], "ms_per_period": v["ms"] / K, "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0)}
+                     for k, v in classes.items()},
+        "by_class_note": "in-stream time between two events around each launch, summed per class: classes overlap each other (five update streams + the state stream), and a launch's time includes its wait for SM slots; riccati_i8_gemm tflops are fp64-equivalent",
+    }
+
+
+def roofline_record(N, K, classes, g, dev_ms_local, peak_tf, peak_i8=None, slices=0):
+    if slices > 0 and classes.get("riccati_i8_gemm", {}).get("launches", 0) > 0:
+        return int8_roofline_record(N, K, classes, g, dev_ms_local, peak_tf, peak_i8, slices)
     g_launches, g_ms, g_flops = g
     paired, kernel_name = riccati_kernel_name(N)
     dom = classes["riccati_gemm"]
@@ -474,6 +523,34 @@ def measure_peak_tf(torch, dev):
     return 2 * 8192**3 / (best * 1e-3) / 1e12
 
 
+def measure_peak_int8(torch, dev):
+    """int8 tensor-core peak for the roofline of the int8 Riccati products: cuBLASLt int8 GEMM (torch._int_mm) 8192^3 measured
+    live; else twice the measured dense bf16 figure of MEASURED_PEAKS.json (the architecture's int8 : bf16 ratio); else nominal."""
+    try:
+        a = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device=dev)
+        b = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device=dev)
+        torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        live = 2 * 8192**3 / (best * 1e-3) / 1e12
+    except Exception:
+        live = None
+    mp = None
+    try:
+        mp = 2.0 * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    if live is not None and (mp is None or live >= 0.5 * mp):
+        return {"value": max(live, mp or 0.0), "source": f"max of: torch._int_mm 8192^3 (cuBLASLt int8 GEMM) measured live, best of 8: {live:.0f} TOP/s; 2 x MEASURED_PEAKS.json bf16_tflops (burst): {mp if mp else float('nan'):.0f} TOP/s"}
+    if mp is not None:
+        return {"value": mp, "source": "2 x bf16_tflops (burst) of MEASURED_PEAKS.json: no int8 entry there, int8 dense rate is twice bf16 on sm_100"}
+    return {"value": 4500.0, "source": "nominal B200 dense int8 (no measured figure available)"}
+
+
 def main():
     global _REAL_STDOUT
     args = parse_args()
@@ -501,6 +578,7 @@ def main():
     N, K, W = args.features, args.steps, args.warmup
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
     peak_tf = measure_peak_tf(torch, dev) if rank == 0 else 0.0
+    peak_i8 = measure_peak_int8(torch, dev) if rank == 0 else {"value": 0.0, "source": ""}
 
     # ---------------- headline: N features, fastRiccati = false, fixed N ----------------
     sampler = ClockSampler(local_rank)
@@ -511,6 +589,7 @@ def main():
     e2e_s, h2d, d2h = ses.end_to_end(flush)
     clocks = sampler.stop()
     classes, g = ses.profiled()
+    slices = ses.f.riccati_int8_slices()
     ses.close()
     total_steps = STEPS_PER_PERIOD * K * world
     value = total_steps / (dev_ms * 1e-3)
@@ -521,6 +600,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "arithmetic": ("state, Sigma and every result in IEEE fp64; the Riccati step's two n x n x n contractions are assembled exactly from int8 tensor-core products "
+                           f"({slices} slices of 7 bits per operand = 55 mantissa bits, int32 accumulation, fp64 recombination: error 7e-16 of |row| |column|, as an fp64 GEMM)"
+                           if slices > 0 else "IEEE fp64 throughout (DMMA tensor instructions for the Sigma contractions)"),
             "data": "synthetic",
             "config": config_dict(N),
             "sessions": f"{world} independent filter session(s), one per GPU" + (", NCCL all-gather of the 8-double pose record per vision frame on the handle's gather stream" if world > 1 else ""),
@@ -530,7 +612,7 @@ def main():
             "gpu_launches": launches,
             "cuda_graphs": {"replays_so_far": graph_replays, "instantiated": graphs_held,
                             "note": "gpu_launches counts this library's kernels, those inside replayed graphs included"},
-            "roofline": roofline_record(N, K, classes, g, dev_ms, peak_tf),
+            "roofline": roofline_record(N, K, classes, g, dev_ms, peak_tf, peak_i8, slices),
             "gflops_dense_equiv": fm["period"] * K * world / (dev_ms * 1e-3) / 1e9,
             "flop_model_period_gflop": fm["period"] / 1e9,
         }
@@ -552,8 +634,8 @@ def main():
         if with_roofline:
             cl, gg = s2.profiled()
             if rank == 0:
-                r = roofline_record(Ns, Ks, cl, gg, ms, peak_tf)
-                rec["roofline"] = {k: r[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "launches", "avg_launch_ms", "kernel_share_of_step", "algorithmic_bytes_per_launch")}
+                r = roofline_record(Ns, Ks, cl, gg, ms, peak_tf, peak_i8, s2.f.riccati_int8_slices())
+                rec["roofline"] = {k: r[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "launches", "avg_launch_ms", "kernel_share_of_step", "algorithmic_bytes_per_launch", "fp64_equivalent") if k in r}
                 rec["roofline"]["by_class"] = r["by_class"]
         s2.close()
         if cpu is not None and rank == 0:

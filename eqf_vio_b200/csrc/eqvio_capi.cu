@@ -60,7 +60,7 @@ static int init_device(int device) {
 }
 
 struct ProfEvent { cudaEvent_t a, b; double flops; int cls; int lane; };
-enum { PROF_RICCATI = 0, PROF_UPDATE = 1, PROF_SCHUR_GEMM = 2, PROF_SCHUR_DIAG = 3, PROF_MISC = 4, PROF_CLASSES = 5 };
+enum { PROF_RICCATI = 0, PROF_UPDATE = 1, PROF_SCHUR_GEMM = 2, PROF_SCHUR_DIAG = 3, PROF_MISC = 4, PROF_RICCATI_I8 = 5, PROF_CLASSES = 6 };
 struct TimelineEntry { double cls, lane, t0, t1, flops; };
 
 static const int STRIP_SLOTS = 2048;   // split-K slots of one strip launch (tiles x k-ranges)
@@ -110,9 +110,12 @@ struct eqvio_filter {
     double* splitk_ws = nullptr;   // partial tiles of the split-K pair launch
     double* strip_ws[2] = {nullptr, nullptr};   // partial tiles / arrival counters of the two split-K strips beside the int8 core block
     int* strip_cnt[2] = {nullptr, nullptr};
-    // EQVIO_OZAKI=S (7..9): the Riccati step's two products on the int8 tensor cores (ozaki_sm100.cuh) for the 128-aligned landmark
-    // block, DMMA strips for the rows / columns in front of it.  0 (default): the fp64 DMMA path.
-    int ozaki_S = 0;
+    // The Riccati step's two products on the int8 tensor cores (ozaki_sm100.cuh) for the 128-aligned landmark block, DMMA strips for
+    // the rows / columns in front of it, with S = 8 slices (fp64-equivalent accuracy) once that block has ozaki_min_tiles 128 x 128
+    // tiles (0.8 of a wave of the 148 SMs; measured: N = 512 1607 -> 1969 steps/s, N = 1024 223 -> 346, N = 384 3384 -> 2758).
+    // EQVIO_OZAKI=S (7..9) selects the slice count, EQVIO_OZAKI=0 the fp64 DMMA path at every size.
+    int ozaki_S = 8;
+    int ozaki_min_tiles = 121;
     int8_t *ozF[2] = {nullptr, nullptr}, *ozS = nullptr, *ozW = nullptr;   // int8 slices of F rows (by tick parity, like F), Sigma columns, W rows
     int *ozeF[2] = {nullptr, nullptr}, *ozeS = nullptr, *ozeW = nullptr;   // their row / column exponents
     int* ozH = nullptr;            // inner-dimension scales, 2^h[k] ~ sqrt(Sigma_kk) (OzKScale); refreshed after every change of Sigma outside the Riccati step
@@ -159,8 +162,8 @@ struct eqvio_filter {
     std::vector<ProfEvent> prof;
     long long prof_launches = 0;
     double prof_ms = 0, prof_flops = 0;
-    long long cls_launches[PROF_CLASSES] = {0, 0, 0, 0, 0};
-    double cls_ms[PROF_CLASSES] = {0, 0, 0, 0, 0}, cls_flops[PROF_CLASSES] = {0, 0, 0, 0, 0};
+    long long cls_launches[PROF_CLASSES] = {0, 0, 0, 0, 0, 0};
+    double cls_ms[PROF_CLASSES] = {0, 0, 0, 0, 0, 0}, cls_flops[PROF_CLASSES] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t prof_base = nullptr;          // time origin of the timeline (recorded by eqvio_profile_enable)
     std::vector<TimelineEntry> timeline;      // filled by eqvio_profile_read while profiling is on
     int prof_cls = PROF_UPDATE;  // class tag applied to the launches that follow
@@ -266,6 +269,7 @@ static void free_device(Filter* f) {
 
 // (Re)allocate every capacity-dependent buffer for `cap` landmarks, preserving Sigma (n x n) and the
 // landmark arrays of the current N.
+static bool ozaki_size(const Filter* f, int N) { const int t = n_of(N) / OZ_TILE; return f->ozaki_S > 0 && t >= 2 && t * t >= f->ozaki_min_tiles; }
 static int ensure_capacity(Filter* f, int needN) {
     if (needN <= f->cap) return EQVIO_OK;
     int cap = f->cap ? f->cap : 64;
@@ -320,7 +324,7 @@ static int ensure_capacity(Filter* f, int needN) {
         CU_TRY(cudaStreamSynchronize(s));
         free_device(&o);
     }
-    if (f->ozaki_S > 0) {
+    if (ozaki_size(f, cap)) {
         const size_t bytes = oz_slices_bytes(n_of(cap), n_of(cap), OZ_MAX_SLICES);
         for (void* q : {(void*)f->ozF[0], (void*)f->ozF[1], (void*)f->ozS, (void*)f->ozW, (void*)f->ozeF[0], (void*)f->ozeF[1], (void*)f->ozeS, (void*)f->ozeW, (void*)f->ozH}) cudaFree(q);
         for (int8_t** q : {&f->ozF[0], &f->ozF[1], &f->ozS, &f->ozW}) { CU_TRY(cudaMalloc((void**)q, bytes)); CU_TRY(cudaMemsetAsync(*q, 0, bytes, s)); }
@@ -569,7 +573,7 @@ static RiccatiOut riccati_out(Filter* f) {
 // leaves over 128) are thin DMMA products.  Reference association kept: W = F Sigma, Sigma' = W F^T + T B_b R B_b^T + T P.
 // Operands are split with the inner-dimension scales ozH (OzKScale): F rows with +h, Sigma columns and W rows with -h.  Each
 // product's epilogue leaves the exponent maxima of its output, so W and the next step's Sigma are split in one pass.
-static bool ozaki_applies(const Filter* f) { return f->ozaki_S > 0 && n_of(f->N) >= 2 * OZ_TILE && f->ozS != nullptr; }
+static bool ozaki_applies(const Filter* f) { return ozaki_size(f, f->N) && f->ozS != nullptr; }
 // A strip in front of the int8 core block: a few rows or columns of the product with the full k loop — tiles x 97 k-tiles on one tile
 // row, far too few CTAs to fill the GPU and each latency-bound (measured 30-57 us per strip) — so every tile is cut into k-ranges.
 static int strip_gemm(Filter* f, const GemmProblem& g, int which, cudaStream_t st) {
@@ -631,7 +635,7 @@ static int riccati_ozaki(Filter* f, double T) {
     {
         const OzExponentsOut exo{f->ozeW, nullptr, f->ozH, m0, m0};
         ProfEvent pe;
-        prof_begin(f, pe, st, PROF_RICCATI, 2.0 * Mc * Mc * n);
+        prof_begin(f, pe, st, PROF_RICCATI_I8, 2.0 * Mc * Mc * n);
         CU_TRY(oz_gemm(oF, oS, Mc, Mc, 1.0, 0.0, nullptr, 0, f->W + m0 + (size_t)m0 * ld, ld, st, nullptr, &exo));
         prof_end(f, pe, st);
         f->launches += 1;
@@ -664,7 +668,7 @@ static int riccati_ozaki(Filter* f, double T) {
         // a warp reduction per column; the split adds one to every exponent to cover a maximum that straddles a power of two)
         const OzExponentsOut exo{f->ozeS, nullptr, f->ozH, m0, m0};
         ProfEvent pe;
-        prof_begin(f, pe, st, PROF_RICCATI, 2.0 * Mc * Mc * n);
+        prof_begin(f, pe, st, PROF_RICCATI_I8, 2.0 * Mc * Mc * n);
         CU_TRY(oz_gemm(oW, oF, Mc, Mc, 1.0, 0.0, nullptr, 0, f->Sigma2 + m0 + (size_t)m0 * ld, ld, st, &ric, &exo));
         prof_end(f, pe, st);
         f->launches += 1;
@@ -1096,6 +1100,7 @@ static int create_impl(Filter* f) {
     }
     if (const char* e = getenv("EQVIO_SIGMA_AFTER_LIFT")) f->sigma_after_lift = atoi(e);
     if (const char* e = getenv("EQVIO_OZAKI")) { f->ozaki_S = atoi(e); if (f->ozaki_S < 7 || f->ozaki_S > OZ_MAX_SLICES) f->ozaki_S = 0; }
+    if (const char* e = getenv("EQVIO_OZAKI_MIN_TILES")) f->ozaki_min_tiles = std::max(4, atoi(e));
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
     if (const char* e = getenv("EQVIO_STAMPS"))
         if (e[0] == '1') { CU_TRY(dalloc(&f->stamps, 512)); CU_TRY(cudaMemset(f->stamps, 0, 512 * 8)); }
@@ -2021,6 +2026,11 @@ int eqvio_profile_timeline(eqvio_handle_t f, double* out, size_t cap_entries, si
         const size_t k = std::min(cap_entries, f->timeline.size());
         memcpy(out, f->timeline.data(), k * sizeof(TimelineEntry));
     }
+    return EQVIO_OK;
+}
+int eqvio_riccati_arith(eqvio_handle_t f, int* int8_slices) {
+    if (!f || !int8_slices) return EQVIO_ERR_ARG;
+    *int8_slices = ozaki_applies(f) ? f->ozaki_S : 0;
     return EQVIO_OK;
 }
 int eqvio_stream(eqvio_handle_t f, void** stream) {

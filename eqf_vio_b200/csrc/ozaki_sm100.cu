@@ -440,6 +440,403 @@ __global__ void k_oz_diag_scale(const double* Sigma, int ld, int n, int* h) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// The Riccati step as two launches of ONE kernel (fused form, see OzFusedParams in the header)
+// ------------------------------------------------------------------------------------------------
+static constexpr int OZF_YC = 12;                                  // short side of a border job (covers the 11 base states in one piece)
+static constexpr int OZF_RED_BYTES = OZ_EPI_WARPS * 32 * OZF_YC * 8;   // partial sums of a border job: [warp][lane][y]
+static constexpr int OZF_TR_LD = 65;                               // row pitch (doubles) of the transposed-store staging
+template <int S> struct OzFusedCfg {
+    static constexpr int STAGE_BYTES = 2 * S * OZ_SLICE_TILE_BYTES;   // A slices then B slices
+    static constexpr int STAGES = 3;
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = PIPE_BYTES + OZF_RED_BYTES + 1024 + 256;
+    static_assert(OZ_EPI_WARPS * 32 * OZF_TR_LD * 8 <= PIPE_BYTES, "transposed-store staging reuses the pipeline stages");
+};
+static constexpr int OZ_EX_RESET = (int)0xC0C0C0C0;               // what oz_reset_exponents' memset leaves: a very negative exponent
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the eight epilogue warps
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One border job on the eight epilogue warps: out(x, y) = sum_k P(x, k) Q(y, k) for 32 x's (one per lane) and up to OZF_YC y's, the k
+// range cut into eight pieces (one per warp) whose partial sums are added in warp order — a fixed order, run to run identical.
+//   P(x, k) at P[x psx + k psk], Q(y, k) at Q[y qsy + k qsk].
+// Returns the value of output t = threadIdx (and t + 256) through `store`.
+struct OzJob { const double* P; long psx, psk; const double* Q; long qsy, qsk; int x0, xmax, y0, ny, n; };
+__device__ __forceinline__ void oz_job_partial(const OzJob& jb, double* red, int tid) {
+    const int w = tid >> 5, l = tid & 31;
+    const int kc = (((jb.n + OZ_EPI_WARPS - 1) / OZ_EPI_WARPS) + 3) & ~3;
+    const int k0 = w * kc, k1 = min(jb.n, k0 + kc);
+    const int x = jb.x0 + l;
+    const bool valid = x < jb.xmax;
+    double acc[OZF_YC];
+#pragma unroll
+    for (int y = 0; y < OZF_YC; ++y) acc[y] = 0.0;
+    const double* Pp = jb.P + (size_t)(valid ? x : jb.x0) * jb.psx;
+    const double* Qp = jb.Q + (size_t)jb.y0 * jb.qsy;
+#pragma unroll 2
+    for (int k = k0; k < k1; ++k) {
+        const double pv = Pp[(size_t)k * jb.psk];
+#pragma unroll
+        for (int y = 0; y < OZF_YC; ++y)
+            if (y < jb.ny) acc[y] = fma(pv, Qp[(size_t)y * jb.qsy + (size_t)k * jb.qsk], acc[y]);
+    }
+#pragma unroll
+    for (int y = 0; y < OZF_YC; ++y) red[(w * 32 + l) * OZF_YC + y] = valid ? acc[y] : 0.0;
+}
+__device__ __forceinline__ double oz_job_sum(const double* red, int l, int y) {
+    double v = red[l * OZF_YC + y];
+#pragma unroll
+    for (int w = 1; w < OZ_EPI_WARPS; ++w) v += red[(w * 32 + l) * OZF_YC + y];
+    return v;
+}
+__device__ __forceinline__ double oz_process_noise(const OzFusedParams& p, int g) {
+    return g < 3 ? p.Pd[0] : g < 6 ? p.Pd[1] : g < 8 ? p.Pd[2] : g < 11 ? p.Pd[3] : p.Pd[4];
+}
+
+// digits of 16 already-scaled values (|x| <= 64): S slices of one 16-byte chunk each
+template <int S>
+__device__ __forceinline__ void oz_emit16(double (&v)[16], uint4* dst) {
+    const double magic = 6755399441055744.0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const double t = v[c] + magic;
+            const double d = t - magic;
+            v[c] = (v[c] - d) * 128.0;
+            w[c >> 2] |= ((uint32_t)__double2loint(t) & 0xffu) << (8 * (c & 3));
+        }
+        dst[(size_t)s * (OZ_SLICE_TILE_BYTES / 16)] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParams p) {
+    using namespace oz;
+    using Cfg = OzFusedCfg<S>;
+    extern __shared__ uint8_t oz_smem_raw[];
+    const uint32_t raw = smem_u32(oz_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = oz_smem_raw + (base - raw);
+    double* red = reinterpret_cast<double*>(smem + Cfg::PIPE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + OZF_RED_BYTES);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* acc_full = empty + Cfg::STAGES;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    int* ticket_slot = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Mt = p.Mt, T = Mt * Mt, KB = p.KB;
+    constexpr int nbatch = (S + OZ_DIAGS_PER_BATCH - 1) / OZ_DIAGS_PER_BATCH;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, OZ_EPI_WARPS);
+        mbar_fence_init();
+        // tiles by ticket: a CTA that waits for its tile row only ever waits for CTAs that started before it or that the hardware can
+        // still start (the lowest unfinished tile row is always completely dispatched), whatever the grid size
+        *ticket_slot = atomicAdd(p.sync, 1);
+    }
+    if (warp == OZ_MMA_WARP) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int ticket = *ticket_slot;
+    const int tile_m = ticket / Mt, tile_n = ticket - tile_m * Mt;
+    // the other tick parity's synchronisation words and exponent maxima (nothing running touches them) are cleared for its next launch
+    if (ticket == 0)
+        for (int i = threadIdx.x; i <= Mt; i += OZ_THREADS) p.syncReset[i] = 0;
+    if (tile_n == 0 && threadIdx.x < OZ_TILE) p.exReset[tile_m * OZ_TILE + threadIdx.x] = OZ_EX_RESET;
+
+    if (warp == OZ_PRODUCER_WARP) {
+        if (lane == 0) {
+            const int8_t* gA = p.slA + (size_t)tile_m * KB * S * OZ_SLICE_TILE_BYTES;
+            const int8_t* gB = p.slB + (size_t)tile_n * KB * S * OZ_SLICE_TILE_BYTES;
+            uint32_t it = 0;
+            for (int b = 0; b < nbatch; ++b) {
+                const int nS = min(OZ_DIAGS_PER_BATCH * (b + 1), S);
+                const uint32_t bytes = (uint32_t)(nS * OZ_SLICE_TILE_BYTES);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % Cfg::STAGES;
+                    mbar_wait(&empty[s], ((it / Cfg::STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], 2 * bytes);
+                    const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + S * OZ_SLICE_TILE_BYTES;
+                    bulk_load(sa, gA + (size_t)kb * S * OZ_SLICE_TILE_BYTES, bytes, &full[s]);
+                    bulk_load(sb, gB + (size_t)kb * S * OZ_SLICE_TILE_BYTES, bytes, &full[s]);
+                }
+            }
+        }
+    } else if (warp == OZ_MMA_WARP) {
+        uint32_t it = 0;
+        const uint64_t adesc0 = smem_desc_sw32(base), bdesc0 = smem_desc_sw32(base + S * OZ_SLICE_TILE_BYTES);
+#pragma unroll
+        for (int b = 0; b < nbatch; ++b) {
+            constexpr int DPB = OZ_DIAGS_PER_BATCH;
+            const int dmin = DPB * b, dmax = (dmin + DPB - 1 < S - 1) ? dmin + DPB - 1 : S - 1;
+            if (b > 0) {
+                mbar_wait(acc_empty, (uint32_t)((b - 1) & 1));
+                tc_fence_after();
+            }
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % Cfg::STAGES;
+                mbar_wait(&full[s], (it / Cfg::STAGES) & 1);
+                tc_fence_after();
+                const uint64_t soff = (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
+                const uint32_t first = kb > 0 ? 1u : 0u;
+                if (elect_one()) {
+#pragma unroll
+                    for (int d = dmin; d <= dmax; ++d) {
+                        const uint32_t acc = tmem_base + (uint32_t)((d - dmin) * OZ_TILE);
+#pragma unroll
+                        for (int a = 0; a <= d; ++a)
+                            mma_i8(acc, adesc0 + soff + (uint64_t)(a * (OZ_SLICE_TILE_BYTES >> 4)), bdesc0 + soff + (uint64_t)((d - a) * (OZ_SLICE_TILE_BYTES >> 4)),
+                                   OZ_IDESC, a > 0 ? 1u : first);
+                    }
+                    tc_commit(&empty[s]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) tc_commit(acc_full);
+            __syncwarp();
+        }
+    } else {
+        // ===== the eight epilogue warps =====
+        const int tid = threadIdx.x;            // 0 .. 255
+        const int q = warp & 3, hh = warp >> 2;
+        const int m0 = p.m0, n = p.n, ld = p.ld;
+        const double* Wx = (p.phase == 2 ? p.X : p.Out) + (size_t)p.n16 * ld;   // T B_b R (six columns behind W)
+        const double* Fx = p.F + (size_t)p.n16 * ld;                            // B_b
+        const double Tstep = p.phase == 2 ? *p.T_dev : 0.0;
+        int* cnt = p.sync + 1;
+
+        // ---- border jobs: the rows / columns in front of the 128-aligned block, in fp64, while the tensor core works.
+        // inner jobs (operand rows of this tile row x border inner indices) feed the exponents and count towards the tile-row barrier
+        const int nch = (m0 + OZF_YC - 1) / OZF_YC;
+        const int nIB = 4 * nch, nOB = ((n + 31) / 32) * nch;
+        const int oq = (Mt - 1 - tile_n) * Mt + tile_m;   // outer jobs start with the CTAs that have no inner job
+        int my_inner = 0, my_outer = 0;
+        for (int j = tile_n; j < nIB; j += Mt) ++my_inner;
+        for (int j = oq; j < nOB; j += T) ++my_outer;
+        const int my_jobs = my_inner + my_outer;
+        const int first_window = nbatch > 1 ? max(1, (my_jobs + 2) / 3) : my_jobs;
+        int done_jobs = 0;
+        auto run_jobs = [&](int upto) {
+            for (; done_jobs < upto; ++done_jobs) {
+                const bool inner = done_jobs < my_inner;
+                const int job = inner ? tile_n + done_jobs * Mt : oq + (done_jobs - my_inner) * T;
+                const int xb = job / nch, ch = job - xb * nch;
+                OzJob jb;
+                jb.n = n; jb.y0 = ch * OZF_YC; jb.ny = min(OZF_YC, m0 - jb.y0); jb.xmax = n;
+                jb.x0 = inner ? m0 + tile_m * OZ_TILE + xb * 32 : xb * 32;
+                bool transposed_out;   // out(x, y) stored at Out[y + ld x] instead of Out[x + ld y]
+                if (p.phase == 1) {
+                    if (inner) { jb.P = p.F; jb.psx = 1; jb.psk = ld; jb.Q = p.X; jb.qsy = ld; jb.qsk = 1; transposed_out = false; }   // W[x, y] = sum_k F[x, k] Sigma[k, y]
+                    else       { jb.P = p.X; jb.psx = ld; jb.psk = 1; jb.Q = p.F; jb.qsy = 1; jb.qsk = ld; transposed_out = true; }    // W[y, x] = sum_k F[y, k] Sigma[k, x]
+                } else {
+                    if (inner) { jb.P = p.F; jb.psx = 1; jb.psk = ld; jb.Q = p.X; jb.qsy = 1; jb.qsk = ld; transposed_out = true; }    // Sigma'[y, x] = sum_k W[y, k] F[x, k]
+                    else       { jb.P = p.X; jb.psx = 1; jb.psk = ld; jb.Q = p.F; jb.qsy = 1; jb.qsk = ld; transposed_out = false; }   // Sigma'[x, y] = sum_k W[x, k] F[y, k]
+                }
+                oz_job_partial(jb, red, tid);
+                epi_bar();
+                for (int t = tid; t < 32 * OZF_YC; t += 256) {
+                    int l, y;
+                    if (transposed_out) { l = t / OZF_YC; y = t - l * OZF_YC; } else { y = t >> 5; l = t & 31; }
+                    const int x = jb.x0 + l, gy = jb.y0 + y;
+                    if (x < jb.xmax && y < jb.ny) {
+                        double v = oz_job_sum(red, l, y);
+                        // Sigma' row index i / column index j of this output
+                        if (p.phase == 2) {
+                            const int gi = transposed_out ? gy : x, gj = transposed_out ? x : gy;
+                            double r6 = 0.0;
+#pragma unroll
+                            for (int c = 0; c < 6; ++c) r6 = fma(Wx[(size_t)gi + (size_t)ld * c], Fx[(size_t)gj + (size_t)ld * c], r6);
+                            v += r6;
+                            if (gi == gj) v += Tstep * oz_process_noise(p, gi);
+                        }
+                        p.Out[transposed_out ? (size_t)gy + (size_t)ld * x : (size_t)x + (size_t)ld * gy] = v;
+                        if (inner) atomicMax(p.exOut + (x - m0), oz_exponent(v) - p.h[gy]);
+                    }
+                }
+                __threadfence();
+                epi_bar();
+                if (inner && tid == 0) atomicAdd(cnt + tile_m, 1);
+            }
+        };
+        run_jobs(first_window);
+
+        double acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+        for (int b = 0; b < nbatch; ++b) {
+            if (b == nbatch - 1) run_jobs(my_jobs);
+            const int dmin = OZ_DIAGS_PER_BATCH * b, dmax = min(dmin + OZ_DIAGS_PER_BATCH - 1, S - 1);
+            mbar_wait(acc_full, (uint32_t)(b & 1));
+            tc_fence_after();
+            for (int d = dmin; d <= dmax; ++d) {
+                const double scale = oz_pow2(-7 * d);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((d - dmin) * OZ_TILE + hh * 64);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + half * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[half * 32 + j] = fma((double)(int)v[j], scale, acc[half * 32 + j]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+        // ---- this tile in fp64: D[row, col], row = operand row (phase 1: row i of W; phase 2: column j of Sigma'), col = inner index
+        const int r = q * 32 + lane;                       // tile-local row
+        const int row = tile_m * OZ_TILE + r, grow = m0 + row;
+        const int col0 = tile_n * OZ_TILE + hh * 64;       // block-local first column
+        {
+            const double ra = oz_pow2(max(p.exA[row], -900) - 12);
+            double fx[6] = {0, 0, 0, 0, 0, 0};
+            if (p.phase == 2) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) fx[c] = Fx[(size_t)grow + (size_t)ld * c];
+            }
+            int e = -2000;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const int col = col0 + j, gcol = m0 + col;
+                double v = (acc[j] * ra) * oz_pow2(max(p.exB[col], -900));
+                if (p.phase == 2) {   // Sigma'[i = gcol, j = grow] += (T B_b R B_b^T)[i, j] + T P on the diagonal (VIOFilter.cpp:188-189)
+                    double r6 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) r6 = fma(Wx[(size_t)gcol + (size_t)ld * c], fx[c], r6);
+                    v += r6;
+                    if (grow == gcol) v += Tstep * oz_process_noise(p, grow);
+                }
+                e = max(e, oz_exponent(v) - p.h[gcol]);
+                acc[j] = v;
+            }
+            atomicMax(p.exOut + row, e);
+        }
+        if (p.phase == 1) {   // W[grow, gcol]: the lanes of a warp are 32 consecutive rows of one column
+#pragma unroll
+            for (int j = 0; j < 64; ++j) p.Out[(size_t)grow + (size_t)ld * (m0 + col0 + j)] = acc[j];
+        } else {              // Sigma'[gcol, grow]: through shared memory (the pipeline stages are idle now) so that lanes are consecutive gcol
+            double* tr = reinterpret_cast<double*>(smem) + (size_t)warp * 32 * OZF_TR_LD;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) tr[lane * OZF_TR_LD + j] = acc[j];
+            __syncwarp();
+            for (int rr = 0; rr < 32; ++rr) {
+                double* dst = p.Out + (size_t)(m0 + col0) + (size_t)ld * (m0 + tile_m * OZ_TILE + q * 32 + rr);
+                dst[lane] = tr[rr * OZF_TR_LD + lane];
+                dst[lane + 32] = tr[rr * OZF_TR_LD + lane + 32];
+            }
+        }
+        // ---- tile-row barrier: every tile of this row of tiles and its inner border jobs have published their maxima
+        __threadfence();
+        epi_bar();
+        if (tid == 0) {
+            atomicAdd(cnt + tile_m, 1);
+            const int expected = Mt + nIB;
+            while (ld_acquire(cnt + tile_m) < expected) __nanosleep(200);
+        }
+        epi_bar();
+        // ---- emission: this tile as int8 slices of the next product's operand (rows = operand rows, inner index = block-local column)
+        {
+            const int e = max(__ldcg(p.exOut + row), -900);
+            const double up = oz_pow2(6 - e);
+            const int sw = (r >> 2) & 1;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int kk = col0 + 16 * c4;             // rotated inner index k' of the chunk's first column
+                double v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = (acc[c4 * 16 + c] * oz_pow2(-p.h[m0 + kk + c])) * up;
+                const size_t tile = ((size_t)tile_m * KB + (kk >> 5)) * S;
+                const int in_tile = r * OZ_KBLOCK + ((((kk & 31) >> 4) ^ sw) << 4);
+                oz_emit16<S>(v, reinterpret_cast<uint4*>(p.slOut + tile * OZ_SLICE_TILE_BYTES + in_tile));
+            }
+        }
+        // the inner border of this tile row (inner indices [0, m0), stored behind the block: k' = Mc + index), zero-padded to a whole k-block
+        if (tile_n == Mt - 1) {
+            const int rb = tid & 127, rowb = tile_m * OZ_TILE + rb, growb = m0 + rowb;
+            const int e = max(__ldcg(p.exOut + rowb), -900);
+            const double up = oz_pow2(6 - e);
+            const int sw = (rb >> 2) & 1;
+            const int nchunk = (KB - p.Mc / OZ_KBLOCK) * 2;       // 16-byte chunks per row
+            for (int ck = tid >> 7; ck < nchunk; ck += 2) {
+                double v[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int idx = ck * 16 + c;                  // border inner index
+                    double x = 0.0;
+                    if (idx < m0) {
+                        x = __ldcg(p.phase == 1 ? p.Out + (size_t)growb + (size_t)ld * idx : p.Out + (size_t)idx + (size_t)ld * growb);
+                        x = (x * oz_pow2(-p.h[idx])) * up;
+                    }
+                    v[c] = x;
+                }
+                const int kk = p.Mc + ck * 16;
+                const size_t tile = ((size_t)tile_m * KB + (kk >> 5)) * S;
+                const int in_tile = rb * OZ_KBLOCK + ((((kk & 31) >> 4) ^ sw) << 4);
+                oz_emit16<S>(v, reinterpret_cast<uint4*>(p.slOut + tile * OZ_SLICE_TILE_BYTES + in_tile));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == OZ_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// F's landmark rows as int8 slices without reading the zeros: row g >= 11 of F = I + T A_b (EqFMatrices.cpp:292-312, VIOFilter.cpp:177-185)
+// holds nine entries — columns 0..2 (-T B_i), 8..10 (T A_iv) and its landmark's own 3 x 3 block (I + T A_ii), exactly what
+// k_feature_step writes — so the split of the rows [m0, n) is nine bytes per row and slice at positions that depend on the row only;
+// every other byte of the (zero-initialised) slice array stays zero.  ex[row] = the row's exponent (entries scaled by 2^(+h[column])).
+__global__ void __launch_bounds__(128) k_oz_split_F_rows(const double* F, int ld, int n, int m0, int Mc, int KB, int S, const int* h, int8_t* slices, int* ex) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;   // block-local row
+    if (row >= Mc) return;
+    const int g = m0 + row;
+    const int b0 = 11 + (g - 11) / 3 * 3;
+    int cols[9] = {0, 1, 2, 8, 9, 10, b0, b0 + 1, b0 + 2};
+    double v[9];
+    int e = -2000;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        v[c] = g < n ? F[(size_t)g + (size_t)ld * cols[c]] * oz_pow2(h[cols[c]]) : 0.0;
+        e = max(e, oz_exponent(v[c]));
+    }
+    ex[row] = e;
+    const double up = oz_pow2(6 - max(e, -900));
+    const double magic = 6755399441055744.0;
+    const int sw = (row >> 2) & 1;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        const int kk = cols[c] >= m0 ? cols[c] - m0 : Mc + cols[c];   // rotated inner index
+        const size_t tile = ((size_t)(row / OZ_TILE) * KB + (kk >> 5)) * S;
+        int8_t* dst = slices + tile * OZ_SLICE_TILE_BYTES + (row % OZ_TILE) * OZ_KBLOCK + ((((kk & 31) >> 4) ^ sw) << 4) + (kk & 15);
+        double x = v[c] * up;
+        for (int s = 0; s < S; ++s) {
+            const double t = x + magic;
+            const double d = t - magic;
+            x = (x - d) * 128.0;
+            dst[(size_t)s * OZ_SLICE_TILE_BYTES] = (int8_t)(__double2loint(t) & 0xff);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static inline int oz_round_up(int a, int b) { return (a + b - 1) / b * b; }

@@ -236,7 +236,7 @@ class VIOFilter:
         abi.check(self._L.eqvio_profile_read(self._h, C.byref(n), C.byref(ms), C.byref(fl), int(reset)), "eqvio_profile_read")
         return n.value, ms.value, fl.value
 
-    PROFILE_CLASSES = ("riccati_gemm", "update_gemm", "schur_gemm", "schur_diag_lu", "small_kernels")
+    PROFILE_CLASSES = ("riccati_gemm", "update_gemm", "schur_gemm", "schur_diag_lu", "small_kernels", "riccati_i8_gemm")
     PROFILE_LANES = ("main", "side", "lift", "main_helper", "lift_helper", "other")
 
     def profile_timeline(self) -> np.ndarray:
@@ -256,6 +256,12 @@ class VIOFilter:
             abi.check(self._L.eqvio_profile_read_class(self._h, cls, C.byref(n), C.byref(ms), C.byref(fl), int(reset)), "eqvio_profile_read_class")
             out[name] = {"launches": n.value, "ms": ms.value, "flops": fl.value}
         return out
+
+    def riccati_int8_slices(self) -> int:
+        """0: the Riccati products run on fp64 DMMA at the current N; S > 0: on the int8 tensor cores with S slices."""
+        s = C.c_int()
+        abi.check(self._L.eqvio_riccati_arith(self._h, C.byref(s)), "eqvio_riccati_arith")
+        return s.value
 
     def stream_ptr(self) -> int:
         p = C.c_void_p()

@@ -255,13 +255,19 @@ int eqvio_profile_read(eqvio_handle_t h, long long* gemm_launches, double* gemm_
                        int reset);
 /* Same, per class of launch: 0 = Riccati GEMMs (F Sigma, W F^T), 1 = update GEMMs (C Sigma, S, Sigma C^T,
  * K, K C, Sigma - K C Sigma), 2 = GEMMs inside the blocked Schur eliminations (S^-1, Sigma_sub^-1),
- * 3 = the diagonal-block LU kernels of those eliminations (flops reported as 0). */
+ * 3 = the diagonal-block LU kernels of those eliminations (flops reported as 0), 4 = the O(N) / O(n m) kernels,
+ * 5 = the Riccati products issued on the int8 tensor cores (fp64-equivalent flops 2 M N K; see eqvio_riccati_arith). */
 int eqvio_profile_read_class(eqvio_handle_t h, int cls, long long* launches, double* ms, double* flops, int reset);
 /* Timeline of every bracketed launch since profiling was enabled: 5 doubles per entry — class (0-3 as
  * above, 4 = the O(N) / O(n m) kernels), stream lane (0 main, 1 side, 2 lift chain, 3 / 4 the chains' helper
  * streams), start ms, end ms (relative to eqvio_profile_enable), flops.  *count receives the number of
  * entries available; at most cap_entries are copied to out (may be NULL). */
 int eqvio_profile_timeline(eqvio_handle_t h, double* out, size_t cap_entries, size_t* count);
+/* Which arithmetic the Riccati step's two Sigma contractions (VIOFilter.cpp:188-189) run on at the current landmark count:
+ * *int8_slices = 0 — fp64 DMMA tiles; S > 0 — the 128-aligned landmark block as an exact sum of S (S + 1) / 2 int8 x int8 -> int32
+ * tensor-core products per fp64 product (tcgen05.mma kind::i8, Ozaki splitting with S slices of 7 bits; S = 8 carries 55 mantissa
+ * bits), the rows / columns in front of that block on fp64 DMMA.  Selected per size (environment EQVIO_OZAKI, 0 = never). */
+int eqvio_riccati_arith(eqvio_handle_t h, int* int8_slices);
 /* The handle's CUDA stream (cudaStream_t as void*), for callers that order their own work after it. */
 int eqvio_stream(eqvio_handle_t h, void** stream);
 const char* eqvio_status_string(int status);

@@ -27,5 +27,12 @@ for b in blocks[1:]:
                 c[k] += 1
                 break
     pretty = dm.get(name, name).replace("eqvio::", "")
-    pretty = re.sub(r"\(.*", "", pretty).replace("void ", "")
+    pretty = pretty.replace("void ", "")
+    depth = 0
+    for i, ch in enumerate(pretty):   # cut the argument list: the first "(" outside the template brackets
+        depth += ch == "<"
+        depth -= ch == ">"
+        if ch == "(" and depth == 0:
+            pretty = pretty[:i]
+            break
     print(f"| `{pretty}` | {len(ins)} | " + " | ".join(str(c[k]) for k in keys) + " |")
