@@ -123,6 +123,15 @@ struct eqvio_filter {
     bool oz_sigma_ex_valid = false;// ozeS holds the column exponents of the current Sigma (left there by the previous Riccati step's epilogue)
     bool oz_F_ready = false;       // the state stream has split this tick's F already
     size_t oz_bytes = 0;
+    // fused form (ozaki_sm100.cuh, OzFusedParams): both products emit their result as the next product's int8 operand themselves; F's
+    // rows are split on the state stream from their nine structural entries.  Exponent arrays and synchronisation words by tick parity.
+    int oz_fused = 1;              // EQVIO_OZAKI_FUSED=0: the unfused sequence (split kernels and DMMA strips between the products)
+    int *oz_exW[2] = {nullptr, nullptr}, *oz_exS[2] = {nullptr, nullptr};
+    int *oz_sync1[2] = {nullptr, nullptr}, *oz_sync2[2] = {nullptr, nullptr};
+    int* oz_words = nullptr;       // one allocation behind the eight arrays above
+    size_t oz_words_count = 0;
+    int oz_valid_par = -1;         // the tick parity the emitted Sigma slices / exponents / cleared words are valid for (the one after the step that left them)
+    int oz_F_layout[2] = {0, 0};   // n for which ozF[parity] was cleared (its non-structural bytes must be zero)
     int par = 0;                   // parity of the current Riccati tick: F == Fpp[par], W == Wpp[par]
     double *Fpp[2] = {nullptr, nullptr}, *Wpp[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -331,6 +340,17 @@ static int ensure_capacity(Filter* f, int needN) {
         for (int** q : {&f->ozeF[0], &f->ozeF[1], &f->ozeS, &f->ozeW, &f->ozH}) { CU_TRY(dalloc(q, (size_t)ld + 256)); CU_TRY(cudaMemsetAsync(*q, 0, ((size_t)ld + 256) * sizeof(int), s)); }
         f->oz_bytes = bytes;
         f->oz_h_valid = f->oz_sigma_ex_valid = f->oz_F_ready = false;
+        cudaFree(f->oz_words);
+        const size_t ex_len = (size_t)ld + 256;
+        f->oz_words_count = 4 * ex_len + 4 * OZ_FUSED_SYNC_INTS;
+        CU_TRY(dalloc(&f->oz_words, f->oz_words_count));
+        for (int i = 0; i < 2; ++i) {
+            f->oz_exW[i] = f->oz_words + (size_t)i * ex_len;
+            f->oz_exS[i] = f->oz_words + (size_t)(2 + i) * ex_len;
+            f->oz_sync1[i] = f->oz_words + 4 * ex_len + (size_t)i * OZ_FUSED_SYNC_INTS;
+            f->oz_sync2[i] = f->oz_words + 4 * ex_len + (size_t)(2 + i) * OZ_FUSED_SYNC_INTS;
+        }
+        f->oz_F_layout[0] = f->oz_F_layout[1] = 0;
     }
     f->cap = cap; f->ld = ld; f->ldm = ldm; f->ld2m = ld2m;
     f->L = L; f->L2 = L2;
@@ -682,8 +702,87 @@ static int riccati_ozaki(Filter* f, double T) {
     return EQVIO_OK;
 }
 
+static bool ozaki_fused_applies(const Filter* f) {
+    return ozaki_applies(f) && f->oz_fused && f->oz_words && oz_fused_supported(f->ozaki_S, n_of(f->N) / OZ_TILE);
+}
+// F's rows [m0, n) as int8 slices (nine structural entries per row) on stream `s`; the rest of the array is cleared when the layout changes
+static int split_F_rows(Filter* f, cudaStream_t s) {
+    const int n = n_of(f->N), m0 = n % OZ_TILE, par = f->par;
+    ProfScope ps(f, s, PROF_MISC);
+    if (f->oz_F_layout[par] != n) {
+        CU_TRY(cudaMemsetAsync(f->ozF[par], 0, f->oz_bytes, s));
+        f->oz_F_layout[par] = n;
+    }
+    CU_TRY(oz_split_F_rows(f->F, f->ld, n, m0, f->ozaki_S, f->ozH, f->ozF[par], f->ozeF[par], s));
+    f->launches += 1;
+    return EQVIO_OK;
+}
+// The Riccati step as two launches of k_oz_riccati (ozaki_sm100.cuh).  Steady state (between vision updates): nothing else — the previous
+// step's second launch left Sigma's slices and exponents, the state stream left F's.  After anything else changed Sigma: the
+// synchronisation words are cleared and Sigma is split by the generic kernels first.
+static int riccati_ozaki_fused(Filter* f, double T) {
+    const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld, S = f->ozaki_S, par = f->par;
+    const int Mc = n / OZ_TILE * OZ_TILE, m0 = n - Mc, Mt = Mc / OZ_TILE, KB = round_up(n, OZ_KBLOCK) / OZ_KBLOCK;
+    cudaStream_t st = f->stream;
+    f->prof_cls = PROF_RICCATI;
+    struct Guard { Filter* f; ~Guard() { f->prof_cls = PROF_UPDATE; f->cur = f->stream; } } guard{f};
+    if (f->oz_valid_par != par) f->oz_sigma_ex_valid = false;   // (kernel-level entry points repeat a parity)
+    if (!f->oz_h_valid) {   // (kernel-level entry points: integrate() refreshes the scales itself)
+        CU_TRY(oz_diag_scale(f->Sigma, ld, n, f->ozH, st));
+        f->launches += 1;
+        f->oz_h_valid = true; f->oz_sigma_ex_valid = false; f->oz_F_ready = false;
+    }
+    if (!f->oz_F_ready) {   // (kernel-level entry points: integrate() splits F on the state stream)
+        int rc = split_F_rows(f, st);
+        if (rc) return rc;
+    }
+    if (!f->oz_sigma_ex_valid) {
+        ProfScope ps(f, st, PROF_MISC);
+        const size_t ex_len = (size_t)ld + 256;
+        CU_TRY(cudaMemsetAsync(f->oz_words, 0xC0, 4 * ex_len * sizeof(int), st));
+        CU_TRY(cudaMemsetAsync(f->oz_words + 4 * ex_len, 0, 4 * OZ_FUSED_SYNC_INTS * sizeof(int), st));
+        const OzKScale kminus{f->ozH, -1};
+        OzOperand oS;
+        CU_TRY(oz_split(f->Sigma + (size_t)m0 * ld, ld, 1, Mc, n, S, &oS, f->ozS, f->oz_exS[par], st, &kminus, false, 0, m0));   // columns m0.. of Sigma, rotated inner index
+        f->launches += 3;
+    }
+    OzFusedParams p;
+    memset(&p, 0, sizeof p);
+    p.Mc = Mc; p.m0 = m0; p.n = n; p.n16 = n16; p.KB = KB; p.Mt = Mt; p.ld = ld;
+    p.slA = f->ozF[par]; p.exA = f->ozeF[par]; p.F = f->F; p.h = f->ozH;
+    p.T_dev = &f->sc->Tpp[par];
+    p.Pd[0] = f->s.biasOmegaProcessVariance; p.Pd[1] = f->s.biasAccelProcessVariance; p.Pd[2] = f->s.gravityProcessVariance;
+    p.Pd[3] = f->s.velocityProcessVariance; p.Pd[4] = f->s.pointProcessVariance;
+    {   // W = F Sigma, emitted as the second product's operand
+        p.phase = 1;
+        p.slB = f->ozS; p.exB = f->oz_exS[par]; p.X = f->Sigma; p.Out = f->W;
+        p.slOut = f->ozW; p.exOut = f->oz_exW[par]; p.exReset = f->oz_exW[par ^ 1];
+        p.sync = f->oz_sync1[par]; p.syncReset = f->oz_sync1[par ^ 1];
+        ProfEvent pe;
+        prof_begin(f, pe, st, PROF_RICCATI_I8, 2.0 * n * n * n);
+        CU_TRY(oz_riccati_fused(p, S, st));
+        prof_end(f, pe, st);
+        f->launches += 1;
+    }
+    {   // Sigma' = W F^T + T B_b R B_b^T + T P (computed as its transpose, F's rows on the A side again), emitted as the next step's operand
+        p.phase = 2;
+        p.slB = f->ozW; p.exB = f->oz_exW[par]; p.X = f->W; p.Out = f->Sigma2;
+        p.slOut = f->ozS; p.exOut = f->oz_exS[par ^ 1]; p.exReset = f->oz_exS[par];
+        p.sync = f->oz_sync2[par]; p.syncReset = f->oz_sync2[par ^ 1];
+        ProfEvent pe;
+        prof_begin(f, pe, st, PROF_RICCATI_I8, 2.0 * n * n * n);
+        CU_TRY(oz_riccati_fused(p, S, st));
+        prof_end(f, pe, st);
+        f->launches += 1;
+    }
+    f->oz_sigma_ex_valid = true;
+    f->oz_valid_par = par ^ 1;
+    return EQVIO_OK;
+}
+
 static int riccati_gemms(Filter* f, double T) {
     const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld;
+    if (ozaki_fused_applies(f)) return riccati_ozaki_fused(f, T);
     if (ozaki_applies(f)) return riccati_ozaki(f, T);
     f->prof_cls = PROF_RICCATI;
     const GemmProblem g1 = make_problem(f, 0, n, n, n, 1.0, f->F, ld, f->Sigma, ld, 0.0, nullptr, 0, f->W, ld, 0, 0.0);
@@ -753,15 +852,21 @@ static int integrate(Filter* f, double newTime, bool doRiccati, const double* om
         launch_feature_step(ss, f->st, f->sc, f->L, f->N, a.do_riccati, a.discrete_lift, ro);
         f->launches += 1;
     }
+    if (oz && a.do_integrate && ozaki_fused_applies(f)) {
+        int rc = split_F_rows(f, ss);
+        if (rc) return rc;
+        f->oz_F_ready = true;
+    }
     // ---- main stream: everything queued there from now on sees this tick's state
     CU_TRY(cudaEventRecord(f->ev_state, ss));
     CU_TRY(cudaStreamWaitEvent(f->stream, f->ev_state, 0));
     if (a.do_integrate) {
         if (a.do_riccati) {
             // the two Sigma GEMMs read T from device memory (written by k_step_prepare): replayable
-            const int gflags = f->par | (oz && f->oz_sigma_ex_valid ? 2 : 0);
+            if (oz && ozaki_fused_applies(f) && f->oz_valid_par != f->par) f->oz_sigma_ex_valid = false;
+            const int gflags = f->par | (oz && f->oz_sigma_ex_valid ? 2 : 0) | (oz && f->oz_F_ready ? 4 : 0);
             const int st = run_graphed(f, GRAPH_RICCATI, gflags, [&]() { return riccati_gemms(f, a.T); });
-            if (oz) { f->oz_sigma_ex_valid = true; f->oz_F_ready = false; }   // (a replayed graph does not run the host code that sets them)
+            if (oz) { f->oz_sigma_ex_valid = true; f->oz_F_ready = false; f->oz_valid_par = f->par ^ 1; }   // (a replayed graph does not run the host code that sets them)
             if (st) return st;
             std::swap(f->Sigma, f->Sigma2);   // the step wrote the twin buffer
             CU_TRY(cudaEventRecord(f->ev_gemm[f->par], f->stream));
@@ -1051,6 +1156,7 @@ static void destroy_filter(Filter* f) {
     cudaFree(f->sk_sync); cudaFree(f->sk_ws); cudaFree(f->splitk_ws);
     for (int i = 0; i < 2; ++i) { cudaFree(f->strip_ws[i]); cudaFree(f->strip_cnt[i]); }
     for (void* q : {(void*)f->ozF[0], (void*)f->ozF[1], (void*)f->ozS, (void*)f->ozW, (void*)f->ozeF[0], (void*)f->ozeF[1], (void*)f->ozeS, (void*)f->ozeW, (void*)f->ozH}) cudaFree(q);
+    cudaFree(f->oz_words);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->pose_pub); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
@@ -1101,6 +1207,7 @@ static int create_impl(Filter* f) {
     if (const char* e = getenv("EQVIO_SIGMA_AFTER_LIFT")) f->sigma_after_lift = atoi(e);
     if (const char* e = getenv("EQVIO_OZAKI")) { f->ozaki_S = atoi(e); if (f->ozaki_S < 7 || f->ozaki_S > OZ_MAX_SLICES) f->ozaki_S = 0; }
     if (const char* e = getenv("EQVIO_OZAKI_MIN_TILES")) f->ozaki_min_tiles = std::max(4, atoi(e));
+    if (const char* e = getenv("EQVIO_OZAKI_FUSED")) f->oz_fused = atoi(e);
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
     if (const char* e = getenv("EQVIO_STAMPS"))
         if (e[0] == '1') { CU_TRY(dalloc(&f->stamps, 512)); CU_TRY(cudaMemset(f->stamps, 0, 512 * 8)); }

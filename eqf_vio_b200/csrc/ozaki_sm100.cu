@@ -346,21 +346,25 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
 __device__ __forceinline__ double oz_kscaled(double x, const int* h, int hsign, int kidx) {
     return h ? x * oz_pow2(hsign * h[kidx]) : x;
 }
-template <int KW>   // tile of 32 rows x KW k (KW = 32 or 128), t[32][KW + 1]
+// stored (rotated) inner index -> source index: the first krot source indices are stored behind the other k - krot
+__device__ __forceinline__ int oz_unrot(int kk, int k, int krot) { return kk < k - krot ? kk + krot : kk - (k - krot); }
+template <int KW>   // tile of 32 rows x KW k (KW = 32 or 128), t[32][KW + 1]; k0 is a STORED index
 __device__ __forceinline__ void oz_load_tile(const double* X, long sr, long sk, int r0, int k0, int rows, int k, const int* h, int hsign,
-                                             double (*t)[KW + 1]) {
+                                             double (*t)[KW + 1], int krot = 0) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     if (sk == 1) {   // k contiguous: a warp reads 32 consecutive k of one row
 #pragma unroll
         for (int i = 0; i < KW / 8; ++i) {
             const int r = ty + 8 * (i & 3), kk = tx + 32 * (i >> 2);
-            t[r][kk] = (r0 + r < rows && k0 + kk < k) ? oz_kscaled(X[(size_t)(r0 + r) * sr + (k0 + kk)], h, hsign, k0 + kk) : 0.0;
+            const int ks = oz_unrot(k0 + kk, k, krot);
+            t[r][kk] = (r0 + r < rows && k0 + kk < k) ? oz_kscaled(X[(size_t)(r0 + r) * sr + ks], h, hsign, ks) : 0.0;
         }
     } else {         // rows contiguous (or general): a warp reads 32 consecutive rows at one k
 #pragma unroll
         for (int i = 0; i < KW / 8; ++i) {
             const int kk = ty + 8 * i;
-            t[tx][kk] = (r0 + tx < rows && k0 + kk < k) ? oz_kscaled(X[(size_t)(r0 + tx) * sr + (size_t)(k0 + kk) * sk], h, hsign, k0 + kk) : 0.0;
+            const int ks = oz_unrot(k0 + kk, k, krot);
+            t[tx][kk] = (r0 + tx < rows && k0 + kk < k) ? oz_kscaled(X[(size_t)(r0 + tx) * sr + (size_t)ks * sk], h, hsign, ks) : 0.0;
         }
     }
 }
@@ -389,11 +393,11 @@ __global__ void __launch_bounds__(256) k_oz_rowmax(const double* X, long sr, lon
 // digits: x 2^-e 2^6 = d0 + r0, |r| <= 1/2; then r 2^7 = d + r' ... every step exact in fp64, every digit in [-64, 64].
 // A block takes 32 rows x 128 k; a thread 16 consecutive k of one row, one 16-byte store per slice (a warp: four full 128-byte lines).
 __global__ void __launch_bounds__(256) k_oz_split(const double* X, long sr, long sk, int rows, int k, const int* h, int hsign, int* ex,
-                                                  int ex_margin, int8_t* slices, int rows_pad, int k_pad, int S) {
+                                                  int ex_margin, int8_t* slices, int rows_pad, int k_pad, int S, int krot) {
     extern __shared__ double oz_split_smem[];
     double(*t)[129] = reinterpret_cast<double(*)[129]>(oz_split_smem);
     const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 128;
-    oz_load_tile<128>(X, sr, sk, r0, k0, rows, k, h, hsign, t);
+    oz_load_tile<128>(X, sr, sk, r0, k0, rows, k, h, hsign, t, krot);
     __syncthreads();
     const int id = threadIdx.y * 32 + threadIdx.x, r = id >> 3, kg = id & 7;
     if (r0 + r >= rows || k0 + 16 * kg >= k_pad) return;
@@ -443,7 +447,7 @@ __global__ void k_oz_diag_scale(const double* Sigma, int ld, int n, int* h) {
 // The Riccati step as two launches of ONE kernel (fused form, see OzFusedParams in the header)
 // ------------------------------------------------------------------------------------------------
 static constexpr int OZF_YC = 12;                                  // short side of a border job (covers the 11 base states in one piece)
-static constexpr int OZF_RED_BYTES = OZ_EPI_WARPS * 32 * OZF_YC * 8;   // partial sums of a border job: [warp][lane][y]
+static constexpr int OZF_RED_BYTES = 0;
 static constexpr int OZF_TR_LD = 65;                               // row pitch (doubles) of the transposed-store staging
 template <int S> struct OzFusedCfg {
     static constexpr int STAGE_BYTES = 2 * S * OZ_SLICE_TILE_BYTES;   // A slices then B slices
@@ -461,36 +465,23 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     return v;
 }
 
-// One border job on the eight epilogue warps: out(x, y) = sum_k P(x, k) Q(y, k) for 32 x's (one per lane) and up to OZF_YC y's, the k
-// range cut into eight pieces (one per warp) whose partial sums are added in warp order — a fixed order, run to run identical.
-//   P(x, k) at P[x psx + k psk], Q(y, k) at Q[y qsy + k qsk].
-// Returns the value of output t = threadIdx (and t + 256) through `store`.
-struct OzJob { const double* P; long psx, psk; const double* Q; long qsy, qsk; int x0, xmax, y0, ny, n; };
-__device__ __forceinline__ void oz_job_partial(const OzJob& jb, double* red, int tid) {
-    const int w = tid >> 5, l = tid & 31;
-    const int kc = (((jb.n + OZ_EPI_WARPS - 1) / OZ_EPI_WARPS) + 3) & ~3;
-    const int k0 = w * kc, k1 = min(jb.n, k0 + kc);
-    const int x = jb.x0 + l;
-    const bool valid = x < jb.xmax;
-    double acc[OZF_YC];
+// Border outputs D[fr, o] = sum_k F[fr, k] B(o, k) (B(o, k) = Sigma[k, o] in phase 1, W[o, k] in phase 2).  Row fr of F = I + T A_b is
+// zero outside the 11 base columns and — for a landmark row — its own 3 x 3 block (EqFMatrices.cpp:289-312: the only couplings are
+// bias / gravity / velocity -> everything and landmark -> itself), so the sum over all k has at most 14 terms that are not exact zeros;
+// they are added in ascending k like the dense loop would.
+__device__ __forceinline__ double oz_border_dot(const OzFusedParams& p, int fr, int o) {
+    const double* Frow = p.F + fr;
+    const bool ph1 = p.phase == 1;
+    const double* B0 = ph1 ? p.X + (size_t)p.ld * o : p.X + o;     // B(o, k) at B0[k * bs]
+    const size_t bs = ph1 ? 1 : (size_t)p.ld;
+    double v = 0.0;
 #pragma unroll
-    for (int y = 0; y < OZF_YC; ++y) acc[y] = 0.0;
-    const double* Pp = jb.P + (size_t)(valid ? x : jb.x0) * jb.psx;
-    const double* Qp = jb.Q + (size_t)jb.y0 * jb.qsy;
-#pragma unroll 2
-    for (int k = k0; k < k1; ++k) {
-        const double pv = Pp[(size_t)k * jb.psk];
+    for (int k = 0; k < 11; ++k) v = fma(Frow[(size_t)p.ld * k], B0[bs * k], v);
+    if (fr >= 11) {
+        const int b0 = 11 + (fr - 11) / 3 * 3;
 #pragma unroll
-        for (int y = 0; y < OZF_YC; ++y)
-            if (y < jb.ny) acc[y] = fma(pv, Qp[(size_t)y * jb.qsy + (size_t)k * jb.qsk], acc[y]);
+        for (int k = 0; k < 3; ++k) v = fma(Frow[(size_t)p.ld * (b0 + k)], B0[bs * (b0 + k)], v);
     }
-#pragma unroll
-    for (int y = 0; y < OZF_YC; ++y) red[(w * 32 + l) * OZF_YC + y] = valid ? acc[y] : 0.0;
-}
-__device__ __forceinline__ double oz_job_sum(const double* red, int l, int y) {
-    double v = red[l * OZF_YC + y];
-#pragma unroll
-    for (int w = 1; w < OZ_EPI_WARPS; ++w) v += red[(w * 32 + l) * OZF_YC + y];
     return v;
 }
 __device__ __forceinline__ double oz_process_noise(const OzFusedParams& p, int g) {
@@ -523,7 +514,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
     const uint32_t raw = smem_u32(oz_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = oz_smem_raw + (base - raw);
-    double* red = reinterpret_cast<double*>(smem + Cfg::PIPE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + OZF_RED_BYTES);
     uint64_t* empty = full + Cfg::STAGES;
     uint64_t* acc_full = empty + Cfg::STAGES;
@@ -629,43 +619,31 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
         for (int j = tile_n; j < nIB; j += Mt) ++my_inner;
         for (int j = oq; j < nOB; j += T) ++my_outer;
         const int my_jobs = my_inner + my_outer;
-        const int first_window = nbatch > 1 ? max(1, (my_jobs + 2) / 3) : my_jobs;
+        const int first_window = nbatch > 1 ? min(my_jobs, max(1, (my_jobs + 2) / 3)) : my_jobs;
         int done_jobs = 0;
         auto run_jobs = [&](int upto) {
             for (; done_jobs < upto; ++done_jobs) {
                 const bool inner = done_jobs < my_inner;
                 const int job = inner ? tile_n + done_jobs * Mt : oq + (done_jobs - my_inner) * T;
                 const int xb = job / nch, ch = job - xb * nch;
-                OzJob jb;
-                jb.n = n; jb.y0 = ch * OZF_YC; jb.ny = min(OZF_YC, m0 - jb.y0); jb.xmax = n;
-                jb.x0 = inner ? m0 + tile_m * OZ_TILE + xb * 32 : xb * 32;
-                bool transposed_out;   // out(x, y) stored at Out[y + ld x] instead of Out[x + ld y]
-                if (p.phase == 1) {
-                    if (inner) { jb.P = p.F; jb.psx = 1; jb.psk = ld; jb.Q = p.X; jb.qsy = ld; jb.qsk = 1; transposed_out = false; }   // W[x, y] = sum_k F[x, k] Sigma[k, y]
-                    else       { jb.P = p.X; jb.psx = ld; jb.psk = 1; jb.Q = p.F; jb.qsy = 1; jb.qsk = ld; transposed_out = true; }    // W[y, x] = sum_k F[y, k] Sigma[k, x]
-                } else {
-                    if (inner) { jb.P = p.F; jb.psx = 1; jb.psk = ld; jb.Q = p.X; jb.qsy = 1; jb.qsk = ld; transposed_out = true; }    // Sigma'[y, x] = sum_k W[y, k] F[x, k]
-                    else       { jb.P = p.X; jb.psx = 1; jb.psk = ld; jb.Q = p.F; jb.qsy = 1; jb.qsk = ld; transposed_out = false; }   // Sigma'[x, y] = sum_k W[x, k] F[y, k]
-                }
-                oz_job_partial(jb, red, tid);
-                epi_bar();
+                // 32 x's (lanes) by up to OZF_YC y's; inner jobs: x = operand row (block row), y = border inner index; outer jobs:
+                // x = any column index, y = border row
+                const int y0 = ch * OZF_YC, ny = min(OZF_YC, m0 - y0);
+                const int x0 = inner ? m0 + tile_m * OZ_TILE + xb * 32 : xb * 32;
                 for (int t = tid; t < 32 * OZF_YC; t += 256) {
-                    int l, y;
-                    if (transposed_out) { l = t / OZF_YC; y = t - l * OZF_YC; } else { y = t >> 5; l = t & 31; }
-                    const int x = jb.x0 + l, gy = jb.y0 + y;
-                    if (x < jb.xmax && y < jb.ny) {
-                        double v = oz_job_sum(red, l, y);
-                        // Sigma' row index i / column index j of this output
-                        if (p.phase == 2) {
-                            const int gi = transposed_out ? gy : x, gj = transposed_out ? x : gy;
+                    const int x = x0 + (t & 31), y = t >> 5;
+                    if (x < n && y < ny) {
+                        const int fr = inner ? x : y0 + y, o = inner ? y0 + y : x;
+                        double v = oz_border_dot(p, fr, o);
+                        if (p.phase == 2) {   // D[fr, o] = Sigma'[o, fr]
                             double r6 = 0.0;
 #pragma unroll
-                            for (int c = 0; c < 6; ++c) r6 = fma(Wx[(size_t)gi + (size_t)ld * c], Fx[(size_t)gj + (size_t)ld * c], r6);
+                            for (int c = 0; c < 6; ++c) r6 = fma(Wx[(size_t)o + (size_t)ld * c], Fx[(size_t)fr + (size_t)ld * c], r6);
                             v += r6;
-                            if (gi == gj) v += Tstep * oz_process_noise(p, gi);
+                            if (o == fr) v += Tstep * oz_process_noise(p, o);
                         }
-                        p.Out[transposed_out ? (size_t)gy + (size_t)ld * x : (size_t)x + (size_t)ld * gy] = v;
-                        if (inner) atomicMax(p.exOut + (x - m0), oz_exponent(v) - p.h[gy]);
+                        p.Out[p.phase == 1 ? (size_t)fr + (size_t)ld * o : (size_t)o + (size_t)ld * fr] = v;
+                        if (inner) atomicMax(p.exOut + (fr - m0), oz_exponent(v) - p.h[o]);
                     }
                 }
                 __threadfence();
@@ -801,19 +779,19 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
 }
 
 // F's landmark rows as int8 slices without reading the zeros: row g >= 11 of F = I + T A_b (EqFMatrices.cpp:292-312, VIOFilter.cpp:177-185)
-// holds nine entries — columns 0..2 (-T B_i), 8..10 (T A_iv) and its landmark's own 3 x 3 block (I + T A_ii), exactly what
-// k_feature_step writes — so the split of the rows [m0, n) is nine bytes per row and slice at positions that depend on the row only;
+// is zero outside the 11 base columns (-T B_i in 0..2, T A_iv in 8..10 are what k_feature_step writes there) and its landmark's own
+// 3 x 3 block (I + T A_ii), so the split of the rows [m0, n) is fourteen bytes per row and slice at positions that depend on the row only;
 // every other byte of the (zero-initialised) slice array stays zero.  ex[row] = the row's exponent (entries scaled by 2^(+h[column])).
 __global__ void __launch_bounds__(128) k_oz_split_F_rows(const double* F, int ld, int n, int m0, int Mc, int KB, int S, const int* h, int8_t* slices, int* ex) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;   // block-local row
     if (row >= Mc) return;
     const int g = m0 + row;
     const int b0 = 11 + (g - 11) / 3 * 3;
-    int cols[9] = {0, 1, 2, 8, 9, 10, b0, b0 + 1, b0 + 2};
-    double v[9];
+    int cols[14] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, b0, b0 + 1, b0 + 2};
+    double v[14];
     int e = -2000;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) {
+    for (int c = 0; c < 14; ++c) {
         v[c] = g < n ? F[(size_t)g + (size_t)ld * cols[c]] * oz_pow2(h[cols[c]]) : 0.0;
         e = max(e, oz_exponent(v[c]));
     }
@@ -822,7 +800,7 @@ __global__ void __launch_bounds__(128) k_oz_split_F_rows(const double* F, int ld
     const double magic = 6755399441055744.0;
     const int sw = (row >> 2) & 1;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) {
+    for (int c = 0; c < 14; ++c) {
         const int kk = cols[c] >= m0 ? cols[c] - m0 : Mc + cols[c];   // rotated inner index
         const size_t tile = ((size_t)(row / OZ_TILE) * KB + (kk >> 5)) * S;
         int8_t* dst = slices + tile * OZ_SLICE_TILE_BYTES + (row % OZ_TILE) * OZ_KBLOCK + ((((kk & 31) >> 4) ^ sw) << 4) + (kk & 15);
@@ -848,12 +826,14 @@ cudaError_t oz_init_device() {
     if (e != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_oz_gemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_oz_gemm<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_oz_riccati<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzFusedCfg<7>::SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_oz_riccati<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzFusedCfg<8>::SMEM_BYTES)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_oz_split, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SPLIT_SMEM);
 }
 
 cudaError_t oz_split(const double* X, long stride_r, long stride_k, int rows, int k, int S, OzOperand* op, int8_t* slices, int* ex,
-                     cudaStream_t stream, const OzKScale* ks, bool ex_ready, int ex_margin) {
-    if (S < 1 || S > OZ_MAX_SLICES || rows < 1 || k < 1) return cudaErrorInvalidValue;
+                     cudaStream_t stream, const OzKScale* ks, bool ex_ready, int ex_margin, int k_rot) {
+    if (S < 1 || S > OZ_MAX_SLICES || rows < 1 || k < 1 || k_rot < 0 || k_rot >= k || (k_rot > 0 && (k - k_rot) % 128 != 0)) return cudaErrorInvalidValue;
     op->slices = slices; op->ex = ex; op->rows = rows; op->k = k; op->S = S; op->ex_margin = ex_margin;
     op->rows_pad = oz_round_up(rows, OZ_TILE); op->k_pad = oz_round_up(k, OZ_KBLOCK);
     const int* h = ks ? ks->h : nullptr;
@@ -864,7 +844,7 @@ cudaError_t oz_split(const double* X, long stride_r, long stride_k, int rows, in
         k_oz_rowmax<<<dim3((k + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, stream>>>(X, stride_r, stride_k, rows, k, h, hsign, ex);
     }
     k_oz_split<<<dim3((op->k_pad + 127) / 128, (rows + 31) / 32), dim3(32, 8), OZ_SPLIT_SMEM, stream>>>(X, stride_r, stride_k, rows, k, h, hsign, ex, ex_margin,
-                                                                                                   slices, op->rows_pad, op->k_pad, S);
+                                                                                                   slices, op->rows_pad, op->k_pad, S, k_rot);
     return cudaGetLastError();
 }
 cudaError_t oz_reset_exponents(int* ex, int count, cudaStream_t stream) {   // a very negative exponent everywhere
@@ -877,6 +857,22 @@ cudaError_t oz_rowmax(const double* X, long stride_r, long stride_k, int rows, i
 }
 cudaError_t oz_diag_scale(const double* Sigma, int ld, int n, int* h, cudaStream_t stream) {
     k_oz_diag_scale<<<(n + 255) / 256, 256, 0, stream>>>(Sigma, ld, n, h);
+    return cudaGetLastError();
+}
+
+bool oz_fused_supported(int S, int Mt) { return (S == 7 || S == 8) && Mt >= 2 && 1 + Mt <= OZ_FUSED_SYNC_INTS; }
+cudaError_t oz_riccati_fused(const OzFusedParams& p, int S, cudaStream_t stream) {
+    if (!oz_fused_supported(S, p.Mt) || p.Mc != p.Mt * OZ_TILE || p.n != p.m0 + p.Mc || p.m0 < 1 || p.KB * OZ_KBLOCK < p.n) return cudaErrorInvalidValue;
+    if ((long long)p.KB * OZ_KBLOCK * 64 * 64 * S >= (1LL << 31)) return cudaErrorInvalidValue;
+    const dim3 grid(p.Mt * p.Mt);
+    if (S == 7) k_oz_riccati<7><<<grid, OZ_THREADS, OzFusedCfg<7>::SMEM_BYTES, stream>>>(p);
+    else k_oz_riccati<8><<<grid, OZ_THREADS, OzFusedCfg<8>::SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t oz_split_F_rows(const double* F, int ld, int n, int m0, int S, const int* h, int8_t* slices, int* ex, cudaStream_t stream) {
+    const int Mc = n - m0, KB = (n + OZ_KBLOCK - 1) / OZ_KBLOCK;
+    if (Mc < OZ_TILE || Mc % OZ_TILE != 0 || m0 < 11) return cudaErrorInvalidValue;
+    k_oz_split_F_rows<<<(Mc + 127) / 128, 128, 0, stream>>>(F, ld, n, m0, Mc, KB, S, h, slices, ex);
     return cudaGetLastError();
 }
 

@@ -67,8 +67,10 @@ struct OzExponentsOut { int* rows_out; int* cols_out; const int* h; int row_off,
 size_t oz_slices_bytes(int rows, int k, int S);
 // Splits X (element (r, k) at X[r * stride_r + k * stride_k]) into S slices; `slices` sized with oz_slices_bytes.  ex_ready: `ex`
 // already holds the rows' exponents (of the scaled entries); else they are computed first (one more pass over X).
+// k_rot > 0: the inner index is stored rotated, k' = k - k_rot for k >= k_rot and k' = (k - k_rot) + k for the first k_rot (they go
+// behind the others); k - k_rot must be a multiple of 128.
 cudaError_t oz_split(const double* X, long stride_r, long stride_k, int rows, int k, int S, OzOperand* op, int8_t* slices, int* ex,
-                     cudaStream_t stream, const OzKScale* ks = nullptr, bool ex_ready = false, int ex_margin = 0);
+                     cudaStream_t stream, const OzKScale* ks = nullptr, bool ex_ready = false, int ex_margin = 0, int k_rot = 0);
 cudaError_t oz_reset_exponents(int* ex, int count, cudaStream_t stream);
 // ex[r] = max(ex[r], largest exponent of row r of X over its k columns)
 cudaError_t oz_rowmax(const double* X, long stride_r, long stride_k, int rows, int k, int* ex, cudaStream_t stream, const OzKScale* ks = nullptr);
@@ -79,5 +81,39 @@ cudaError_t oz_diag_scale(const double* Sigma, int ld, int n, int* h, cudaStream
 cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double alpha, double beta, const double* Cin, int ldcin, double* D,
                     int ldd, cudaStream_t stream, const OzRiccatiEpilogue* ric = nullptr, const OzExponentsOut* exo = nullptr);
 cudaError_t oz_init_device();
+
+// ---- the Riccati step as two launches of one kernel ------------------------------------------------------------------------------
+// Sigma (n x n, n = m0 + Mc) = [border: the first m0 = n mod 128 rows / columns | block: Mc = 128 Mt].  Both products of
+// VIOFilter.cpp:188-189 are computed for the block on the int8 tensor cores with F's rows as the A operand:
+//   phase 1:  D[i, c] = W[i, c]       = sum_k F[i, k] Sigma[k, c]         B operand = Sigma's columns  (X = Sigma, Out = W)
+//   phase 2:  D[j, i] = Sigma'[i, j]  = sum_k F[j, k] W[i, k] + ...       B operand = W's rows         (X = W, Out = Sigma', stored transposed)
+// so that in both phases the rows of D are the operand rows of the NEXT product (W's rows for phase 2, Sigma''s columns for the next
+// step's phase 1) and the epilogue writes them out as int8 slices directly: every tile publishes its rows' exponent maxima, waits for
+// the other tiles of its tile row (tiles are taken by ticket in row-major order, so the wait cannot deadlock at any grid size) and then
+// emits its 128 x 128 block of digits from registers — no separate split pass, exact exponents.  The inner index of all slice arrays
+// is rotated, k' = k - m0 for the block and k' = Mc + k for the border, so that a tile's columns are whole 32-deep k-blocks.
+// The border rows / columns (2 m0 n outputs per phase, 0.7 % of the work at N = 512) are fp64 dot products done by the epilogue
+// warps while the tensor core runs ("border jobs"); those that are inner-border entries of operand rows are emitted as well.
+// Synchronisation words and exponent arrays exist twice (by tick parity): each launch clears the set the other parity uses next.
+struct OzFusedParams {
+    int Mc, m0, n, n16, KB, Mt, phase, ld;
+    const int8_t* slA; const int* exA;      // F rows [m0, n), scaled 2^(+h)
+    const int8_t* slB; const int* exB;      // phase 1: Sigma columns [m0, n); phase 2: W rows [m0, n); scaled 2^(-h)
+    const double* F;                        // [F | B_b] (B_b in columns n16 .. n16+5)
+    const double* X;                        // phase 1: Sigma; phase 2: [W | T B_b R]
+    double* Out;                            // phase 1: W; phase 2: Sigma'
+    int8_t* slOut; int* exOut;              // the output as the next product's B operand
+    const int* h;
+    int* exReset;                           // Mc exponents to clear
+    int* sync;                              // [0] ticket counter, [1 + tile row] arrivals; zero at launch
+    int* syncReset;                         // 1 + Mt words to clear
+    const double* T_dev;                    // phase 2: the step length (device memory, written by k_step_prepare)
+    double Pd[5];                           // process variances: bias omega, bias accel, gravity, velocity, point
+};
+static const int OZ_FUSED_SYNC_INTS = 64;   // >= 1 + Mt
+bool oz_fused_supported(int S, int Mt);
+cudaError_t oz_riccati_fused(const OzFusedParams& p, int S, cudaStream_t stream);
+// F's rows [m0, n) as slices from their nine structural entries per row (see k_oz_split_F_rows); `slices` must be zero elsewhere.
+cudaError_t oz_split_F_rows(const double* F, int ld, int n, int m0, int S, const int* h, int8_t* slices, int* ex, cudaStream_t stream);
 
 }  // namespace eqvio

@@ -71,3 +71,92 @@ def test_ozaki_rejects_what_it_cannot_do():
     A = np.ones((128, 128))
     with pytest.raises(abi.EqvioError):
         dgemm_ozaki(A, A, slices=12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# The Riccati step of the filter on the int8 tensor cores (VIOFilter.cpp:188-189): fused form (two launches of k_oz_riccati, each
+# emitting its result as the next product's int8 operand), unfused form (split kernels + DMMA strips between the products) and the
+# fp64 DMMA path must agree to round-off with each other and with the CPU oracle.
+# ---------------------------------------------------------------------------------------------------------------------------------
+_MID = {}
+
+
+def _events_after_vision(seq, j):
+    ev = list(seq.events())
+    k = max(i for i, (kind, idx) in enumerate(ev) if kind == "vision" and idx == j)
+    return ev[: k + 1], ev[k + 1 :]
+
+
+def _riccati_run(monkeypatch, N, env, ticks):
+    """Seeds a filter with the state behind the first vision update (computed once per N on the fp64 DMMA path) and runs `ticks`
+    IMU ticks with the environment `env`; returns (seed snapshot, final snapshot, int8 slices in use)."""
+    from eqf_vio_b200.filter import VIOFilter
+    from eqf_vio_b200.settings import conditioned_settings
+    from eqf_vio_b200.synthetic import period_sequence
+    from helpers import feed
+
+    for k in ("EQVIO_OZAKI", "EQVIO_OZAKI_FUSED", "EQVIO_OZAKI_MIN_TILES"):
+        monkeypatch.delenv(k, raising=False)
+    s = conditioned_settings(outlierThreshold=1e9)
+    seq = period_sequence(N, 3, camera_offset=tuple(s.cameraOffset))
+    head, tail = _events_after_vision(seq, 1)
+    if N not in _MID:
+        monkeypatch.setenv("EQVIO_OZAKI", "0")
+        f = VIOFilter(s, device=0)
+        for kind, i in head:
+            feed(f, seq, kind, i)
+        _MID[N] = f.get_snapshot()
+        f.close()
+        monkeypatch.delenv("EQVIO_OZAKI")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    f = VIOFilter(s, device=0)
+    f.set_snapshot(_MID[N])
+    slices = None
+    for kind, i in tail[:ticks]:
+        assert kind == "imu"
+        feed(f, seq, kind, i)
+        slices = f.riccati_int8_slices()
+    out = f.get_snapshot()
+    f.close()
+    return _MID[N], out, slices
+
+
+@pytest.mark.parametrize("N", [512, 500, 470])
+def test_fused_riccati_matches_unfused_dmma_and_oracle(monkeypatch, N):
+    """N = 512: n = 1547 = 11 + 12 x 128 (the border is the 11 base states).  N = 500: n = 1511 = 103 + 11 x 128 and N = 470:
+    n = 1421 = 13 + 11 x 128 — the border holds landmark rows as well, several border jobs per tile row.  Nine IMU ticks behind the
+    first vision update: the first tick splits Sigma with the generic kernels, the others run on what the previous launch emitted."""
+    from eqf_vio_b200.settings import conditioned_settings
+    from eqf_vio_b200.synthetic import period_sequence
+    from helpers import feed, split_snapshot
+    from oracle.c_oracle import COracleFilter
+
+    mid, out_f, sl_f = _riccati_run(monkeypatch, N, {}, 9)
+    _, out_u, sl_u = _riccati_run(monkeypatch, N, {"EQVIO_OZAKI_FUSED": "0"}, 9)
+    _, out_d, sl_d = _riccati_run(monkeypatch, N, {"EQVIO_OZAKI": "0"}, 9)
+    assert sl_f == 8 and sl_u == 8 and sl_d == 0
+    hf, Sf = split_snapshot(out_f); hu, Su = split_snapshot(out_u); hd, Sd = split_snapshot(out_d)
+    assert np.array_equal(hf, hd) and np.array_equal(hu, hd)                  # the state propagate does not depend on Sigma
+    assert rel(Sf, Sd) < 2e-14 and rel(Su, Sd) < 2e-14 and rel(Sf, Su) < 2e-14, (rel(Sf, Sd), rel(Su, Sd), rel(Sf, Su))
+    # entry by entry, relative to sqrt(Sigma_ii Sigma_jj) — the scale the inner-dimension equilibration guarantees
+    d = np.sqrt(np.abs(np.diag(Sd)))
+    ent = np.abs(Sf - Sd) / (d[:, None] * d[None, :])
+    assert ent.max() < 1e-12, ent.max()
+    # and against the oracle seeded with the same state
+    s = conditioned_settings(outlierThreshold=1e9)
+    seq = period_sequence(N, 3, camera_offset=tuple(s.cameraOffset))
+    _, tail = _events_after_vision(seq, 1)
+    o = COracleFilter(s)
+    o.set_snapshot(mid)
+    for kind, i in tail[:9]:
+        feed(o, seq, kind, i)
+    ho, So = split_snapshot(o.get_snapshot())
+    assert rel(Sf, So) < 1e-12 and np.abs(hf - ho).max() < 1e-9, (rel(Sf, So), np.abs(hf - ho).max())
+
+
+def test_fused_riccati_is_deterministic(monkeypatch):
+    """Atomic maxima, tickets and tile-row barriers order nothing that reaches the result: two runs agree bit for bit."""
+    a = _riccati_run(monkeypatch, 512, {}, 10)[1]
+    b = _riccati_run(monkeypatch, 512, {}, 10)[1]
+    assert np.array_equal(a, b)
