@@ -63,6 +63,7 @@ SIGNATURES = {
     "eqvio_profile_read_class": (C.c_int, [_h, C.c_int, C.POINTER(C.c_longlong), _dp, _dp, C.c_int]),
     "eqvio_profile_timeline": (C.c_int, [_h, _dp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "eqvio_riccati_arith": (C.c_int, [_h, _ip]),
+    "eqvio_oz_stamps": (C.c_int, [_h, C.POINTER(C.c_longlong), C.c_size_t, C.POINTER(C.c_size_t)]),
     "eqvio_stream": (C.c_int, [_h, C.POINTER(C.c_void_p)]),
     "eqvio_status_string": (C.c_char_p, [C.c_int]),
     "eqvio_version": (C.c_char_p, []),

@@ -130,6 +130,7 @@ struct eqvio_filter {
     int *oz_sync1[2] = {nullptr, nullptr}, *oz_sync2[2] = {nullptr, nullptr};
     int* oz_words = nullptr;       // one allocation behind the eight arrays above
     size_t oz_words_count = 0;
+    long long* oz_stamps = nullptr; // EQVIO_OZ_STAMPS=1: clock stamps of the last two fused launches (2 x tiles x OZ_STAMPS), eqvio_oz_stamps
     int oz_valid_par = -1;         // the tick parity the emitted Sigma slices / exponents / cleared words are valid for (the one after the step that left them)
     int oz_F_layout[2] = {0, 0};   // n for which ozF[parity] was cleared (its non-structural bytes must be zero)
     int par = 0;                   // parity of the current Riccati tick: F == Fpp[par], W == Wpp[par]
@@ -758,6 +759,7 @@ static int riccati_ozaki_fused(Filter* f, double T) {
         p.slB = f->ozS; p.exB = f->oz_exS[par]; p.X = f->Sigma; p.Out = f->W;
         p.slOut = f->ozW; p.exOut = f->oz_exW[par]; p.exReset = f->oz_exW[par ^ 1];
         p.sync = f->oz_sync1[par]; p.syncReset = f->oz_sync1[par ^ 1];
+        p.stamps = (f->oz_stamps && Mt * Mt <= 1024) ? f->oz_stamps : nullptr;
         ProfEvent pe;
         prof_begin(f, pe, st, PROF_RICCATI_I8, 2.0 * n * n * n);
         CU_TRY(oz_riccati_fused(p, S, st));
@@ -769,6 +771,7 @@ static int riccati_ozaki_fused(Filter* f, double T) {
         p.slB = f->ozW; p.exB = f->oz_exW[par]; p.X = f->W; p.Out = f->Sigma2;
         p.slOut = f->ozS; p.exOut = f->oz_exS[par ^ 1]; p.exReset = f->oz_exS[par];
         p.sync = f->oz_sync2[par]; p.syncReset = f->oz_sync2[par ^ 1];
+        p.stamps = (f->oz_stamps && Mt * Mt <= 1024) ? f->oz_stamps + (size_t)1024 * OZ_STAMPS : nullptr;
         ProfEvent pe;
         prof_begin(f, pe, st, PROF_RICCATI_I8, 2.0 * n * n * n);
         CU_TRY(oz_riccati_fused(p, S, st));
@@ -1156,7 +1159,7 @@ static void destroy_filter(Filter* f) {
     cudaFree(f->sk_sync); cudaFree(f->sk_ws); cudaFree(f->splitk_ws);
     for (int i = 0; i < 2; ++i) { cudaFree(f->strip_ws[i]); cudaFree(f->strip_cnt[i]); }
     for (void* q : {(void*)f->ozF[0], (void*)f->ozF[1], (void*)f->ozS, (void*)f->ozW, (void*)f->ozeF[0], (void*)f->ozeF[1], (void*)f->ozeS, (void*)f->ozeW, (void*)f->ozH}) cudaFree(q);
-    cudaFree(f->oz_words);
+    cudaFree(f->oz_words); cudaFree(f->oz_stamps);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->pose_pub); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
@@ -1208,6 +1211,8 @@ static int create_impl(Filter* f) {
     if (const char* e = getenv("EQVIO_OZAKI")) { f->ozaki_S = atoi(e); if (f->ozaki_S < 7 || f->ozaki_S > OZ_MAX_SLICES) f->ozaki_S = 0; }
     if (const char* e = getenv("EQVIO_OZAKI_MIN_TILES")) f->ozaki_min_tiles = std::max(4, atoi(e));
     if (const char* e = getenv("EQVIO_OZAKI_FUSED")) f->oz_fused = atoi(e);
+    if (const char* e = getenv("EQVIO_OZ_STAMPS"))
+        if (e[0] == '1') { CU_TRY(cudaMalloc((void**)&f->oz_stamps, (size_t)2 * 1024 * OZ_STAMPS * 8)); CU_TRY(cudaMemset(f->oz_stamps, 0, (size_t)2 * 1024 * OZ_STAMPS * 8)); }
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
     if (const char* e = getenv("EQVIO_STAMPS"))
         if (e[0] == '1') { CU_TRY(dalloc(&f->stamps, 512)); CU_TRY(cudaMemset(f->stamps, 0, 512 * 8)); }
@@ -2132,6 +2137,16 @@ int eqvio_profile_timeline(eqvio_handle_t f, double* out, size_t cap_entries, si
     if (out) {
         const size_t k = std::min(cap_entries, f->timeline.size());
         memcpy(out, f->timeline.data(), k * sizeof(TimelineEntry));
+    }
+    return EQVIO_OK;
+}
+int eqvio_oz_stamps(eqvio_handle_t f, long long* out, size_t cap_words, size_t* count) {
+    if (!f || !count) return EQVIO_ERR_ARG;
+    *count = f->oz_stamps ? (size_t)2 * 1024 * OZ_STAMPS : 0;
+    if (out && f->oz_stamps) {
+        CU_TRY(cudaSetDevice(f->device));
+        CU_TRY(cudaStreamSynchronize(f->stream));
+        CU_TRY(cudaMemcpy(out, f->oz_stamps, std::min(cap_words, *count) * 8, cudaMemcpyDeviceToHost));
     }
     return EQVIO_OK;
 }

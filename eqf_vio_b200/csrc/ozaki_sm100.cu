@@ -447,18 +447,8 @@ __global__ void k_oz_diag_scale(const double* Sigma, int ld, int n, int* h) {
 // The Riccati step as two launches of ONE kernel (fused form, see OzFusedParams in the header)
 // ------------------------------------------------------------------------------------------------
 static constexpr int OZF_YC = 12;                                  // short side of a border job (covers the 11 base states in one piece)
-static constexpr int OZF_RED_BYTES = 0;
-static constexpr int OZF_TR_LD = 65;                               // row pitch (doubles) of the transposed-store staging
-template <int S> struct OzFusedCfg {
-    static constexpr int STAGE_BYTES = 2 * S * OZ_SLICE_TILE_BYTES;   // A slices then B slices
-    static constexpr int STAGES = 3;
-    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-    static constexpr int SMEM_BYTES = PIPE_BYTES + OZF_RED_BYTES + 1024 + 256;
-    static_assert(OZ_EPI_WARPS * 32 * OZF_TR_LD * 8 <= PIPE_BYTES, "transposed-store staging reuses the pipeline stages");
-};
 static constexpr int OZ_EX_RESET = (int)0xC0C0C0C0;               // what oz_reset_exponents' memset leaves: a very negative exponent
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the eight epilogue warps
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -488,33 +478,72 @@ __device__ __forceinline__ double oz_process_noise(const OzFusedParams& p, int g
     return g < 3 ? p.Pd[0] : g < 6 ? p.Pd[1] : g < 8 ? p.Pd[2] : g < 11 ? p.Pd[3] : p.Pd[4];
 }
 
-// digits of 16 already-scaled values (|x| <= 64): S slices of one 16-byte chunk each
+// Digits of 16 values x (|x| <= 64) as S slices of one 16-byte chunk each.  Slices are taken four at a time from one value:
+// adding M_s = 1.5 * 2^(52 - 7s) rounds x to a multiple of 2^(-7s) and leaves R_s = round(x 2^(7s)) as a two's-complement integer in
+// the low word of the sum, and digit_s = R_s - 128 R_(s-1) (|digit| <= 64) is the balanced base-128 digit the sequential algorithm
+// (k_oz_split) produces — one fp64 addition and one integer multiply-add per digit instead of four dependent fp64 operations; after
+// four digits the exact residual x - R_3 2^(-21) is rescaled by 2^28 and the next four follow.
+__device__ __forceinline__ uint32_t oz_pack4(int a, int b, int c, int d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
 template <int S>
-__device__ __forceinline__ void oz_emit16(double (&v)[16], uint4* dst) {
-    const double magic = 6755399441055744.0;
+__device__ __forceinline__ void oz_emit16(const double* x, uint4* dst) {
+    int dig[S][16];
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        uint32_t w[4] = {0, 0, 0, 0};
+    for (int c = 0; c < 16; ++c) {
+        double v = x[c];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const double t = v[c] + magic;
-            const double d = t - magic;
-            v[c] = (v[c] - d) * 128.0;
-            w[c >> 2] |= ((uint32_t)__double2loint(t) & 0xffu) << (8 * (c & 3));
+        for (int g = 0; g < S; g += 4) {
+            int prev = 0;
+            double t = 0.0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (g + s < S) {
+                    const double M = __hiloint2double((1023 + 52 - 7 * s) << 20 | 0x80000, 0);   // 1.5 * 2^(52 - 7 s)
+                    t = v + M;
+                    const int R = __double2loint(t);
+                    dig[g + s][c] = s == 0 ? R : R - (prev << 7);
+                    prev = R;
+                    if (s == 3 && g + 4 < S) v = (v - (t - M)) * 268435456.0;   // 2^28: the residual behind four digits
+                }
+            }
         }
-        dst[(size_t)s * (OZ_SLICE_TILE_BYTES / 16)] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+        dst[(size_t)s * (OZ_SLICE_TILE_BYTES / 16)] = make_uint4(oz_pack4(dig[s][0], dig[s][1], dig[s][2], dig[s][3]), oz_pack4(dig[s][4], dig[s][5], dig[s][6], dig[s][7]),
+                                                               oz_pack4(dig[s][8], dig[s][9], dig[s][10], dig[s][11]), oz_pack4(dig[s][12], dig[s][13], dig[s][14], dig[s][15]));
 }
 
+// Warp roles of the fused kernel: sixteen epilogue warps (lane quarter = warp % 4, column quarter = warp / 4: 32 accumulator columns per
+// thread — the epilogue is dependent fp64 / integer chains, more warps hide them), one producer, one MMA issuer.
+static constexpr int OZF_EPI_WARPS = 16, OZF_PRODUCER_WARP = 16, OZF_MMA_WARP = 17, OZF_THREADS = 576, OZF_EPI_THREADS = OZF_EPI_WARPS * 32;
+static constexpr int OZF_TR_LD = 33;                               // row pitch (doubles) of the transposed-store staging
+static constexpr int OZF_AUX_BYTES = 128 * 8 * 2 + 128 * 4 + 6 * 128 * 8;   // per tile column: 2^exB, 2^-h, h, and (phase 2) T B_b R
+template <int S> struct OzFusedCfg {
+    static constexpr int STAGE_BYTES = 2 * S * OZ_SLICE_TILE_BYTES;   // A slices then B slices
+    static constexpr int STAGES = 3;
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = PIPE_BYTES + OZF_AUX_BYTES + 1024 + 256;
+    static_assert(OZF_EPI_WARPS * 32 * OZF_TR_LD * 8 <= PIPE_BYTES, "transposed-store staging reuses the pipeline stages");
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the sixteen epilogue warps
+
+#define OZ_STAMP(i) do { if (p.stamps && lane == 0 && (warp == 0 || warp == OZF_MMA_WARP)) p.stamps[(size_t)ticket * OZ_STAMPS + (i)] = clock64(); } while (0)
 template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParams p) {
+__global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedParams p) {
     using namespace oz;
     using Cfg = OzFusedCfg<S>;
     extern __shared__ uint8_t oz_smem_raw[];
     const uint32_t raw = smem_u32(oz_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = oz_smem_raw + (base - raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + OZF_RED_BYTES);
+    double* s_cb = reinterpret_cast<double*>(smem + Cfg::PIPE_BYTES);   // 2^exB[col]
+    double* s_ch = s_cb + 128;                                          // 2^-h[col]
+    double* s_wx = s_ch + 128;                                          // [6][128] T B_b R rows of the tile's columns (phase 2)
+    int* s_h = reinterpret_cast<int*>(s_wx + 6 * 128);                  // h[col]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + OZF_AUX_BYTES);
     uint64_t* empty = full + Cfg::STAGES;
     uint64_t* acc_full = empty + Cfg::STAGES;
     uint64_t* acc_empty = acc_full + 1;
@@ -528,13 +557,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, OZ_EPI_WARPS);
+        mbar_init(acc_empty, OZF_EPI_WARPS);
         mbar_fence_init();
         // tiles by ticket: a CTA that waits for its tile row only ever waits for CTAs that started before it or that the hardware can
         // still start (the lowest unfinished tile row is always completely dispatched), whatever the grid size
         *ticket_slot = atomicAdd(p.sync, 1);
     }
-    if (warp == OZ_MMA_WARP) {
+    if (warp == OZF_MMA_WARP) {
         tmem_alloc(smem_u32(tmem_slot), 512);
         tmem_relinquish();
     }
@@ -546,10 +575,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
     const int tile_m = ticket / Mt, tile_n = ticket - tile_m * Mt;
     // the other tick parity's synchronisation words and exponent maxima (nothing running touches them) are cleared for its next launch
     if (ticket == 0)
-        for (int i = threadIdx.x; i <= Mt; i += OZ_THREADS) p.syncReset[i] = 0;
+        for (int i = threadIdx.x; i <= Mt; i += OZF_THREADS) p.syncReset[i] = 0;
     if (tile_n == 0 && threadIdx.x < OZ_TILE) p.exReset[tile_m * OZ_TILE + threadIdx.x] = OZ_EX_RESET;
+    OZ_STAMP(0);
 
-    if (warp == OZ_PRODUCER_WARP) {
+    if (warp == OZF_PRODUCER_WARP) {
         if (lane == 0) {
             const int8_t* gA = p.slA + (size_t)tile_m * KB * S * OZ_SLICE_TILE_BYTES;
             const int8_t* gB = p.slB + (size_t)tile_n * KB * S * OZ_SLICE_TILE_BYTES;
@@ -567,7 +597,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
                 }
             }
         }
-    } else if (warp == OZ_MMA_WARP) {
+    } else if (warp == OZF_MMA_WARP) {
         uint32_t it = 0;
         const uint64_t adesc0 = smem_desc_sw32(base), bdesc0 = smem_desc_sw32(base + S * OZ_SLICE_TILE_BYTES);
 #pragma unroll
@@ -575,12 +605,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
             constexpr int DPB = OZ_DIAGS_PER_BATCH;
             const int dmin = DPB * b, dmax = (dmin + DPB - 1 < S - 1) ? dmin + DPB - 1 : S - 1;
             if (b > 0) {
+                OZ_STAMP(12);
                 mbar_wait(acc_empty, (uint32_t)((b - 1) & 1));
                 tc_fence_after();
+                OZ_STAMP(13);
             }
+            long long waited = 0;
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int s = it % Cfg::STAGES;
+                const long long w0 = p.stamps ? clock64() : 0;
                 mbar_wait(&full[s], (it / Cfg::STAGES) & 1);
+                if (p.stamps) waited += clock64() - w0;
                 tc_fence_after();
                 const uint64_t soff = (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
                 const uint32_t first = kb > 0 ? 1u : 0u;
@@ -599,16 +634,30 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
             }
             if (elect_one()) tc_commit(acc_full);
             __syncwarp();
+            if (p.stamps && lane == 0) p.stamps[(size_t)ticket * OZ_STAMPS + 9 + b] = waited;   // 9, 10: cycles the issuer waited for operands
+            if (b == nbatch - 1) OZ_STAMP(14);
         }
     } else {
-        // ===== the eight epilogue warps =====
-        const int tid = threadIdx.x;            // 0 .. 255
-        const int q = warp & 3, hh = warp >> 2;
+        // ===== the sixteen epilogue warps =====
+        const int tid = threadIdx.x;            // 0 .. 511
+        const int q = warp & 3, cq = warp >> 2;
         const int m0 = p.m0, n = p.n, ld = p.ld;
         const double* Wx = (p.phase == 2 ? p.X : p.Out) + (size_t)p.n16 * ld;   // T B_b R (six columns behind W)
         const double* Fx = p.F + (size_t)p.n16 * ld;                            // B_b
         const double Tstep = p.phase == 2 ? *p.T_dev : 0.0;
         int* cnt = p.sync + 1;
+
+        // ---- per-column factors of this tile, staged once: 2^exB, 2^-h, h and (phase 2) the six entries of T B_b R
+        if (tid < OZ_TILE) {
+            const int col = tile_n * OZ_TILE + tid;
+            const int hc = p.h[m0 + col];
+            s_cb[tid] = oz_pow2(max(p.exB[col], -900));
+            s_ch[tid] = oz_pow2(-hc);
+            s_h[tid] = hc;
+        } else if (p.phase == 2 && tid < OZ_TILE + 6 * 32) {
+            const int c = (tid - OZ_TILE) >> 5, l = tid & 31;
+            for (int j = l; j < OZ_TILE; j += 32) s_wx[c * 128 + j] = Wx[(size_t)(m0 + tile_n * OZ_TILE + j) + (size_t)ld * c];
+        }
 
         // ---- border jobs: the rows / columns in front of the 128-aligned block, in fp64, while the tensor core works.
         // inner jobs (operand rows of this tile row x border inner indices) feed the exponents and count towards the tile-row barrier
@@ -619,129 +668,125 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
         for (int j = tile_n; j < nIB; j += Mt) ++my_inner;
         for (int j = oq; j < nOB; j += T) ++my_outer;
         const int my_jobs = my_inner + my_outer;
-        const int first_window = nbatch > 1 ? min(my_jobs, max(1, (my_jobs + 2) / 3)) : my_jobs;
-        int done_jobs = 0;
-        auto run_jobs = [&](int upto) {
-            for (; done_jobs < upto; ++done_jobs) {
-                const bool inner = done_jobs < my_inner;
-                const int job = inner ? tile_n + done_jobs * Mt : oq + (done_jobs - my_inner) * T;
-                const int xb = job / nch, ch = job - xb * nch;
-                // 32 x's (lanes) by up to OZF_YC y's; inner jobs: x = operand row (block row), y = border inner index; outer jobs:
-                // x = any column index, y = border row
-                const int y0 = ch * OZF_YC, ny = min(OZF_YC, m0 - y0);
-                const int x0 = inner ? m0 + tile_m * OZ_TILE + xb * 32 : xb * 32;
-                for (int t = tid; t < 32 * OZF_YC; t += 256) {
-                    const int x = x0 + (t & 31), y = t >> 5;
-                    if (x < n && y < ny) {
-                        const int fr = inner ? x : y0 + y, o = inner ? y0 + y : x;
-                        double v = oz_border_dot(p, fr, o);
-                        if (p.phase == 2) {   // D[fr, o] = Sigma'[o, fr]
-                            double r6 = 0.0;
+        for (int done_jobs = 0; done_jobs < my_jobs; ++done_jobs) {
+            const bool inner = done_jobs < my_inner;
+            const int job = inner ? tile_n + done_jobs * Mt : oq + (done_jobs - my_inner) * T;
+            const int xb = job / nch, ch = job - xb * nch;
+            // 32 x's (lanes) by up to OZF_YC y's; inner jobs: x = operand row (block row), y = border inner index; outer jobs:
+            // x = any column index, y = border row
+            const int y0 = ch * OZF_YC, ny = min(OZF_YC, m0 - y0);
+            const int x0 = inner ? m0 + tile_m * OZ_TILE + xb * 32 : xb * 32;
+            if (tid < 32 * OZF_YC) {
+                const int x = x0 + (tid & 31), y = tid >> 5;
+                if (x < n && y < ny) {
+                    const int fr = inner ? x : y0 + y, o = inner ? y0 + y : x;
+                    double v = oz_border_dot(p, fr, o);
+                    if (p.phase == 2) {   // D[fr, o] = Sigma'[o, fr]
+                        double r6 = 0.0;
 #pragma unroll
-                            for (int c = 0; c < 6; ++c) r6 = fma(Wx[(size_t)o + (size_t)ld * c], Fx[(size_t)fr + (size_t)ld * c], r6);
-                            v += r6;
-                            if (o == fr) v += Tstep * oz_process_noise(p, o);
-                        }
-                        p.Out[p.phase == 1 ? (size_t)fr + (size_t)ld * o : (size_t)o + (size_t)ld * fr] = v;
-                        if (inner) atomicMax(p.exOut + (fr - m0), oz_exponent(v) - p.h[o]);
+                        for (int c = 0; c < 6; ++c) r6 = fma(Wx[(size_t)o + (size_t)ld * c], Fx[(size_t)fr + (size_t)ld * c], r6);
+                        v += r6;
+                        if (o == fr) v += Tstep * oz_process_noise(p, o);
                     }
+                    p.Out[p.phase == 1 ? (size_t)fr + (size_t)ld * o : (size_t)o + (size_t)ld * fr] = v;
+                    if (inner) atomicMax(p.exOut + (fr - m0), oz_exponent(v) - p.h[o]);
                 }
-                __threadfence();
-                epi_bar();
-                if (inner && tid == 0) atomicAdd(cnt + tile_m, 1);
             }
-        };
-        run_jobs(first_window);
+            __threadfence();
+            epi_bar();
+            if (inner && tid == 0) atomicAdd(cnt + tile_m, 1);
+        }
+        epi_bar();   // (the staged column factors are visible to every epilogue warp)
+        OZ_STAMP(1);
 
-        double acc[64];
+        double acc[32];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+        for (int j = 0; j < 32; ++j) acc[j] = 0.0;
         for (int b = 0; b < nbatch; ++b) {
-            if (b == nbatch - 1) run_jobs(my_jobs);
             const int dmin = OZ_DIAGS_PER_BATCH * b, dmax = min(dmin + OZ_DIAGS_PER_BATCH - 1, S - 1);
             mbar_wait(acc_full, (uint32_t)(b & 1));
             tc_fence_after();
+            OZ_STAMP(2 + 2 * b);
             for (int d = dmin; d <= dmax; ++d) {
                 const double scale = oz_pow2(-7 * d);
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((d - dmin) * OZ_TILE + hh * 64);
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((d - dmin) * OZ_TILE + cq * 32), v);
+                tmem_ld_wait();
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + half * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[half * 32 + j] = fma((double)(int)v[j], scale, acc[half * 32 + j]);
-                }
+                for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int)v[j], scale, acc[j]);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
+            OZ_STAMP(3 + 2 * b);
         }
         // ---- this tile in fp64: D[row, col], row = operand row (phase 1: row i of W; phase 2: column j of Sigma'), col = inner index
         const int r = q * 32 + lane;                       // tile-local row
         const int row = tile_m * OZ_TILE + r, grow = m0 + row;
-        const int col0 = tile_n * OZ_TILE + hh * 64;       // block-local first column
+        const int lc0 = cq * 32;                           // tile-local first column of this thread
+        const int gcol0 = m0 + tile_n * OZ_TILE + lc0;     // its index in Sigma
+        double* tr = reinterpret_cast<double*>(smem) + (size_t)warp * 32 * OZF_TR_LD;   // (phase 2) the pipeline stages are idle now
         {
             const double ra = oz_pow2(max(p.exA[row], -900) - 12);
             double fx[6] = {0, 0, 0, 0, 0, 0};
+            double tp = 0.0;
             if (p.phase == 2) {
 #pragma unroll
                 for (int c = 0; c < 6; ++c) fx[c] = Fx[(size_t)grow + (size_t)ld * c];
+                tp = Tstep * oz_process_noise(p, grow);
             }
-            int e = -2000;
+            int emax = 0;   // largest high word (sign cleared) of the entries scaled by 2^-h: its exponent field is the row's maximum
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int col = col0 + j, gcol = m0 + col;
-                double v = (acc[j] * ra) * oz_pow2(max(p.exB[col], -900));
+            for (int j = 0; j < 32; ++j) {
+                double v = (acc[j] * ra) * s_cb[lc0 + j];
                 if (p.phase == 2) {   // Sigma'[i = gcol, j = grow] += (T B_b R B_b^T)[i, j] + T P on the diagonal (VIOFilter.cpp:188-189)
                     double r6 = 0.0;
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) r6 = fma(Wx[(size_t)gcol + (size_t)ld * c], fx[c], r6);
+                    for (int c = 0; c < 6; ++c) r6 = fma(s_wx[c * 128 + lc0 + j], fx[c], r6);
                     v += r6;
-                    if (grow == gcol) v += Tstep * oz_process_noise(p, grow);
+                    if (grow == gcol0 + j) v += tp;
+                    tr[lane * OZF_TR_LD + j] = v;
+                } else {
+                    p.Out[(size_t)grow + (size_t)ld * (gcol0 + j)] = v;   // W[grow, gcol]: the lanes of a warp are 32 consecutive rows of one column
                 }
-                e = max(e, oz_exponent(v) - p.h[gcol]);
-                acc[j] = v;
+                const double vs = v * s_ch[lc0 + j];
+                emax = max(emax, __double2hiint(vs) & 0x7fffffff);
+                acc[j] = vs;
             }
-            atomicMax(p.exOut + row, e);
+            const int be = emax >> 20;
+            atomicMax(p.exOut + row, be == 0 ? -2000 : be - 1022);
         }
-        if (p.phase == 1) {   // W[grow, gcol]: the lanes of a warp are 32 consecutive rows of one column
-#pragma unroll
-            for (int j = 0; j < 64; ++j) p.Out[(size_t)grow + (size_t)ld * (m0 + col0 + j)] = acc[j];
-        } else {              // Sigma'[gcol, grow]: through shared memory (the pipeline stages are idle now) so that lanes are consecutive gcol
-            double* tr = reinterpret_cast<double*>(smem) + (size_t)warp * 32 * OZF_TR_LD;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) tr[lane * OZF_TR_LD + j] = acc[j];
+        if (p.phase == 2) {   // Sigma'[gcol, grow] through shared memory so that the lanes of a warp are 32 consecutive gcol
             __syncwarp();
-            for (int rr = 0; rr < 32; ++rr) {
-                double* dst = p.Out + (size_t)(m0 + col0) + (size_t)ld * (m0 + tile_m * OZ_TILE + q * 32 + rr);
-                dst[lane] = tr[rr * OZF_TR_LD + lane];
-                dst[lane + 32] = tr[rr * OZF_TR_LD + lane + 32];
-            }
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr)
+                p.Out[(size_t)(gcol0 + lane) + (size_t)ld * (m0 + tile_m * OZ_TILE + q * 32 + rr)] = tr[rr * OZF_TR_LD + lane];
         }
         // ---- tile-row barrier: every tile of this row of tiles and its inner border jobs have published their maxima
         __threadfence();
+        OZ_STAMP(6);
         epi_bar();
         if (tid == 0) {
             atomicAdd(cnt + tile_m, 1);
             const int expected = Mt + nIB;
-            while (ld_acquire(cnt + tile_m) < expected) __nanosleep(200);
+            while (ld_acquire(cnt + tile_m) < expected) __nanosleep(100);
         }
         epi_bar();
+        OZ_STAMP(7);
         // ---- emission: this tile as int8 slices of the next product's operand (rows = operand rows, inner index = block-local column)
         {
             const int e = max(__ldcg(p.exOut + row), -900);
             const double up = oz_pow2(6 - e);
             const int sw = (r >> 2) & 1;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const int kk = col0 + 16 * c4;             // rotated inner index k' of the chunk's first column
-                double v[16];
+            for (int c2 = 0; c2 < 2; ++c2) {
+                const int kk = tile_n * OZ_TILE + lc0 + 16 * c2;   // rotated inner index k' of the chunk's first column
+                double x[16];
 #pragma unroll
-                for (int c = 0; c < 16; ++c) v[c] = (acc[c4 * 16 + c] * oz_pow2(-p.h[m0 + kk + c])) * up;
+                for (int c = 0; c < 16; ++c) x[c] = acc[c2 * 16 + c] * up;
                 const size_t tile = ((size_t)tile_m * KB + (kk >> 5)) * S;
                 const int in_tile = r * OZ_KBLOCK + ((((kk & 31) >> 4) ^ sw) << 4);
-                oz_emit16<S>(v, reinterpret_cast<uint4*>(p.slOut + tile * OZ_SLICE_TILE_BYTES + in_tile));
+                oz_emit16<S>(x, reinterpret_cast<uint4*>(p.slOut + tile * OZ_SLICE_TILE_BYTES + in_tile));
             }
         }
         // the inner border of this tile row (inner indices [0, m0), stored behind the block: k' = Mc + index), zero-padded to a whole k-block
@@ -751,28 +796,29 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_riccati(const OzFusedParam
             const double up = oz_pow2(6 - e);
             const int sw = (rb >> 2) & 1;
             const int nchunk = (KB - p.Mc / OZ_KBLOCK) * 2;       // 16-byte chunks per row
-            for (int ck = tid >> 7; ck < nchunk; ck += 2) {
-                double v[16];
+            for (int ck = tid >> 7; ck < nchunk; ck += OZF_EPI_THREADS / 128) {
+                double x[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const int idx = ck * 16 + c;                  // border inner index
-                    double x = 0.0;
+                    double xv = 0.0;
                     if (idx < m0) {
-                        x = __ldcg(p.phase == 1 ? p.Out + (size_t)growb + (size_t)ld * idx : p.Out + (size_t)idx + (size_t)ld * growb);
-                        x = (x * oz_pow2(-p.h[idx])) * up;
+                        xv = __ldcg(p.phase == 1 ? p.Out + (size_t)growb + (size_t)ld * idx : p.Out + (size_t)idx + (size_t)ld * growb);
+                        xv = (xv * oz_pow2(-p.h[idx])) * up;
                     }
-                    v[c] = x;
+                    x[c] = xv;
                 }
                 const int kk = p.Mc + ck * 16;
                 const size_t tile = ((size_t)tile_m * KB + (kk >> 5)) * S;
                 const int in_tile = rb * OZ_KBLOCK + ((((kk & 31) >> 4) ^ sw) << 4);
-                oz_emit16<S>(v, reinterpret_cast<uint4*>(p.slOut + tile * OZ_SLICE_TILE_BYTES + in_tile));
+                oz_emit16<S>(x, reinterpret_cast<uint4*>(p.slOut + tile * OZ_SLICE_TILE_BYTES + in_tile));
             }
         }
     }
+    OZ_STAMP(8);
     tc_fence_before();
     __syncthreads();
-    if (warp == OZ_MMA_WARP) {
+    if (warp == OZF_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -865,8 +911,8 @@ cudaError_t oz_riccati_fused(const OzFusedParams& p, int S, cudaStream_t stream)
     if (!oz_fused_supported(S, p.Mt) || p.Mc != p.Mt * OZ_TILE || p.n != p.m0 + p.Mc || p.m0 < 1 || p.KB * OZ_KBLOCK < p.n) return cudaErrorInvalidValue;
     if ((long long)p.KB * OZ_KBLOCK * 64 * 64 * S >= (1LL << 31)) return cudaErrorInvalidValue;
     const dim3 grid(p.Mt * p.Mt);
-    if (S == 7) k_oz_riccati<7><<<grid, OZ_THREADS, OzFusedCfg<7>::SMEM_BYTES, stream>>>(p);
-    else k_oz_riccati<8><<<grid, OZ_THREADS, OzFusedCfg<8>::SMEM_BYTES, stream>>>(p);
+    if (S == 7) k_oz_riccati<7><<<grid, OZF_THREADS, OzFusedCfg<7>::SMEM_BYTES, stream>>>(p);
+    else k_oz_riccati<8><<<grid, OZF_THREADS, OzFusedCfg<8>::SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 cudaError_t oz_split_F_rows(const double* F, int ld, int n, int m0, int S, const int* h, int8_t* slices, int* ex, cudaStream_t stream) {

@@ -109,7 +109,9 @@ struct OzFusedParams {
     int* syncReset;                         // 1 + Mt words to clear
     const double* T_dev;                    // phase 2: the step length (device memory, written by k_step_prepare)
     double Pd[5];                           // process variances: bias omega, bias accel, gravity, velocity, point
+    long long* stamps;                      // diagnostics (may be null): OZ_STAMPS clock64 stamps per CTA, see tools/oz_stamps.py
 };
+static const int OZ_STAMPS = 16;
 static const int OZ_FUSED_SYNC_INTS = 64;   // >= 1 + Mt
 bool oz_fused_supported(int S, int Mt);
 cudaError_t oz_riccati_fused(const OzFusedParams& p, int S, cudaStream_t stream);
