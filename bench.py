@@ -449,16 +449,16 @@ def int8_roofline_record(N, K, classes, g, dev_ms_local, peak_tf, peak_i8, slice
             traffic = None
     return {
         "bound": "tensor",
-        "kernel": f"eqvio::k_oz_gemm<{slices}> (tcgen05.mma.cta_group::1.kind::i8 128x128x32, int32 accumulators in TMEM, bulk-copy staged pre-swizzled int8 slice tiles): "
-                  f"the {mc} x {mc} landmark block of W = F Sigma and of Sigma' = W F^T + T B R B^T + T P, each fp64 product an exact sum of {pairs} int8 products ({slices} slices of 7 bits per operand); "
-                  "the rows / columns in front of the block run on fp64 DMMA strips (class riccati_gemm)",
+        "kernel": f"eqvio::k_oz_riccati<{slices}> (tcgen05.mma.cta_group::1.kind::i8 128x128x32, int32 accumulators in TMEM, bulk-copy staged pre-swizzled int8 slice tiles): "
+                  f"two launches per Riccati step, W = F Sigma and Sigma' = W F^T + T B R B^T + T P; the {mc} x {mc} landmark block of each fp64 product is an exact sum of {pairs} int8 products "
+                  f"({slices} slices of 7 bits per operand), the rows / columns in front of it are fp64 dots in the same launch, and the epilogue emits the result as the next product's int8 operand",
         "achieved": tops, "peak": peak_i8["value"], "unit": "TOP/s (int8 dense)", "frac": tops / peak_i8["value"] if peak_i8["value"] else None,
         "peak_source": peak_i8["source"],
         "traffic": traffic, "traffic_source": traffic_src,
         "launches": d_launches, "avg_launch_ms": d_ms / d_launches if d_launches else None,
         "int8_ops_per_launch": 2.0 * mc * mc * n_sigma * pairs,
-        "algorithmic_bytes_per_launch": 2 * slices * mc * kpad + 8 * mc * mc,
-        "algorithmic_bytes_note": "both operands' int8 slice arrays read once + the fp64 result block written once",
+        "algorithmic_bytes_per_launch": 3 * slices * mc * kpad + 8 * mc * mc,
+        "algorithmic_bytes_note": "both operands' int8 slice arrays read once + the fp64 result block and its int8 slices (the next product's operand) written once",
         "fp64_equivalent": {"achieved_tflops": eq_tf, "dgemm_peak_tflops": peak_tf, "ratio": eq_tf / peak_tf if peak_tf else None,
                             "note": "2 M N K of the fp64 product the int8 launches stand for, over their time; the DMMA pipe tops out at 37.1 TFLOP/s (profiles/r01_dmma_microbench.md)"},
         "riccati_step_fp64_equivalent_tflops": (sum(v["flops"] for v in whole.values()) / (K * STEPS_PER_PERIOD)) / 1e12,

@@ -112,10 +112,11 @@ struct eqvio_filter {
     int* strip_cnt[2] = {nullptr, nullptr};
     // The Riccati step's two products on the int8 tensor cores (ozaki_sm100.cuh) for the 128-aligned landmark block, DMMA strips for
     // the rows / columns in front of it, with S = 8 slices (fp64-equivalent accuracy) once that block has ozaki_min_tiles 128 x 128
-    // tiles (0.8 of a wave of the 148 SMs; measured: N = 512 1607 -> 1969 steps/s, N = 1024 223 -> 346, N = 384 3384 -> 2758).
+    // tiles (0.55 of a wave of the 148 SMs; measured with the fused kernel, steps/s DMMA -> int8: N = 1024 223 -> 424, N = 512 1607 -> 2632,
+    // N = 470 2009 -> 2942, N = 384 3370 -> 3823; N = 320 4922 -> 3678 and N = 256 8299 -> 5645 stay on DMMA).
     // EQVIO_OZAKI=S (7..9) selects the slice count, EQVIO_OZAKI=0 the fp64 DMMA path at every size.
     int ozaki_S = 8;
-    int ozaki_min_tiles = 121;
+    int ozaki_min_tiles = 81;
     int8_t *ozF[2] = {nullptr, nullptr}, *ozS = nullptr, *ozW = nullptr;   // int8 slices of F rows (by tick parity, like F), Sigma columns, W rows
     int *ozeF[2] = {nullptr, nullptr}, *ozeS = nullptr, *ozeW = nullptr;   // their row / column exponents
     int* ozH = nullptr;            // inner-dimension scales, 2^h[k] ~ sqrt(Sigma_kk) (OzKScale); refreshed after every change of Sigma outside the Riccati step

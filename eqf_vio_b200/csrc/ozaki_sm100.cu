@@ -668,34 +668,34 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
         for (int j = tile_n; j < nIB; j += Mt) ++my_inner;
         for (int j = oq; j < nOB; j += T) ++my_outer;
         const int my_jobs = my_inner + my_outer;
-        for (int done_jobs = 0; done_jobs < my_jobs; ++done_jobs) {
-            const bool inner = done_jobs < my_inner;
-            const int job = inner ? tile_n + done_jobs * Mt : oq + (done_jobs - my_inner) * T;
+        // all of this CTA's jobs as one flat loop over their outputs (no barrier between jobs: a thread has several independent dots in flight)
+        for (int t = tid; t < my_jobs * 32 * OZF_YC; t += OZF_EPI_THREADS) {
+            const int jn = t / (32 * OZF_YC), tt = t - jn * (32 * OZF_YC);
+            const bool inner = jn < my_inner;
+            const int job = inner ? tile_n + jn * Mt : oq + (jn - my_inner) * T;
             const int xb = job / nch, ch = job - xb * nch;
             // 32 x's (lanes) by up to OZF_YC y's; inner jobs: x = operand row (block row), y = border inner index; outer jobs:
             // x = any column index, y = border row
             const int y0 = ch * OZF_YC, ny = min(OZF_YC, m0 - y0);
             const int x0 = inner ? m0 + tile_m * OZ_TILE + xb * 32 : xb * 32;
-            if (tid < 32 * OZF_YC) {
-                const int x = x0 + (tid & 31), y = tid >> 5;
-                if (x < n && y < ny) {
-                    const int fr = inner ? x : y0 + y, o = inner ? y0 + y : x;
-                    double v = oz_border_dot(p, fr, o);
-                    if (p.phase == 2) {   // D[fr, o] = Sigma'[o, fr]
-                        double r6 = 0.0;
+            const int x = x0 + (tt & 31), y = tt >> 5;
+            if (x < n && y < ny) {
+                const int fr = inner ? x : y0 + y, o = inner ? y0 + y : x;
+                double v = oz_border_dot(p, fr, o);
+                if (p.phase == 2) {   // D[fr, o] = Sigma'[o, fr]
+                    double r6 = 0.0;
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) r6 = fma(Wx[(size_t)o + (size_t)ld * c], Fx[(size_t)fr + (size_t)ld * c], r6);
-                        v += r6;
-                        if (o == fr) v += Tstep * oz_process_noise(p, o);
-                    }
-                    p.Out[p.phase == 1 ? (size_t)fr + (size_t)ld * o : (size_t)o + (size_t)ld * fr] = v;
-                    if (inner) atomicMax(p.exOut + (fr - m0), oz_exponent(v) - p.h[o]);
+                    for (int c = 0; c < 6; ++c) r6 = fma(Wx[(size_t)o + (size_t)ld * c], Fx[(size_t)fr + (size_t)ld * c], r6);
+                    v += r6;
+                    if (o == fr) v += Tstep * oz_process_noise(p, o);
                 }
+                p.Out[p.phase == 1 ? (size_t)fr + (size_t)ld * o : (size_t)o + (size_t)ld * fr] = v;
+                if (inner) atomicMax(p.exOut + (fr - m0), oz_exponent(v) - p.h[o]);
             }
-            __threadfence();
-            epi_bar();
-            if (inner && tid == 0) atomicAdd(cnt + tile_m, 1);
         }
+        __threadfence();
+        epi_bar();
+        if (my_inner > 0 && tid == 0) atomicAdd(cnt + tile_m, my_inner);
         epi_bar();   // (the staged column factors are visible to every epilogue warp)
         OZ_STAMP(1);
 

@@ -1,11 +1,12 @@
 #!/bin/bash
-# Where the int8 Riccati path pays: steps/s with EQVIO_OZAKI=8 vs 0 over a range of N.  Usage: tools/gpu_oz_threshold.sh <tag> "<N list>"
-tag=${1:-ozth}; NL=${2:-"128 192 256 384 1024"}
+# Where the int8 Riccati path pays: steps/s with the int8 path forced on (EQVIO_OZAKI_MIN_TILES=4) vs off (EQVIO_OZAKI=0) over a range of N.
+# Usage: tools/gpu_oz_threshold.sh <tag> "<N list>"
+tag=${1:-ozth}; NL=${2:-"192 256 320 384"}
 mkdir -p gpurun_out
 for N in $NL; do
   for S in 0 8; do
     K=20; [ $N -ge 1024 ] && K=6
-    EQVIO_OZAKI=$S python bench.py --features $N --steps $K --warmup 3 --no-sub-configs --no-cpu-baseline > gpurun_out/${tag}_n${N}_oz$S.json 2> gpurun_out/${tag}_n${N}_oz$S.err
+    EQVIO_OZAKI=$S EQVIO_OZAKI_MIN_TILES=4 python bench.py --features $N --steps $K --warmup 3 --no-sub-configs --no-cpu-baseline > gpurun_out/${tag}_n${N}_oz$S.json 2> gpurun_out/${tag}_n${N}_oz$S.err
     python - <<PY
 import json
 d=json.load(open("gpurun_out/${tag}_n${N}_oz$S.json"))

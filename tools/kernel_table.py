@@ -38,13 +38,14 @@ for r in rows[1:]:
     if m.startswith("dram__bytes"):
         v = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
     per[lid][m] = v
-agg = defaultdict(lambda: dict(n=0, us=0.0, dmma=0.0, rd=0.0, wr=0.0, regs=0, waves=0.0, warps=0.0, grid=0.0))
+agg = defaultdict(lambda: dict(n=0, us=0.0, dmma=0.0, imma=0.0, rd=0.0, wr=0.0, regs=0, waves=0.0, warps=0.0, grid=0.0))
 for lid, m in per.items():
     a = agg[kname[lid]]
     us = m.get("gpu__time_duration.sum", 0.0)
     a["n"] += 1
     a["us"] += us
     a["dmma"] += us * m.get("sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", 0.0)
+    a["imma"] += us * m.get("sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active", 0.0)
     a["warps"] += us * m.get("sm__warps_active.avg.pct_of_peak_sustained_active", 0.0)
     a["rd"] += m.get("dram__bytes_read.sum", 0.0)
     a["wr"] += m.get("dram__bytes_write.sum", 0.0)
@@ -52,10 +53,10 @@ for lid, m in per.items():
     a["waves"] = max(a["waves"], m.get("launch__waves_per_multiprocessor", 0.0))
     a["grid"] = max(a["grid"], m.get("launch__grid_size", 0.0))
 tot = sum(a["us"] for a in agg.values())
-print("| kernel | launches | avg us | share | DMMA pipe %% | DRAM rd+wr per launch | DRAM GB/s (of %.1f measured) | regs | max grid | max waves/SM | warps active %% |" % hbm)
-print("|---|---|---|---|---|---|---|---|---|---|---|")
+print("| kernel | launches | avg us | share | DMMA pipe %% | int8 tensor pipe (tcgen05) %% | DRAM rd+wr per launch | DRAM GB/s (of %.1f measured) | regs | max grid | max waves/SM | warps active %% |" % hbm)
+print("|---|---|---|---|---|---|---|---|---|---|---|---|")
 for k, a in sorted(agg.items(), key=lambda x: -x[1]["us"]):
     us = a["us"] / a["n"]
     by = (a["rd"] + a["wr"]) / a["n"]
     gbs = (a["rd"] + a["wr"]) / (a["us"] * 1e-6) / 1e9 if a["us"] > 0 else 0.0
-    print(f"| `{k}` | {a['n']} | {us:.1f} | {100 * a['us'] / tot:.1f} % | {a['dmma'] / a['us'] if a['us'] else 0:.1f} | {by / 1e6:.3f} MB | {gbs:.0f} ({100 * gbs / hbm:.1f} %) | {a['regs']} | {int(a['grid'])} | {a['waves']:.2f} | {a['warps'] / a['us'] if a['us'] else 0:.1f} |")
+    print(f"| `{k}` | {a['n']} | {us:.1f} | {100 * a['us'] / tot:.1f} % | {a['dmma'] / a['us'] if a['us'] else 0:.1f} | {a['imma'] / a['us'] if a['us'] else 0:.1f} | {by / 1e6:.3f} MB | {gbs:.0f} ({100 * gbs / hbm:.1f} %) | {a['regs']} | {int(a['grid'])} | {a['waves']:.2f} | {a['warps'] / a['us'] if a['us'] else 0:.1f} |")

@@ -18,7 +18,7 @@ print("|---|---|" + "---|" * len(keys))
 blocks = re.split(r"\n\s*Function : ", out)
 for b in blocks[1:]:
     name = b.split("\n", 1)[0].strip()
-    ins = re.findall(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", b, flags=re.M)
+    ins = re.findall(r"^\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", b, flags=re.M)
     c = Counter()
     for i in ins:
         base = i.split(".")[0]
