@@ -530,6 +530,38 @@ template <int S> struct OzFusedCfg {
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the sixteen epilogue warps
 
+// The inner border of a tile row as int8 slices (inner indices [0, m0), stored behind the block: k' = Mc + index, zero-padded to a whole
+// k-block): done by the producer warp, which is idle once the last stage is in flight, while the epilogue warps emit the tile itself.
+// The tile row's 128 rows are shared out among its Mt CTAs.
+template <int S>
+__device__ __forceinline__ void oz_emit_inner_border(const OzFusedParams& p, int tile_m, int tile_n, int lane) {
+    const int Mt = p.Mt, m0 = p.m0, ld = p.ld, KB = p.KB;
+    const int rb_lo = tile_n * OZ_TILE / Mt, rb_n = (tile_n + 1) * OZ_TILE / Mt - rb_lo;
+    const int nchunk = (KB - p.Mc / OZ_KBLOCK) * 2;           // 16-byte chunks per row
+    for (int item = lane; item < rb_n * nchunk; item += 32) {
+        const int rb = rb_lo + item % rb_n, ck = item / rb_n;
+        const int rowb = tile_m * OZ_TILE + rb, growb = m0 + rowb;
+        const int e = max(__ldcg(p.exOut + rowb), -900);
+        const double up = oz_pow2(6 - e);
+        const int sw = (rb >> 2) & 1;
+        double x[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int idx = ck * 16 + c;                      // border inner index
+            double xv = 0.0;
+            if (idx < m0) {
+                xv = __ldcg(p.phase == 1 ? p.Out + (size_t)growb + (size_t)ld * idx : p.Out + (size_t)idx + (size_t)ld * growb);
+                xv = (xv * oz_pow2(-p.h[idx])) * up;
+            }
+            x[c] = xv;
+        }
+        const int kk = p.Mc + ck * 16;
+        const size_t tile = ((size_t)tile_m * KB + (kk >> 5)) * S;
+        const int in_tile = rb * OZ_KBLOCK + ((((kk & 31) >> 4) ^ sw) << 4);
+        oz_emit16<S>(x, reinterpret_cast<uint4*>(p.slOut + tile * OZ_SLICE_TILE_BYTES + in_tile));
+    }
+}
+
 #define OZ_STAMP(i) do { if (p.stamps && lane == 0 && (warp == 0 || warp == OZF_MMA_WARP)) p.stamps[(size_t)ticket * OZ_STAMPS + (i)] = clock64(); } while (0)
 template <int S>
 __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedParams p) {
@@ -559,13 +591,19 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, OZF_EPI_WARPS);
         mbar_fence_init();
-        // tiles by ticket: a CTA that waits for its tile row only ever waits for CTAs that started before it or that the hardware can
-        // still start (the lowest unfinished tile row is always completely dispatched), whatever the grid size
-        *ticket_slot = atomicAdd(p.sync, 1);
     }
     if (warp == OZF_MMA_WARP) {
         tmem_alloc(smem_u32(tmem_slot), 512);
         tmem_relinquish();
+    }
+    // launched with programmatic stream serialisation (oz_riccati_fused, pdl): everything above overlaps the previous launch's tail;
+    // its results (and the words it clears) are only touched behind this wait.  Without the attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) {
+        // tiles by ticket: a CTA that waits for its tile row only ever waits for CTAs that started before it or that the hardware can
+        // still start (the lowest unfinished tile row is always completely dispatched), whatever the grid size
+        *ticket_slot = atomicAdd(p.sync, 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -597,6 +635,14 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
                 }
             }
         }
+        __syncwarp();
+        // the tile-row barrier, observed from this warp: the rows' exponents and the inner-border values are final
+        {
+            const int nch = (p.m0 + OZF_YC - 1) / OZF_YC;
+            const int expected = Mt + 4 * nch;
+            while (ld_acquire(p.sync + 1 + tile_m) < expected) __nanosleep(200);
+        }
+        oz_emit_inner_border<S>(p, tile_m, tile_n, lane);
     } else if (warp == OZF_MMA_WARP) {
         uint32_t it = 0;
         const uint64_t adesc0 = smem_desc_sw32(base), bdesc0 = smem_desc_sw32(base + S * OZ_SLICE_TILE_BYTES);
@@ -712,8 +758,9 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((d - dmin) * OZ_TILE + cq * 32), v);
                 tmem_ld_wait();
+                // int32 -> fp64 without the conversion unit: 2^52 + 2^31 + x has x + 2^31 in its low mantissa word
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int)v[j], scale, acc[j]);
+                for (int j = 0; j < 32; ++j) acc[j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0, scale, acc[j]);
             }
             tc_fence_before();
             __syncwarp();
@@ -786,31 +833,6 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
                 for (int c = 0; c < 16; ++c) x[c] = acc[c2 * 16 + c] * up;
                 const size_t tile = ((size_t)tile_m * KB + (kk >> 5)) * S;
                 const int in_tile = r * OZ_KBLOCK + ((((kk & 31) >> 4) ^ sw) << 4);
-                oz_emit16<S>(x, reinterpret_cast<uint4*>(p.slOut + tile * OZ_SLICE_TILE_BYTES + in_tile));
-            }
-        }
-        // the inner border of this tile row (inner indices [0, m0), stored behind the block: k' = Mc + index), zero-padded to a whole k-block
-        if (tile_n == Mt - 1) {
-            const int rb = tid & 127, rowb = tile_m * OZ_TILE + rb, growb = m0 + rowb;
-            const int e = max(__ldcg(p.exOut + rowb), -900);
-            const double up = oz_pow2(6 - e);
-            const int sw = (rb >> 2) & 1;
-            const int nchunk = (KB - p.Mc / OZ_KBLOCK) * 2;       // 16-byte chunks per row
-            for (int ck = tid >> 7; ck < nchunk; ck += OZF_EPI_THREADS / 128) {
-                double x[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int idx = ck * 16 + c;                  // border inner index
-                    double xv = 0.0;
-                    if (idx < m0) {
-                        xv = __ldcg(p.phase == 1 ? p.Out + (size_t)growb + (size_t)ld * idx : p.Out + (size_t)idx + (size_t)ld * growb);
-                        xv = (xv * oz_pow2(-p.h[idx])) * up;
-                    }
-                    x[c] = xv;
-                }
-                const int kk = p.Mc + ck * 16;
-                const size_t tile = ((size_t)tile_m * KB + (kk >> 5)) * S;
-                const int in_tile = rb * OZ_KBLOCK + ((((kk & 31) >> 4) ^ sw) << 4);
                 oz_emit16<S>(x, reinterpret_cast<uint4*>(p.slOut + tile * OZ_SLICE_TILE_BYTES + in_tile));
             }
         }
@@ -907,13 +929,18 @@ cudaError_t oz_diag_scale(const double* Sigma, int ld, int n, int* h, cudaStream
 }
 
 bool oz_fused_supported(int S, int Mt) { return (S == 7 || S == 8) && Mt >= 2 && 1 + Mt <= OZ_FUSED_SYNC_INTS; }
-cudaError_t oz_riccati_fused(const OzFusedParams& p, int S, cudaStream_t stream) {
+cudaError_t oz_riccati_fused(const OzFusedParams& p, int S, cudaStream_t stream, bool pdl) {
     if (!oz_fused_supported(S, p.Mt) || p.Mc != p.Mt * OZ_TILE || p.n != p.m0 + p.Mc || p.m0 < 1 || p.KB * OZ_KBLOCK < p.n) return cudaErrorInvalidValue;
     if ((long long)p.KB * OZ_KBLOCK * 64 * 64 * S >= (1LL << 31)) return cudaErrorInvalidValue;
-    const dim3 grid(p.Mt * p.Mt);
-    if (S == 7) k_oz_riccati<7><<<grid, OZF_THREADS, OzFusedCfg<7>::SMEM_BYTES, stream>>>(p);
-    else k_oz_riccati<8><<<grid, OZF_THREADS, OzFusedCfg<8>::SMEM_BYTES, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(p.Mt * p.Mt); cfg.blockDim = dim3(OZF_THREADS); cfg.stream = stream;
+    cfg.dynamicSmemBytes = S == 7 ? OzFusedCfg<7>::SMEM_BYTES : OzFusedCfg<8>::SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return S == 7 ? cudaLaunchKernelEx(&cfg, k_oz_riccati<7>, p) : cudaLaunchKernelEx(&cfg, k_oz_riccati<8>, p);
 }
 cudaError_t oz_split_F_rows(const double* F, int ld, int n, int m0, int S, const int* h, int8_t* slices, int* ex, cudaStream_t stream) {
     const int Mc = n - m0, KB = (n + OZ_KBLOCK - 1) / OZ_KBLOCK;

@@ -114,7 +114,8 @@ struct OzFusedParams {
 static const int OZ_STAMPS = 16;
 static const int OZ_FUSED_SYNC_INTS = 64;   // >= 1 + Mt
 bool oz_fused_supported(int S, int Mt);
-cudaError_t oz_riccati_fused(const OzFusedParams& p, int S, cudaStream_t stream);
+// pdl: programmatic dependent launch behind the previous kernel of the stream (the prologue overlaps that kernel's tail)
+cudaError_t oz_riccati_fused(const OzFusedParams& p, int S, cudaStream_t stream, bool pdl = false);
 // F's rows [m0, n) as slices from their nine structural entries per row (see k_oz_split_F_rows); `slices` must be zero elsewhere.
 cudaError_t oz_split_F_rows(const double* F, int ld, int n, int m0, int S, const int* h, int8_t* slices, int* ex, cudaStream_t stream);
 
