@@ -126,6 +126,15 @@ struct eqvio_filter {
     size_t oz_bytes = 0;
     // fused form (ozaki_sm100.cuh, OzFusedParams): both products emit their result as the next product's int8 operand themselves; F's
     // rows are split on the state stream from their nine structural entries.  Exponent arrays and synchronisation words by tick parity.
+    // The covariance update's two products, K C and (K C) Sigma (VIOFilter.cpp:297), on the int8 tensor cores as well when the last Riccati
+    // launch's slices of the prior Sigma are still valid (no bookkeeping changed Sigma since): (K C) Sigma takes them as its B operand.
+    int oz_update = 0;             // EQVIO_OZ_UPDATE=1 turns it on.  Measured at N = 512 with the unfused product + split kernels: 2774 -> 2784 steps/s only —
+                                   // the split passes and the 222 KB CTAs waiting for whole SMs under the lift chain's GEMMs eat the gain; off by default
+    bool upd_oz = false;           // decided per update (part of the graph key)
+    int upd_oz_par = 0;            // which exponent array holds the prior Sigma's column exponents
+    int8_t* ozC = nullptr;         // slices of C's columns (B operand of K C)
+    int* ozeC = nullptr;
+    cudaEvent_t ev_oz_a = nullptr, ev_oz_b = nullptr;
     int oz_pdl = 1;                // the second launch of a step starts programmatically behind the first (EQVIO_OZ_PDL=0: plain stream order); N = 512: 2667 -> 2701 steps/s
     int oz_fused = 1;              // EQVIO_OZAKI_FUSED=0: the unfused sequence (split kernels and DMMA strips between the products)
     int *oz_exW[2] = {nullptr, nullptr}, *oz_exS[2] = {nullptr, nullptr};
@@ -343,6 +352,10 @@ static int ensure_capacity(Filter* f, int needN) {
         for (int** q : {&f->ozeF[0], &f->ozeF[1], &f->ozeS, &f->ozeW, &f->ozH}) { CU_TRY(dalloc(q, (size_t)ld + 256)); CU_TRY(cudaMemsetAsync(*q, 0, ((size_t)ld + 256) * sizeof(int), s)); }
         f->oz_bytes = bytes;
         f->oz_h_valid = f->oz_sigma_ex_valid = f->oz_F_ready = false;
+        cudaFree(f->ozC); cudaFree(f->ozeC);
+        CU_TRY(cudaMalloc((void**)&f->ozC, bytes));
+        CU_TRY(cudaMemsetAsync(f->ozC, 0, bytes, s));
+        CU_TRY(dalloc(&f->ozeC, (size_t)ld + 256));
         cudaFree(f->oz_words);
         const size_t ex_len = (size_t)ld + 256;
         f->oz_words_count = 4 * ex_len + 4 * OZ_FUSED_SYNC_INTS;
@@ -951,6 +964,65 @@ static void lift_solve(Filter* f, cudaStream_t s, int use_lift, int discrete, do
 
 // The measurement update, VIOFilter.cpp:264-297, on matched bearings f->y (3N, device).
 // want_lift = 0 stops after gamma / Sigma update (kernel-level entry point).
+// Sigma' = Sigma - (K C) Sigma (VIOFilter.cpp:297) with both products' 128-aligned blocks on the int8 tensor cores (reference association
+// kept).  On the side stream (f->cur):  split K's rows and C's columns -> K C block -> split its rows -> (K C) Sigma block against the
+// slices of the prior Sigma the last Riccati launch emitted (same rotated inner index, scales 2^(-h)); the m0 rows / columns in front
+// of the blocks are DMMA strips on the S chain's (by now idle) helper stream.
+static int sigma_update_ozaki(Filter* f) {
+    const int N = f->N, n = n_of(N), m = 2 * N, ld = f->ld, ldm = f->ldm, S = f->ozaki_S;
+    const int Mc = n / OZ_TILE * OZ_TILE, m0 = n - Mc;
+    cudaStream_t st = f->cur, sh = f->main_h;
+    double* KC = f->Wpp[0];
+    int rc;
+    // ---- K C: rows [m0, n) x columns [m0, n) on int8; rows [0, m0) (all columns) and columns [0, m0) (zero: C's base columns are) as strips
+    CU_TRY(cudaEventRecord(f->ev_oz_a, st));
+    CU_TRY(cudaStreamWaitEvent(sh, f->ev_oz_a, 0));
+    f->cur = sh;
+    if ((rc = gemm(f, 0, m0, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, KC, ld))) return rc;
+    if ((rc = gemm(f, 0, n, m0, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, KC, ld))) return rc;   // (TMA wants 16-byte aligned bases: whole columns; the corner is written twice)
+    f->cur = st;
+    OzOperand oK, oC, oKC, oS;
+    {
+        ProfScope ps(f, st, PROF_MISC);
+        CU_TRY(oz_split(f->K + m0, 1, ld, Mc, m, S, &oK, f->ozW, f->ozeW, st));                          // rows m0.. of K, inner index = measurement row
+        CU_TRY(oz_split(f->C + (size_t)m0 * ldm, ldm, 1, Mc, m, S, &oC, f->ozC, f->ozeC, st));          // columns m0.. of C
+        f->launches += 6;
+    }
+    {
+        ProfEvent pe;
+        prof_begin(f, pe, st, PROF_UPDATE, 2.0 * Mc * Mc * m);
+        CU_TRY(oz_gemm(oK, oC, Mc, Mc, 1.0, 0.0, nullptr, 0, KC + m0 + (size_t)m0 * ld, ld, st));
+        prof_end(f, pe, st);
+        f->launches += 1;
+    }
+    // ---- (K C) Sigma: rows [m0, n) of K C as the A operand (inner index = Sigma's row index, rotated, scaled 2^(+h)); B = the prior Sigma's slices
+    CU_TRY(cudaEventRecord(f->ev_oz_b, sh));
+    CU_TRY(cudaStreamWaitEvent(st, f->ev_oz_b, 0));       // the strips of K C (its columns [0, m0) are inner indices of the split below)
+    {
+        ProfScope ps(f, st, PROF_MISC);
+        const OzKScale kplus{f->ozH, +1};
+        CU_TRY(oz_split(KC + m0, 1, ld, Mc, n, S, &oKC, f->ozW, f->ozeW, st, &kplus, false, 0, m0));
+        f->launches += 3;
+    }
+    CU_TRY(cudaEventRecord(f->ev_oz_a, st));
+    CU_TRY(cudaStreamWaitEvent(sh, f->ev_oz_a, 0));        // K C is complete: the strips of the second product
+    f->cur = sh;
+    if ((rc = gemm(f, 0, m0, n, n, -1.0, KC, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld))) return rc;
+    if ((rc = gemm(f, 0, n, m0, n, -1.0, KC, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld))) return rc;
+    CU_TRY(cudaEventRecord(f->ev_oz_b, sh));
+    f->cur = st;
+    oS.slices = f->ozS; oS.ex = f->oz_exS[f->upd_oz_par]; oS.rows = Mc; oS.k = n; oS.rows_pad = Mc; oS.k_pad = round_up(n, OZ_KBLOCK); oS.S = S; oS.ex_margin = 0;
+    {
+        ProfEvent pe;
+        prof_begin(f, pe, st, PROF_UPDATE, 2.0 * Mc * Mc * n);
+        CU_TRY(oz_gemm(oKC, oS, Mc, Mc, -1.0, 1.0, f->Sigma + m0 + (size_t)m0 * ld, ld, f->Sigma2 + m0 + (size_t)m0 * ld, ld, st));
+        prof_end(f, pe, st);
+        f->launches += 1;
+    }
+    CU_TRY(cudaStreamWaitEvent(st, f->ev_oz_b, 0));
+    return EQVIO_OK;
+}
+
 static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     const int N = f->N, n = n_of(N), m = 2 * N, p = 5 + 3 * N, pb = round_up(p, 16), ld = f->ld, ldm = f->ldm;
     int st;
@@ -1022,6 +1094,9 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
             for (int d = 0; d < f->trail_delay; ++d) { launch_nop(f->side); f->launches += 1; }
         }
         double* KC = f->Wpp[0];   // columns [0, n) of a Riccati work buffer; fixed (not parity-dependent) so that the update graph's key is not
+        if (f->upd_oz) {
+            if ((st = sigma_update_ozaki(f))) return st;
+        } else
         if ((st = gemm_pair(f, make_problem(f, 0, n, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, KC, ld, 0, 0.0),
                             make_problem(f, 0, n, n, n, -1.0, KC, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld, 0, 0.0), PAIR_SIGMA))) return st;
         stamp(f, f->side, ST_SIDE2_DONE);
@@ -1060,10 +1135,13 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
 
 static int update(Filter* f, bool do_lift, bool do_sigma) {
     f->main_dirty = true;
+    // the slices of the prior Sigma the last Riccati launch emitted serve the covariance update, if nothing else touched Sigma since
+    f->upd_oz = do_sigma && f->oz_update && ozaki_fused_applies(f) && f->oz_sigma_ex_valid && f->oz_h_valid && f->oz_valid_par >= 0;
+    f->upd_oz_par = f->upd_oz ? f->oz_valid_par : 0;
     f->oz_h_valid = f->oz_sigma_ex_valid = false;   // Sigma changes outside the Riccati step
     int st = prepare_layout(f);
     if (st) return st;
-    const int flags = (do_lift ? 1 : 0) | (do_sigma ? 2 : 0);
+    const int flags = (do_lift ? 1 : 0) | (do_sigma ? 2 : 0) | (f->upd_oz ? 4 | (f->upd_oz_par << 3) : 0);
     if ((st = run_graphed(f, GRAPH_UPDATE, flags, [&]() { return update_launches(f, do_lift, do_sigma); }))) return st;
     if (do_sigma) std::swap(f->Sigma, f->Sigma2);   // the update wrote the twin buffer
     return EQVIO_OK;
@@ -1161,7 +1239,9 @@ static void destroy_filter(Filter* f) {
     cudaFree(f->sk_sync); cudaFree(f->sk_ws); cudaFree(f->splitk_ws);
     for (int i = 0; i < 2; ++i) { cudaFree(f->strip_ws[i]); cudaFree(f->strip_cnt[i]); }
     for (void* q : {(void*)f->ozF[0], (void*)f->ozF[1], (void*)f->ozS, (void*)f->ozW, (void*)f->ozeF[0], (void*)f->ozeF[1], (void*)f->ozeS, (void*)f->ozeW, (void*)f->ozH}) cudaFree(q);
-    cudaFree(f->oz_words); cudaFree(f->oz_stamps);
+    cudaFree(f->oz_words); cudaFree(f->oz_stamps); cudaFree(f->ozC); cudaFree(f->ozeC);
+    if (f->ev_oz_a) cudaEventDestroy(f->ev_oz_a);
+    if (f->ev_oz_b) cudaEventDestroy(f->ev_oz_b);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->pose_pub); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
     if (f->h_stage) cudaFreeHost(f->h_stage);
     if (f->h_istage) cudaFreeHost(f->h_istage);
@@ -1214,6 +1294,9 @@ static int create_impl(Filter* f) {
     if (const char* e = getenv("EQVIO_OZAKI_MIN_TILES")) f->ozaki_min_tiles = std::max(4, atoi(e));
     if (const char* e = getenv("EQVIO_OZAKI_FUSED")) f->oz_fused = atoi(e);
     if (const char* e = getenv("EQVIO_OZ_PDL")) f->oz_pdl = atoi(e);
+    if (const char* e = getenv("EQVIO_OZ_UPDATE")) f->oz_update = atoi(e);
+    CU_TRY(cudaEventCreateWithFlags(&f->ev_oz_a, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&f->ev_oz_b, cudaEventDisableTiming));
     if (const char* e = getenv("EQVIO_OZ_STAMPS"))
         if (e[0] == '1') { CU_TRY(cudaMalloc((void**)&f->oz_stamps, (size_t)2 * 1024 * OZ_STAMPS * 8)); CU_TRY(cudaMemset(f->oz_stamps, 0, (size_t)2 * 1024 * OZ_STAMPS * 8)); }
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
