@@ -436,7 +436,7 @@ def int8_roofline_record(N, K, classes, g, dev_ms_local, peak_tf, peak_i8, slice
     tops = d_flops * pairs / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
     eq_tf = d_flops / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
     n_sigma = 11 + 3 * N
-    mc = n_sigma // 128 * 128
+    mc = (n_sigma - 11) // 128 * 128
     kpad = (n_sigma + 31) // 32 * 32
     whole = {k: classes[k] for k in ("riccati_gemm", "riccati_i8_gemm")}
     traffic, traffic_src = None, None

@@ -290,7 +290,10 @@ static void free_device(Filter* f) {
 
 // (Re)allocate every capacity-dependent buffer for `cap` landmarks, preserving Sigma (n x n) and the
 // landmark arrays of the current N.
-static bool ozaki_size(const Filter* f, int N) { const int t = n_of(N) / OZ_TILE; return f->ozaki_S > 0 && t >= 2 && t * t >= f->ozaki_min_tiles; }
+// The 128-aligned block of the int8 path covers landmark states only: Mc = 128 floor(3N / 128); the border in front of it — the 11 base
+// states and what 3N leaves over 128 — has m0 = n - Mc in [11, 138] rows / columns.
+static int oz_core(int n) { return (n - EQVIO_SIGMA_BASE_SIZE) / OZ_TILE * OZ_TILE; }
+static bool ozaki_size(const Filter* f, int N) { const int t = oz_core(n_of(N)) / OZ_TILE; return f->ozaki_S > 0 && t >= 2 && t * t >= f->ozaki_min_tiles; }
 static int ensure_capacity(Filter* f, int needN) {
     if (needN <= f->cap) return EQVIO_OK;
     int cap = f->cap ? f->cap : 64;
@@ -631,7 +634,7 @@ static int strip_gemm(Filter* f, const GemmProblem& g, int which, cudaStream_t s
 // ->  product 2  ->  border maxima.
 static int riccati_ozaki(Filter* f, double T) {
     const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld, S = f->ozaki_S;
-    const int Mc = n / OZ_TILE * OZ_TILE, m0 = n - Mc;
+    const int Mc = oz_core(n), m0 = n - Mc;
     cudaStream_t st = f->stream, s2 = f->side, s3 = f->lift;
     int rc;
     f->prof_cls = PROF_RICCATI;
@@ -719,11 +722,11 @@ static int riccati_ozaki(Filter* f, double T) {
 }
 
 static bool ozaki_fused_applies(const Filter* f) {
-    return ozaki_applies(f) && f->oz_fused && f->oz_words && oz_fused_supported(f->ozaki_S, n_of(f->N) / OZ_TILE);
+    return ozaki_applies(f) && f->oz_fused && f->oz_words && oz_fused_supported(f->ozaki_S, oz_core(n_of(f->N)) / OZ_TILE);
 }
 // F's rows [m0, n) as int8 slices (nine structural entries per row) on stream `s`; the rest of the array is cleared when the layout changes
 static int split_F_rows(Filter* f, cudaStream_t s) {
-    const int n = n_of(f->N), m0 = n % OZ_TILE, par = f->par;
+    const int n = n_of(f->N), m0 = n - oz_core(n), par = f->par;
     ProfScope ps(f, s, PROF_MISC);
     if (f->oz_F_layout[par] != n) {
         CU_TRY(cudaMemsetAsync(f->ozF[par], 0, f->oz_bytes, s));
@@ -738,7 +741,7 @@ static int split_F_rows(Filter* f, cudaStream_t s) {
 // synchronisation words are cleared and Sigma is split by the generic kernels first.
 static int riccati_ozaki_fused(Filter* f, double T) {
     const int n = n_of(f->N), n16 = round_up(n, 16), ld = f->ld, S = f->ozaki_S, par = f->par;
-    const int Mc = n / OZ_TILE * OZ_TILE, m0 = n - Mc, Mt = Mc / OZ_TILE, KB = round_up(n, OZ_KBLOCK) / OZ_KBLOCK;
+    const int Mc = oz_core(n), m0 = n - Mc, Mt = Mc / OZ_TILE, KB = round_up(n, OZ_KBLOCK) / OZ_KBLOCK;
     cudaStream_t st = f->stream;
     f->prof_cls = PROF_RICCATI;
     struct Guard { Filter* f; ~Guard() { f->prof_cls = PROF_UPDATE; f->cur = f->stream; } } guard{f};
@@ -970,7 +973,7 @@ static void lift_solve(Filter* f, cudaStream_t s, int use_lift, int discrete, do
 // of the blocks are DMMA strips on the S chain's (by now idle) helper stream.
 static int sigma_update_ozaki(Filter* f) {
     const int N = f->N, n = n_of(N), m = 2 * N, ld = f->ld, ldm = f->ldm, S = f->ozaki_S;
-    const int Mc = n / OZ_TILE * OZ_TILE, m0 = n - Mc;
+    const int Mc = oz_core(n), m0 = n - Mc;
     cudaStream_t st = f->cur, sh = f->main_h;
     double* KC = f->Wpp[0];
     int rc;

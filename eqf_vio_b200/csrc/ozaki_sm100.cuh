@@ -83,7 +83,7 @@ cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double
 cudaError_t oz_init_device();
 
 // ---- the Riccati step as two launches of one kernel ------------------------------------------------------------------------------
-// Sigma (n x n, n = m0 + Mc) = [border: the first m0 = n mod 128 rows / columns | block: Mc = 128 Mt].  Both products of
+// Sigma (n x n, n = m0 + Mc) = [border: the first m0 = 11 + (3N mod 128) rows / columns, i.e. at least the base states | block: Mc = 128 Mt of landmark states].  Both products of
 // VIOFilter.cpp:188-189 are computed for the block on the int8 tensor cores with F's rows as the A operand:
 //   phase 1:  D[i, c] = W[i, c]       = sum_k F[i, k] Sigma[k, c]         B operand = Sigma's columns  (X = Sigma, Out = W)
 //   phase 2:  D[j, i] = Sigma'[i, j]  = sum_k F[j, k] W[i, k] + ...       B operand = W's rows         (X = W, Out = Sigma', stored transposed)

@@ -122,10 +122,11 @@ def _riccati_run(monkeypatch, N, env, ticks):
     return _MID[N], out, slices
 
 
-@pytest.mark.parametrize("N", [512, 500, 470])
+@pytest.mark.parametrize("N", [512, 500, 470, 511])
 def test_fused_riccati_matches_unfused_dmma_and_oracle(monkeypatch, N):
     """N = 512: n = 1547 = 11 + 12 x 128 (the border is the 11 base states).  N = 500: n = 1511 = 103 + 11 x 128 and N = 470:
-    n = 1421 = 13 + 11 x 128 — the border holds landmark rows as well, several border jobs per tile row.  Nine IMU ticks behind the
+    n = 1421 = 13 + 11 x 128 — the border holds landmark rows as well, several border jobs per tile row.  N = 511: n = 1544 =
+    12 x 128 + 8, where n mod 128 is smaller than the 11 base states (the block is 128 floor(3N / 128) = 1408, the border 136).  Nine IMU ticks behind the
     first vision update: the first tick splits Sigma with the generic kernels, the others run on what the previous launch emitted."""
     from eqf_vio_b200.settings import conditioned_settings
     from eqf_vio_b200.synthetic import period_sequence

@@ -27,7 +27,7 @@ abi.check(L.eqvio_oz_stamps(f._h, None, 0, C.byref(cnt)), "stamps")
 buf = np.zeros(cnt.value, dtype=np.int64)
 abi.check(L.eqvio_oz_stamps(f._h, buf.ctypes.data_as(C.POINTER(C.c_longlong)), cnt.value, C.byref(cnt)), "stamps")
 n = 11 + 3 * N
-T = (n // 128) ** 2
+T = ((n - 11) // 128) ** 2
 names = ["start", "jobs0 done", "acc0 full", "acc0 read", "acc1 full", "acc1 read", "fp64 stored", "row barrier passed", "emitted"]
 for ph in range(2):
     st = buf[ph * 1024 * 16:(ph * 1024 + T) * 16].reshape(T, 16)
