@@ -43,3 +43,20 @@ print("chain block", np.isfinite(LU).all())
 A = rng.standard_normal((45, 37)); B = rng.standard_normal((37, 50))
 C, _ = dgemm(A, B)
 print("gemm", np.abs(C - A @ B).max())
+# the int8 tensor-core Riccati path at a size a sanitizer can afford (forced on: 4 tiles, border with landmark rows): fused kernel
+# (tickets, tile-row barriers, emission), structural split of F, generic split kernels behind each update, and the unfused product
+if os.environ.get("EQVIO_SANITIZE_INT8", "1") != "0":
+    os.environ["EQVIO_OZAKI_MIN_TILES"] = "4"
+    s = conditioned_settings(outlierThreshold=1e9)
+    seq = period_sequence(90, 3, camera_offset=tuple(s.cameraOffset))
+    f = VIOFilter(s)
+    for kind, i in seq.events():
+        if kind == "imu":
+            f.processIMUData(seq.imu[i, 0], seq.imu[i, 1:4], seq.imu[i, 4:7])
+        else:
+            f.processVisionData(seq.vision_stamps[i], seq.ids, seq.bearings[i])
+    print("N 90 int8 slices", f.riccati_int8_slices(), "finite", np.isfinite(f.stateCovariance()).all(), "graph replays", f.graph_stats())
+    from eqf_vio_b200.filter import dgemm_ozaki
+    A = rng.standard_normal((139, 150)); B = rng.standard_normal((150, 260))
+    C, _, _ = dgemm_ozaki(A, B, slices=8)
+    print("ozaki gemm", np.abs(C - A @ B).max())
