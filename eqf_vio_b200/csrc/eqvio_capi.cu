@@ -770,6 +770,7 @@ static int riccati_ozaki_fused(Filter* f, double T) {
     p.Mc = Mc; p.m0 = m0; p.n = n; p.n16 = n16; p.KB = KB; p.Mt = Mt; p.ld = ld;
     p.slA = f->ozF[par]; p.exA = f->ozeF[par]; p.F = f->F; p.h = f->ozH;
     p.T_dev = &f->sc->Tpp[par];
+    p.err = &f->st->flags;   // a wait that gives up surfaces as EQVIO_ERR_NAN through the asynchronous error model (eqvio_get_flags)
     p.Pd[0] = f->s.biasOmegaProcessVariance; p.Pd[1] = f->s.biasAccelProcessVariance; p.Pd[2] = f->s.gravityProcessVariance;
     p.Pd[3] = f->s.velocityProcessVariance; p.Pd[4] = f->s.pointProcessVariance;
     {   // W = F Sigma, emitted as the second product's operand

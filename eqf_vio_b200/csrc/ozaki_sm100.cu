@@ -455,6 +455,19 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     return v;
 }
 
+// Bounded wait for a counter other CTAs of the launch advance (release side: __threadfence + atomicAdd).  Tiles are taken by ticket, so
+// the wait ends as soon as the hardware has run the CTAs in front; if it does not within ~2^31 clocks (about a second: a fault in
+// another CTA, the context losing its SMs) the wait gives up and raises the filter's NaN flag instead of hanging the GPU — the
+// launch's results are then invalid and the host sees EQVIO_ERR_NAN at its next status read.
+__device__ __forceinline__ void oz_wait_ge(const int* ctr, int target, int* err) {
+    if (ld_acquire(ctr) >= target) return;
+    const long long t0 = clock64();
+    while (ld_acquire(ctr) < target) {
+        __nanosleep(100);
+        if (clock64() - t0 > (1LL << 31)) { if (err) atomicOr(err, 2); return; }   // (2 = FLAG_NAN of the filter's device flags)
+    }
+}
+
 // Border outputs D[fr, o] = sum_k F[fr, k] B(o, k) (B(o, k) = Sigma[k, o] in phase 1, W[o, k] in phase 2).  Row fr of F = I + T A_b is
 // zero outside the 11 base columns and — for a landmark row — its own 3 x 3 block (EqFMatrices.cpp:289-312: the only couplings are
 // bias / gravity / velocity -> everything and landmark -> itself), so the sum over all k has at most 14 terms that are not exact zeros;
@@ -639,8 +652,7 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
         // the tile-row barrier, observed from this warp: the rows' exponents and the inner-border values are final
         {
             const int nch = (p.m0 + OZF_YC - 1) / OZF_YC;
-            const int expected = Mt + 4 * nch;
-            while (ld_acquire(p.sync + 1 + tile_m) < expected) __nanosleep(200);
+            oz_wait_ge(p.sync + 1 + tile_m, Mt + 4 * nch, p.err);
         }
         oz_emit_inner_border<S>(p, tile_m, tile_n, lane);
     } else if (warp == OZF_MMA_WARP) {
@@ -815,8 +827,7 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
         epi_bar();
         if (tid == 0) {
             atomicAdd(cnt + tile_m, 1);
-            const int expected = Mt + nIB;
-            while (ld_acquire(cnt + tile_m) < expected) __nanosleep(100);
+            oz_wait_ge(cnt + tile_m, Mt + nIB, p.err);
         }
         epi_bar();
         OZ_STAMP(7);

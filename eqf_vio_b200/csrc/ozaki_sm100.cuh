@@ -109,6 +109,7 @@ struct OzFusedParams {
     int* syncReset;                         // 1 + Mt words to clear
     const double* T_dev;                    // phase 2: the step length (device memory, written by k_step_prepare)
     double Pd[5];                           // process variances: bias omega, bias accel, gravity, velocity, point
+    int* err;                               // device flags word: bit 1 (FLAG_NAN) is raised if an in-kernel wait gives up after about a second
     long long* stamps;                      // diagnostics (may be null): OZ_STAMPS clock64 stamps per CTA, see tools/oz_stamps.py
 };
 static const int OZ_STAMPS = 16;
