@@ -778,7 +778,7 @@ static int riccati_ozaki_fused(Filter* f, double T) {
         p.slB = f->ozS; p.exB = f->oz_exS[par]; p.X = f->Sigma; p.Out = f->W;
         p.slOut = f->ozW; p.exOut = f->oz_exW[par]; p.exReset = f->oz_exW[par ^ 1];
         p.sync = f->oz_sync1[par]; p.syncReset = f->oz_sync1[par ^ 1];
-        p.stamps = (f->oz_stamps && Mt * Mt <= 1024) ? f->oz_stamps : nullptr;
+        p.stamps = (f->oz_stamps && Mt * Mt <= 1024) ? f->oz_stamps + (size_t)(2 * par) * 1024 * OZ_STAMPS : nullptr;   // (by tick parity: the last two steps are kept)
         ProfEvent pe;
         prof_begin(f, pe, st, PROF_RICCATI_I8, 2.0 * n * n * n);
         CU_TRY(oz_riccati_fused(p, S, st));
@@ -790,7 +790,7 @@ static int riccati_ozaki_fused(Filter* f, double T) {
         p.slB = f->ozW; p.exB = f->oz_exW[par]; p.X = f->W; p.Out = f->Sigma2;
         p.slOut = f->ozS; p.exOut = f->oz_exS[par ^ 1]; p.exReset = f->oz_exS[par];
         p.sync = f->oz_sync2[par]; p.syncReset = f->oz_sync2[par ^ 1];
-        p.stamps = (f->oz_stamps && Mt * Mt <= 1024) ? f->oz_stamps + (size_t)1024 * OZ_STAMPS : nullptr;
+        p.stamps = (f->oz_stamps && Mt * Mt <= 1024) ? f->oz_stamps + (size_t)(2 * par + 1) * 1024 * OZ_STAMPS : nullptr;
         ProfEvent pe;
         prof_begin(f, pe, st, PROF_RICCATI_I8, 2.0 * n * n * n);
         CU_TRY(oz_riccati_fused(p, S, st, f->oz_pdl != 0));
@@ -1302,7 +1302,7 @@ static int create_impl(Filter* f) {
     CU_TRY(cudaEventCreateWithFlags(&f->ev_oz_a, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&f->ev_oz_b, cudaEventDisableTiming));
     if (const char* e = getenv("EQVIO_OZ_STAMPS"))
-        if (e[0] == '1') { CU_TRY(cudaMalloc((void**)&f->oz_stamps, (size_t)2 * 1024 * OZ_STAMPS * 8)); CU_TRY(cudaMemset(f->oz_stamps, 0, (size_t)2 * 1024 * OZ_STAMPS * 8)); }
+        if (e[0] == '1') { CU_TRY(cudaMalloc((void**)&f->oz_stamps, (size_t)4 * 1024 * OZ_STAMPS * 8)); CU_TRY(cudaMemset(f->oz_stamps, 0, (size_t)4 * 1024 * OZ_STAMPS * 8)); }
     if (const char* e = getenv("EQVIO_TRAIL_DELAY")) f->trail_delay = std::max(0, std::min(16, atoi(e)));
     if (const char* e = getenv("EQVIO_STAMPS"))
         if (e[0] == '1') { CU_TRY(dalloc(&f->stamps, 512)); CU_TRY(cudaMemset(f->stamps, 0, 512 * 8)); }
@@ -2232,7 +2232,7 @@ int eqvio_profile_timeline(eqvio_handle_t f, double* out, size_t cap_entries, si
 }
 int eqvio_oz_stamps(eqvio_handle_t f, long long* out, size_t cap_words, size_t* count) {
     if (!f || !count) return EQVIO_ERR_ARG;
-    *count = f->oz_stamps ? (size_t)2 * 1024 * OZ_STAMPS : 0;
+    *count = f->oz_stamps ? (size_t)4 * 1024 * OZ_STAMPS : 0;
     if (out && f->oz_stamps) {
         CU_TRY(cudaSetDevice(f->device));
         CU_TRY(cudaStreamSynchronize(f->stream));

@@ -629,6 +629,7 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
         for (int i = threadIdx.x; i <= Mt; i += OZF_THREADS) p.syncReset[i] = 0;
     if (tile_n == 0 && threadIdx.x < OZ_TILE) p.exReset[tile_m * OZ_TILE + threadIdx.x] = OZ_EX_RESET;
     OZ_STAMP(0);
+    if (p.stamps && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); p.stamps[(size_t)ticket * OZ_STAMPS + 11] = (long long)g; }
 
     if (warp == OZF_PRODUCER_WARP) {
         if (lane == 0) {
@@ -855,6 +856,7 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+    if (p.stamps && threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); p.stamps[(size_t)ticket * OZ_STAMPS + 15] = (long long)g; }
 }
 
 // F's landmark rows as int8 slices without reading the zeros: row g >= 11 of F = I + T A_b (EqFMatrices.cpp:292-312, VIOFilter.cpp:177-185)

@@ -269,7 +269,7 @@ int eqvio_profile_timeline(eqvio_handle_t h, double* out, size_t cap_entries, si
  * bits), the rows / columns in front of that block on fp64 DMMA.  Selected per size (environment EQVIO_OZAKI, 0 = never). */
 int eqvio_riccati_arith(eqvio_handle_t h, int* int8_slices);
 /* Diagnostics of the int8 Riccati kernel (environment EQVIO_OZ_STAMPS=1 at eqvio_create, else *count = 0): per-CTA clock stamps of
- * the last two launches, 2 x 1024 x 16 words (tools/oz_stamps.py names them). */
+ * the last two steps (four launches, by tick parity), 4 x 1024 x 16 words (tools/oz_stamps.py names them). */
 int eqvio_oz_stamps(eqvio_handle_t h, long long* out, size_t cap_words, size_t* count);
 /* The handle's CUDA stream (cudaStream_t as void*), for callers that order their own work after it. */
 int eqvio_stream(eqvio_handle_t h, void** stream);
