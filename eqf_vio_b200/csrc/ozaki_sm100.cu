@@ -806,8 +806,10 @@ __global__ void __launch_bounds__(OZF_THREADS, 1) k_oz_riccati(const OzFusedPara
                     v += r6;
                     if (grow == gcol0 + j) v += tp;
                     tr[lane * OZF_TR_LD + j] = v;
-                } else {
-                    p.Out[(size_t)grow + (size_t)ld * (gcol0 + j)] = v;   // W[grow, gcol]: the lanes of a warp are 32 consecutive rows of one column
+                } else if (gcol0 + j < m0 + 2) {
+                    // W's block is consumed as int8 slices only; in fp64 the second product's border dots read W's border columns (written
+                    // by the border jobs) and — for a landmark row that ends the border — at most the block's first two columns
+                    p.Out[(size_t)grow + (size_t)ld * (gcol0 + j)] = v;
                 }
                 const double vs = v * s_ch[lc0 + j];
                 emax = max(emax, __double2hiint(vs) & 0x7fffffff);
