@@ -128,12 +128,22 @@ struct eqvio_filter {
     // rows are split on the state stream from their nine structural entries.  Exponent arrays and synchronisation words by tick parity.
     // The covariance update's two products, K C and (K C) Sigma (VIOFilter.cpp:297), on the int8 tensor cores as well when the last Riccati
     // launch's slices of the prior Sigma are still valid (no bookkeeping changed Sigma since): (K C) Sigma takes them as its B operand.
-    int oz_update = 0;             // EQVIO_OZ_UPDATE=1 turns it on.  Measured at N = 512 with the unfused product + split kernels: 2774 -> 2784 steps/s only —
-                                   // the split passes and the 222 KB CTAs waiting for whole SMs under the lift chain's GEMMs eat the gain; off by default
+    int oz_sct = -1;               // Sigma C^T and K = (Sigma C^T) S^-1 (VIOFilter.cpp:277) on the int8 path as well: -1 = where the block has oz_all_min_tiles tiles
+                                   // (EQVIO_OZ_SCT=0 / 1: never / always).  Measured, steps/s with S formation only -> + these two -> + the covariance update:
+                                   // N = 512 2917 -> 2966 -> 3012, N = 1024 448 -> 451 -> 490, N = 384 4125 -> 4064 -> 3991
+    int oz_all_min_tiles = 121;
+    int oz_pre = 1;                // C Sigma and (C Sigma) C^T (VIOFilter.cpp:276) on the int8 path too (same validity condition as oz_update; EQVIO_OZ_PRE=0: DMMA).
+                                   // Not faster than the DMMA pair in itself, but one CTA per SM on 96 + 64 SMs leaves the lift chain free SMs: N = 512 2809 -> 2917 steps/s
+    bool upd_oz_pre = false, upd_oz_sct = false;
+    int oz_update = -1;            // K C and (K C) Sigma: -1 = where the block has oz_all_min_tiles tiles (EQVIO_OZ_UPDATE=0 / 1: never / always).  Alone it gains nothing
+                                   // (N = 512: 2774 -> 2784: its 222 KB CTAs wait for whole SMs under the lift chain's DMMA GEMMs); behind the int8 S formation,
+                                   // which lets the lift chain finish 170 us earlier, it does (2966 -> 3012)
     bool upd_oz = false;           // decided per update (part of the graph key)
     int upd_oz_par = 0;            // which exponent array holds the prior Sigma's column exponents
-    int8_t* ozC = nullptr;         // slices of C's columns (B operand of K C)
+    int8_t* ozC = nullptr;         // slices of C's rows (S, Sigma C^T) / columns (K C)
     int* ozeC = nullptr;
+    int8_t *ozR = nullptr, *ozT = nullptr;   // slices of Sigma's rows (Sigma C^T) and of S^-1's columns (K)
+    int *ozeR = nullptr, *ozeT = nullptr;
     cudaEvent_t ev_oz_a = nullptr, ev_oz_b = nullptr;
     int oz_pdl = 1;                // the second launch of a step starts programmatically behind the first (EQVIO_OZ_PDL=0: plain stream order); N = 512: 2667 -> 2701 steps/s
     int oz_fused = 1;              // EQVIO_OZAKI_FUSED=0: the unfused sequence (split kernels and DMMA strips between the products)
@@ -355,10 +365,9 @@ static int ensure_capacity(Filter* f, int needN) {
         for (int** q : {&f->ozeF[0], &f->ozeF[1], &f->ozeS, &f->ozeW, &f->ozH}) { CU_TRY(dalloc(q, (size_t)ld + 256)); CU_TRY(cudaMemsetAsync(*q, 0, ((size_t)ld + 256) * sizeof(int), s)); }
         f->oz_bytes = bytes;
         f->oz_h_valid = f->oz_sigma_ex_valid = f->oz_F_ready = false;
-        cudaFree(f->ozC); cudaFree(f->ozeC);
-        CU_TRY(cudaMalloc((void**)&f->ozC, bytes));
-        CU_TRY(cudaMemsetAsync(f->ozC, 0, bytes, s));
-        CU_TRY(dalloc(&f->ozeC, (size_t)ld + 256));
+        cudaFree(f->ozC); cudaFree(f->ozeC); cudaFree(f->ozR); cudaFree(f->ozeR); cudaFree(f->ozT); cudaFree(f->ozeT);
+        for (int8_t** q : {&f->ozC, &f->ozR, &f->ozT}) { CU_TRY(cudaMalloc((void**)q, bytes)); CU_TRY(cudaMemsetAsync(*q, 0, bytes, s)); }
+        for (int** q : {&f->ozeC, &f->ozeR, &f->ozeT}) CU_TRY(dalloc(q, (size_t)ld + 256));
         cudaFree(f->oz_words);
         const size_t ex_len = (size_t)ld + 256;
         f->oz_words_count = 4 * ex_len + 4 * OZ_FUSED_SYNC_INTS;
@@ -1027,6 +1036,54 @@ static int sigma_update_ozaki(Filter* f) {
     return EQVIO_OK;
 }
 
+// S = (C Sigma) C^T (VIOFilter.cpp:276, reference association) with both products on the int8 tensor cores: C's rows are split once
+// (rotated inner index, scales 2^(+h)) and serve as the A operand of C Sigma — against the slices of the prior Sigma the last Riccati
+// launch emitted — and as the B operand of (C Sigma) C^T, whose A operand is the split of C Sigma (scales 2^(-h)).  One CTA per SM on
+// 96 + 64 SMs: the lift chain's kernels keep finding free SMs while S is formed (with the DMMA GEMMs its first links take 100-140 us).
+static int form_S_ozaki(Filter* f) {
+    const int N = f->N, n = n_of(N), m = 2 * N, ld = f->ld, ldm = f->ldm, S = f->ozaki_S;
+    const int Mc = oz_core(n), m0 = n - Mc;
+    cudaStream_t st = f->cur;
+    const OzKScale kplus{f->ozH, +1}, kminus{f->ozH, -1};
+    OzOperand oC, oS, oCS;
+    int rc;
+    CU_TRY(cudaEventRecord(f->ev_oz_a, st));
+    CU_TRY(cudaStreamWaitEvent(f->main_h, f->ev_oz_a, 0));
+    f->cur = f->main_h;
+    rc = gemm(f, 0, m, m0, n, 1.0, f->C, ldm, f->Sigma, ld, 0.0, nullptr, 0, f->CS, ldm);
+    f->cur = st;
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(f->ev_oz_b, f->main_h));
+    {
+        ProfScope ps(f, st, PROF_MISC);
+        CU_TRY(oz_split(f->C, 1, ldm, m, n, S, &oC, f->ozC, f->ozeC, st, &kplus, false, 0, m0));      // rows of C
+        f->launches += 3;
+    }
+    oS.slices = f->ozS; oS.ex = f->oz_exS[f->upd_oz_par]; oS.rows = Mc; oS.k = n; oS.rows_pad = Mc; oS.k_pad = round_up(n, OZ_KBLOCK); oS.S = S; oS.ex_margin = 0;
+    {
+        ProfEvent pe;
+        prof_begin(f, pe, st, PROF_UPDATE, 2.0 * m * Mc * n);
+        CU_TRY(oz_gemm(oC, oS, m, Mc, 1.0, 0.0, nullptr, 0, f->CS + (size_t)m0 * ldm, ldm, st));       // columns m0.. of C Sigma
+        prof_end(f, pe, st);
+        f->launches += 1;
+    }
+    // its first m0 columns: a thin DMMA product on the (still idle) helper stream of the S chain, beside everything above
+    CU_TRY(cudaStreamWaitEvent(st, f->ev_oz_b, 0));
+    {
+        ProfScope ps(f, st, PROF_MISC);
+        CU_TRY(oz_split(f->CS, 1, ldm, m, n, S, &oCS, f->ozW, f->ozeW, st, &kminus, false, 0, m0));   // rows of C Sigma
+        f->launches += 3;
+    }
+    {
+        ProfEvent pe;
+        prof_begin(f, pe, st, PROF_UPDATE, 2.0 * m * m * n);
+        CU_TRY(oz_gemm(oCS, oC, m, m, 1.0, 0.0, nullptr, 0, f->Saug, f->ld2m, st));
+        prof_end(f, pe, st);
+        f->launches += 1;
+    }
+    return EQVIO_OK;
+}
+
 static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     const int N = f->N, n = n_of(N), m = 2 * N, p = 5 + 3 * N, pb = round_up(p, 16), ld = f->ld, ldm = f->ldm;
     int st;
@@ -1049,6 +1106,9 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     f->launches += 1;
     stamp(f, s, ST_C_DELTA);
     // S = (C Sigma) C^T + Q                                        VIOFilter.cpp:276
+    if (f->upd_oz_pre) {
+        if ((st = form_S_ozaki(f))) return st;
+    } else
     if ((st = gemm_pair(f, make_problem(f, 0, m, n, n, 1.0, f->C, ldm, f->Sigma, ld, 0.0, nullptr, 0, f->CS, ldm, 0, 0.0),
                         make_problem(f, 1, m, m, n, 1.0, f->CS, ldm, f->C, ldm, 0.0, nullptr, 0, f->Saug, f->ld2m, 0, 0.0), PAIR_S))) return st;
     {
@@ -1069,6 +1129,33 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     // (a few empty kernels first: the S chain's first kernel becomes ready at the same moment and must get its SM
     // before this GEMM's 2400 CTAs occupy every slot for the next 170 us)
     for (int d = 0; d < f->trail_delay; ++d) { launch_nop(f->side); f->launches += 1; }
+    if (f->upd_oz_pre && f->upd_oz_sct) {
+        // Sigma C^T: rows [m0, n) of Sigma as the A operand (split here: rotated inner index, scales 2^(-h)), C's rows (already split for S)
+        // as B; the m0 rows in front as a thin DMMA product behind it
+        const int Mc = oz_core(n), m0 = n - Mc, S8 = f->ozaki_S;
+        const OzKScale kminus{f->ozH, -1};
+        OzOperand oSr, oCr;
+        oCr.slices = f->ozC; oCr.ex = f->ozeC; oCr.rows = m; oCr.k = n; oCr.rows_pad = round_up(m, OZ_TILE); oCr.k_pad = round_up(n, OZ_KBLOCK); oCr.S = S8; oCr.ex_margin = 0;
+        {
+            ProfScope ps(f, f->side, PROF_MISC);
+            CU_TRY(oz_split(f->Sigma + m0, 1, ld, Mc, n, S8, &oSr, f->ozR, f->ozeR, f->side, &kminus, false, 0, m0));
+            f->launches += 3;
+        }
+        {
+            ProfEvent pe;
+            prof_begin(f, pe, f->side, PROF_UPDATE, 2.0 * Mc * m * n);
+            CU_TRY(oz_gemm(oSr, oCr, Mc, m, 1.0, 0.0, nullptr, 0, f->SCt + m0, ld, f->side));
+            prof_end(f, pe, f->side);
+            f->launches += 1;
+        }
+        if ((st = gemm(f, 1, m0, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
+        {   // ... and its rows [m0, n) as the A operand of K = (Sigma C^T) S^-1 (inner index = measurement row; nothing to equilibrate)
+            ProfScope ps(f, f->side, PROF_MISC);
+            OzOperand tmp;
+            CU_TRY(oz_split(f->SCt + m0, 1, ld, Mc, m, S8, &tmp, f->ozR, f->ozeR, f->side));
+            f->launches += 3;
+        }
+    } else
     if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
     stamp(f, f->side, ST_SIDE1_DONE);
     if ((st = end_side(f))) return st;
@@ -1077,6 +1164,31 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     stamp(f, s, ST_S_CHAIN);
     if ((st = join_side(f))) return st;
     // K = (Sigma C^T) S^-1                                           :277
+    if (f->upd_oz_pre && f->upd_oz_sct) {
+        const int Mc = oz_core(n), m0 = n - Mc, S8 = f->ozaki_S;
+        OzOperand oA, oB;
+        oA.slices = f->ozR; oA.ex = f->ozeR; oA.rows = Mc; oA.k = m; oA.rows_pad = Mc; oA.k_pad = round_up(m, OZ_KBLOCK); oA.S = S8; oA.ex_margin = 0;
+        CU_TRY(cudaEventRecord(f->ev_oz_a, s));
+        CU_TRY(cudaStreamWaitEvent(f->main_h, f->ev_oz_a, 0));
+        f->cur = f->main_h;
+        st = gemm(f, 0, m0, m, m, -1.0, f->SCt, ld, negSinv, f->ld2m, 0.0, nullptr, 0, f->K, ld);   // the m0 rows in front: thin DMMA product beside
+        f->cur = s;
+        if (st) return st;
+        CU_TRY(cudaEventRecord(f->ev_oz_b, f->main_h));
+        {
+            ProfScope ps(f, s, PROF_MISC);
+            CU_TRY(oz_split(negSinv, f->ld2m, 1, m, m, S8, &oB, f->ozT, f->ozeT, s));                // columns of -S^-1
+            f->launches += 3;
+        }
+        {
+            ProfEvent pe;
+            prof_begin(f, pe, s, PROF_UPDATE, 2.0 * Mc * m * m);
+            CU_TRY(oz_gemm(oA, oB, Mc, m, -1.0, 0.0, nullptr, 0, f->K + m0, ld, s));
+            prof_end(f, pe, s);
+            f->launches += 1;
+        }
+        CU_TRY(cudaStreamWaitEvent(s, f->ev_oz_b, 0));
+    } else
     if ((st = gemm(f, 0, n, m, m, -1.0, f->SCt, ld, negSinv, f->ld2m, 0.0, nullptr, 0, f->K, ld))) return st;
     stamp(f, s, ST_K);
     {
@@ -1140,12 +1252,16 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
 static int update(Filter* f, bool do_lift, bool do_sigma) {
     f->main_dirty = true;
     // the slices of the prior Sigma the last Riccati launch emitted serve the covariance update, if nothing else touched Sigma since
-    f->upd_oz = do_sigma && f->oz_update && ozaki_fused_applies(f) && f->oz_sigma_ex_valid && f->oz_h_valid && f->oz_valid_par >= 0;
-    f->upd_oz_par = f->upd_oz ? f->oz_valid_par : 0;
+    const int oz_tiles = (oz_core(n_of(f->N)) / OZ_TILE) * (oz_core(n_of(f->N)) / OZ_TILE);
+    const bool oz_all = oz_tiles >= f->oz_all_min_tiles;
+    f->upd_oz = do_sigma && (f->oz_update < 0 ? oz_all : f->oz_update != 0) && ozaki_fused_applies(f) && f->oz_sigma_ex_valid && f->oz_h_valid && f->oz_valid_par >= 0;
+    f->upd_oz_sct = f->oz_sct < 0 ? oz_all : f->oz_sct != 0;
+    f->upd_oz_pre = f->oz_pre && ozaki_fused_applies(f) && f->oz_sigma_ex_valid && f->oz_h_valid && f->oz_valid_par >= 0;
+    f->upd_oz_par = (f->upd_oz || f->upd_oz_pre) ? f->oz_valid_par : 0;
     f->oz_h_valid = f->oz_sigma_ex_valid = false;   // Sigma changes outside the Riccati step
     int st = prepare_layout(f);
     if (st) return st;
-    const int flags = (do_lift ? 1 : 0) | (do_sigma ? 2 : 0) | (f->upd_oz ? 4 | (f->upd_oz_par << 3) : 0);
+    const int flags = (do_lift ? 1 : 0) | (do_sigma ? 2 : 0) | (f->upd_oz ? 4 : 0) | (f->upd_oz_pre ? 16 : 0) | (f->upd_oz_pre && f->upd_oz_sct ? 32 : 0) | ((f->upd_oz || f->upd_oz_pre) ? (f->upd_oz_par << 3) : 0);
     if ((st = run_graphed(f, GRAPH_UPDATE, flags, [&]() { return update_launches(f, do_lift, do_sigma); }))) return st;
     if (do_sigma) std::swap(f->Sigma, f->Sigma2);   // the update wrote the twin buffer
     return EQVIO_OK;
@@ -1243,7 +1359,7 @@ static void destroy_filter(Filter* f) {
     cudaFree(f->sk_sync); cudaFree(f->sk_ws); cudaFree(f->splitk_ws);
     for (int i = 0; i < 2; ++i) { cudaFree(f->strip_ws[i]); cudaFree(f->strip_cnt[i]); }
     for (void* q : {(void*)f->ozF[0], (void*)f->ozF[1], (void*)f->ozS, (void*)f->ozW, (void*)f->ozeF[0], (void*)f->ozeF[1], (void*)f->ozeS, (void*)f->ozeW, (void*)f->ozH}) cudaFree(q);
-    cudaFree(f->oz_words); cudaFree(f->oz_stamps); cudaFree(f->ozC); cudaFree(f->ozeC);
+    cudaFree(f->oz_words); cudaFree(f->oz_stamps); cudaFree(f->ozC); cudaFree(f->ozeC); cudaFree(f->ozR); cudaFree(f->ozeR); cudaFree(f->ozT); cudaFree(f->ozeT);
     if (f->ev_oz_a) cudaEventDestroy(f->ev_oz_a);
     if (f->ev_oz_b) cudaEventDestroy(f->ev_oz_b);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->pose_pub); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);
@@ -1299,6 +1415,8 @@ static int create_impl(Filter* f) {
     if (const char* e = getenv("EQVIO_OZAKI_FUSED")) f->oz_fused = atoi(e);
     if (const char* e = getenv("EQVIO_OZ_PDL")) f->oz_pdl = atoi(e);
     if (const char* e = getenv("EQVIO_OZ_UPDATE")) f->oz_update = atoi(e);
+    if (const char* e = getenv("EQVIO_OZ_PRE")) f->oz_pre = atoi(e);
+    if (const char* e = getenv("EQVIO_OZ_SCT")) f->oz_sct = atoi(e);
     CU_TRY(cudaEventCreateWithFlags(&f->ev_oz_a, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&f->ev_oz_b, cudaEventDisableTiming));
     if (const char* e = getenv("EQVIO_OZ_STAMPS"))

@@ -165,9 +165,10 @@ def test_fused_riccati_is_deterministic(monkeypatch):
 
 @pytest.mark.parametrize("N", [512, 470])
 def test_int8_covariance_update_matches_dmma(monkeypatch, N):
-    """Sigma <- Sigma - (K C) Sigma (VIOFilter.cpp:297) with K C and (K C) Sigma on the int8 tensor cores — the second product against the
-    slices of the prior Sigma left by the last Riccati launch — against the same update on fp64 DMMA: one whole vision period
-    (10 IMU ticks + the frame's own propagate + the update) from the same state, Riccati steps on int8 in both runs."""
+    """The vision update's six dense products — C Sigma, (C Sigma) C^T, Sigma C^T, (Sigma C^T) S^-1, K C, (K C) Sigma (VIOFilter.cpp:276-277,
+    297; reference association) — on the int8 tensor cores, C Sigma and (K C) Sigma against the slices of the prior Sigma left by the last
+    Riccati launch, against the same update on fp64 DMMA: one whole vision period (10 IMU ticks + the frame's own propagate + the
+    update) from the same state, Riccati steps on int8 in both runs."""
     from eqf_vio_b200.filter import VIOFilter
     from eqf_vio_b200.settings import conditioned_settings
     from eqf_vio_b200.synthetic import period_sequence
@@ -178,8 +179,10 @@ def test_int8_covariance_update_matches_dmma(monkeypatch, N):
     seq = period_sequence(N, 3, camera_offset=tuple(s.cameraOffset))
     _, tail = _events_after_vision(seq, 1)
     outs = []
-    for upd in ("1", "0"):   # (opt-in: EQVIO_OZ_UPDATE=1)
+    for upd in ("1", "0"):
         monkeypatch.setenv("EQVIO_OZ_UPDATE", upd)
+        monkeypatch.setenv("EQVIO_OZ_PRE", upd)
+        monkeypatch.setenv("EQVIO_OZ_SCT", upd)
         f = VIOFilter(s, device=0)
         f.set_snapshot(mid)
         for kind, i in tail[:11]:
@@ -187,9 +190,10 @@ def test_int8_covariance_update_matches_dmma(monkeypatch, N):
         assert tail[10][0] == "vision"
         outs.append(f.get_snapshot())
         f.close()
-    monkeypatch.delenv("EQVIO_OZ_UPDATE")
+    for k in ("EQVIO_OZ_UPDATE", "EQVIO_OZ_PRE", "EQVIO_OZ_SCT"):
+        monkeypatch.delenv(k)
     (h1, S1), (h0, S0) = split_snapshot(outs[0]), split_snapshot(outs[1])
-    assert np.array_equal(h1, h0)                       # K, gamma and the lift do not depend on how Sigma' is formed
+    assert np.abs(h1 - h0).max() < 1e-10, np.abs(h1 - h0).max()   # S, K and gamma come from int8 products in one run, from DMMA in the other
     assert not np.array_equal(S1, S0)                   # (the int8 path was taken)
     d = np.sqrt(np.abs(np.diag(S0)))
-    assert rel(S1, S0) < 1e-13 and (np.abs(S1 - S0) / (d[:, None] * d[None, :])).max() < 1e-11, (rel(S1, S0), (np.abs(S1 - S0) / (d[:, None] * d[None, :])).max())
+    assert rel(S1, S0) < 1e-11 and (np.abs(S1 - S0) / (d[:, None] * d[None, :])).max() < 1e-10, (rel(S1, S0), (np.abs(S1 - S0) / (d[:, None] * d[None, :])).max())
