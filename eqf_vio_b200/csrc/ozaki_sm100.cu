@@ -126,10 +126,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr) {
 static constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_TILE >> 3) << 17) | ((uint32_t)(OZ_TILE >> 4) << 24);
 
 static constexpr int OZ_SLICE_TILE_BYTES = OZ_TILE * OZ_KBLOCK;                     // 4096
-static constexpr int OZ_STAGE_BYTES = 2 * OZ_MAX_SLICES * OZ_SLICE_TILE_BYTES;      // A slices then B slices: 73728
 static constexpr int OZ_STAGES = 3;
-static constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 + 256;
-static constexpr int OZ_EPI_WARPS = 8, OZ_PRODUCER_WARP = 8, OZ_MMA_WARP = 9, OZ_THREADS = 320;
 static constexpr int OZ_DIAGS_PER_BATCH = 4;   // 4 x 128 TMEM columns
 static constexpr int OZ_SPLIT_SMEM = 32 * 129 * 8;
 
@@ -152,15 +149,30 @@ __device__ __forceinline__ double oz_pow2(int e) {   // 2^e for e in the normal 
 }
 __device__ __forceinline__ int oz_exponent(double x);
 
+// Warp roles: sixteen epilogue warps (lane quarter = warp % 4, column quarter = warp / 4: 32 accumulator columns per thread — the epilogue
+// is dependent fp64 / integer chains, more warps hide them; the first version had eight warps of 64 columns, 168 registers and spills,
+// and took 30 us of a 100 us launch), one producer, one MMA issuer.
+static constexpr int OZG_EPI_WARPS = 16, OZG_PRODUCER_WARP = 16, OZG_MMA_WARP = 17, OZG_THREADS = 576;
+static constexpr int OZG_AUX_BYTES = 128 * 8 + 128 * 4 + 6 * 128 * 8;   // per tile column: 2^(exB + margin), h (exponent outputs), B_b (Riccati epilogue)
+template <int S> struct OzGemmCfg {
+    static constexpr int STAGE_BYTES = 2 * S * OZ_SLICE_TILE_BYTES;   // A slices then B slices
+    static constexpr int PIPE_BYTES = OZ_STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = PIPE_BYTES + OZG_AUX_BYTES + 1024 + 256;
+};
+
 template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 1)
+__global__ void __launch_bounds__(OZG_THREADS, 1)
 k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const OzParams p) {
     using namespace oz;
+    using Cfg = OzGemmCfg<S>;
     extern __shared__ uint8_t oz_smem_raw[];
     const uint32_t raw = smem_u32(oz_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = oz_smem_raw + (base - raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
+    double* s_cb = reinterpret_cast<double*>(smem + Cfg::PIPE_BYTES);   // 2^(exB[col] + marginB)
+    double* s_fx = s_cb + 128;                                          // [6][128] B_b rows of the tile's columns (Riccati epilogue)
+    int* s_h = reinterpret_cast<int*>(s_fx + 6 * 128);                  // h[col + col_off] (exponent outputs)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::PIPE_BYTES + OZG_AUX_BYTES);
     uint64_t* empty = full + OZ_STAGES;
     uint64_t* acc_full = empty + OZ_STAGES;
     uint64_t* acc_empty = acc_full + 1;
@@ -175,10 +187,10 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
     if (threadIdx.x == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, OZ_EPI_WARPS);
+        mbar_init(acc_empty, OZG_EPI_WARPS);
         mbar_fence_init();
     }
-    if (warp == OZ_MMA_WARP) {   // one warp allocates all 512 TMEM columns (one CTA per SM: 216 KB of shared memory) and frees them at the end
+    if (warp == OZG_MMA_WARP) {   // one warp allocates all 512 TMEM columns (one CTA per SM) and frees them at the end
         tmem_alloc(smem_u32(tmem_slot), 512);
         tmem_relinquish();
     }
@@ -187,7 +199,7 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == OZ_PRODUCER_WARP) {
+    if (warp == OZG_PRODUCER_WARP) {
         if (lane == 0) {
             // the slice arrays are tiled [row tile][k-block][slice][128 rows x 32 B, pre-swizzled]: the nS slice tiles a batch needs for one
             // k-block are ONE contiguous run of nS x 4 KB per operand — two bulk copies per stage
@@ -201,19 +213,18 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
                     const int s = it % OZ_STAGES;
                     mbar_wait(&empty[s], ((it / OZ_STAGES) & 1) ^ 1);
                     mbar_expect_tx(&full[s], 2 * bytes);
-                    const uint32_t sa = base + s * OZ_STAGE_BYTES, sb = sa + OZ_MAX_SLICES * OZ_SLICE_TILE_BYTES;
+                    const uint32_t sa = base + s * Cfg::STAGE_BYTES, sb = sa + S * OZ_SLICE_TILE_BYTES;
                     bulk_load(sa, gA + (size_t)kb * S * OZ_SLICE_TILE_BYTES, bytes, &full[s]);
                     bulk_load(sb, gB + (size_t)kb * S * OZ_SLICE_TILE_BYTES, bytes, &full[s]);
                 }
             }
         }
-    } else if (warp == OZ_MMA_WARP) {
+    } else if (warp == OZG_MMA_WARP) {
         // The whole warp walks the loop (waits included) and ONE elected lane issues: with a single lane inside a divergent branch
         // every descriptor had to be moved from vector to uniform registers per instruction and the issue loop ran at ~160 clk per MMA
         // against the 64 clk the tensor core needs (first version: 43 % tensor-pipe active, producer never the one waited for).
         uint32_t it = 0;
-        // descriptors of slice 0 of stage 0; slice a of stage s is + (s * stage + a * tile) / 16 in the 14-bit start-address field
-        const uint64_t adesc0 = smem_desc_sw32(base), bdesc0 = smem_desc_sw32(base + OZ_MAX_SLICES * OZ_SLICE_TILE_BYTES);
+        const uint64_t adesc0 = smem_desc_sw32(base), bdesc0 = smem_desc_sw32(base + S * OZ_SLICE_TILE_BYTES);
 #pragma unroll
         for (int b = 0; b < nbatch; ++b) {
             constexpr int DPB = OZ_DIAGS_PER_BATCH;
@@ -226,7 +237,7 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
                 const int s = it % OZ_STAGES;
                 mbar_wait(&full[s], (it / OZ_STAGES) & 1);
                 tc_fence_after();
-                const uint64_t soff = (uint64_t)((s * OZ_STAGE_BYTES) >> 4);
+                const uint64_t soff = (uint64_t)((s * Cfg::STAGE_BYTES) >> 4);
                 const uint32_t first = kb > 0 ? 1u : 0u;
                 if (elect_one()) {
 #pragma unroll
@@ -245,84 +256,84 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
             __syncwarp();
         }
     } else {
-        // ===== epilogue warps: lane quarter q (TMEM lanes 32q .. 32q+31 = tile rows), column half h =====
-        const int q = warp & 3, h = warp >> 2;
-        double acc[64];
+        // ===== epilogue warps: lane quarter q (TMEM lanes 32q .. 32q+31 = tile rows), column quarter cq =====
+        const int tid = threadIdx.x;
+        const int q = warp & 3, cq = warp >> 2;
+        const bool ric = p.ric.on != 0;
+        // per-column factors of this tile, staged once while the tensor core works
+        if (tid < OZ_TILE) {
+            const int col = tile_n * OZ_TILE + tid;
+            s_cb[tid] = col < p.N ? oz_pow2(max(p.exB[col], -900) + p.marginB) : 0.0;
+            s_h[tid] = (p.exo.h && col < p.N) ? p.exo.h[col + p.exo.col_off] : 0;
+        } else if (ric && tid < OZ_TILE + 6 * 32) {
+            const int c = (tid - OZ_TILE) >> 5, l = tid & 31;
+            for (int j = l; j < OZ_TILE; j += 32) {
+                const int col = tile_n * OZ_TILE + j;
+                s_fx[c * 128 + j] = col < p.N ? p.ric.Fx[(size_t)(col + p.ric.col_off) + (size_t)p.ric.ldx * c] : 0.0;
+            }
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        double acc[32];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+        for (int j = 0; j < 32; ++j) acc[j] = 0.0;
         for (int b = 0; b < nbatch; ++b) {
             const int dmin = OZ_DIAGS_PER_BATCH * b, dmax = min(dmin + OZ_DIAGS_PER_BATCH - 1, S - 1);
             mbar_wait(acc_full, (uint32_t)(b & 1));
             tc_fence_after();
             for (int d = dmin; d <= dmax; ++d) {
                 const double scale = oz_pow2(-7 * d);
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((d - dmin) * OZ_TILE + h * 64);
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((d - dmin) * OZ_TILE + cq * 32), v);
+                tmem_ld_wait();
+                // int32 -> fp64 without the conversion unit: 2^52 + 2^31 + x has x + 2^31 in its low mantissa word
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + half * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[half * 32 + j] = fma((double)(int)v[j], scale, acc[half * 32 + j]);
-                }
+                for (int j = 0; j < 32; ++j) acc[j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0, scale, acc[j]);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
         }
         const int row = tile_m * OZ_TILE + q * 32 + lane;
-        if (row < p.M) {
-            const double ra = oz_pow2(max(p.exA[row], -900) + p.marginA - 12);
-            const int col0 = tile_n * OZ_TILE + h * 64;
-            // Riccati epilogue (VIOFilter.cpp:188-189): + T (B_b R B_b^T) as six products of the border columns, + T P on the diagonal
-            const bool ric = p.ric.on != 0;
-            const int gm = row + p.ric.row_off;
-            double wx[6] = {0, 0, 0, 0, 0, 0}, Tstep = 0.0;
-            if (ric) {
-                Tstep = *p.ric.T_dev;
+        const int lc0 = cq * 32, col0 = tile_n * OZ_TILE + lc0;
+        const bool row_ok = row < p.M;
+        const double ra = row_ok ? oz_pow2(max(p.exA[row], -900) + p.marginA - 12) : 0.0;
+        // Riccati epilogue (VIOFilter.cpp:188-189): + T (B_b R B_b^T) as six products of the border columns, + T P on the diagonal
+        const int gm = row + p.ric.row_off;
+        double wx[6] = {0, 0, 0, 0, 0, 0}, Tstep = 0.0;
+        if (ric && row_ok) {
+            Tstep = *p.ric.T_dev;
 #pragma unroll
-                for (int c = 0; c < 6; ++c) wx[c] = p.ric.Wx[(size_t)gm + (size_t)p.ric.ldx * c];
-            }
+            for (int c = 0; c < 6; ++c) wx[c] = p.ric.Wx[(size_t)gm + (size_t)p.ric.ldx * c];
+        }
+        int emax = -2000;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                const int col = col0 + j;
-                if (col < p.N) {
-                    double v = p.alpha * ((acc[j] * ra) * oz_pow2(max(p.exB[col], -900) + p.marginB));
-                    if (p.beta != 0.0) v += p.beta * p.Cin[(size_t)row + (size_t)p.ldcin * col];
-                    if (ric) {
-                        const int gn = col + p.ric.col_off;
-                        double r6 = 0.0;
+        for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            double v = 0.0;
+            if (row_ok && col < p.N) {
+                v = p.alpha * ((acc[j] * ra) * s_cb[lc0 + j]);
+                if (p.beta != 0.0) v += p.beta * p.Cin[(size_t)row + (size_t)p.ldcin * col];
+                if (ric) {
+                    const int gn = col + p.ric.col_off;
+                    double r6 = 0.0;
 #pragma unroll
-                        for (int c = 0; c < 6; ++c) r6 = fma(wx[c], p.ric.Fx[(size_t)gn + (size_t)p.ric.ldx * c], r6);
-                        v += r6;
-                        if (gm == gn) v += Tstep * (gm < 3 ? p.ric.Pd[0] : gm < 6 ? p.ric.Pd[1] : gm < 8 ? p.ric.Pd[2] : gm < 11 ? p.ric.Pd[3] : p.ric.Pd[4]);
-                    }
-                    p.D[(size_t)row + (size_t)p.ldd * col] = v;
-                    acc[j] = v;
-                } else {
-                    acc[j] = 0.0;
+                    for (int c = 0; c < 6; ++c) r6 = fma(wx[c], s_fx[c * 128 + lc0 + j], r6);
+                    v += r6;
+                    if (gm == gn) v += Tstep * (gm < 3 ? p.ric.Pd[0] : gm < 6 ? p.ric.Pd[1] : gm < 8 ? p.ric.Pd[2] : gm < 11 ? p.ric.Pd[3] : p.ric.Pd[4]);
                 }
+                p.D[(size_t)row + (size_t)p.ldd * col] = v;
+                emax = max(emax, oz_exponent(v) - s_h[lc0 + j]);
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+            acc[j] = v;
         }
         // Exponents of what was just written, for the split of this output as the next product's operand: row maxima over the columns
         // (each entry scaled by 2^(-h[column]) first) and / or column maxima over the rows (scaled by 2^(-h[row])).
-        if (p.exo.rows_out != nullptr && row < p.M) {
-            const int col0 = tile_n * OZ_TILE + h * 64;
-            int e = -2000;
-#pragma unroll
-            for (int j = 0; j < 64; ++j)
-                if (col0 + j < p.N) e = max(e, oz_exponent(acc[j]) - (p.exo.h ? p.exo.h[col0 + j + p.exo.col_off] : 0));
-            atomicMax(p.exo.rows_out + row, e);
-        }
+        if (p.exo.rows_out != nullptr && row_ok) atomicMax(p.exo.rows_out + row, emax);
         if (p.exo.cols_out != nullptr) {
-            const int col0 = tile_n * OZ_TILE + h * 64;
-            const int hr = (p.exo.h && row < p.M) ? p.exo.h[row + p.exo.row_off] : 0;
+            const int hr = (p.exo.h && row_ok) ? p.exo.h[row + p.exo.row_off] : 0;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) {
-                int e = oz_exponent(acc[j]) - hr;
+            for (int j = 0; j < 32; ++j) {
+                int e = row_ok ? oz_exponent(acc[j]) - hr : -2000;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
                 if (lane == 0 && col0 + j < p.N) atomicMax(p.exo.cols_out + col0 + j, e);
@@ -331,7 +342,7 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == OZ_MMA_WARP) {
+    if (warp == OZG_MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -905,10 +916,10 @@ static inline int oz_round_up(int a, int b) { return (a + b - 1) / b * b; }
 size_t oz_slices_bytes(int rows, int k, int S) { return (size_t)S * oz_round_up(rows, OZ_TILE) * oz_round_up(k, OZ_KBLOCK); }
 
 cudaError_t oz_init_device() {
-    cudaError_t e = cudaFuncSetAttribute(k_oz_gemm<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_oz_gemm<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzGemmCfg<7>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_oz_gemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_oz_gemm<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_oz_gemm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzGemmCfg<8>::SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_oz_gemm<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzGemmCfg<9>::SMEM_BYTES)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_oz_riccati<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzFusedCfg<7>::SMEM_BYTES)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_oz_riccati<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzFusedCfg<8>::SMEM_BYTES)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_oz_split, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SPLIT_SMEM);
@@ -977,9 +988,9 @@ cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double
     const int Mt = (M + OZ_TILE - 1) / OZ_TILE, Nt = (N + OZ_TILE - 1) / OZ_TILE;
     const dim3 grid(Mt * Nt);
     switch (A.S) {
-        case 7: k_oz_gemm<7><<<grid, OZ_THREADS, OZ_SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
-        case 8: k_oz_gemm<8><<<grid, OZ_THREADS, OZ_SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
-        case 9: k_oz_gemm<9><<<grid, OZ_THREADS, OZ_SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
+        case 7: k_oz_gemm<7><<<grid, OZG_THREADS, OzGemmCfg<7>::SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
+        case 8: k_oz_gemm<8><<<grid, OZG_THREADS, OzGemmCfg<8>::SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
+        case 9: k_oz_gemm<9><<<grid, OZG_THREADS, OzGemmCfg<9>::SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
