@@ -128,6 +128,7 @@ struct eqvio_filter {
     // rows are split on the state stream from their nine structural entries.  Exponent arrays and synchronisation words by tick parity.
     // The covariance update's two products, K C and (K C) Sigma (VIOFilter.cpp:297), on the int8 tensor cores as well when the last Riccati
     // launch's slices of the prior Sigma are still valid (no bookkeeping changed Sigma since): (K C) Sigma takes them as its B operand.
+    int sct_after = -1;            // EQVIO_SCT_AFTER=k: link of the S chain behind which Sigma C^T is queued on the int8 path (-1: 5/8 of the chain)
     int oz_sct = -1;               // Sigma C^T and K = (Sigma C^T) S^-1 (VIOFilter.cpp:277) on the int8 path as well: -1 = where the block has oz_all_min_tiles tiles
                                    // (EQVIO_OZ_SCT=0 / 1: never / always).  Measured, steps/s with S formation only -> + these two -> + the covariance update:
                                    // N = 512 2917 -> 2966 -> 3012, N = 1024 448 -> 451 -> 490, N = 384 4125 -> 4064 -> 3991
@@ -550,7 +551,7 @@ static int join_side(Filter* f) { CU_TRY(cudaStreamWaitEvent(f->stream, f->ev_jo
 //   ch.s: column panel  X U = B  as GEMM with U^-1      |  ch.h: row panel  L X = B  as GEMM with L^-1
 //   ch.h: trailing update, minus the next diagonal block        (overlaps the next chain kernel)
 // The chain is kernel -> panel -> kernel; the diagonal blocks of Aug itself are left stale (nothing reads them).
-static int schur_lu(Filter* f, const SchurChain& ch, double* Aug, int lda, int k, int r, int c) {
+static int schur_lu(Filter* f, const SchurChain& ch, double* Aug, int lda, int k, int r, int c, int hook_block = -1, const std::function<int()>* hook = nullptr) {
     struct Guard { Filter* f; cudaStream_t prev; ~Guard() { f->prof_cls = PROF_UPDATE; f->cur = prev; } } guard{f, f->cur};
     f->prof_cls = PROF_SCHUR_GEMM;
     int st;
@@ -568,6 +569,12 @@ static int schur_lu(Filter* f, const SchurChain& ch, double* Aug, int lda, int k
             CU_TRY(launch_chain_block(ch.s, Aug, lda, j, nb, j > 0 ? 64 : 0, nullptr, 0, nullptr, 0, Linv, Uinv, &f->st->flags));
         }
         f->launches += 1;
+        if (hook && j / 64 == hook_block) {   // work queued behind this link of the chain (see update_launches)
+            cudaStream_t keep = f->cur;
+            const int hs = (*hook)();
+            f->cur = keep;
+            if (hs) return hs;
+        }
         const int sbase = (ch.keep_linv ? 32 : 272) + 3 * (j / 64);   // debug stamps: chain kernel / column panel / trailing update
         if (sbase + 2 < 512) stamp(f, ch.s, sbase);
         double* Lp = Aug + (j + nb) + (size_t)lda * j;         // rows x nb, below the diagonal block
@@ -1123,43 +1130,53 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     }
     f->launches += 2;
     stamp(f, s, ST_S_FORMED);
+    const std::function<int()> sct_work = [&]() -> int {
+        int st;
     // Sigma C^T does not depend on S^-1: it runs on the side stream under the (latency-bound) elimination.  (Queued
-    // earlier, next to the two products that form S, it was measured 0.2 - 1 % slower at N = 256 / 512 / 1024.)
-    if ((st = fork_side(f))) return st;
-    // (a few empty kernels first: the S chain's first kernel becomes ready at the same moment and must get its SM
-    // before this GEMM's 2400 CTAs occupy every slot for the next 170 us)
-    for (int d = 0; d < f->trail_delay; ++d) { launch_nop(f->side); f->launches += 1; }
-    if (f->upd_oz_pre && f->upd_oz_sct) {
-        // Sigma C^T: rows [m0, n) of Sigma as the A operand (split here: rotated inner index, scales 2^(-h)), C's rows (already split for S)
-        // as B; the m0 rows in front as a thin DMMA product behind it
-        const int Mc = oz_core(n), m0 = n - Mc, S8 = f->ozaki_S;
-        const OzKScale kminus{f->ozH, -1};
-        OzOperand oSr, oCr;
-        oCr.slices = f->ozC; oCr.ex = f->ozeC; oCr.rows = m; oCr.k = n; oCr.rows_pad = round_up(m, OZ_TILE); oCr.k_pad = round_up(n, OZ_KBLOCK); oCr.S = S8; oCr.ex_margin = 0;
-        {
-            ProfScope ps(f, f->side, PROF_MISC);
-            CU_TRY(oz_split(f->Sigma + m0, 1, ld, Mc, n, S8, &oSr, f->ozR, f->ozeR, f->side, &kminus, false, 0, m0));
-            f->launches += 3;
-        }
-        {
-            ProfEvent pe;
-            prof_begin(f, pe, f->side, PROF_UPDATE, 2.0 * Mc * m * n);
-            CU_TRY(oz_gemm(oSr, oCr, Mc, m, 1.0, 0.0, nullptr, 0, f->SCt + m0, ld, f->side));
-            prof_end(f, pe, f->side);
-            f->launches += 1;
-        }
-        if ((st = gemm(f, 1, m0, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
-        {   // ... and its rows [m0, n) as the A operand of K = (Sigma C^T) S^-1 (inner index = measurement row; nothing to equilibrate)
-            ProfScope ps(f, f->side, PROF_MISC);
-            OzOperand tmp;
-            CU_TRY(oz_split(f->SCt + m0, 1, ld, Mc, m, S8, &tmp, f->ozR, f->ozeR, f->side));
-            f->launches += 3;
-        }
-    } else
-    if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
-    stamp(f, f->side, ST_SIDE1_DONE);
-    if ((st = end_side(f))) return st;
-    if ((st = schur_lu(f, SchurChain{f->stream, f->main_h, f->ev_sa, f->ev_sb, f->ev_st, f->Linv, f->Uinv, false}, f->Saug, f->ld2m, mp, m, m))) return st;
+        // earlier, next to the two products that form S, it was measured 0.2 - 1 % slower at N = 256 / 512 / 1024.)
+        if ((st = fork_side(f))) return st;
+        // (a few empty kernels first: the S chain's first kernel becomes ready at the same moment and must get its SM
+        // before this GEMM's 2400 CTAs occupy every slot for the next 170 us)
+        for (int d = 0; d < f->trail_delay; ++d) { launch_nop(f->side); f->launches += 1; }
+        if (f->upd_oz_pre && f->upd_oz_sct) {
+            // Sigma C^T: rows [m0, n) of Sigma as the A operand (split here: rotated inner index, scales 2^(-h)), C's rows (already split for S)
+            // as B; the m0 rows in front as a thin DMMA product behind it
+            const int Mc = oz_core(n), m0 = n - Mc, S8 = f->ozaki_S;
+            const OzKScale kminus{f->ozH, -1};
+            OzOperand oSr, oCr;
+            oCr.slices = f->ozC; oCr.ex = f->ozeC; oCr.rows = m; oCr.k = n; oCr.rows_pad = round_up(m, OZ_TILE); oCr.k_pad = round_up(n, OZ_KBLOCK); oCr.S = S8; oCr.ex_margin = 0;
+            {
+                ProfScope ps(f, f->side, PROF_MISC);
+                CU_TRY(oz_split(f->Sigma + m0, 1, ld, Mc, n, S8, &oSr, f->ozR, f->ozeR, f->side, &kminus, false, 0, m0));
+                f->launches += 3;
+            }
+            {
+                ProfEvent pe;
+                prof_begin(f, pe, f->side, PROF_UPDATE, 2.0 * Mc * m * n);
+                CU_TRY(oz_gemm(oSr, oCr, Mc, m, 1.0, 0.0, nullptr, 0, f->SCt + m0, ld, f->side));
+                prof_end(f, pe, f->side);
+                f->launches += 1;
+            }
+            if ((st = gemm(f, 1, m0, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
+            {   // ... and its rows [m0, n) as the A operand of K = (Sigma C^T) S^-1 (inner index = measurement row; nothing to equilibrate)
+                ProfScope ps(f, f->side, PROF_MISC);
+                OzOperand tmp;
+                CU_TRY(oz_split(f->SCt + m0, 1, ld, Mc, m, S8, &tmp, f->ozR, f->ozeR, f->side));
+                f->launches += 3;
+            }
+        } else
+        if ((st = gemm(f, 1, n, m, n, 1.0, f->Sigma, ld, f->C, ldm, 0.0, nullptr, 0, f->SCt, ld))) return st;
+        stamp(f, f->side, ST_SIDE1_DONE);
+        if ((st = end_side(f))) return st;
+        return EQVIO_OK;
+    };
+    // Where the update's big products run on the int8 path, Sigma C^T is queued behind link `sct_after` of the S chain instead of next to its
+    // first link: the chain is then the critical path of the update, its first links carry the largest trailing updates, and Sigma C^T
+    // (needed by K only) fits under the last links, whose trailing updates leave the GPU almost idle.
+    const int links = (mp + 63) / 64;
+    const int sct_after = (f->upd_oz_pre && f->upd_oz_sct) ? std::min(f->sct_after < 0 ? links * 5 / 8 : f->sct_after, links - 1) : -1;
+    if (sct_after < 0 && (st = sct_work())) return st;
+    if ((st = schur_lu(f, SchurChain{f->stream, f->main_h, f->ev_sa, f->ev_sb, f->ev_st, f->Linv, f->Uinv, false}, f->Saug, f->ld2m, mp, m, m, sct_after, sct_after >= 0 ? &sct_work : nullptr))) return st;
     const double* negSinv = f->Saug + mp + (size_t)f->ld2m * mp;
     stamp(f, s, ST_S_CHAIN);
     if ((st = join_side(f))) return st;
@@ -1417,6 +1434,7 @@ static int create_impl(Filter* f) {
     if (const char* e = getenv("EQVIO_OZ_UPDATE")) f->oz_update = atoi(e);
     if (const char* e = getenv("EQVIO_OZ_PRE")) f->oz_pre = atoi(e);
     if (const char* e = getenv("EQVIO_OZ_SCT")) f->oz_sct = atoi(e);
+    if (const char* e = getenv("EQVIO_SCT_AFTER")) f->sct_after = atoi(e);
     CU_TRY(cudaEventCreateWithFlags(&f->ev_oz_a, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&f->ev_oz_b, cudaEventDisableTiming));
     if (const char* e = getenv("EQVIO_OZ_STAMPS"))
