@@ -145,6 +145,9 @@ struct eqvio_filter {
     int* ozeC = nullptr;
     int8_t *ozR = nullptr, *ozT = nullptr;   // slices of Sigma's rows (Sigma C^T) and of S^-1's columns (K)
     int *ozeR = nullptr, *ozeT = nullptr;
+    int8_t* ozCc = nullptr;        // slices of C's columns (ozC holds its rows); both are written at their structural positions only
+    int* ozeCc = nullptr;
+    int oz_Cr_layout = 0, oz_Cc_layout = 0;   // n for which ozC / ozCc were cleared
     cudaEvent_t ev_oz_a = nullptr, ev_oz_b = nullptr;
     int oz_pdl = 1;                // the second launch of a step starts programmatically behind the first (EQVIO_OZ_PDL=0: plain stream order); N = 512: 2667 -> 2701 steps/s
     int oz_fused = 1;              // EQVIO_OZAKI_FUSED=0: the unfused sequence (split kernels and DMMA strips between the products)
@@ -366,9 +369,10 @@ static int ensure_capacity(Filter* f, int needN) {
         for (int** q : {&f->ozeF[0], &f->ozeF[1], &f->ozeS, &f->ozeW, &f->ozH}) { CU_TRY(dalloc(q, (size_t)ld + 256)); CU_TRY(cudaMemsetAsync(*q, 0, ((size_t)ld + 256) * sizeof(int), s)); }
         f->oz_bytes = bytes;
         f->oz_h_valid = f->oz_sigma_ex_valid = f->oz_F_ready = false;
-        cudaFree(f->ozC); cudaFree(f->ozeC); cudaFree(f->ozR); cudaFree(f->ozeR); cudaFree(f->ozT); cudaFree(f->ozeT);
-        for (int8_t** q : {&f->ozC, &f->ozR, &f->ozT}) { CU_TRY(cudaMalloc((void**)q, bytes)); CU_TRY(cudaMemsetAsync(*q, 0, bytes, s)); }
-        for (int** q : {&f->ozeC, &f->ozeR, &f->ozeT}) CU_TRY(dalloc(q, (size_t)ld + 256));
+        cudaFree(f->ozC); cudaFree(f->ozeC); cudaFree(f->ozR); cudaFree(f->ozeR); cudaFree(f->ozT); cudaFree(f->ozeT); cudaFree(f->ozCc); cudaFree(f->ozeCc);
+        for (int8_t** q : {&f->ozC, &f->ozR, &f->ozT, &f->ozCc}) { CU_TRY(cudaMalloc((void**)q, bytes)); CU_TRY(cudaMemsetAsync(*q, 0, bytes, s)); }
+        for (int** q : {&f->ozeC, &f->ozeR, &f->ozeT, &f->ozeCc}) CU_TRY(dalloc(q, (size_t)ld + 256));
+        f->oz_Cr_layout = f->oz_Cc_layout = 0;
         cudaFree(f->oz_words);
         const size_t ex_len = (size_t)ld + 256;
         f->oz_words_count = 4 * ex_len + 4 * OZ_FUSED_SYNC_INTS;
@@ -1005,8 +1009,9 @@ static int sigma_update_ozaki(Filter* f) {
     {
         ProfScope ps(f, st, PROF_MISC);
         CU_TRY(oz_split(f->K + m0, 1, ld, Mc, m, S, &oK, f->ozW, f->ozeW, st));                          // rows m0.. of K, inner index = measurement row
-        CU_TRY(oz_split(f->C + (size_t)m0 * ldm, ldm, 1, Mc, m, S, &oC, f->ozC, f->ozeC, st));          // columns m0.. of C
-        f->launches += 6;
+        if (f->oz_Cc_layout != n) { CU_TRY(cudaMemsetAsync(f->ozCc, 0, f->oz_bytes, st)); f->oz_Cc_layout = n; }
+        CU_TRY(oz_split_C_cols(f->C, ldm, m, n, m0, S, &oC, f->ozCc, f->ozeCc, st));                    // columns m0.. of C, from their two entries each
+        f->launches += 4;
     }
     {
         ProfEvent pe;
@@ -1063,8 +1068,9 @@ static int form_S_ozaki(Filter* f) {
     CU_TRY(cudaEventRecord(f->ev_oz_b, f->main_h));
     {
         ProfScope ps(f, st, PROF_MISC);
-        CU_TRY(oz_split(f->C, 1, ldm, m, n, S, &oC, f->ozC, f->ozeC, st, &kplus, false, 0, m0));      // rows of C
-        f->launches += 3;
+        if (f->oz_Cr_layout != n) { CU_TRY(cudaMemsetAsync(f->ozC, 0, f->oz_bytes, st)); f->oz_Cr_layout = n; }
+        CU_TRY(oz_split_C_rows(f->C, ldm, m, n, m0, S, &kplus, &oC, f->ozC, f->ozeC, st));            // rows of C, from their three entries each
+        f->launches += 1;
     }
     oS.slices = f->ozS; oS.ex = f->oz_exS[f->upd_oz_par]; oS.rows = Mc; oS.k = n; oS.rows_pad = Mc; oS.k_pad = round_up(n, OZ_KBLOCK); oS.S = S; oS.ex_margin = 0;
     {
@@ -1376,7 +1382,7 @@ static void destroy_filter(Filter* f) {
     cudaFree(f->sk_sync); cudaFree(f->sk_ws); cudaFree(f->splitk_ws);
     for (int i = 0; i < 2; ++i) { cudaFree(f->strip_ws[i]); cudaFree(f->strip_cnt[i]); }
     for (void* q : {(void*)f->ozF[0], (void*)f->ozF[1], (void*)f->ozS, (void*)f->ozW, (void*)f->ozeF[0], (void*)f->ozeF[1], (void*)f->ozeS, (void*)f->ozeW, (void*)f->ozH}) cudaFree(q);
-    cudaFree(f->oz_words); cudaFree(f->oz_stamps); cudaFree(f->ozC); cudaFree(f->ozeC); cudaFree(f->ozR); cudaFree(f->ozeR); cudaFree(f->ozT); cudaFree(f->ozeT);
+    cudaFree(f->oz_words); cudaFree(f->oz_stamps); cudaFree(f->ozC); cudaFree(f->ozeC); cudaFree(f->ozR); cudaFree(f->ozeR); cudaFree(f->ozT); cudaFree(f->ozeT); cudaFree(f->ozCc); cudaFree(f->ozeCc);
     if (f->ev_oz_a) cudaEventDestroy(f->ev_oz_a);
     if (f->ev_oz_b) cudaEventDestroy(f->ev_oz_b);
     cudaFree(f->st); cudaFree(f->sc); cudaFree(f->pose_pub); cudaFree(f->Linv); cudaFree(f->Uinv); cudaFree(f->UinvL);

@@ -81,6 +81,11 @@ cudaError_t oz_diag_scale(const double* Sigma, int ld, int n, int* h, cudaStream
 cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double alpha, double beta, const double* Cin, int ldcin, double* D,
                     int ldd, cudaStream_t stream, const OzRiccatiEpilogue* ric = nullptr, const OzExponentsOut* exo = nullptr);
 cudaError_t oz_init_device();
+// C (m x n = 2N x (11 + 3N), one 2 x 3 block per landmark) split from its structural entries: its rows (inner index = column, rotated
+// by m0, scaled by `ks`) or its columns [m0, n) (inner index = row).  `slices` must be zero outside the structural positions (they
+// depend on m, n only).
+cudaError_t oz_split_C_rows(const double* C, int ldm, int m, int n, int m0, int S, const OzKScale* ks, OzOperand* op, int8_t* slices, int* ex, cudaStream_t stream);
+cudaError_t oz_split_C_cols(const double* C, int ldm, int m, int n, int m0, int S, OzOperand* op, int8_t* slices, int* ex, cudaStream_t stream);
 
 // ---- the Riccati step as two launches of one kernel ------------------------------------------------------------------------------
 // Sigma (n x n, n = m0 + Mc) = [border: the first m0 = 11 + (3N mod 128) rows / columns, i.e. at least the base states | block: Mc = 128 Mt of landmark states].  Both products of
