@@ -1090,7 +1090,11 @@ static int form_S_ozaki(Filter* f) {
     {
         ProfEvent pe;
         prof_begin(f, pe, st, PROF_UPDATE, 2.0 * m * m * n);
-        CU_TRY(oz_gemm(oCS, oC, m, m, 1.0, 0.0, nullptr, 0, f->Saug, f->ld2m, st));
+        // (m / 128)^2 = 64 tiles at N = 512.  EQVIO_OZ_SSPLIT=1: two CTAs share a tile's k-blocks and add into the zeroed block — S is
+        // formed 23 us earlier, but 128 busy SMs instead of 64 slow the lift chain more than that (3158 -> 3127 steps/s): off
+        const int mt = (m + OZ_TILE - 1) / OZ_TILE, ks = (2 * mt * mt <= 148 && getenv("EQVIO_OZ_SSPLIT")) ? 2 : 1;
+        if (ks == 2) CU_TRY(cudaMemset2DAsync(f->Saug, (size_t)f->ld2m * 8, 0, (size_t)m * 8, m, st));
+        CU_TRY(oz_gemm(oCS, oC, m, m, 1.0, 0.0, nullptr, 0, f->Saug, f->ld2m, st, nullptr, nullptr, ks));
         prof_end(f, pe, st);
         f->launches += 1;
     }

@@ -142,6 +142,7 @@ struct OzParams {
     int ldd;
     OzRiccatiEpilogue ric;
     OzExponentsOut exo;
+    int ksplit;   // 1, or 2: every tile's k-blocks are shared by two CTAs whose fp64 results are added into a zeroed D (a + b = b + a: the order cannot matter)
 };
 
 __device__ __forceinline__ double oz_pow2(int e) {   // 2^e for e in the normal range
@@ -180,8 +181,10 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Mt = (p.M + OZ_TILE - 1) / OZ_TILE;
-    const int tile_m = blockIdx.x % Mt, tile_n = blockIdx.x / Mt;
-    const int KB = p.KB;
+    const int tile_id = (int)blockIdx.x / p.ksplit, khalf = (int)blockIdx.x - tile_id * p.ksplit;
+    const int tile_m = tile_id % Mt, tile_n = tile_id / Mt;
+    const int kb_lo = khalf * ((p.KB + p.ksplit - 1) / p.ksplit), kb_hi = min(p.KB, kb_lo + (p.KB + p.ksplit - 1) / p.ksplit);
+    const int KB = kb_hi - kb_lo;   // this CTA's k-blocks
     constexpr int nbatch = (S + OZ_DIAGS_PER_BATCH - 1) / OZ_DIAGS_PER_BATCH;
 
     if (threadIdx.x == 0) {
@@ -203,8 +206,8 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
         if (lane == 0) {
             // the slice arrays are tiled [row tile][k-block][slice][128 rows x 32 B, pre-swizzled]: the nS slice tiles a batch needs for one
             // k-block are ONE contiguous run of nS x 4 KB per operand — two bulk copies per stage
-            const int8_t* gA = slA + (size_t)tile_m * KB * S * OZ_SLICE_TILE_BYTES;
-            const int8_t* gB = slB + (size_t)tile_n * KB * S * OZ_SLICE_TILE_BYTES;
+            const int8_t* gA = slA + ((size_t)tile_m * p.KB + kb_lo) * S * OZ_SLICE_TILE_BYTES;
+            const int8_t* gB = slB + ((size_t)tile_n * p.KB + kb_lo) * S * OZ_SLICE_TILE_BYTES;
             uint32_t it = 0;
             for (int b = 0; b < nbatch; ++b) {
                 const int nS = min(OZ_DIAGS_PER_BATCH * (b + 1), S);   // slices 0 .. nS-1 of both operands take part in this batch's diagonals
@@ -321,7 +324,8 @@ k_oz_gemm(const int8_t* __restrict__ slA, const int8_t* __restrict__ slB, const 
                     v += r6;
                     if (gm == gn) v += Tstep * (gm < 3 ? p.ric.Pd[0] : gm < 6 ? p.ric.Pd[1] : gm < 8 ? p.ric.Pd[2] : gm < 11 ? p.ric.Pd[3] : p.ric.Pd[4]);
                 }
-                p.D[(size_t)row + (size_t)p.ldd * col] = v;
+                if (p.ksplit > 1) atomicAdd(p.D + (size_t)row + (size_t)p.ldd * col, v);
+                else p.D[(size_t)row + (size_t)p.ldd * col] = v;
                 emax = max(emax, oz_exponent(v) - s_h[lc0 + j]);
             }
             acc[j] = v;
@@ -1062,7 +1066,8 @@ cudaError_t oz_split_C_cols(const double* C, int ldm, int m, int n, int m0, int 
 }
 
 cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double alpha, double beta, const double* Cin, int ldcin, double* D,
-                    int ldd, cudaStream_t stream, const OzRiccatiEpilogue* ric, const OzExponentsOut* exo) {
+                    int ldd, cudaStream_t stream, const OzRiccatiEpilogue* ric, const OzExponentsOut* exo, int ksplit) {
+    if (ksplit < 1 || ksplit > 2 || (ksplit == 2 && (Cin || ric || exo))) return cudaErrorInvalidValue;   // (a split product only adds into a zeroed D)
     if (A.k_pad != B.k_pad || A.S != B.S || M > A.rows_pad || N > B.rows_pad || M < 1 || N < 1) return cudaErrorInvalidValue;
     if ((long long)A.k_pad * 64 * 64 * A.S >= (1LL << 31)) return cudaErrorInvalidValue;   // int32 accumulation of one diagonal must be exact
     OzParams p;
@@ -1072,7 +1077,8 @@ cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double
     if (ric) p.ric = *ric; else { memset(&p.ric, 0, sizeof p.ric); }
     if (exo) p.exo = *exo; else { memset(&p.exo, 0, sizeof p.exo); }
     const int Mt = (M + OZ_TILE - 1) / OZ_TILE, Nt = (N + OZ_TILE - 1) / OZ_TILE;
-    const dim3 grid(Mt * Nt);
+    p.ksplit = ksplit;
+    const dim3 grid(Mt * Nt * ksplit);
     switch (A.S) {
         case 7: k_oz_gemm<7><<<grid, OZG_THREADS, OzGemmCfg<7>::SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;
         case 8: k_oz_gemm<8><<<grid, OZG_THREADS, OzGemmCfg<8>::SMEM_BYTES, stream>>>(A.slices, B.slices, p); break;

@@ -78,8 +78,10 @@ cudaError_t oz_rowmax(const double* X, long stride_r, long stride_k, int rows, i
 cudaError_t oz_diag_scale(const double* Sigma, int ld, int n, int* h, cudaStream_t stream);
 // D[0:M, 0:N] (column-major, ldd) = alpha * A * B + beta * Cin for the split operands (A: M rows, B: N "rows" = columns of B), M and N
 // multiples of 128 up to the padding (rows beyond M / N are computed on zero slices and not stored).
+// ksplit = 2: every tile's k-blocks are shared by two CTAs that ADD their fp64 results into D, which the caller has zeroed (two terms:
+// the order of the additions cannot matter) — for products with too few tiles to fill the GPU; no Cin / ric / exo then.
 cudaError_t oz_gemm(const OzOperand& A, const OzOperand& B, int M, int N, double alpha, double beta, const double* Cin, int ldcin, double* D,
-                    int ldd, cudaStream_t stream, const OzRiccatiEpilogue* ric = nullptr, const OzExponentsOut* exo = nullptr);
+                    int ldd, cudaStream_t stream, const OzRiccatiEpilogue* ric = nullptr, const OzExponentsOut* exo = nullptr, int ksplit = 1);
 cudaError_t oz_init_device();
 // C (m x n = 2N x (11 + 3N), one 2 x 3 block per landmark) split from its structural entries: its rows (inner index = column, rotated
 // by m0, scaled by `ks`) or its columns [m0, n) (inner index = row).  `slices` must be zero outside the structural positions (they
