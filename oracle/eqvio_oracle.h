@@ -13,7 +13,7 @@
  *       place against a minimal Eigen-API stand-in (oracle/refshim/ -> oracle/_ref/libeqvio_ref.so) and
  *       compared with this restatement on identical inputs: free functions to <=1e-13, whole sequences
  *       in every Settings mode to <=1e-12, landmark bookkeeping to identical id sets
- *       (tests/test_oracle_vs_reference.py); the committed golden vectors (tests/golden/*.npz) are
+ *       (tests/test_oracle_vs_reference.py); the committed golden vectors (tests/golden/<name>.npz) are
  *       recorded from that build.  What this cannot pin is Eigen's internal kernels (the stand-in uses
  *       plain loops, LU with partial pivoting for dynamic inverse(), cofactors for 3x3).
  *   (2) the reference's own property tests (test/test_EqFMatrices.cpp, test_VIOLift.cpp,
