@@ -9,7 +9,7 @@
  * PARITY PIN STATUS: pinned against the reference's own code, not against reference-shipped vectors.
  * The reference ships no golden vectors or known-answer tests for the filter recursion (SURVEY.md §4,
  * §8c) and cannot be built as shipped (Eigen3, yaml-cpp, googletest absent, no network).  Pins:
- *   (1) the reference's UNMODIFIED translation units (eqf_vio/src/*.cpp, libs/core/src/*.cpp) compiled in
+ *   (1) the reference's UNMODIFIED translation units (every .cpp under eqf_vio/src and libs/core/src) compiled in
  *       place against a minimal Eigen-API stand-in (oracle/refshim/ -> oracle/_ref/libeqvio_ref.so) and
  *       compared with this restatement on identical inputs: free functions to <=1e-13, whole sequences
  *       in every Settings mode to <=1e-12, landmark bookkeeping to identical id sets
