@@ -135,7 +135,7 @@ struct eqvio_filter {
     int oz_all_min_tiles = 121;
     int oz_pre = 1;                // C Sigma and (C Sigma) C^T (VIOFilter.cpp:276) on the int8 path too (same validity condition as oz_update; EQVIO_OZ_PRE=0: DMMA).
                                    // Not faster than the DMMA pair in itself, but one CTA per SM on 96 + 64 SMs leaves the lift chain free SMs: N = 512 2809 -> 2917 steps/s
-    bool upd_oz_pre = false, upd_oz_sct = false;
+    bool upd_oz_pre = false, upd_oz_sct = false, upd_oz_fresh = false;
     int oz_update = -1;            // K C and (K C) Sigma: -1 = where the block has oz_all_min_tiles tiles (EQVIO_OZ_UPDATE=0 / 1: never / always).  Alone it gains nothing
                                    // (N = 512: 2774 -> 2784: its 222 KB CTAs wait for whole SMs under the lift chain's DMMA GEMMs); behind the int8 S formation,
                                    // which lets the lift chain finish 170 us earlier, it does (2966 -> 3012)
@@ -1059,6 +1059,12 @@ static int form_S_ozaki(Filter* f) {
     const OzKScale kplus{f->ozH, +1}, kminus{f->ozH, -1};
     OzOperand oC, oS, oCS;
     int rc;
+    if (f->upd_oz_fresh) {   // no slices of the prior Sigma left by a Riccati launch: scales and a generic split of its columns first
+        ProfScope ps(f, st, PROF_MISC);
+        CU_TRY(oz_diag_scale(f->Sigma, ld, n, f->ozH, st));
+        CU_TRY(oz_split(f->Sigma + (size_t)m0 * ld, ld, 1, Mc, n, S, &oS, f->ozS, f->oz_exS[f->upd_oz_par], st, &kminus, false, 0, m0));
+        f->launches += 4;
+    }
     CU_TRY(cudaEventRecord(f->ev_oz_a, st));
     CU_TRY(cudaStreamWaitEvent(f->main_h, f->ev_oz_a, 0));
     f->cur = f->main_h;
@@ -1281,14 +1287,21 @@ static int update(Filter* f, bool do_lift, bool do_sigma) {
     // the slices of the prior Sigma the last Riccati launch emitted serve the covariance update, if nothing else touched Sigma since
     const int oz_tiles = (oz_core(n_of(f->N)) / OZ_TILE) * (oz_core(n_of(f->N)) / OZ_TILE);
     const bool oz_all = oz_tiles >= f->oz_all_min_tiles;
-    f->upd_oz = do_sigma && (f->oz_update < 0 ? oz_all : f->oz_update != 0) && ozaki_fused_applies(f) && f->oz_sigma_ex_valid && f->oz_h_valid && f->oz_valid_par >= 0;
+    // The update's products on the int8 path need the prior Sigma's column slices: those the last Riccati launch emitted if nothing touched
+    // Sigma since, else (landmarks came or went, a snapshot was loaded ...) a fresh split at the head of the update — 45 us against the
+    // 390 us the int8 products save.
+    const bool oz_ok = ozaki_fused_applies(f);
+    const bool oz_have = oz_ok && f->oz_sigma_ex_valid && f->oz_h_valid && f->oz_valid_par >= 0;
+    f->upd_oz_fresh = oz_ok && !oz_have && oz_all && f->oz_pre && f->oz_update != 0 && f->oz_sct != 0;
+    const bool oz_slices = oz_have || f->upd_oz_fresh;
+    f->upd_oz = do_sigma && (f->oz_update < 0 ? oz_all : f->oz_update != 0) && oz_slices;
     f->upd_oz_sct = f->oz_sct < 0 ? oz_all : f->oz_sct != 0;
-    f->upd_oz_pre = f->oz_pre && ozaki_fused_applies(f) && f->oz_sigma_ex_valid && f->oz_h_valid && f->oz_valid_par >= 0;
-    f->upd_oz_par = (f->upd_oz || f->upd_oz_pre) ? f->oz_valid_par : 0;
+    f->upd_oz_pre = f->oz_pre && oz_slices;
+    f->upd_oz_par = oz_have ? f->oz_valid_par : 0;
     f->oz_h_valid = f->oz_sigma_ex_valid = false;   // Sigma changes outside the Riccati step
     int st = prepare_layout(f);
     if (st) return st;
-    const int flags = (do_lift ? 1 : 0) | (do_sigma ? 2 : 0) | (f->upd_oz ? 4 : 0) | (f->upd_oz_pre ? 16 : 0) | (f->upd_oz_pre && f->upd_oz_sct ? 32 : 0) | ((f->upd_oz || f->upd_oz_pre) ? (f->upd_oz_par << 3) : 0);
+    const int flags = (do_lift ? 1 : 0) | (do_sigma ? 2 : 0) | (f->upd_oz ? 4 : 0) | (f->upd_oz_pre ? 16 : 0) | (f->upd_oz_pre && f->upd_oz_sct ? 32 : 0) | (f->upd_oz_fresh ? 64 : 0) | ((f->upd_oz || f->upd_oz_pre) ? (f->upd_oz_par << 3) : 0);
     if ((st = run_graphed(f, GRAPH_UPDATE, flags, [&]() { return update_launches(f, do_lift, do_sigma); }))) return st;
     if (do_sigma) std::swap(f->Sigma, f->Sigma2);   // the update wrote the twin buffer
     return EQVIO_OK;
