@@ -47,6 +47,8 @@ print("gemm", np.abs(C - A @ B).max())
 # (tickets, tile-row barriers, emission), structural split of F, generic split kernels behind each update, and the unfused product
 if os.environ.get("EQVIO_SANITIZE_INT8", "1") != "0":
     os.environ["EQVIO_OZAKI_MIN_TILES"] = "4"
+    os.environ["EQVIO_OZ_SCT"] = "1"      # ... and the vision update's six products on the int8 path as well (structural splits of C,
+    os.environ["EQVIO_OZ_UPDATE"] = "1"   # generic splits, k_oz_gemm, thin DMMA products on the helper stream)
     s = conditioned_settings(outlierThreshold=1e9)
     seq = period_sequence(90, 3, camera_offset=tuple(s.cameraOffset))
     f = VIOFilter(s)
