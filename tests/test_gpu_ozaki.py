@@ -197,3 +197,45 @@ def test_int8_covariance_update_matches_dmma(monkeypatch, N):
     assert not np.array_equal(S1, S0)                   # (the int8 path was taken)
     d = np.sqrt(np.abs(np.diag(S0)))
     assert rel(S1, S0) < 1e-11 and (np.abs(S1 - S0) / (d[:, None] * d[None, :])).max() < 1e-10, (rel(S1, S0), (np.abs(S1 - S0) / (d[:, None] * d[None, :])).max())
+
+
+def test_int8_paths_when_landmarks_come_and_go(monkeypatch):
+    """N = 500 features; after five stable frames (their launch sequences are captured as CUDA graphs) ten ids drop out for one frame and
+    come back: Sigma is compacted and grown, the slice layouts of every int8 operand follow n, the update splits Sigma itself because
+    the Riccati launch's slices are stale.  (i) Graph replay and direct launches must agree bit for bit — what a captured sequence
+    depends on (which slice arrays must be cleared first, which exponent array is current ...) is part of its key; (ii) the int8 paths
+    must agree with the fp64 DMMA paths to round-off."""
+    from eqf_vio_b200.filter import VIOFilter
+    from eqf_vio_b200.settings import conditioned_settings
+    from eqf_vio_b200.synthetic import period_sequence
+    from helpers import split_snapshot
+
+    N = 500
+    s = conditioned_settings(outlierThreshold=1e9)
+    seq = period_sequence(N, 12, camera_offset=tuple(s.cameraOffset))
+    drop = np.arange(40, 50)
+
+    def run_it(env):
+        for k in ("EQVIO_OZAKI", "EQVIO_GRAPHS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        f = VIOFilter(s, device=0)
+        for kind, i in seq.events():
+            if kind == "imu":
+                f.processIMUData(seq.imu[i, 0], seq.imu[i, 1:4], seq.imu[i, 4:7])
+            else:
+                sel = np.setdiff1d(np.arange(N), drop) if i in (6, 9) else np.arange(N)
+                f.processVisionData(seq.vision_stamps[i], seq.ids[sel], seq.bearings[i][sel])
+        out = f.get_snapshot(), f.graph_stats(), f.riccati_int8_slices()
+        f.close()
+        return out
+
+    g, gstats, sl = run_it({})
+    d, dstats, _ = run_it({"EQVIO_GRAPHS": "0"})
+    x, _, slx = run_it({"EQVIO_OZAKI": "0"})
+    assert sl == 8 and slx == 0 and gstats[0] > 0 and dstats[0] == 0
+    assert np.array_equal(g, d)
+    (hg, Sg), (hx, Sx) = split_snapshot(g), split_snapshot(x)
+    assert int(g[0]) == N
+    assert rel(Sg, Sx) < 1e-10 and np.abs(hg - hx).max() < 1e-9, (rel(Sg, Sx), np.abs(hg - hx).max())
