@@ -993,6 +993,7 @@ cudaError_t oz_init_device() {
     if ((e = cudaFuncSetAttribute(k_oz_gemm<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzGemmCfg<9>::SMEM_BYTES)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_oz_riccati<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzFusedCfg<7>::SMEM_BYTES)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_oz_riccati<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzFusedCfg<8>::SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_oz_riccati<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzFusedCfg<9>::SMEM_BYTES)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_oz_split, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SPLIT_SMEM);
 }
 
@@ -1025,19 +1026,19 @@ cudaError_t oz_diag_scale(const double* Sigma, int ld, int n, int* h, cudaStream
     return cudaGetLastError();
 }
 
-bool oz_fused_supported(int S, int Mt) { return (S == 7 || S == 8) && Mt >= 2 && 1 + Mt <= OZ_FUSED_SYNC_INTS; }
+bool oz_fused_supported(int S, int Mt) { return S >= 7 && S <= 9 && Mt >= 2 && 1 + Mt <= OZ_FUSED_SYNC_INTS; }
 cudaError_t oz_riccati_fused(const OzFusedParams& p, int S, cudaStream_t stream, bool pdl) {
     if (!oz_fused_supported(S, p.Mt) || p.Mc != p.Mt * OZ_TILE || p.n != p.m0 + p.Mc || p.m0 < 1 || p.KB * OZ_KBLOCK < p.n) return cudaErrorInvalidValue;
     if ((long long)p.KB * OZ_KBLOCK * 64 * 64 * S >= (1LL << 31)) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(p.Mt * p.Mt); cfg.blockDim = dim3(OZF_THREADS); cfg.stream = stream;
-    cfg.dynamicSmemBytes = S == 7 ? OzFusedCfg<7>::SMEM_BYTES : OzFusedCfg<8>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = S == 7 ? OzFusedCfg<7>::SMEM_BYTES : S == 8 ? OzFusedCfg<8>::SMEM_BYTES : OzFusedCfg<9>::SMEM_BYTES;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return S == 7 ? cudaLaunchKernelEx(&cfg, k_oz_riccati<7>, p) : cudaLaunchKernelEx(&cfg, k_oz_riccati<8>, p);
+    return S == 7 ? cudaLaunchKernelEx(&cfg, k_oz_riccati<7>, p) : S == 8 ? cudaLaunchKernelEx(&cfg, k_oz_riccati<8>, p) : cudaLaunchKernelEx(&cfg, k_oz_riccati<9>, p);
 }
 cudaError_t oz_split_F_rows(const double* F, int ld, int n, int m0, int S, const int* h, int8_t* slices, int* ex, cudaStream_t stream) {
     const int Mc = n - m0, KB = (n + OZ_KBLOCK - 1) / OZ_KBLOCK;

@@ -21,7 +21,7 @@ h2, S2 = split_snapshot(o.get_snapshot())
 print("| update's products | Riccati step | rel-Frobenius(Sigma) vs C oracle | max state error / max(1, |entry|) |")
 print("|---|---|---|---|")
 for label, env in (("int8, 8 slices (default)", {}), ("fp64 DMMA", {"EQVIO_OZ_PRE": "0", "EQVIO_OZ_SCT": "0", "EQVIO_OZ_UPDATE": "0"}), ("fp64 DMMA", {"EQVIO_OZAKI": "0"}),
-                   ("int8, 7 slices", {"EQVIO_OZAKI": "7"}), ("int8, 9 slices (unfused Riccati kernels)", {"EQVIO_OZAKI": "9"})):
+                   ("int8, 7 slices", {"EQVIO_OZAKI": "7"}), ("int8, 9 slices", {"EQVIO_OZAKI": "9"})):
     for k in ("EQVIO_OZ_PRE", "EQVIO_OZ_SCT", "EQVIO_OZ_UPDATE", "EQVIO_OZAKI"):
         os.environ.pop(k, None)
     os.environ.update(env)
