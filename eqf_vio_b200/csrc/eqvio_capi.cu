@@ -137,6 +137,7 @@ struct eqvio_filter {
                                    // Not faster than the DMMA pair in itself, but one CTA per SM on 96 + 64 SMs leaves the lift chain free SMs: N = 512 2809 -> 2917 steps/s
     bool upd_oz_pre = false, upd_oz_sct = false, upd_oz_fresh = false;
     bool upd_clear_cr = false, upd_clear_cc = false;   // the structural slice arrays of C must be cleared first (their layout follows n)
+    int sigma_kcs = 1;             // Sigma - K (C Sigma) with the C Sigma of the S formation (one product) instead of the reference's association (K C) Sigma (two); EQVIO_SIGMA_KCS=0: the latter
     int oz_update = -1;            // K C and (K C) Sigma: -1 = where the block has oz_all_min_tiles tiles (EQVIO_OZ_UPDATE=0 / 1: never / always).  Alone it gains nothing
                                    // (N = 512: 2774 -> 2784: its 222 KB CTAs wait for whole SMs under the lift chain's DMMA GEMMs); behind the int8 S formation,
                                    // which lets the lift chain finish 170 us earlier, it does (2966 -> 3012)
@@ -1055,6 +1056,42 @@ static int sigma_update_ozaki(Filter* f) {
     return EQVIO_OK;
 }
 
+// Sigma' = Sigma - K (C Sigma): the same matrix as the reference's Sigma - (K C) Sigma (VIOFilter.cpp:297) by associativity, with the
+// C Sigma that S = (C Sigma) C^T was formed from (VIOFilter.cpp:276; f->CS, complete since the head of the update) — ONE product with
+// inner dimension m = 2N in place of K C (inner m) + a split + (K C) Sigma (inner n).  Rows [m0, n) x columns [m0, n) on int8: K's rows
+// and C Sigma's columns are split over the measurement index (nothing to equilibrate); the m0 rows / columns in front are DMMA
+// strips on the helper stream.  The two associations differ by rounding only (5e-15 rel-Frobenius at the ill-conditioned template
+// start-up, both 3-5e-15 from a long-double evaluation; tools/sigma_update_association.py).
+static int sigma_update_kcs_ozaki(Filter* f) {
+    const int N = f->N, n = n_of(N), m = 2 * N, ld = f->ld, ldm = f->ldm, S = f->ozaki_S;
+    const int Mc = oz_core(n), m0 = n - Mc;
+    cudaStream_t st = f->cur, sh = f->main_h;
+    int rc;
+    CU_TRY(cudaEventRecord(f->ev_oz_a, st));
+    CU_TRY(cudaStreamWaitEvent(sh, f->ev_oz_a, 0));
+    f->cur = sh;
+    if ((rc = gemm(f, 0, m0, n, m, -1.0, f->K, ld, f->CS, ldm, 1.0, f->Sigma, ld, f->Sigma2, ld))) return rc;
+    if ((rc = gemm(f, 0, n, m0, m, -1.0, f->K, ld, f->CS, ldm, 1.0, f->Sigma, ld, f->Sigma2, ld))) return rc;   // (whole columns: TMA wants 16-byte aligned bases; the corner is written twice)
+    CU_TRY(cudaEventRecord(f->ev_oz_b, sh));
+    f->cur = st;
+    OzOperand oK, oZ;
+    {
+        ProfScope ps(f, st, PROF_MISC);
+        CU_TRY(oz_split(f->K + m0, 1, ld, Mc, m, S, &oK, f->ozW, f->ozeW, st));                              // rows m0.. of K
+        CU_TRY(oz_split(f->CS + (size_t)m0 * ldm, ldm, 1, Mc, m, S, &oZ, f->ozCc, f->ozeCc, st));           // columns m0.. of C Sigma
+        f->launches += 6;
+    }
+    {
+        ProfEvent pe;
+        prof_begin(f, pe, st, PROF_UPDATE, 2.0 * Mc * Mc * m);
+        CU_TRY(oz_gemm(oK, oZ, Mc, Mc, -1.0, 1.0, f->Sigma + m0 + (size_t)m0 * ld, ld, f->Sigma2 + m0 + (size_t)m0 * ld, ld, st));
+        prof_end(f, pe, st);
+        f->launches += 1;
+    }
+    CU_TRY(cudaStreamWaitEvent(st, f->ev_oz_b, 0));
+    return EQVIO_OK;
+}
+
 // S = (C Sigma) C^T (VIOFilter.cpp:276, reference association) with both products on the int8 tensor cores: C's rows are split once
 // (rotated inner index, scales 2^(+h)) and serve as the A operand of C Sigma — against the slices of the prior Sigma the last Riccati
 // launch emitted — and as the B operand of (C Sigma) C^T, whose A operand is the split of C Sigma (scales 2^(-h)).  One CTA per SM on
@@ -1251,7 +1288,9 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
         }
         double* KC = f->Wpp[0];   // columns [0, n) of a Riccati work buffer; fixed (not parity-dependent) so that the update graph's key is not
         if (f->upd_oz) {
-            if ((st = sigma_update_ozaki(f))) return st;
+            if ((st = f->sigma_kcs ? sigma_update_kcs_ozaki(f) : sigma_update_ozaki(f))) return st;
+        } else if (f->sigma_kcs) {
+            if ((st = gemm(f, 0, n, n, m, -1.0, f->K, ld, f->CS, ldm, 1.0, f->Sigma, ld, f->Sigma2, ld))) return st;   // Sigma - K (C Sigma)
         } else
         if ((st = gemm_pair(f, make_problem(f, 0, n, n, m, 1.0, f->K, ld, f->C, ldm, 0.0, nullptr, 0, KC, ld, 0, 0.0),
                             make_problem(f, 0, n, n, n, -1.0, KC, ld, f->Sigma, ld, 1.0, f->Sigma, ld, f->Sigma2, ld, 0, 0.0), PAIR_SIGMA))) return st;
@@ -1301,16 +1340,16 @@ static int update(Filter* f, bool do_lift, bool do_sigma) {
     const bool oz_have = oz_ok && f->oz_sigma_ex_valid && f->oz_h_valid && f->oz_valid_par >= 0;
     f->upd_oz_fresh = oz_ok && !oz_have && oz_all && f->oz_pre && f->oz_update != 0 && f->oz_sct != 0;
     const bool oz_slices = oz_have || f->upd_oz_fresh;
-    f->upd_oz = do_sigma && (f->oz_update < 0 ? oz_all : f->oz_update != 0) && oz_slices;
+    f->upd_oz = do_sigma && (f->oz_update < 0 ? oz_all : f->oz_update != 0) && (f->sigma_kcs ? oz_ok : oz_slices);   // (K (C Sigma) needs no slices of Sigma)
     f->upd_oz_sct = f->oz_sct < 0 ? oz_all : f->oz_sct != 0;
     f->upd_oz_pre = f->oz_pre && oz_slices;
     f->upd_oz_par = oz_have ? f->oz_valid_par : 0;
     // (host state a captured launch sequence depends on must be in its graph key: a replayed graph does not re-evaluate it)
     const int n_now = n_of(f->N);
     f->upd_clear_cr = f->upd_oz_pre && f->oz_Cr_layout != n_now;
-    f->upd_clear_cc = f->upd_oz && f->oz_Cc_layout != n_now;
+    f->upd_clear_cc = f->upd_oz && !f->sigma_kcs && f->oz_Cc_layout != n_now;
     if (f->upd_oz_pre) f->oz_Cr_layout = n_now;
-    if (f->upd_oz) f->oz_Cc_layout = n_now;
+    if (f->upd_oz) f->oz_Cc_layout = f->sigma_kcs ? 0 : n_now;   // (the generic split of C Sigma's columns overwrites the structural layout)
     f->oz_h_valid = f->oz_sigma_ex_valid = false;   // Sigma changes outside the Riccati step
     int st = prepare_layout(f);
     if (st) return st;
@@ -1469,6 +1508,7 @@ static int create_impl(Filter* f) {
     if (const char* e = getenv("EQVIO_OZ_PDL")) f->oz_pdl = atoi(e);
     if (const char* e = getenv("EQVIO_GRAPH_CACHE")) f->graph_cache = std::max(2, atoi(e));
     if (const char* e = getenv("EQVIO_OZ_UPDATE")) f->oz_update = atoi(e);
+    if (const char* e = getenv("EQVIO_SIGMA_KCS")) f->sigma_kcs = atoi(e) != 0;
     if (const char* e = getenv("EQVIO_OZ_PRE")) f->oz_pre = atoi(e);
     if (const char* e = getenv("EQVIO_OZ_SCT")) f->oz_sct = atoi(e);
     if (const char* e = getenv("EQVIO_SCT_AFTER")) f->sct_after = atoi(e);
