@@ -136,6 +136,7 @@ struct eqvio_filter {
     int oz_pre = 1;                // C Sigma and (C Sigma) C^T (VIOFilter.cpp:276) on the int8 path too (same validity condition as oz_update; EQVIO_OZ_PRE=0: DMMA).
                                    // Not faster than the DMMA pair in itself, but one CTA per SM on 96 + 64 SMs leaves the lift chain free SMs: N = 512 2809 -> 2917 steps/s
     bool upd_oz_pre = false, upd_oz_sct = false, upd_oz_fresh = false;
+    bool upd_z_split = false;      // (within one update_launches call) C Sigma's columns were split under the S chain
     bool upd_clear_cr = false, upd_clear_cc = false;   // the structural slice arrays of C must be cleared first (their layout follows n)
     int sigma_kcs = 1;             // Sigma - K (C Sigma) with the C Sigma of the S formation (one product) instead of the reference's association (K C) Sigma (two); EQVIO_SIGMA_KCS=0: the latter
     int oz_update = -1;            // K C and (K C) Sigma: -1 = where the block has oz_all_min_tiles tiles (EQVIO_OZ_UPDATE=0 / 1: never / always).  Alone it gains nothing
@@ -151,6 +152,7 @@ struct eqvio_filter {
     int* ozeCc = nullptr;
     int oz_Cr_layout = 0, oz_Cc_layout = 0;   // n for which ozC / ozCc were cleared
     cudaEvent_t ev_oz_a = nullptr, ev_oz_b = nullptr;
+    int graph_stable = 2;          // frames without a landmark change before new graphs are captured (EQVIO_GRAPH_STABLE)
     int stable_frames = 0;         // consecutive vision frames that neither removed nor added a landmark
     int graph_cache = 16;          // cached graph executables (EQVIO_GRAPH_CACHE)
     int oz_pdl = 1;                // the second launch of a step starts programmatically behind the first (EQVIO_OZ_PDL=0: plain stream order); N = 512: 2667 -> 2701 steps/s
@@ -180,7 +182,6 @@ struct eqvio_filter {
     double *Linv = nullptr, *Uinv = nullptr;  // 64 x 64 triangular inverses of the current pivot block (S chain)
     double *LinvL = nullptr, *UinvL = nullptr;  // lift chain: every block's L_jj^-1 is kept (forward substitution), U_jj^-1 scratch
     double *yo = nullptr, *Rt = nullptr;       // D obs (p) and Ym^T Sigma_sub^-1 (4 x pb, row-major)
-    int* wave = nullptr;                        // per-block ready flags of k_lift_rsolve
     Landmarks L{nullptr, 0}, L2{nullptr, 0};
     double *Sigma = nullptr, *Sigma2 = nullptr, *F = nullptr, *W = nullptr, *Bb = nullptr, *Aug = nullptr;
     double *C = nullptr, *CS = nullptr, *SCt = nullptr, *K = nullptr, *Saug = nullptr, *Sinv = nullptr;
@@ -249,7 +250,7 @@ static int run_graphed(Filter* f, int kind, int flags, const std::function<int()
     // While landmarks come and go the keys keep changing (N, buffer parities): capturing and instantiating a graph that is replayed
     // once or never costs more than direct launches (measured under 5 % churn per frame: 2189 steps/s with captures, 2397 without
     // graphs).  Existing graphs are still replayed; new ones are captured once the landmark set has been stable for two frames.
-    if (!e->exec && f->stable_frames < 2) return body();
+    if (!e->exec && f->stable_frames < f->graph_stable) return body();
     if (!e->exec) {
         const long long before = f->launches;
         if (cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -301,8 +302,8 @@ static void free_device(Filter* f) {
     cudaFree(f->C); cudaFree(f->CS); cudaFree(f->SCt); cudaFree(f->K); cudaFree(f->Saug); cudaFree(f->Sinv);
     cudaFree(f->delta); cudaFree(f->gamma); cudaFree(f->y_in); cudaFree(f->y); cudaFree(f->scratch); cudaFree(f->Gamma);
     cudaFree(f->gemv_part); cudaFree(f->gemv_cnt); f->gemv_part = nullptr; f->gemv_cnt = nullptr;
-    cudaFree(f->d_flags); cudaFree(f->d_map); cudaFree(f->LinvL); cudaFree(f->yo); cudaFree(f->Rt); cudaFree(f->wave);
-    f->LinvL = f->yo = f->Rt = nullptr; f->wave = nullptr;
+    cudaFree(f->d_flags); cudaFree(f->d_map); cudaFree(f->LinvL); cudaFree(f->yo); cudaFree(f->Rt);
+    f->LinvL = f->yo = f->Rt = nullptr;
     f->L.base = f->L2.base = nullptr;
     f->Fpp[0] = f->Fpp[1] = f->Wpp[0] = f->Wpp[1] = nullptr;
     f->Sigma = f->Sigma2 = f->F = f->W = f->Bb = f->Aug = f->C = f->CS = f->SCt = f->K = f->Saug = f->Sinv = nullptr;
@@ -330,9 +331,7 @@ static int ensure_capacity(Filter* f, int needN) {
     double *Sigma, *Sigma2, *F, *W, *F1, *W1, *Bb, *Aug, *C, *CS, *SCt, *K, *Saug, *Sinv, *delta, *gamma, *y_in, *y, *scratch, *Gamma;
     int *d_flags, *d_map;
     double *LinvL, *yo, *Rt;
-    int* wave;
     CU_TRY(dalloc(&Rt, (size_t)4 * (ld + 64) + 64));
-    CU_TRY(dalloc(&wave, (size_t)ld / 64 + 8));
     CU_TRY(dalloc(&LinvL, (size_t)(ld / 64 + 2) * 4096 + 1024));
     CU_TRY(dalloc(&yo, (size_t)ld + 64));
     CU_TRY(dalloc(&L.base, (size_t)LM_FIELDS * cap));
@@ -403,7 +402,7 @@ static int ensure_capacity(Filter* f, int needN) {
     f->d_flags = d_flags; f->d_map = d_map;
     f->gemv_part = gemv_part; f->gemv_cnt = gemv_cnt;
     f->lift_wide = lift_wide;
-    f->LinvL = LinvL; f->yo = yo; f->Rt = Rt; f->wave = wave;
+    f->LinvL = LinvL; f->yo = yo; f->Rt = Rt;
     f->layoutN = -1;
     f->main_dirty = true;
     // pinned staging sized for the capacity
@@ -970,6 +969,7 @@ static int lift_eliminate(Filter* f, const SchurChain& ch) {
         launch_schur_setup(ch.s, f->Aug, ld, p, pb, 4, 4, 0);
         if (f->lift_wide) { launch_schur_identity_cols(ch.s, f->Aug, ld, pb + 4, p, pb + 4, pb); f->launches += 1; }
         launch_lift_features(ch.s, f->sc, f->L, N, nullptr, f->Aug, ld, pb, f->yo);
+        if (!f->lift_wide) { launch_lift_rsolve_reset(ch.s, f->Rt, pb); f->launches += 1; }
     }
     f->launches += 4;
     CU_TRY(cudaEventRecord(f->ev_lift_setup, ch.s));   // the gamma-dependent right-hand side reads what k_lift_prepare(nullptr) left in the scratch
@@ -979,7 +979,7 @@ static int lift_eliminate(Filter* f, const SchurChain& ch) {
     CU_TRY(cudaEventRecord(f->ev_lift_elim, ch.s));
     if (!f->lift_wide) {
         ProfScope ps(f, ch.s, PROF_MISC);
-        CU_TRY(launch_lift_rsolve(ch.s, f->Aug, ld, pb, f->LinvL, f->Rt, f->wave));
+        CU_TRY(launch_lift_rsolve(ch.s, f->Aug, ld, pb, f->LinvL, f->Rt, &f->st->flags));
         f->launches += 1;
     }
     stamp(f, ch.s, ST_LIFT_RSOLVE);
@@ -1078,8 +1078,13 @@ static int sigma_update_kcs_ozaki(Filter* f) {
     {
         ProfScope ps(f, st, PROF_MISC);
         CU_TRY(oz_split(f->K + m0, 1, ld, Mc, m, S, &oK, f->ozW, f->ozeW, st));                              // rows m0.. of K
-        CU_TRY(oz_split(f->CS + (size_t)m0 * ldm, ldm, 1, Mc, m, S, &oZ, f->ozCc, f->ozeCc, st));           // columns m0.. of C Sigma
-        f->launches += 6;
+        if (f->upd_z_split) {   // (already split on the side stream under the S chain)
+            oZ.slices = f->ozCc; oZ.ex = f->ozeCc; oZ.rows = Mc; oZ.k = m; oZ.rows_pad = Mc; oZ.k_pad = round_up(m, OZ_KBLOCK); oZ.S = S; oZ.ex_margin = 0;
+        } else {
+            CU_TRY(oz_split(f->CS + (size_t)m0 * ldm, ldm, 1, Mc, m, S, &oZ, f->ozCc, f->ozeCc, st));       // columns m0.. of C Sigma
+            f->launches += 3;
+        }
+        f->launches += 3;
     }
     {
         ProfEvent pe;
@@ -1157,6 +1162,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     cudaStream_t s = f->stream;
     const bool lift_chain = do_lift && f->s.useInnovationLift;
     stamp(f, s, ST_BEGIN);
+    f->upd_z_split = false;
     if (lift_chain) {
         // bundleLift's elimination of Sigma_sub (the PRIOR Sigma block, :285 precedes :297) does not depend on
         // the innovation except through one border column, so it runs on its own stream while the main stream
@@ -1209,6 +1215,13 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
                 ProfScope ps(f, f->side, PROF_MISC);
                 CU_TRY(oz_split(f->Sigma + m0, 1, ld, Mc, n, S8, &oSr, f->ozR, f->ozeR, f->side, &kminus, false, 0, m0));
                 f->launches += 3;
+                if (do_sigma && f->upd_oz && f->sigma_kcs) {
+                    // columns m0.. of C Sigma, the B operand of Sigma - K (C Sigma): split here, under the S chain, not behind K
+                    OzOperand oZ;
+                    CU_TRY(oz_split(f->CS + (size_t)m0 * ldm, ldm, 1, Mc, m, S8, &oZ, f->ozCc, f->ozeCc, f->side));
+                    f->launches += 3;
+                    f->upd_z_split = true;
+                }
             }
             {
                 ProfEvent pe;
@@ -1509,6 +1522,7 @@ static int create_impl(Filter* f) {
     if (const char* e = getenv("EQVIO_GRAPH_CACHE")) f->graph_cache = std::max(2, atoi(e));
     if (const char* e = getenv("EQVIO_OZ_UPDATE")) f->oz_update = atoi(e);
     if (const char* e = getenv("EQVIO_SIGMA_KCS")) f->sigma_kcs = atoi(e) != 0;
+    if (const char* e = getenv("EQVIO_GRAPH_STABLE")) f->graph_stable = atoi(e);
     if (const char* e = getenv("EQVIO_OZ_PRE")) f->oz_pre = atoi(e);
     if (const char* e = getenv("EQVIO_OZ_SCT")) f->oz_sct = atoi(e);
     if (const char* e = getenv("EQVIO_SCT_AFTER")) f->sct_after = atoi(e);

@@ -418,70 +418,100 @@ __global__ void __launch_bounds__(128) k_lift_features(const StepScratch* sc, La
 // Aug (with every L_jj^-1 kept), so R^T = G L^-1 is a block back-substitution from the right:
 //     R_j = (G_j - sum_{i > j} R_i L_ij) L_jj^-1,      j = last block ... 0.
 // One CTA per 64-wide block, all launched together: CTA c owns block j = nblk-1-c, streams its L_ij tiles through
-// shared memory and consumes R_i in the order they are published (release / acquire flag per block), so the
-// only serial part is one 4 x 64 x 64 product per link instead of a whole single-CTA sweep.  CTAs only wait on
-// lower-numbered CTAs, which the hardware dispatches first: no co-residency requirement.
+// shared memory and consumes R_i in the order they are published, so the only serial part is one 4 x 64 x 64
+// product per link instead of a whole single-CTA sweep.  CTAs only wait on lower-numbered CTAs, which the hardware
+// dispatches first: no co-residency requirement.
+// Hand-over: the data validates itself.  R^T is pre-filled with a NaN payload no computation produces
+// (LIFT_RT_PENDING, by k_fill_u64 at the head of the lift chain); a producer stores its 8-byte entries with plain
+// L2 stores, consumer thread (a, c) polls its own entry of R_i until it is no longer the sentinel.  One L2 write + one
+// L2 read per link instead of store, fence, release-flag, acquire-poll, load (four round trips: 6.6 -> 3.4 us per link
+// under the load of the covariance update's products).  A wait that gives up (~1 s) raises FLAG_NAN.
 // Runs on the lift stream behind the elimination, before the innovation exists; once gamma is known
 // M^T W obs = R^T yo is four dot products (k_lift_solve).
+static constexpr unsigned long long LIFT_RT_PENDING = 0xFFF8DEADBEEF5A5Aull;
+__global__ void k_fill_u64(unsigned long long* p, int n, unsigned long long v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 __global__ void __launch_bounds__(256) k_lift_rsolve(const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt,
-                                                     int* ready) {
+                                                     int* err) {
     extern __shared__ double sm_rs[];
-    double* tiles = sm_rs;                    // two L_ij buffers, 64 x 64, ld 65: the next tile loads while the flag is awaited
-    double* linv = sm_rs + 2 * 64 * 65;       // L_jj^-1, loaded once up front
-    double(*Ri)[64] = reinterpret_cast<double(*)[64]>(sm_rs + 3 * 64 * 65);
+    double* tiles = sm_rs;                    // three L_ij buffers, 64 x 64, ld 65: two tiles in flight (cp.async) under the product of a third
+    double* linv = sm_rs + 3 * 64 * 65;       // L_jj^-1, loaded once up front
+    double(*Ri)[4][64] = reinterpret_cast<double(*)[4][64]>(sm_rs + 4 * 64 * 65);   // R_i, double-buffered: one barrier per tile
     const int nblk = (pb + 63) >> 6, j = nblk - 1 - (int)blockIdx.x, j0 = j << 6, nbj = min(64, pb - j0);
     const int tid = threadIdx.x, a = tid >> 6, c = tid & 63;   // thread (a, c): entry (a, j0 + c) of R^T
     double acc = (c < nbj) ? Aug[(pb + a) + (size_t)lda * (j0 + c)] : 0.0;
-    auto load_tile = [&](int i, double* dst) {
-        const int i0 = i << 6, nbi = min(64, pb - i0);
-        for (int idx = tid; idx < 64 * 64; idx += 256) {
-            const int r = idx & 63, cc = idx >> 6;
-            dst[r + 65 * cc] = (r < nbi && cc < nbj) ? Aug[(i0 + r) + (size_t)lda * (j0 + cc)] : 0.0;
+    const unsigned tiles_s = (unsigned)__cvta_generic_to_shared(tiles);
+    const int nt = nblk - 1 - j;   // tiles L_ij to consume, i = nblk-1 ... j+1 (tile t <-> i = nblk-1-t): known up front, so the
+    // loads run two tiles ahead of the products whatever the state of the chain.  (One tile in flight, loaded through registers,
+    // made a CTA's per-tile time — not the hand-over — the period of the whole wavefront: 6.2 us per link.)
+    auto issue_tile = [&](int t) {
+        if (t < nt) {
+            const int i0 = (nblk - 1 - t) << 6, nbi = min(64, pb - i0);
+            const unsigned dst = tiles_s + (unsigned)(t % 3) * (64 * 65 * 8);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int idx = tid + 256 * u, r = idx & 63, cc = idx >> 6;
+                const bool in = r < nbi && cc < nbj;
+                const double* src = in ? Aug + (i0 + r) + (size_t)lda * (j0 + cc) : Aug;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8u * (r + 65 * cc)), "l"(src), "r"(in ? 8 : 0) : "memory");
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group past the last tile keeps the count below uniform)
     };
+    issue_tile(0);
+    issue_tile(1);
     {
         const double* Li = LinvBlocks + (size_t)j * 4096;
         for (int idx = tid; idx < 64 * 64; idx += 256) linv[(idx & 63) + 65 * (idx >> 6)] = Li[idx];
     }
-    if (nblk - 1 > j) load_tile(nblk - 1, tiles);
-    for (int i = nblk - 1; i > j; --i) {
-        const int i0 = i << 6, nbi = min(64, pb - i0);
-        const double* tile = tiles + ((nblk - 1 - i) & 1) * 64 * 65;
-        __syncthreads();   // the other buffer and R_i of the previous iteration are consumed
-        if (i - 1 > j) load_tile(i - 1, tiles + ((nblk - i) & 1) * 64 * 65);
-        if (tid == 0) {
-            int v;
-            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ready + i) : "memory"); } while (v == 0);
+    for (int t = 0; t < nt; ++t) {
+        const int i0 = (nblk - 1 - t) << 6, nbi = min(64, pb - i0);
+        const double* tile = tiles + (t % 3) * 64 * 65;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's copies of tile t have landed
+        {
+            unsigned long long v = 0ull;
+            if (c < nbi) {
+                const unsigned long long* src = reinterpret_cast<const unsigned long long*>(Rt + (size_t)a * pb + i0 + c);
+                long long spins = 0;
+                do {
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+                    if (v == LIFT_RT_PENDING && ++spins > (1ll << 26)) { atomicOr(err, FLAG_NAN); v = 0ull; }
+                } while (v == LIFT_RT_PENDING);
+            }
+            Ri[t & 1][a][c] = __longlong_as_double((long long)v);
         }
-        __syncthreads();
-        Ri[a][c] = (c < nbi) ? __ldcg(Rt + (size_t)a * pb + i0 + c) : 0.0;
-        __syncthreads();
+        __syncthreads();   // tile t and R_i are in shared memory; every thread is past the product of tile t-1
+        issue_tile(t + 2);   // into the buffer of tile t-1
         double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll 4
         for (int q = 0; q < 64; q += 4) {
-            p0 = fma(Ri[a][q], tile[q + 65 * c], p0);
-            p1 = fma(Ri[a][q + 1], tile[q + 1 + 65 * c], p1);
-            p2 = fma(Ri[a][q + 2], tile[q + 2 + 65 * c], p2);
-            p3 = fma(Ri[a][q + 3], tile[q + 3 + 65 * c], p3);
+            p0 = fma(Ri[t & 1][a][q], tile[q + 65 * c], p0);
+            p1 = fma(Ri[t & 1][a][q + 1], tile[q + 1 + 65 * c], p1);
+            p2 = fma(Ri[t & 1][a][q + 2], tile[q + 2 + 65 * c], p2);
+            p3 = fma(Ri[t & 1][a][q + 3], tile[q + 3 + 65 * c], p3);
         }
         acc -= (p0 + p1) + (p2 + p3);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     // R_j = acc * L_jj^-1 (64 x 64, identity-padded)
-    Ri[a][c] = acc;
+    Ri[0][a][c] = acc;
     __syncthreads();
     double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll 4
     for (int q = 0; q < 64; q += 4) {
-        p0 = fma(Ri[a][q], linv[q + 65 * c], p0);
-        p1 = fma(Ri[a][q + 1], linv[q + 1 + 65 * c], p1);
-        p2 = fma(Ri[a][q + 2], linv[q + 2 + 65 * c], p2);
-        p3 = fma(Ri[a][q + 3], linv[q + 3 + 65 * c], p3);
+        p0 = fma(Ri[0][a][q], linv[q + 65 * c], p0);
+        p1 = fma(Ri[0][a][q + 1], linv[q + 1 + 65 * c], p1);
+        p2 = fma(Ri[0][a][q + 2], linv[q + 2 + 65 * c], p2);
+        p3 = fma(Ri[0][a][q + 3], linv[q + 3 + 65 * c], p3);
     }
-    if (c < nbj) __stcg(Rt + (size_t)a * pb + j0 + c, (p0 + p1) + (p2 + p3));
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready + j), "r"(1) : "memory");
+    if (c < nbj) {
+        unsigned long long v = (unsigned long long)__double_as_longlong((p0 + p1) + (p2 + p3));
+        if (v == LIFT_RT_PENDING) v = 0x7FF8000000000000ull;   // (cannot come out of arithmetic; kept for the proof that no consumer waits forever)
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(Rt + (size_t)a * pb + j0 + c), "l"(v) : "memory");
+    }
 }
 
 // 4x4 Householder QR solve (EqFMatrices.cpp:240-242)
@@ -1061,7 +1091,7 @@ __global__ void k_set_inertial_points(const BaseState* st, Landmarks L, int N, c
 // ------------------------------------------------------------------------------------------------
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-static const int LIFT_RSOLVE_SMEM = (3 * 64 * 65 + 4 * 64) * (int)sizeof(double);
+static const int LIFT_RSOLVE_SMEM = (4 * 64 * 65 + 2 * 4 * 64) * (int)sizeof(double);
 static const int CHAIN_BLOCK_SMEM = (4 * 64 * LDW + 64) * (int)sizeof(double);
 // The > 48 KB dynamic shared-memory opt-in is a per-device function attribute: once per device, with it current.
 cudaError_t kernels_init_device() {
@@ -1091,11 +1121,13 @@ void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, in
                           int lda, int pb, double* yo) {
     k_lift_features<<<cdiv(N > 16 ? N : 16, 128), 128, 0, s>>>(sc, L, N, gamma, Aug, lda, pb, yo);
 }
-cudaError_t launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt, int* ready) {
+// (before the lift chain, off the critical path: every entry of R^T "pending")
+void launch_lift_rsolve_reset(cudaStream_t s, double* Rt, int pb) {
+    k_fill_u64<<<cdiv(4 * pb, 256), 256, 0, s>>>(reinterpret_cast<unsigned long long*>(Rt), 4 * pb, LIFT_RT_PENDING);
+}
+cudaError_t launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt, int* err) {
     const int nblk = (pb + 63) / 64;
-    cudaError_t e = cudaMemsetAsync(ready, 0, (size_t)nblk * sizeof(int), s);
-    if (e != cudaSuccess) return e;
-    k_lift_rsolve<<<nblk, 256, LIFT_RSOLVE_SMEM, s>>>(Aug, lda, pb, LinvBlocks, Rt, ready);
+    k_lift_rsolve<<<nblk, 256, LIFT_RSOLVE_SMEM, s>>>(Aug, lda, pb, LinvBlocks, Rt, err);
     return cudaGetLastError();
 }
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p, long rt_rs, long rt_cs, double rt_sign,

@@ -15,7 +15,8 @@ void launch_gemv(cudaStream_t s, const double* K, int ldk, int n, int m, const d
 void launch_lift_prepare(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma);
 void launch_lift_features(cudaStream_t s, const StepScratch* sc, Landmarks L, int N, const double* gamma, double* Aug,
                           int lda, int pb, double* yo);
-cudaError_t launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt, int* ready);
+void launch_lift_rsolve_reset(cudaStream_t s, double* Rt, int pb);
+cudaError_t launch_lift_rsolve(cudaStream_t s, const double* Aug, int lda, int pb, const double* LinvBlocks, double* Rt, int* err);
 // R^T = Ym^T Sigma_sub^-1, entry (a, col) = rt_sign * Rt[a * rt_rs + col * rt_cs]
 void launch_lift_solve(cudaStream_t s, BaseState* st, StepScratch* sc, const double* gamma, const double* Aug, int lda, int p, long rt_rs, long rt_cs, double rt_sign,
                        const double* Rt, const double* yo, int use_lift, int discrete, double* Gamma_out, int apply);

@@ -1,9 +1,8 @@
 #!/bin/bash
-# Round of the one-product covariance update Sigma - K (C Sigma): the whole GPU suite, then A/B against the reference's association.
+# Round after a change in the update: the whole GPU suite, the headline sizes, the in-graph timestamps of the update.
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-bash tools/gpu_ab.sh kcs EQVIO_SIGMA_KCS "0 1 0 1" 512
-bash tools/gpu_ab.sh kcs EQVIO_SIGMA_KCS "0 1" 256
-bash tools/gpu_ab.sh kcs EQVIO_SIGMA_KCS "0 1" 1024
-bash tools/gpu_ab.sh kcs EQVIO_SIGMA_KCS "0 1" 64
-timeout 200 python tools/graph_stamps.py --features 512 > gpurun_out/kcs_update_stamps_n512.txt 2>&1; tail -16 gpurun_out/kcs_update_stamps_n512.txt
+bash tools/gpu_ab.sh upd EQVIO_SIGMA_KCS "1 1" 512
+bash tools/gpu_ab.sh upd EQVIO_SIGMA_KCS "1" 256
+bash tools/gpu_ab.sh upd EQVIO_SIGMA_KCS "1" 1024
+timeout 200 python tools/graph_stamps.py --features 512 > gpurun_out/upd_update_stamps_n512.txt 2>&1; tail -16 gpurun_out/upd_update_stamps_n512.txt
