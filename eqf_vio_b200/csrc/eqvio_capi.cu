@@ -136,7 +136,7 @@ struct eqvio_filter {
     int oz_pre = 1;                // C Sigma and (C Sigma) C^T (VIOFilter.cpp:276) on the int8 path too (same validity condition as oz_update; EQVIO_OZ_PRE=0: DMMA).
                                    // Not faster than the DMMA pair in itself, but one CTA per SM on 96 + 64 SMs leaves the lift chain free SMs: N = 512 2809 -> 2917 steps/s
     bool upd_oz_pre = false, upd_oz_sct = false, upd_oz_fresh = false;
-    bool upd_z_split = false;      // (within one update_launches call) C Sigma's columns were split under the S chain
+    bool upd_z_split = false, upd_k_ex = false;   // (within one update_launches call) C Sigma's columns were split under the S chain; K's row exponents came with the K product
     bool upd_clear_cr = false, upd_clear_cc = false;   // the structural slice arrays of C must be cleared first (their layout follows n)
     int sigma_kcs = 1;             // Sigma - K (C Sigma) with the C Sigma of the S formation (one product) instead of the reference's association (K C) Sigma (two); EQVIO_SIGMA_KCS=0: the latter
     int oz_update = -1;            // K C and (K C) Sigma: -1 = where the block has oz_all_min_tiles tiles (EQVIO_OZ_UPDATE=0 / 1: never / always).  Alone it gains nothing
@@ -1077,7 +1077,7 @@ static int sigma_update_kcs_ozaki(Filter* f) {
     OzOperand oK, oZ;
     {
         ProfScope ps(f, st, PROF_MISC);
-        CU_TRY(oz_split(f->K + m0, 1, ld, Mc, m, S, &oK, f->ozW, f->ozeW, st));                              // rows m0.. of K
+        CU_TRY(oz_split(f->K + m0, 1, ld, Mc, m, S, &oK, f->ozW, f->ozeW, st, nullptr, f->upd_k_ex));      // rows m0.. of K (exponents: from the K product's epilogue if it ran on int8)
         if (f->upd_z_split) {   // (already split on the side stream under the S chain)
             oZ.slices = f->ozCc; oZ.ex = f->ozeCc; oZ.rows = Mc; oZ.k = m; oZ.rows_pad = Mc; oZ.k_pad = round_up(m, OZ_KBLOCK); oZ.S = S; oZ.ex_margin = 0;
         } else {
@@ -1162,7 +1162,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     cudaStream_t s = f->stream;
     const bool lift_chain = do_lift && f->s.useInnovationLift;
     stamp(f, s, ST_BEGIN);
-    f->upd_z_split = false;
+    f->upd_z_split = f->upd_k_ex = false;
     if (lift_chain) {
         // bundleLift's elimination of Sigma_sub (the PRIOR Sigma block, :285 precedes :297) does not depend on
         // the innovation except through one border column, so it runs on its own stream while the main stream
@@ -1195,6 +1195,10 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
         launch_schur_setup(s, f->Saug, f->ld2m, m, mp, m, m, 1);
     }
     f->launches += 2;
+    if (do_sigma && f->upd_oz && f->sigma_kcs && f->upd_oz_pre && f->upd_oz_sct) {
+        // ozeW is free from here (the split of C Sigma's rows has been consumed) until the K product maxes K's row exponents into it
+        CU_TRY(oz_reset_exponents(f->ozeW, round_up(oz_core(n), OZ_TILE), s));
+    }
     stamp(f, s, ST_S_FORMED);
     const std::function<int()> sct_work = [&]() -> int {
         int st;
@@ -1273,7 +1277,11 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
         {
             ProfEvent pe;
             prof_begin(f, pe, s, PROF_UPDATE, 2.0 * Mc * m * m);
-            CU_TRY(oz_gemm(oA, oB, Mc, m, -1.0, 0.0, nullptr, 0, f->K + m0, ld, s));
+            // (with the exponent maxima of K's rows for the split at the head of the covariance update: no separate pass over K there)
+            const OzExponentsOut exo{f->ozeW, nullptr, nullptr, 0, 0};
+            const bool k_ex = do_sigma && f->upd_oz && f->sigma_kcs;
+            CU_TRY(oz_gemm(oA, oB, Mc, m, -1.0, 0.0, nullptr, 0, f->K + m0, ld, s, nullptr, k_ex ? &exo : nullptr));
+            f->upd_k_ex = k_ex;
             prof_end(f, pe, s);
             f->launches += 1;
         }
@@ -1281,6 +1289,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     } else
     if ((st = gemm(f, 0, n, m, m, -1.0, f->SCt, ld, negSinv, f->ld2m, 0.0, nullptr, 0, f->K, ld))) return st;
     stamp(f, s, ST_K);
+    if (do_sigma) CU_TRY(cudaEventRecord(f->ev_fork, s));   // the covariance update needs K, not gamma: its fork point
     {
         ProfScope ps(f, s, PROF_MISC);
         launch_gemv(s, f->K, ld, n, m, f->delta, f->gamma, f->gemv_part, f->gemv_cnt);  // :279
@@ -1291,7 +1300,8 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
     // (:285-296) reads the prior Sigma and gamma and writes X.  Independent: the two GEMMs go to the side
     // stream and run under the lift's Schur elimination.
     if (do_sigma) {
-        if ((st = fork_side(f))) return st;
+        CU_TRY(cudaStreamWaitEvent(f->side, f->ev_fork, 0));   // (recorded behind K, in front of the gamma product)
+        f->cur = f->side;
         if (lift_chain && (f->sigma_after_lift == 1 || (f->sigma_after_lift < 0 && n >= 1024))) {
             // ... but (for large n) not before that elimination is through: its chain kernels (one CTA, 139 KB of shared memory) cannot
             // get an SM while 2400 long-lived GEMM CTAs keep every slot taken, and a stalled chain costs more than the
