@@ -30,6 +30,20 @@ for kind, i in seq.events():
     else:
         f.processVisionData(seq.vision_stamps[i], seq.ids, seq.bearings[i])
 print("N 40 fixed: graph replays", f.graph_stats(), "finite", np.isfinite(f.stateCovariance()).all())
+# the narrow lift form of capacities > 256 at a size a sanitizer can afford (forced): k_fill_u64 + k_lift_rsolve (cp.async tile ring,
+# self-validating hand-over of R between its CTAs) behind the elimination, 5 blocks
+os.environ["EQVIO_LIFT_NARROW"] = "1"
+s = conditioned_settings(outlierThreshold=1e9)
+seq = period_sequence(90, 3, camera_offset=tuple(s.cameraOffset))
+f = VIOFilter(s)
+for kind, i in seq.events():
+    if kind == "imu":
+        f.processIMUData(seq.imu[i, 0], seq.imu[i, 1:4], seq.imu[i, 4:7])
+    else:
+        f.processVisionData(seq.vision_stamps[i], seq.ids, seq.bearings[i])
+print("N 90 narrow lift: finite", np.isfinite(f.stateCovariance()).all(), "device flags", f.deviceFlags())
+f.close()
+del os.environ["EQVIO_LIFT_NARROW"]
 # the pair kernel (ticket + row-block counters between CTAs) at a ragged multi-row-block size, both second-product layouts
 from eqf_vio_b200.filter import dgemm_pair
 for tB2 in (True, False):
