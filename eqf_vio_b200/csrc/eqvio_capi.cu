@@ -459,7 +459,8 @@ static void prof_end(Filter* f, ProfEvent& pe, cudaStream_t s) {
 }
 
 enum { ST_BEGIN = 0, ST_LIFT_SETUP, ST_LIFT_CHAIN, ST_LIFT_RSOLVE, ST_C_DELTA, ST_S_FORMED, ST_S_CHAIN, ST_K, ST_GAMMA,
-       ST_SIDE1_DONE, ST_LIFT_JOIN, ST_LIFT_FEATURES, ST_LIFT_APPLIED, ST_SIDE2_DONE, ST_END, ST_COUNT };
+       ST_SIDE1_DONE, ST_LIFT_JOIN, ST_LIFT_FEATURES, ST_LIFT_APPLIED, ST_SIDE2_DONE, ST_END,
+       ST_SIG_SPLIT, ST_SIG_STRIPS, ST_SINV_SPLIT, ST_CS_DONE, ST_CS_SPLIT, ST_COUNT };
 static void stamp(Filter* f, cudaStream_t s, int idx) {
     if (f->stamps) { launch_stamp(s, f->stamps + idx); f->launches += 1; }
 }
@@ -1072,6 +1073,7 @@ static int sigma_update_kcs_ozaki(Filter* f) {
     f->cur = sh;
     if ((rc = gemm(f, 0, m0, n, m, -1.0, f->K, ld, f->CS, ldm, 1.0, f->Sigma, ld, f->Sigma2, ld))) return rc;
     if ((rc = gemm(f, 0, n, m0, m, -1.0, f->K, ld, f->CS, ldm, 1.0, f->Sigma, ld, f->Sigma2, ld))) return rc;   // (whole columns: TMA wants 16-byte aligned bases; the corner is written twice)
+    stamp(f, sh, ST_SIG_STRIPS);
     CU_TRY(cudaEventRecord(f->ev_oz_b, sh));
     f->cur = st;
     OzOperand oK, oZ;
@@ -1086,6 +1088,7 @@ static int sigma_update_kcs_ozaki(Filter* f) {
         }
         f->launches += 3;
     }
+    stamp(f, st, ST_SIG_SPLIT);
     {
         ProfEvent pe;
         prof_begin(f, pe, st, PROF_UPDATE, 2.0 * Mc * Mc * m);
@@ -1135,6 +1138,7 @@ static int form_S_ozaki(Filter* f) {
         prof_end(f, pe, st);
         f->launches += 1;
     }
+    stamp(f, st, ST_CS_DONE);
     // its first m0 columns: a thin DMMA product on the (still idle) helper stream of the S chain, beside everything above
     CU_TRY(cudaStreamWaitEvent(st, f->ev_oz_b, 0));
     {
@@ -1142,6 +1146,7 @@ static int form_S_ozaki(Filter* f) {
         CU_TRY(oz_split(f->CS, 1, ldm, m, n, S, &oCS, f->ozW, f->ozeW, st, &kminus, false, 0, m0));   // rows of C Sigma
         f->launches += 3;
     }
+    stamp(f, st, ST_CS_SPLIT);
     {
         ProfEvent pe;
         prof_begin(f, pe, st, PROF_UPDATE, 2.0 * m * m * n);
@@ -1274,6 +1279,7 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
             CU_TRY(oz_split(negSinv, f->ld2m, 1, m, m, S8, &oB, f->ozT, f->ozeT, s));                // columns of -S^-1
             f->launches += 3;
         }
+        stamp(f, s, ST_SINV_SPLIT);
         {
             ProfEvent pe;
             prof_begin(f, pe, s, PROF_UPDATE, 2.0 * Mc * m * m);
@@ -1306,6 +1312,9 @@ static int update_launches(Filter* f, bool do_lift, bool do_sigma) {
             // ... but (for large n) not before that elimination is through: its chain kernels (one CTA, 139 KB of shared memory) cannot
             // get an SM while 2400 long-lived GEMM CTAs keep every slot taken, and a stalled chain costs more than the
             // GEMMs gain by starting early.  The R^T back-substitution that follows the elimination starts first.
+            // (Still the rule with the one int8 product of Sigma - K (C Sigma), N = 512: no wait 3331 -> 3308 steps/s (elimination
+            // +70 us under 144 one-per-SM CTAs); only the product waiting, as two launches of 72 tiles: 3296; the block shrunk to
+            // 11 x 11 tiles with 139-wide strips: 3303 — profiles/r02u_sigma_update_placement.md.)
             CU_TRY(cudaStreamWaitEvent(f->side, f->ev_lift_elim, 0));
             for (int d = 0; d < f->trail_delay; ++d) { launch_nop(f->side); f->launches += 1; }
         }
