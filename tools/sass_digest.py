@@ -1,7 +1,7 @@
 """Per-kernel SASS digest of the shipped library: instruction counts that show which hardware paths a kernel uses.
     python tools/sass_digest.py eqf_vio_b200/csrc/libeqvio_b200.so > profiles/r02_sass_digest.md
 UTMALDG = TMA tile load (cp.async.bulk.tensor), SYNCS = mbarrier, DMMA = fp64 tensor core (mma.sync m8n8k4.f64),
-UTC*MMA / LDTM = tcgen05 MMA / TMEM load, LDS.64 / STS = shared-memory traffic, BAR = CTA barriers."""
+UTC*MMA / LDTM = tcgen05 MMA / TMEM load, LDGSTS = cp.async, UBLKCP = cp.async.bulk, LDS / STS = shared-memory traffic, BAR = CTA barriers."""
 import re
 import subprocess
 import sys
@@ -12,7 +12,7 @@ out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True
 demangle = subprocess.run(["cu++filt"], input="\n".join(re.findall(r"Function : (\S+)", out)), capture_output=True, text=True).stdout.split("\n")
 names = re.findall(r"Function : (\S+)", out)
 dm = dict(zip(names, demangle))
-keys = ["UTMALDG", "UTMASTG", "SYNCS", "DMMA", "UTC", "LDTM", "STTM", "IMMA", "LDS", "STS", "LDG", "STG", "BAR", "ATOM", "RED", "MUFU", "DFMA", "DADD", "DMUL", "SHFL"]
+keys = ["UTMALDG", "UTMASTG", "SYNCS", "DMMA", "UTC", "LDTM", "STTM", "IMMA", "LDS", "STS", "LDGSTS", "UBLKCP", "LDG", "STG", "BAR", "ATOM", "RED", "MUFU", "DFMA", "DADD", "DMUL", "SHFL"]
 print("| kernel | SASS instr | " + " | ".join(keys) + " |")
 print("|---|---|" + "---|" * len(keys))
 blocks = re.split(r"\n\s*Function : ", out)
