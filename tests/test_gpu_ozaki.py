@@ -165,10 +165,10 @@ def test_fused_riccati_is_deterministic(monkeypatch):
 
 @pytest.mark.parametrize("N", [512, 470])
 def test_int8_covariance_update_matches_dmma(monkeypatch, N):
-    """The vision update's six dense products — C Sigma, (C Sigma) C^T, Sigma C^T, (Sigma C^T) S^-1, K C, (K C) Sigma (VIOFilter.cpp:276-277,
-    297; reference association) — on the int8 tensor cores, C Sigma and (K C) Sigma against the slices of the prior Sigma left by the last
-    Riccati launch, against the same update on fp64 DMMA: one whole vision period (10 IMU ticks + the frame's own propagate + the
-    update) from the same state, Riccati steps on int8 in both runs."""
+    """The vision update's dense products — C Sigma, (C Sigma) C^T, Sigma C^T, (Sigma C^T) S^-1 and K (C Sigma) (VIOFilter.cpp:276-277,
+    297) — on the int8 tensor cores, C Sigma against the slices of the prior Sigma left by the last Riccati launch, against the same
+    update on fp64 DMMA: one whole vision period (10 IMU ticks + the frame's own propagate + the update) from the same state, Riccati
+    steps on int8 in both runs."""
     from eqf_vio_b200.filter import VIOFilter
     from eqf_vio_b200.settings import conditioned_settings
     from eqf_vio_b200.synthetic import period_sequence
@@ -239,3 +239,59 @@ def test_int8_paths_when_landmarks_come_and_go(monkeypatch):
     (hg, Sg), (hx, Sx) = split_snapshot(g), split_snapshot(x)
     assert int(g[0]) == N
     assert rel(Sg, Sx) < 1e-10 and np.abs(hg - hx).max() < 1e-9, (rel(Sg, Sx), np.abs(hg - hx).max())
+
+
+@pytest.mark.parametrize("N", [512, 64])
+def test_covariance_update_associations_agree(monkeypatch, N):
+    """Sigma - K (C Sigma) (what the path evaluates: one product, C Sigma from the S formation) against the reference's evaluation order
+    Sigma - (K C) Sigma (VIOFilter.cpp:297; EQVIO_SIGMA_KCS=0), on the int8 path (N = 512) and on DMMA (N = 64): the same matrix up
+    to rounding, the lifted state (which does not depend on the covariance update) bit for bit."""
+    from eqf_vio_b200.filter import VIOFilter
+    from eqf_vio_b200.settings import conditioned_settings
+    from eqf_vio_b200.synthetic import period_sequence
+    from helpers import feed, split_snapshot
+
+    s = conditioned_settings(outlierThreshold=1e9)
+    seq = period_sequence(N, 2, camera_offset=tuple(s.cameraOffset))
+    outs = []
+    for kcs in ("1", "0"):
+        monkeypatch.setenv("EQVIO_SIGMA_KCS", kcs)
+        f = VIOFilter(s, device=0)
+        for kind, i in seq.events():
+            feed(f, seq, kind, i)
+        outs.append(f.get_snapshot())
+        f.close()
+    monkeypatch.delenv("EQVIO_SIGMA_KCS")
+    (h1, S1), (h0, S0) = split_snapshot(outs[0]), split_snapshot(outs[1])
+    assert not np.array_equal(S1, S0)                   # (two different evaluation orders ran)
+    d = np.sqrt(np.abs(np.diag(S0)))
+    assert rel(S1, S0) < 1e-12 and (np.abs(S1 - S0) / (d[:, None] * d[None, :])).max() < 1e-10, (rel(S1, S0), (np.abs(S1 - S0) / (d[:, None] * d[None, :])).max())
+    assert np.abs(h1 - h0).max() < 1e-10, np.abs(h1 - h0).max()
+
+
+def test_narrow_lift_back_substitution_matches_wide_form(monkeypatch):
+    """bundleLift's R^T = Ym^T Sigma_sub^-1 (EqFMatrices.cpp:239-242) by k_lift_rsolve (the form of capacities > 256, forced here at
+    N = 90: five CTAs with their cp.async tile rings handing R over through self-validating entries) against the identity-bordered
+    elimination of capacities <= 256, two vision periods."""
+    from eqf_vio_b200.filter import VIOFilter
+    from eqf_vio_b200.settings import conditioned_settings
+    from eqf_vio_b200.synthetic import period_sequence
+    from helpers import feed, split_snapshot
+
+    s = conditioned_settings(outlierThreshold=1e9)
+    seq = period_sequence(90, 2, camera_offset=tuple(s.cameraOffset))
+    outs = []
+    for narrow in (True, False):
+        if narrow:
+            monkeypatch.setenv("EQVIO_LIFT_NARROW", "1")
+        f = VIOFilter(s, device=0)
+        for kind, i in seq.events():
+            feed(f, seq, kind, i)
+        assert f.deviceFlags() == 0
+        outs.append(f.get_snapshot())
+        f.close()
+        if narrow:
+            monkeypatch.delenv("EQVIO_LIFT_NARROW")
+    (h1, S1), (h0, S0) = split_snapshot(outs[0]), split_snapshot(outs[1])
+    assert not np.array_equal(h1, h0)                   # (two different forms ran)
+    assert np.abs(h1 - h0).max() < 1e-9 and rel(S1, S0) < 1e-11, (np.abs(h1 - h0).max(), rel(S1, S0))
