@@ -170,7 +170,8 @@ def config_dict(N: int, variant: str = "") -> dict:
                     "BASELINE.md section 7)",
         "step": "one vision period = 10 IMU ticks + 1 vision frame = 11 filter steps, 11 Riccati propagates + 1 update",
         "l2": "flushed between bench steps (256 MiB write, untimed)",
-        "association": "reference order: (F Sigma) F^T, (C Sigma) C^T, (Sigma C^T) S^-1, (K C) Sigma",
+        "association": "reference order for (F Sigma) F^T, (C Sigma) C^T, (Sigma C^T) S^-1; the covariance update K C Sigma is evaluated as (K C) Sigma by the "
+                       "reference arm and as K (C Sigma), with the C Sigma of the S formation, by the B200 arm (same matrix by associativity, 5e-15 apart)",
     }
     if variant:
         d["variant"] = variant
